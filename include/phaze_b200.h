@@ -1,0 +1,136 @@
+/*
+ * phaze_b200.h — C ABI of the B200-native batched phase-vocoder pitch shifter.
+ *
+ * This library replaces ONE path of olvb/phaze: the per-quantum
+ *     process(inputs, outputs, {pitchFactor})
+ * of its AudioWorklet processor, i.e.
+ *     /root/reference/src/ola-processor.js:159-171   (OLAProcessor.process)
+ *     /root/reference/src/phase-vocoder.js:45-72     (PhaseVocoderProcessor.processOLA)
+ * including everything those call (Hann window, fft.js realTransform /
+ * completeSpectrum / inverseTransform, peak picking, region shifting, the
+ * overlap-add ring).  All compute runs in hand-written sm_100a CUDA kernels;
+ * there is no CPU fallback: every entry point fails with PVB_ERR_CUDA when no
+ * usable device is present.
+ *
+ * The signatures are plain C (pointers and sizes, no torch / CUDA types) so the
+ * same shared object is bound by the Node N-API shim (addon/phaze_napi.c), by
+ * ctypes (phaze_b200/_lib.py) and by C/C++ hosts.  One handle == one
+ * PhaseVocoderProcessor instance with all of its channels flattened
+ * (inputs x channels) into `num_channels` independent mono streams.
+ *
+ * Threading: like the reference (one audio render thread), a handle is NOT
+ * thread-safe; use one caller thread per handle.
+ */
+#ifndef PHAZE_B200_H
+#define PHAZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVB_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define PVB_API __attribute__((visibility("default")))
+#else
+#define PVB_API
+#endif
+
+/* error codes (0 == success) */
+enum {
+    PVB_OK = 0,
+    PVB_ERR_BAD_SIZE = -1,   /* frame size not a power of two in [256, 4096]  (fft.js ctor throw,
+                                www/phase-vocoder.js:6-7), hop does not divide it or hop % 4 != 0 */
+    PVB_ERR_BAD_ARG = -2,    /* NULL handle / pointer, negative channel count, bad state blob      */
+    PVB_ERR_CUDA = -3,       /* CUDA runtime / driver error, or no sm_100 device                   */
+    PVB_ERR_NOMEM = -4       /* host or device allocation failed                                   */
+};
+
+typedef struct pvb_processor pvb_processor;
+
+/* Replaces the constructor options of PhaseVocoderProcessor / OLAProcessor
+ * (phase-vocoder.js:24-43, ola-processor.js:7-34).  The reference hard-codes
+ * frame 2048 (phase-vocoder.js:6) and hop 128 (ola-processor.js:3,15); both are
+ * parameters here and frame_size == 0 / hop_size == 0 select those defaults. */
+typedef struct pvb_config {
+    int32_t frame_size;    /* BUFFERED_BLOCK_SIZE; power of two, 256..4096; 0 -> 2048         */
+    int32_t hop_size;      /* WEBAUDIO_BLOCK_SIZE == samples per process() call; 0 -> 128     */
+    int32_t num_channels;  /* flattened inputs x channels handled by this handle (>= 0)       */
+    int32_t device;        /* CUDA device ordinal; -1 -> current device                       */
+} pvb_config;
+
+PVB_API int32_t pvb_version(void);
+PVB_API const char *pvb_error_string(int32_t code);
+
+/* new PhaseVocoderProcessor(options) — phase-vocoder.js:24-43.  State (input
+ * history, overlap-add accumulator, timeCursor) starts at zero like the JS. */
+PVB_API int32_t pvb_create(const pvb_config *cfg, pvb_processor **out);
+/* garbage collection of the processor */
+PVB_API void pvb_destroy(pvb_processor *p);
+/* text of the last error seen on this handle (never NULL) */
+PVB_API const char *pvb_last_error(const pvb_processor *p);
+
+/* process(inputs, outputs, parameters) — ola-processor.js:159-171 — on HOST
+ * buffers.  in / out: [num_channels][hop_size] float32, packed.  `in` is not
+ * modified (ola-processor.js:105 copies first), `out` is fully overwritten
+ * (ola-processor.js:115).  in == NULL is the paused case: every channel gets a
+ * block of zeros and timeCursor still advances (ola-processor.js:93-100).
+ * pitch_factor is the LAST element of parameters.pitchFactor
+ * (phase-vocoder.js:47), a float32 like every AudioParam value.
+ * Synchronous: `out` is valid on return, as in the JS. */
+PVB_API int32_t pvb_process(pvb_processor *p, const float *in, float *out, float pitch_factor);
+
+/* Same call on DEVICE buffers, asynchronous on `stream` (a cudaStream_t passed
+ * as void*; NULL -> the handle's own stream).  Used by hosts that already keep
+ * audio in HBM (the multi-GPU sharded host, the benchmark).  in == NULL: paused. */
+PVB_API int32_t pvb_process_device(pvb_processor *p, const float *in_dev, float *out_dev,
+                           float pitch_factor, void *stream);
+
+/* K consecutive process() calls of one pitch factor in a single submission
+ * (in/out: [K][num_channels][hop_size]); bit-identical to K pvb_process_device
+ * calls.  Host variant copies once each way. */
+PVB_API int32_t pvb_process_many_device(pvb_processor *p, const float *in_dev, float *out_dev,
+                                int32_t num_calls, float pitch_factor, void *stream);
+PVB_API int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t num_calls,
+                         float pitch_factor);
+
+/* wait for everything submitted on the handle's own stream */
+PVB_API int32_t pvb_sync(pvb_processor *p);
+
+/* reallocateChannelsIfNeeded — ola-processor.js:38-52: a changed channel count
+ * re-allocates the buffers (state -> 0) and keeps timeCursor. */
+PVB_API int32_t pvb_resize(pvb_processor *p, int32_t num_channels);
+/* back to the freshly constructed state (all zero, timeCursor 0) */
+PVB_API int32_t pvb_reset(pvb_processor *p);
+
+/* introspection */
+PVB_API int32_t pvb_frame_size(const pvb_processor *p);
+PVB_API int32_t pvb_hop_size(const pvb_processor *p);
+PVB_API int32_t pvb_num_channels(const pvb_processor *p);
+/* this.timeCursor (phase-vocoder.js:31,71): hop_size * (process calls so far) */
+PVB_API double pvb_time_cursor(const pvb_processor *p);
+PVB_API int32_t pvb_set_time_cursor(pvb_processor *p, double samples);
+/* number of CUDA kernels this handle has launched since creation */
+PVB_API int64_t pvb_kernel_launches(const pvb_processor *p);
+
+/* checkpoint / resume of the per-channel state.  Blob layout (float32):
+ * [num_channels][frame_size] input history in time order (oldest first),
+ * then [num_channels][frame_size] overlap-add accumulator in time order, i.e.
+ * exactly inputBuffers[..][0..N) and outputBuffers[..][0..N) of the reference
+ * after a process() call.  pvb_state_bytes() == 2*C*N*4. */
+PVB_API size_t pvb_state_bytes(const pvb_processor *p);
+PVB_API int32_t pvb_get_state(pvb_processor *p, float *blob_host);
+PVB_API int32_t pvb_set_state(pvb_processor *p, const float *blob_host);
+
+/* pinned host memory for callers that want the host<->device copies of
+ * pvb_process() to run at full PCIe speed */
+PVB_API void *pvb_alloc_host(size_t bytes);
+PVB_API void pvb_free_host(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHAZE_B200_H */

@@ -1,0 +1,422 @@
+// pv_api.cu — host side of the C ABI declared in include/phaze_b200.h.
+//
+// Owns the per-handle device state (history ring, overlap-add ring, tables), the
+// stream, and the launch of the fused kernel in pv_kernel.cuh.  No compute happens on
+// the host: if there is no CUDA device every entry point reports PVB_ERR_CUDA.
+#include "../../include/phaze_b200.h"
+#include "pv_kernel.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+struct pvb_processor {
+    int n = 0, hop = 0, overlaps = 0, channels = 0, device = 0;
+    uint64_t ring_calls = 0;     // process() calls since the rings were last zeroed / set
+    uint64_t cursor_calls = 0;   // timeCursor / hop (pv:31,71)
+    float *d_hist = nullptr, *d_acc = nullptr, *d_window = nullptr;
+    float2 *d_tw = nullptr;
+    float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
+    size_t staging_floats = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    char err[256] = "";
+};
+
+namespace {
+
+thread_local char g_create_err[256] = "";
+
+int fail(pvb_processor *p, int code, const char *fmt, ...) {
+    char *dst = p ? p->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PVB_CUDA(p, call)                                                              \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return fail((p), PVB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+bool valid_frame(int n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
+
+template <int N>
+cudaError_t launch_n(const pvb::FrameParams &fp, cudaStream_t s) {
+    using G = pvb::Geo<N>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_kernel<N>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(G::SMEM_BYTES));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int pairs = (fp.num_channels + 1) / 2;
+    const int grid = (pairs + G::G - 1) / G::G;
+    if (grid == 0) return cudaSuccess;
+    pvb::pv_process_kernel<N><<<grid, G::THREADS, G::SMEM_BYTES, s>>>(fp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch(int n, const pvb::FrameParams &fp, cudaStream_t s) {
+    switch (n) {
+        case 256: return launch_n<256>(fp, s);
+        case 512: return launch_n<512>(fp, s);
+        case 1024: return launch_n<1024>(fp, s);
+        case 2048: return launch_n<2048>(fp, s);
+        case 4096: return launch_n<4096>(fp, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// number of source bins that can land inside [0, nb): for pitchFactor >= 1 only bins
+// 0..N/2 (delta >= 0); below 1 the last region reaches up to nb + nb*(1-pf) (pv:133,150).
+int source_limit(int n, float pitch_factor) {
+    const int nb = n / 2 + 1;
+    if (!(pitch_factor < 1.0f)) return nb;
+    double lim = double(nb) + std::ceil(double(nb) * (1.0 - double(pitch_factor))) + 2.0;
+    if (!(lim < double(n))) return n;      // also catches NaN / negative factors
+    if (lim < nb) lim = nb;
+    return int(lim);
+}
+
+int alloc_state(pvb_processor *p, int channels) {
+    cudaFree(p->d_hist);
+    cudaFree(p->d_acc);
+    p->d_hist = p->d_acc = nullptr;
+    p->channels = channels;
+    const size_t bytes = size_t(channels > 0 ? channels : 1) * size_t(p->n) * sizeof(float);
+    if (cudaMalloc(&p->d_hist, bytes) != cudaSuccess || cudaMalloc(&p->d_acc, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(p, PVB_ERR_NOMEM, "cudaMalloc of %zu state bytes failed", 2 * bytes);
+    }
+    PVB_CUDA(p, cudaMemsetAsync(p->d_hist, 0, bytes, p->stream));
+    PVB_CUDA(p, cudaMemsetAsync(p->d_acc, 0, bytes, p->stream));
+    p->ring_calls = 0;
+    return PVB_OK;
+}
+
+int ensure_staging(pvb_processor *p, size_t floats) {
+    if (floats <= p->staging_floats) return PVB_OK;
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    cudaFree(p->d_in);
+    cudaFree(p->d_out);
+    p->d_in = p->d_out = nullptr;
+    p->staging_floats = 0;
+    if (cudaMalloc(&p->d_in, floats * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->d_out, floats * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(p, PVB_ERR_NOMEM, "cudaMalloc of staging buffers failed");
+    }
+    p->staging_floats = floats;
+    return PVB_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls, float pf,
+           cudaStream_t s) {
+    const size_t block = size_t(p->channels) * size_t(p->hop);
+    for (int k = 0; k < num_calls; k++) {
+        pvb::FrameParams fp;
+        fp.in = in_dev ? in_dev + size_t(k) * block : nullptr;
+        fp.out = out_dev + size_t(k) * block;
+        fp.hist = p->d_hist;
+        fp.acc = p->d_acc;
+        fp.window = p->d_window;
+        fp.tw = p->d_tw;
+        fp.num_channels = p->channels;
+        fp.hop = p->hop;
+        fp.overlaps = p->overlaps;
+        fp.ring_base = int(p->ring_calls % uint64_t(p->overlaps)) * p->hop;
+        fp.step_mod_r = int(p->cursor_calls % uint64_t(p->overlaps));
+        fp.src_limit = source_limit(p->n, pf);
+        fp.pitch_factor = pf;
+        if (p->channels > 0) {
+            PVB_CUDA(p, launch(p->n, fp, s));
+            p->launches++;
+        }
+        p->ring_calls++;
+        p->cursor_calls++;   // pv:71, once per call for all channels
+    }
+    return PVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pvb_version(void) { return PVB_VERSION; }
+
+const char *pvb_error_string(int32_t code) {
+    switch (code) {
+        case PVB_OK: return "ok";
+        case PVB_ERR_BAD_SIZE: return "FFT size must be a power of two in [256, 4096] and hop must divide it";
+        case PVB_ERR_BAD_ARG: return "bad argument";
+        case PVB_ERR_CUDA: return "CUDA error (no CPU fallback exists)";
+        case PVB_ERR_NOMEM: return "out of memory";
+    }
+    return "unknown error";
+}
+
+const char *pvb_last_error(const pvb_processor *p) { return p ? p->err : g_create_err; }
+
+int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
+    if (!cfg || !out) return fail(nullptr, PVB_ERR_BAD_ARG, "pvb_create: NULL argument");
+    *out = nullptr;
+    const int n = cfg->frame_size ? cfg->frame_size : 2048;    // pv:6
+    const int hop = cfg->hop_size ? cfg->hop_size : 128;       // ola:3
+    if (!valid_frame(n))
+        return fail(nullptr, PVB_ERR_BAD_SIZE, "FFT size must be a power of two in [256, 4096], got %d", n);
+    if (hop < 4 || hop > n || n % hop != 0 || hop % 4 != 0)
+        return fail(nullptr, PVB_ERR_BAD_SIZE, "hop %d must divide frame %d and be a multiple of 4", hop, n);
+    if (cfg->num_channels < 0) return fail(nullptr, PVB_ERR_BAD_ARG, "negative channel count");
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, PVB_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    int dev = cfg->device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= count) return fail(nullptr, PVB_ERR_BAD_ARG, "device %d out of range (%d devices)", dev, count);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major < 10)
+        return fail(nullptr, PVB_ERR_CUDA, "device %d is not sm_100 class (kernels are sm_100a only)", dev);
+
+    pvb_processor *p = new (std::nothrow) pvb_processor();
+    if (!p) return fail(nullptr, PVB_ERR_NOMEM, "host allocation failed");
+    p->n = n;
+    p->hop = hop;
+    p->overlaps = n / hop;     // ola:17
+    p->device = dev;
+    DeviceGuard guard(dev);
+
+    auto bail = [&](int code) { strncpy(g_create_err, p->err, 255); pvb_destroy(p); return code; };
+    if (cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(p, PVB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail(PVB_ERR_CUDA);
+    }
+
+    // tables, computed in double like the JS and rounded once to float32
+    std::vector<float> win(n);
+    std::vector<float2> tw(n);
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < n; i++) win[i] = float(0.5 * (1 - std::cos(2 * pi * i / n)));   // pv:10-12
+    for (int j = 0; j < n; j++) {
+        double c = std::cos(2 * pi * j / n), s = -std::sin(2 * pi * j / n);
+        if (j % (n / 4) == 0) {    // exact quarter turns
+            const int qd = j / (n / 4);
+            c = (qd == 0) ? 1 : (qd == 2) ? -1 : 0;
+            s = (qd == 1) ? -1 : (qd == 3) ? 1 : 0;
+        }
+        tw[j] = make_float2(float(c), float(s));
+    }
+    if (cudaMalloc(&p->d_window, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->d_tw, n * sizeof(float2)) != cudaSuccess) {
+        fail(p, PVB_ERR_NOMEM, "cudaMalloc of tables failed");
+        return bail(PVB_ERR_NOMEM);
+    }
+    if (cudaMemcpy(p->d_window, win.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(p, PVB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail(PVB_ERR_CUDA);
+    }
+    int rc = alloc_state(p, cfg->num_channels);
+    if (rc != PVB_OK) return bail(rc);
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) {
+        fail(p, PVB_ERR_CUDA, "state initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail(PVB_ERR_CUDA);
+    }
+    *out = p;
+    return PVB_OK;
+}
+
+void pvb_destroy(pvb_processor *p) {
+    if (!p) return;
+    DeviceGuard guard(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    cudaFree(p->d_hist);
+    cudaFree(p->d_acc);
+    cudaFree(p->d_window);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_in);
+    cudaFree(p->d_out);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int32_t pvb_process_many_device(pvb_processor *p, const float *in_dev, float *out_dev,
+                                int32_t num_calls, float pitch_factor, void *stream) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    if (!out_dev || num_calls < 0) return fail(p, PVB_ERR_BAD_ARG, "pvb_process: bad argument");
+    DeviceGuard guard(p->device);
+    return submit(p, in_dev, out_dev, num_calls, pitch_factor,
+                  stream ? static_cast<cudaStream_t>(stream) : p->stream);
+}
+
+int32_t pvb_process_device(pvb_processor *p, const float *in_dev, float *out_dev,
+                           float pitch_factor, void *stream) {
+    return pvb_process_many_device(p, in_dev, out_dev, 1, pitch_factor, stream);
+}
+
+int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t num_calls,
+                         float pitch_factor) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    if (!out || num_calls < 0) return fail(p, PVB_ERR_BAD_ARG, "pvb_process: bad argument");
+    DeviceGuard guard(p->device);
+    const size_t floats = size_t(p->channels) * size_t(p->hop) * size_t(num_calls);
+    if (floats == 0) {
+        p->ring_calls += num_calls;
+        p->cursor_calls += num_calls;
+        return PVB_OK;
+    }
+    int rc = ensure_staging(p, floats);
+    if (rc != PVB_OK) return rc;
+    if (in) PVB_CUDA(p, cudaMemcpyAsync(p->d_in, in, floats * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    rc = submit(p, in ? p->d_in : nullptr, p->d_out, num_calls, pitch_factor, p->stream);
+    if (rc != PVB_OK) return rc;
+    PVB_CUDA(p, cudaMemcpyAsync(out, p->d_out, floats * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    return PVB_OK;
+}
+
+int32_t pvb_process(pvb_processor *p, const float *in, float *out, float pitch_factor) {
+    return pvb_process_many(p, in, out, 1, pitch_factor);
+}
+
+int32_t pvb_sync(pvb_processor *p) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    DeviceGuard guard(p->device);
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    return PVB_OK;
+}
+
+int32_t pvb_resize(pvb_processor *p, int32_t num_channels) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    if (num_channels < 0) return fail(p, PVB_ERR_BAD_ARG, "negative channel count");
+    DeviceGuard guard(p->device);
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    cudaFree(p->d_in);
+    cudaFree(p->d_out);
+    p->d_in = p->d_out = nullptr;
+    p->staging_floats = 0;
+    int rc = alloc_state(p, num_channels);     // ola:54-88: fresh zeroed buffers
+    if (rc != PVB_OK) return rc;
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    return PVB_OK;
+}
+
+int32_t pvb_reset(pvb_processor *p) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    DeviceGuard guard(p->device);
+    const size_t bytes = size_t(p->channels > 0 ? p->channels : 1) * size_t(p->n) * sizeof(float);
+    PVB_CUDA(p, cudaMemsetAsync(p->d_hist, 0, bytes, p->stream));
+    PVB_CUDA(p, cudaMemsetAsync(p->d_acc, 0, bytes, p->stream));
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    p->ring_calls = 0;
+    p->cursor_calls = 0;
+    return PVB_OK;
+}
+
+int32_t pvb_frame_size(const pvb_processor *p) { return p ? p->n : PVB_ERR_BAD_ARG; }
+int32_t pvb_hop_size(const pvb_processor *p) { return p ? p->hop : PVB_ERR_BAD_ARG; }
+int32_t pvb_num_channels(const pvb_processor *p) { return p ? p->channels : PVB_ERR_BAD_ARG; }
+double pvb_time_cursor(const pvb_processor *p) { return p ? double(p->cursor_calls) * p->hop : 0.0; }
+int64_t pvb_kernel_launches(const pvb_processor *p) { return p ? p->launches : 0; }
+
+int32_t pvb_set_time_cursor(pvb_processor *p, double samples) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    // the reference only ever holds multiples of hopSize here (pv:71)
+    const double calls = samples / p->hop;
+    if (!(samples >= 0) || calls != std::floor(calls) || calls > 9.0e15)
+        return fail(p, PVB_ERR_BAD_ARG, "timeCursor must be a non-negative multiple of the hop size");
+    p->cursor_calls = uint64_t(calls);
+    return PVB_OK;
+}
+
+size_t pvb_state_bytes(const pvb_processor *p) {
+    return p ? size_t(2) * size_t(p->channels) * size_t(p->n) * sizeof(float) : 0;
+}
+
+int32_t pvb_get_state(pvb_processor *p, float *blob) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    if (!blob) return fail(p, PVB_ERR_BAD_ARG, "NULL state blob");
+    DeviceGuard guard(p->device);
+    const size_t cn = size_t(p->channels) * size_t(p->n);
+    if (cn == 0) return PVB_OK;
+    std::vector<float> ring(2 * cn);
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    PVB_CUDA(p, cudaMemcpy(ring.data(), p->d_hist, cn * sizeof(float), cudaMemcpyDeviceToHost));
+    PVB_CUDA(p, cudaMemcpy(ring.data() + cn, p->d_acc, cn * sizeof(float), cudaMemcpyDeviceToHost));
+    const int n = p->n, hop = p->hop;
+    const int rb = int(p->ring_calls % uint64_t(p->overlaps)) * hop;
+    for (int c = 0; c < p->channels; c++) {
+        const float *h = ring.data() + size_t(c) * n, *a = ring.data() + cn + size_t(c) * n;
+        float *ho = blob + size_t(c) * n, *ao = blob + cn + size_t(c) * n;
+        for (int j = 0; j < n; j++) {
+            ho[j] = h[(j + rb) & (n - 1)];
+            ao[j] = (j < n - hop) ? a[(j + rb) & (n - 1)] : 0.0f;    // ola:134: the tail is zero
+        }
+    }
+    return PVB_OK;
+}
+
+int32_t pvb_set_state(pvb_processor *p, const float *blob) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    if (!blob) return fail(p, PVB_ERR_BAD_ARG, "NULL state blob");
+    DeviceGuard guard(p->device);
+    const size_t cn = size_t(p->channels) * size_t(p->n);
+    if (cn == 0) return PVB_OK;
+    std::vector<float> ring(2 * cn);
+    const int n = p->n, hop = p->hop;
+    const int rb = int(p->ring_calls % uint64_t(p->overlaps)) * hop;
+    for (int c = 0; c < p->channels; c++) {
+        float *h = ring.data() + size_t(c) * n, *a = ring.data() + cn + size_t(c) * n;
+        const float *hi = blob + size_t(c) * n, *ai = blob + cn + size_t(c) * n;
+        for (int j = 0; j < n; j++) {
+            h[(j + rb) & (n - 1)] = hi[j];
+            a[(j + rb) & (n - 1)] = (j < n - hop) ? ai[j] : 0.0f;
+        }
+    }
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    PVB_CUDA(p, cudaMemcpy(p->d_hist, ring.data(), cn * sizeof(float), cudaMemcpyHostToDevice));
+    PVB_CUDA(p, cudaMemcpy(p->d_acc, ring.data() + cn, cn * sizeof(float), cudaMemcpyHostToDevice));
+    return PVB_OK;
+}
+
+void *pvb_alloc_host(size_t bytes) {
+    void *ptr = nullptr;
+    if (cudaMallocHost(&ptr, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return ptr;
+}
+
+void pvb_free_host(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,221 @@
+"""Host-side mirror of the reference's processor interface, over the C ABI.
+
+The reference's public surface for this path is one class,
+``PhaseVocoderProcessor extends OLAProcessor`` (src/phase-vocoder.js:16-176,
+src/ola-processor.js:6-176), registered as "phase-vocoder-processor", with
+
+    static get parameterDescriptors()        -> [{name: 'pitchFactor', defaultValue: 1.0}]
+    constructor(options)                     options.numberOfInputs / numberOfOutputs
+    process(inputs, outputs, parameters)     -> true
+
+Node is not available in this image, so this module is the host layer the tests drive;
+``addon/`` holds the N-API shim + JS class a Node host would load instead (same C ABI).
+Names and argument meaning follow the JS; arrays are numpy float32 instead of Float32Array.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+
+PROCESSOR_NAME = "phase-vocoder-processor"       # phase-vocoder.js:176
+BUFFERED_BLOCK_SIZE = 2048                       # phase-vocoder.js:6
+WEBAUDIO_BLOCK_SIZE = 128                        # ola-processor.js:3
+
+
+class BatchedPhaseVocoder:
+    """One C-ABI handle: `num_channels` independent mono streams, packed [C][hop] blocks.
+
+    This is the fast path a host with many streams uses (pvb_process / pvb_process_device).
+    """
+
+    def __init__(self, num_channels: int, frame_size: int = BUFFERED_BLOCK_SIZE,
+                 hop_size: int = WEBAUDIO_BLOCK_SIZE, device: int = -1):
+        self._lib = _lib.load()
+        cfg = _lib.PvbConfig(frame_size, hop_size, num_channels, device)
+        h = C.c_void_p()
+        rc = self._lib.pvb_create(C.byref(cfg), C.byref(h))
+        if rc != _lib.PVB_OK:
+            _lib.check(None, rc)
+        self._h = h
+        self.frame_size = self._lib.pvb_frame_size(h)
+        self.hop_size = self._lib.pvb_hop_size(h)
+
+    # -- lifetime ---------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pvb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- properties -------------------------------------------------------------------
+    @property
+    def num_channels(self) -> int:
+        return self._lib.pvb_num_channels(self._h)
+
+    @property
+    def time_cursor(self) -> float:
+        return self._lib.pvb_time_cursor(self._h)
+
+    @time_cursor.setter
+    def time_cursor(self, samples: float):
+        _lib.check(self._h, self._lib.pvb_set_time_cursor(self._h, float(samples)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return self._lib.pvb_kernel_launches(self._h)
+
+    # -- process ----------------------------------------------------------------------
+    def process(self, block: np.ndarray | None, pitch_factor: float,
+                out: np.ndarray | None = None) -> np.ndarray:
+        """One process() call on host arrays: block [C][hop] float32 (None == paused)."""
+        Cn, hop = self.num_channels, self.hop_size
+        if out is None:
+            out = np.empty((Cn, hop), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (Cn, hop)
+        inp = None
+        if block is not None:
+            block = np.ascontiguousarray(block, np.float32)
+            if block.shape != (Cn, hop):
+                raise ValueError(f"expected block of shape {(Cn, hop)}, got {block.shape}")
+            inp = block.ctypes.data
+        rc = self._lib.pvb_process(self._h, inp, out.ctypes.data, np.float32(pitch_factor))
+        _lib.check(self._h, rc)
+        return out
+
+    def process_many(self, blocks: np.ndarray, pitch_factor: float,
+                     out: np.ndarray | None = None) -> np.ndarray:
+        """K consecutive process() calls: blocks [K][C][hop] float32."""
+        blocks = np.ascontiguousarray(blocks, np.float32)
+        K = blocks.shape[0]
+        if blocks.shape != (K, self.num_channels, self.hop_size):
+            raise ValueError(f"expected [K][{self.num_channels}][{self.hop_size}], got {blocks.shape}")
+        if out is None:
+            out = np.empty_like(blocks)
+        rc = self._lib.pvb_process_many(self._h, blocks.ctypes.data, out.ctypes.data, K,
+                                        np.float32(pitch_factor))
+        _lib.check(self._h, rc)
+        return out
+
+    def run(self, signal: np.ndarray, pitch_factor: float, calls_per_submit: int = 16) -> np.ndarray:
+        """signal [C][T*hop] -> [C][T*hop], i.e. T consecutive process() calls."""
+        signal = np.ascontiguousarray(signal, np.float32)
+        Cn, total = signal.shape
+        hop = self.hop_size
+        assert Cn == self.num_channels and total % hop == 0
+        T = total // hop
+        blocks = np.ascontiguousarray(signal.reshape(Cn, T, hop).transpose(1, 0, 2))
+        out = np.empty_like(blocks)
+        for k in range(0, T, calls_per_submit):
+            self.process_many(blocks[k:k + calls_per_submit], pitch_factor, out[k:k + calls_per_submit])
+        return np.ascontiguousarray(out.transpose(1, 0, 2)).reshape(Cn, total)
+
+    def process_device(self, in_ptr: int | None, out_ptr: int, pitch_factor: float,
+                       stream: int | None = None, num_calls: int = 1):
+        """Asynchronous call(s) on device pointers (e.g. torch tensor .data_ptr())."""
+        rc = self._lib.pvb_process_many_device(self._h, in_ptr, out_ptr, num_calls,
+                                               np.float32(pitch_factor), stream)
+        _lib.check(self._h, rc)
+
+    def sync(self):
+        _lib.check(self._h, self._lib.pvb_sync(self._h))
+
+    def resize(self, num_channels: int):
+        _lib.check(self._h, self._lib.pvb_resize(self._h, num_channels))
+
+    def reset(self):
+        _lib.check(self._h, self._lib.pvb_reset(self._h))
+
+    # -- checkpoint / resume ----------------------------------------------------------
+    def get_state(self) -> dict:
+        Cn, N = self.num_channels, self.frame_size
+        blob = np.empty((2, Cn, N), np.float32)
+        _lib.check(self._h, self._lib.pvb_get_state(self._h, blob.ctypes.data))
+        return {"input_history": blob[0].copy(), "output_accumulator": blob[1].copy(),
+                "time_cursor": self.time_cursor}
+
+    def set_state(self, state: dict):
+        Cn, N = self.num_channels, self.frame_size
+        blob = np.empty((2, Cn, N), np.float32)
+        blob[0] = state["input_history"]
+        blob[1] = state["output_accumulator"]
+        _lib.check(self._h, self._lib.pvb_set_state(self._h, blob.ctypes.data))
+        self.time_cursor = state["time_cursor"]
+
+
+class PhaseVocoderProcessor:
+    """Drop-in mirror of the reference class (phase-vocoder.js:16-174).
+
+    ``process(inputs, outputs, parameters)`` takes the Web Audio nesting:
+    inputs[i][j] / outputs[i][j] are float32 arrays of one render quantum for input i,
+    channel j; parameters["pitchFactor"] is an array of length 1 or hop whose LAST
+    element is used (phase-vocoder.js:47).  Returns True (ola-processor.js:170).
+    """
+
+    @staticmethod
+    def parameterDescriptors():
+        return [{"name": "pitchFactor", "defaultValue": 1.0}]        # phase-vocoder.js:17-22
+
+    def __init__(self, options: dict | None = None):
+        options = dict(options or {})
+        # The reference overwrites processorOptions with {blockSize: 2048} (phase-vocoder.js:25-27)
+        # and fixes the hop at 128 (ola-processor.js:15).  frameSize / hopSize are an
+        # extension; leaving them out reproduces the reference.
+        po = options.get("processorOptions") or {}
+        self.blockSize = int(po.get("frameSize", BUFFERED_BLOCK_SIZE))
+        self.hopSize = int(po.get("hopSize", WEBAUDIO_BLOCK_SIZE))
+        self.nbInputs = int(options.get("numberOfInputs", 1))          # ola-processor.js:10
+        self.nbOutputs = int(options.get("numberOfOutputs", 1))        # ola-processor.js:11
+        self.nbOverlaps = self.blockSize // self.hopSize               # ola-processor.js:17
+        self.fftSize = self.blockSize
+        self._device = int(options.get("device", -1))
+        # one handle per input, 1 channel each until we know more (ola-processor.js:23-26)
+        self._inputs = [BatchedPhaseVocoder(1, self.blockSize, self.hopSize, self._device)
+                        for _ in range(self.nbInputs)]
+
+    @property
+    def timeCursor(self) -> float:
+        return self._inputs[0].time_cursor if self._inputs else 0.0
+
+    def close(self):
+        for h in self._inputs:
+            h.close()
+        self._inputs = []
+
+    def process(self, inputs: Sequence[Sequence[np.ndarray]], outputs: Sequence[Sequence[np.ndarray]],
+                parameters: dict) -> bool:
+        pf_arr = np.asarray(parameters["pitchFactor"], np.float32).reshape(-1)
+        pitch_factor = pf_arr[-1]                                       # phase-vocoder.js:47
+        # paused playback: zero-length blocks on the first input (ola-processor.js:93)
+        paused = len(inputs[0]) > 0 and len(inputs[0][0]) == 0
+        for i in range(self.nbInputs):
+            chans = inputs[i]
+            h = self._inputs[i]
+            if len(chans) != h.num_channels:                            # ola-processor.js:38-45
+                cursor = h.time_cursor
+                h.resize(len(chans))
+                h.time_cursor = cursor
+            if len(chans) == 0:
+                h.process(None, pitch_factor)                           # keeps timeCursor in step
+                continue
+            if len(outputs[i]) < len(chans):
+                raise TypeError("outputs[%d] has fewer channels than inputs[%d]" % (i, i))
+            block = None if paused else np.stack([np.asarray(c, np.float32) for c in chans])
+            res = h.process(block, pitch_factor)
+            for j in range(len(chans)):                                 # ola-processor.js:111-118
+                outputs[i][j][...] = res[j]
+        return True                                                     # ola-processor.js:170

@@ -1,0 +1,56 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bar (BASELINE.json north_star): RMS error <= 1e-4 in float32."""
+import numpy as np
+import pytest
+
+from phaze_b200 import signals
+
+pytestmark = pytest.mark.gpu
+
+RMS_BAR = 1e-4          # north_star: "within 1e-4 RMS (float32)"
+RMS_EXPECTED = 2e-6     # what a correct float32 pipeline actually achieves on these inputs
+
+
+def _run_both(oracle, N, hop, C, pf, calls, first_channel=0, sig=None):
+    from phaze_b200 import BatchedPhaseVocoder
+    x = signals.channels(first_channel, C, calls * hop) if sig is None else sig
+    ref = oracle.OracleProcessor(N, hop, C).run(x, pf)
+    with BatchedPhaseVocoder(C, N, hop) as pv:
+        got = pv.run(x, pf)
+        launches = pv.kernel_launches
+    assert launches == calls
+    return x, ref, got
+
+
+def _rms(a):
+    return float(np.sqrt(np.mean(np.square(a.astype(np.float64)))))
+
+
+@pytest.mark.parametrize("N,hop,C,pf", [
+    (1024, 256, 1, 1.2),      # BASELINE config 1 (mono)
+    (1024, 256, 8, 0.8),      # config 2 arithmetic (stale upper bins, colliding regions)
+    (2048, 512, 6, 1.5),      # config 3 arithmetic
+    (1024, 256, 7, 1.25),     # config 4 arithmetic, odd channel count
+    (2048, 128, 4, 1.2),      # the reference's native 2048 / 128
+    (2048, 128, 4, 0.8),
+    (1024, 256, 4, 1.0),
+])
+def test_parity_configs(oracle, N, hop, C, pf):
+    calls = 3 * (N // hop) + 5
+    x, ref, got = _run_both(oracle, N, hop, C, np.float32(pf), calls)
+    err = _rms(got - ref)
+    print(f"N={N} hop={hop} C={C} pf={pf}: rms err {err:.3e}, out rms {_rms(ref):.3e}, "
+          f"max abs {np.abs(got - ref).max():.3e}")
+    assert _rms(ref) > 1e-2
+    assert err <= RMS_BAR
+    assert err <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("pf", [1.2, 0.8])
+def test_parity_frame_size_sweep(oracle, N, pf):
+    hop = N // 4
+    x, ref, got = _run_both(oracle, N, hop, 4, np.float32(pf), 14)
+    err = _rms(got - ref)
+    print(f"N={N} pf={pf}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
