@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — STFT frames/s of the phase-vocoder hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): 4096 mono channels PER GPU, frame 1024 / hop 256,
+pitchFactor 0.8.  One "step" == one process() call over one 4096-channel batch == 4096
+STFT frames (window -> FFT -> peak shift -> IFFT -> overlap-add, 12*N algorithmic bytes
+each).  State of one batch (32 MiB) would fit in the 126 MB L2, so the
+timed loop rotates over `rotate` independent 4096-channel processor instances whose
+combined state exceeds L2 (timing rule: inputs larger than L2).
+
+Prints ONE JSON line (rank 0).  `value` = frames/s over all GPUs with inputs resident in
+HBM; `e2e` = the same through the host-buffer C-ABI call (pvb_process_many, pinned host
+memory, H2D + D2H inside the timed region); `roofline` = algorithmic GB/s of the fused
+kernel against the measured HBM copy peak; `cpu_baseline` = the CPU oracle (a C port of
+the reference JS; no JS engine exists in this image) on the box's host cores.
+
+--impl reference times that CPU port as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "STFT frames/sec (1024-pt, hop 256) at 4096 ch; achieved HBM GB/s vs peak"
+UNIT = "frames/s"
+FRAME, HOP, CHANNELS, PITCH = 1024, 256, 4096, 0.8
+L2_BYTES = 126e6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frame", type=int, default=FRAME)
+    ap.add_argument("--hop", type=int, default=0, help="default: frame/4")
+    ap.add_argument("--channels", type=int, default=CHANNELS, help="channels per GPU per step")
+    ap.add_argument("--pitch", type=float, default=PITCH)
+    ap.add_argument("--rotate", type=int, default=0,
+                    help="processor instances rotated through (0: enough to exceed 2x L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------
+# clocks: NVML sampler thread running across the timed region
+# ------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+        0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+        0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.ok, self._stop = [], False, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:       # pragma: no cover
+            self.err = repr(e)
+        self.t0 = self.t1 = None
+        self.th = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.ok:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        self._stop.set()
+        if self.th:
+            self.th.join(timeout=1.0)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvml unavailable"}
+        inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
+        note = None
+        if not inside:            # timed region shorter than the sampling period
+            inside = self.samples[-3:]
+            note = "timed region shorter than sampler period; nearest samples used"
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "note": "no samples"}
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = [n for b, n in self.REASONS.items() if bits & b and n != "gpu_idle"]
+        out = {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons,
+               "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
+
+
+# ------------------------------------------------------------------------------------
+# CPU baseline: the oracle (C port of the reference JS) on the host cores
+# ------------------------------------------------------------------------------------
+def cpu_port_rate(frame, hop, pitch, channels, calls, threads):
+    """frames/s of the CPU oracle: `channels` split over `threads` processor instances,
+    `calls` process() calls each.  Returns (frames_per_s, seconds)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle_lib
+    from phaze_b200 import signals
+
+    oracle_lib.build()
+    per = [channels // threads + (1 if i < channels % threads else 0) for i in range(threads)]
+    per = [c for c in per if c > 0]
+    procs = [oracle_lib.OracleProcessor(frame, hop, c) for c in per]
+    nblk = 8
+    blocks = [signals.channels(0, max(per), nblk * hop).reshape(max(per), nblk, hop)
+              .transpose(1, 0, 2).copy()]
+    blk = blocks[0]
+
+    def work(i):
+        p, c = procs[i], per[i]
+        for k in range(calls):
+            p.process_packed(blk[k % nblk, :c], pitch)     # ctypes releases the GIL
+
+    # prime history so every frame is full
+    with ThreadPoolExecutor(len(per)) as ex:
+        list(ex.map(lambda i: [procs[i].process_packed(blk[k % nblk, :per[i]], pitch)
+                               for k in range(frame // hop)], range(len(per))))
+        t0 = time.perf_counter()
+        list(ex.map(work, range(len(per))))
+        dt = time.perf_counter() - t0
+    for p in procs:
+        p.close()
+    return channels * calls / dt, dt
+
+
+def cpu_baseline(frame, hop, pitch, seconds):
+    import numpy as np
+    threads = os.cpu_count() or 1
+    channels = 16 * threads
+    rate, _ = cpu_port_rate(frame, hop, np.float32(pitch), channels, 8, threads)     # calibration
+    calls = max(8, int(rate * seconds / channels))
+    rate, dt = cpu_port_rate(frame, hop, np.float32(pitch), channels, calls, threads)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{channels} channels x {calls} process() calls ({channels * calls} frames, "
+                      f"{dt:.1f} s) of the {frame}/{hop} pf={pitch} workload; C port of the reference "
+                      f"JS (oracle/phaze_oracle.c, -O2), one processor instance per thread"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+    No JS engine exists in this image, so it is the oracle port (kind: port)."""
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frame, hop = args.frame, (args.hop or args.frame // 4)
+    threads = os.cpu_count() or 1
+    pitch = np.float32(args.pitch)
+    # one step == one process() call over a bounded sample of the per-GPU batch
+    probe, _ = cpu_port_rate(frame, hop, pitch, 8 * threads, 8, threads)
+    budget_s = 120.0
+    total = args.steps + args.warmup
+    chans = int(min(args.channels, max(threads, probe * budget_s / max(total, 1))))
+    chans = max(threads, chans - chans % threads)
+    if args.warmup:
+        cpu_port_rate(frame, hop, pitch, chans, args.warmup, threads)
+    rate, dt = cpu_port_rate(frame, hop, pitch, chans, args.steps, threads)
+    sample = (f"each step = one process() call over {chans} of the {args.channels} channels "
+              f"({frame}/{hop}, pf={args.pitch}); {threads} host threads, one processor instance each")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.channels} mono channels, frame {frame} / hop {hop}, "
+                               f"pitchFactor {args.pitch} (BASELINE configs[1])",
+                   "frame": frame, "hop": hop, "pitch_factor": args.pitch,
+                   "channels_per_step": chans},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "C port of the reference JS (oracle/phaze_oracle.c); Node/V8 is not present in this image",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import phaze_b200
+    from phaze_b200 import signals
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; phaze_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    frame, hop = args.frame, (args.hop or args.frame // 4)
+    C, K, W = args.channels, args.steps, args.warmup
+    R = frame // hop
+    pitch = np.float32(args.pitch)
+    state_bytes = 2 * C * frame * 4 + 2 * C * hop * 4
+    rotate = args.rotate or max(2, int(np.ceil(2.2 * L2_BYTES / state_bytes)))
+    first_channel = rank * C          # weak scaling: every rank owns its own channel range
+
+    # synthetic input: 8 distinct blocks per channel, resident in HBM before timing
+    nblk = 8
+    host = signals.channels(first_channel, C, nblk * hop)
+    blocks_np = np.ascontiguousarray(host.reshape(C, nblk, hop).transpose(1, 0, 2))
+    blocks = torch.from_numpy(blocks_np).cuda()
+    outs = [torch.empty((C, hop), dtype=torch.float32, device="cuda") for _ in range(rotate)]
+    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local) for _ in range(rotate)]
+    # a real (non-NULL) stream: NULL would select the handle's own stream and the events
+    # below would not bracket the kernels
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+
+    def step(i):
+        procs[i % rotate].process_device(blocks[i % nblk].data_ptr(), outs[i % rotate].data_ptr(),
+                                         pitch, sptr)
+
+    # prime: fill every instance's history so all frames carry signal
+    for i in range(rotate * R):
+        step(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    launches0 = sum(p.kernel_launches for p in procs)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
+    ev0.record(stream)
+    for i in range(K):
+        step(i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    sampler.mark_end()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = sum(p.kernel_launches for p in procs) - launches0
+    sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    frames_total = world * K * C
+    value = frames_total / (ms_max * 1e-3)
+
+    # L2-resident variant (single instance, state stays in L2): reported for context only
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for i in range(min(W, 50)):
+        procs[0].process_device(blocks[i % nblk].data_ptr(), outs[0].data_ptr(), pitch, sptr)
+    ev2.record(stream)
+    for i in range(K):
+        procs[0].process_device(blocks[i % nblk].data_ptr(), outs[0].data_ptr(), pitch, sptr)
+    ev3.record(stream)
+    torch.cuda.synchronize()
+    l2_value = K * C / (ev2.elapsed_time(ev3) * 1e-3)
+
+    # e2e: host buffers through pvb_process_many (pinned), H2D + D2H in the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(procs, blocks_np, C, hop, pitch, K, dist)
+
+    peak, peak_src = measured_peak()
+    kernel_ms = ms / max(launches, 1)                 # this rank's average launch duration
+    achieved = 12.0 * frame * C / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
+                "peak_source": peak_src, "kernel": f"pvb::pv_process_kernel<{frame}>",
+                "algorithmic_bytes_per_launch": 12 * frame * C,
+                "avg_launch_us": kernel_ms * 1e3}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(frame, hop, args.pitch, args.cpu_seconds)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{C} mono channels per GPU, frame {frame} / hop {hop}, "
+                                   f"pitchFactor {args.pitch} (BASELINE configs[1])",
+                       "frame": frame, "hop": hop, "pitch_factor": args.pitch,
+                       "channels_per_gpu": C, "frames_per_step": C * world,
+                       "l2_policy": f"inputs larger than L2: {rotate} processor instances "
+                                    f"({rotate * state_bytes / 2**20:.0f} MiB of state+io) rotated per step",
+                       "parallelism": f"channel-sharded x{world}, no data-path collective"},
+            "roofline": roofline,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "l2_resident_value": l2_value,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    for p in procs:
+        p.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
+    """Same metric through the host-buffer entry point: every step copies its input block
+    from pinned host memory and reads its output block back."""
+    import ctypes as Ct
+
+    import numpy as np
+    import torch
+
+    lib = phaze_b200_lib()
+    nbytes = C * hop * 4
+    hin = lib.pvb_alloc_host(nbytes * blocks_np.shape[0])
+    hout = lib.pvb_alloc_host(nbytes)
+    Ct.memmove(hin, blocks_np.ctypes.data, nbytes * blocks_np.shape[0])
+    steps = int(min(K, 400))
+    p0 = procs[0]
+
+    def one(i):
+        rc = lib.pvb_process(procs[i % len(procs)]._h, hin + (i % blocks_np.shape[0]) * nbytes,
+                             hout, pitch)
+        assert rc == 0, rc
+
+    for i in range(5):
+        one(i)
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    world = 1
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        world = dist.get_world_size()
+    dt = float(t.item())
+    check = float(np.ctypeslib.as_array(Ct.cast(hout, Ct.POINTER(Ct.c_float)), (C * hop,)).std())
+    lib.pvb_free_host(hin)
+    lib.pvb_free_host(hout)
+    return {"value": world * steps * C / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+            "d2h_bytes_per_step": nbytes, "steps": steps,
+            "api": "pvb_process(handle, in_host, out_host, pitch) - synchronous, pinned host buffers",
+            "out_std": check}
+
+
+def phaze_b200_lib():
+    import phaze_b200
+    return phaze_b200.load_library()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the
+# committed `ncu --set full` capture (profiles/), for the default workload; None until captured.
+NCU_TRAFFIC_BYTES = None
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,6 +5,7 @@
 // the host: if there is no CUDA device every entry point reports PVB_ERR_CUDA.
 #include "../../include/phaze_b200.h"
 #include "pv_kernel.cuh"
+#include "pv_kernel_warp.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -30,6 +31,21 @@ struct pvb_processor {
 namespace {
 
 thread_local char g_create_err[256] = "";
+bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
+
+// pitch_factor == mant * 2^-shift exactly; shift outside [1, 62] -> 0 (kernel uses float64)
+void split_pitch_factor(float pf, int *mant, int *shift) {
+    *mant = 0;
+    *shift = 0;
+    if (!std::isfinite(pf) || pf == 0.0f) return;
+    int e = 0;
+    const float fr = std::frexp(pf, &e);               // pf = fr * 2^e, |fr| in [0.5, 1)
+    const int m = int(std::ldexp(fr, 24));             // exact: 24-bit mantissa
+    const int sh = 24 - e;
+    if (sh < 1 || sh > 62) return;
+    *mant = m;
+    *shift = sh;
+}
 
 int fail(pvb_processor *p, int code, const char *fmt, ...) {
     char *dst = p ? p->err : g_create_err;
@@ -69,7 +85,34 @@ cudaError_t launch_n(const pvb::FrameParams &fp, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// warp-synchronous kernel: frame 1024, pitch factors in [2/3, 64] (see pv_kernel_warp.cuh)
+bool warp_kernel_applies(int n, const pvb::FrameParams &fp) {
+    return n == 1024 && fp.pf_shift >= 1 && fp.pitch_factor >= 0.67f && fp.pitch_factor <= 64.0f;
+}
+
+cudaError_t launch_warp(const pvb::FrameParams &fp, cudaStream_t s) {
+    using W = pvb::WarpGeo;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_warp_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(W::SMEM_BYTES));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int pairs = (fp.num_channels + 1) / 2;
+    const int grid = (pairs + W::WARPS - 1) / W::WARPS;
+    if (grid == 0) return cudaSuccess;
+    pvb::WarpParams wp;
+    wp.f = fp;
+    pvb::pv_process_warp_kernel<<<grid, W::THREADS, W::SMEM_BYTES, s>>>(wp);
+    return cudaGetLastError();
+}
+
 cudaError_t launch(int n, const pvb::FrameParams &fp, cudaStream_t s) {
+    if (warp_kernel_applies(n, fp) && !g_force_generic) return launch_warp(fp, s);
     switch (n) {
         case 256: return launch_n<256>(fp, s);
         case 512: return launch_n<512>(fp, s);
@@ -151,6 +194,7 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         fp.step_mod_r = int(p->cursor_calls % uint64_t(p->overlaps));
         fp.src_limit = source_limit(p->n, pf);
         fp.pitch_factor = pf;
+        split_pitch_factor(pf, &fp.pf_mant, &fp.pf_shift);
         if (p->channels > 0) {
             PVB_CUDA(p, launch(p->n, fp, s));
             p->launches++;
@@ -191,6 +235,7 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         return fail(nullptr, PVB_ERR_BAD_SIZE, "hop %d must divide frame %d and be a multiple of 4", hop, n);
     if (cfg->num_channels < 0) return fail(nullptr, PVB_ERR_BAD_ARG, "negative channel count");
 
+    if (const char *env = std::getenv("PVB_FORCE_GENERIC")) g_force_generic = env[0] == '1';
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {

@@ -41,7 +41,19 @@ struct FrameParams {
     int step_mod_r;        // calls mod R == (timeCursor / hop) mod R
     int src_limit;         // source bins [0, src_limit) can land inside [0, nb)
     float pitch_factor;
+    int pf_mant;           // pitch_factor == pf_mant * 2^-pf_shift exactly (float32 mantissa)
+    int pf_shift;          // in [1, 62] when the integer form is usable, else 0 (use float64)
 };
+
+// Math.round(p * pitchFactor) (pv:125): round half up of an exact product
+__device__ __forceinline__ int round_shifted_peak(int p, const FrameParams &fp) {
+    if (fp.pf_shift > 0) {
+        const long long v = (long long)fp.pf_mant * p + (1ll << (fp.pf_shift - 1));
+        const long long r = v >> fp.pf_shift;
+        return r > 0x3fffffff ? 0x3fffffff : (r < -0x3fffffff ? -0x3fffffff : int(r));
+    }
+    return __double2int_rd(fma(double(p), double(fp.pitch_factor), 0.5));
+}
 
 // ---------------------------------------------------------------------------
 // packed two-channel arithmetic (x = channel 0, y = channel 1)
@@ -389,7 +401,6 @@ pv_process_kernel(const FrameParams p) {
     {
         const int limit = p.src_limit;
         const bool contract = p.pitch_factor < 1.0f;     // only then two sources can hit one bin
-        const double pf = double(p.pitch_factor);
         const int rmask = p.overlaps - 1;
         const int rstride = N / p.overlaps;
         for (int idx = t; idx < 2 * limit; idx += T) {
@@ -398,7 +409,7 @@ pv_process_kernel(const FrameParams p) {
             const uint32_t *pkc = pk + ch * NWORDS;
             const int pi = owner_peak(pkc, b, NWORDS);
             if (pi < 0) continue;                                        // no peaks at all
-            const int ps = __double2int_rd(fma(double(pi), pf, 0.5));    // Math.round, pv:125
+            const int ps = round_shifted_peak(pi, p);                    // Math.round, pv:125
             if (ps > NB) continue;                                       // pv:127
             const int delta = ps - pi;
             const int d = b + delta;

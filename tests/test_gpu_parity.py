@@ -54,3 +54,29 @@ def test_parity_frame_size_sweep(oracle, N, pf):
     err = _rms(got - ref)
     print(f"N={N} pf={pf}: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("pf", [0.8, 0.67, 0.7, 0.75, 0.9, 1.0, 1.2, 1.5, 2.0, 3.0])
+@pytest.mark.parametrize("force_generic", ["0", "1"])
+def test_parity_1024_both_kernels(oracle, monkeypatch, pf, force_generic):
+    """frame 1024 has two CUDA paths (warp-synchronous kernel for pf >= 2/3, generic kernel
+    otherwise); both must match the oracle."""
+    monkeypatch.setenv("PVB_FORCE_GENERIC", force_generic)
+    x, ref, got = _run_both(oracle, 1024, 256, 5, np.float32(pf), 17)
+    err = _rms(got - ref)
+    print(f"pf={pf} generic={force_generic}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("pf", [0.5, 0.6, 0.34])
+def test_parity_deep_stale(oracle, pf):
+    """pitch factors below 0.75 read past the first level of stale upper bins."""
+    x, ref, got = _run_both(oracle, 1024, 256, 4, np.float32(pf), 14)
+    err = _rms(got - ref)
+    print(f"pf={pf}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+def test_parity_hop128_warp_kernel(oracle):
+    x, ref, got = _run_both(oracle, 1024, 128, 3, np.float32(0.8), 30)
+    assert _rms(got - ref) <= RMS_EXPECTED
