@@ -19,7 +19,8 @@ struct pvb_processor {
     int n = 0, hop = 0, overlaps = 0, channels = 0, device = 0;
     uint64_t ring_calls = 0;     // process() calls since the rings were last zeroed / set
     uint64_t cursor_calls = 0;   // timeCursor / hop (pv:31,71)
-    float *d_hist = nullptr, *d_acc = nullptr, *d_window = nullptr;
+    float *d_hist = nullptr, *d_acc = nullptr, *d_window = nullptr, *d_window_out = nullptr;
+    int num_sms = 148;
     float2 *d_tw = nullptr;
     float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
     size_t staging_floats = 0;
@@ -85,12 +86,29 @@ cudaError_t launch_n(const pvb::FrameParams &fp, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// warp-synchronous kernel: frame 1024, pitch factors in [2/3, 64] (see pv_kernel_warp.cuh)
+// warp-synchronous kernel: frame 1024, pitch factors in [0.75, 64], R <= 32 (pv_kernel_warp.cuh)
 bool warp_kernel_applies(int n, const pvb::FrameParams &fp) {
-    return n == 1024 && fp.pf_shift >= 1 && fp.pitch_factor >= 0.67f && fp.pitch_factor <= 64.0f;
+    return n == 1024 && fp.pf_shift >= 1 && fp.pitch_factor >= 0.75f && fp.pitch_factor <= 64.0f &&
+           fp.overlaps <= 32;
 }
 
-cudaError_t launch_warp(const pvb::FrameParams &fp, cudaStream_t s) {
+// warps (channel pairs) per CTA: the choice that leaves the most even load per SM
+int pick_warps_per_cta(int pairs, int num_sms) {
+    int best = 7;
+    long best_cost = -1;
+    for (int w = 4; w <= pvb::WarpGeo::MAX_WARPS; w++) {
+        const long ctas = (pairs + w - 1) / w;
+        const long cost = ((ctas + num_sms - 1) / num_sms) * w;     // warps on the busiest SM
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && w > best)) {
+            best = w;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
+
+cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int num_sms,
+                        cudaStream_t s) {
     using W = pvb::WarpGeo;
     static bool configured[64] = {};
     int dev = 0;
@@ -98,21 +116,25 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, cudaStream_t s) {
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_warp_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(W::SMEM_BYTES));
+                                             int(W::MAX_WARPS * W::WARP_BYTES));
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     const int pairs = (fp.num_channels + 1) / 2;
-    const int grid = (pairs + W::WARPS - 1) / W::WARPS;
-    if (grid == 0) return cudaSuccess;
+    if (pairs == 0) return cudaSuccess;
+    const int wpc = pick_warps_per_cta(pairs, num_sms);
+    const int grid = (pairs + wpc - 1) / wpc;
     pvb::WarpParams wp;
     wp.f = fp;
-    pvb::pv_process_warp_kernel<<<grid, W::THREADS, W::SMEM_BYTES, s>>>(wp);
+    wp.window_out = window_out;
+    pvb::pv_process_warp_kernel<<<grid, wpc * 32, size_t(wpc) * W::WARP_BYTES, s>>>(wp);
     return cudaGetLastError();
 }
 
-cudaError_t launch(int n, const pvb::FrameParams &fp, cudaStream_t s) {
-    if (warp_kernel_applies(n, fp) && !g_force_generic) return launch_warp(fp, s);
+cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+    const int n = h->n;
+    if (warp_kernel_applies(n, fp) && !g_force_generic)
+        return launch_warp(fp, h->d_window_out, h->num_sms, s);
     switch (n) {
         case 256: return launch_n<256>(fp, s);
         case 512: return launch_n<512>(fp, s);
@@ -196,7 +218,7 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         fp.pitch_factor = pf;
         split_pitch_factor(pf, &fp.pf_mant, &fp.pf_shift);
         if (p->channels > 0) {
-            PVB_CUDA(p, launch(p->n, fp, s));
+            PVB_CUDA(p, launch(p, fp, s));
             p->launches++;
         }
         p->ring_calls++;
@@ -265,10 +287,15 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
     }
 
     // tables, computed in double like the JS and rounded once to float32
-    std::vector<float> win(n);
+    std::vector<float> win(n), win_out(n);
     std::vector<float2> tw(n);
     const double pi = 3.14159265358979323846;
-    for (int i = 0; i < n; i++) win[i] = float(0.5 * (1 - std::cos(2 * pi * i / n)));   // pv:10-12
+    for (int i = 0; i < n; i++) {
+        win[i] = float(0.5 * (1 - std::cos(2 * pi * i / n)));                          // pv:10-12
+        // synthesis window with 1/N (inverseTransform), the two folded 1/2 of the real-split and
+        // 1/nbOverlaps (ola:153) folded in; all powers of two, so the product is exact
+        win_out[i] = win[i] * (1.0f / float(2 * n)) * (1.0f / float(p->overlaps));
+    }
     for (int j = 0; j < n; j++) {
         double c = std::cos(2 * pi * j / n), s = -std::sin(2 * pi * j / n);
         if (j % (n / 4) == 0) {    // exact quarter turns
@@ -278,12 +305,15 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         }
         tw[j] = make_float2(float(c), float(s));
     }
+    cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaMalloc(&p->d_window, n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->d_window_out, n * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&p->d_tw, n * sizeof(float2)) != cudaSuccess) {
         fail(p, PVB_ERR_NOMEM, "cudaMalloc of tables failed");
         return bail(PVB_ERR_NOMEM);
     }
     if (cudaMemcpy(p->d_window, win.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_window_out, win_out.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(p->d_tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
         fail(p, PVB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(PVB_ERR_CUDA);
@@ -305,6 +335,7 @@ void pvb_destroy(pvb_processor *p) {
     cudaFree(p->d_hist);
     cudaFree(p->d_acc);
     cudaFree(p->d_window);
+    cudaFree(p->d_window_out);
     cudaFree(p->d_tw);
     cudaFree(p->d_in);
     cudaFree(p->d_out);

@@ -1,25 +1,31 @@
 // pv_kernel_warp.cuh — warp-synchronous fused kernel for frame size 1024 (sm_100a).
 //
-// Same arithmetic as pv_kernel.cuh (one launch == one process() call, reference lines
-// cited there), re-laid-out so that ONE WARP owns one channel pair end to end:
+// Same arithmetic as pv_kernel.cuh (one launch == one process() call; the reference lines
+// are cited there), laid out so that ONE WARP owns one channel pair end to end:
 //
 //   * no __syncthreads(): every exchange is shared memory + __syncwarp(), so warps drift
 //     apart and the scheduler overlaps FFT math of one pair with the integer-heavy peak /
 //     shift phases of another;
-//   * the frame goes global memory -> registers -> (2 exchanges) -> registers for both FFTs:
-//     first-pass inputs are read straight from the history ring (coalesced 8-byte lanes),
-//     last-pass outputs of the inverse go straight to the overlap-add ring;
+//   * both FFTs run global -> registers -> 2 shared-memory exchanges -> registers: first-pass
+//     inputs come straight from the history ring, last-pass outputs of the inverse go straight
+//     to the overlap-add ring; the two channels ride in the halves of f32x2 registers;
 //   * the last forward pass gives every lane both Z[k] and Z[M-k], so the real-split (and its
 //     mirror, the Hermitian C2R pre-pass) happens in registers;
-//   * exchanges use an XOR swizzle (slot = 64a + 8b + (c ^ b)): all three access patterns of
-//     the radix-8 passes are bank-conflict free without padding;
-//   * peak picking walks 16-bin runs per lane (vector loads), regions get 32-bit descriptors
-//     indexed by a prefix-popcount of a region-start bitmap, Math.round(p * pitchFactor) is
-//     exact integer arithmetic on the float32 mantissa (no FP64, no XU pipe).
+//   * exchange buffer = separate re / im planes of float2 (ch0, ch1) with an XOR swizzle
+//     slot(a,b,c) = 64a + 8(b ^ (a&1)) + (c ^ b): every 64-bit access pattern of the three
+//     radix-8 passes is bank-conflict free and needs no register shuffling;
+//   * peak picking: 16-bin runs per lane, |X|^2 compared as integers, mask built with funnel
+//     shifts; regions get 32-bit descriptors indexed by a prefix-popcount of a region-start
+//     bitmap kept in registers; Math.round(p * pitchFactor) is exact integer arithmetic;
+//   * the shift is done IN PLACE: the sweep reads X[b], zeroes it, and writes the rotated value
+//     to Y[b + delta] in the same buffer (ascending bins when contracting, descending when
+//     expanding), so one 8 KB buffer per warp serves Z (forward), X, Y and Z (inverse).
+//     13.5 KB of shared memory per warp -> 14-16 resident warps per SM.
 //
-// Valid for pitch factors >= 2/3 (right halves of consecutive regions, and left halves, are
-// then pairwise disjoint after the shift, so two ordered sub-steps replace atomics); the host
-// routes other factors and other frame sizes to the generic kernel in pv_kernel.cuh.
+// Valid for pitch factors in [0.75, 64] and hop >= 32 (R <= 32): then (a) only the first level
+// of stale upper bins is read, (b) right halves of consecutive regions, and left halves, stay
+// pairwise disjoint after the shift, so two ordered sub-steps replace atomics.  The host routes
+// everything else (and other frame sizes) to the generic kernel in pv_kernel.cuh.
 #pragma once
 
 #include "pv_kernel.cuh"
@@ -28,35 +34,36 @@ namespace pvb {
 
 struct WarpGeo {
     static constexpr int N = 1024, M = 512, NB = 513;
-    static constexpr int BUF_BYTES = 8256;                 // >= 513 * 16
+    static constexpr int PLANE = 512;                      // float2 slots per plane
+    static constexpr int XCH = 516;                        // float2 slots per channel of X / Y
+    static constexpr int BUF_BYTES = 2 * XCH * 8;          // 8256 >= 2 planes (8192)
     static constexpr int MAG_FLOATS = 656;                 // per channel, padded layout (see mag_idx)
+    static constexpr int MAG_BYTES = 2 * MAG_FLOATS * 4;   // 5248
     static constexpr int MAXPK = 176;                      // > 509 / 3 peaks
     static constexpr int SWORDS = 20;                      // region-start bitmap words (bins 0..639)
-    static constexpr int OFF_A = 0;                        // Zbuf (forward) / X
-    static constexpr int OFF_B = BUF_BYTES;                // mag + peak list / Y / Zbuf (inverse)
-    static constexpr int OFF_DESC = 2 * BUF_BYTES;         // [2][MAXPK] u32
-    static constexpr int OFF_S = OFF_DESC + 2 * MAXPK * 4; // [2][SWORDS] u32
-    static constexpr int OFF_PS = OFF_S + 2 * SWORDS * 4;  // [2][SWORDS] u32 prefix counts
-    static constexpr int WARP_BYTES = OFF_PS + 2 * SWORDS * 4;   // 18240
-    static constexpr int OFF_LIST = OFF_B + 2 * MAG_FLOATS * 4;  // [2][MAXPK] u16, dead before Y is cleared
-    static constexpr int WARPS = 4;                        // warps (pairs) per CTA
-    static constexpr int THREADS = WARPS * 32;
-    static constexpr size_t SMEM_BYTES = size_t(WARPS) * WARP_BYTES;
+    static constexpr int OFF_BUF = 0;
+    static constexpr int OFF_MAG = BUF_BYTES;
+    static constexpr int WARP_BYTES = BUF_BYTES + MAG_BYTES;     // 13504
+    // descriptors / bitmap of channel c live in the (dead) mag space of channel c
+    static constexpr int DESC_OFF = 0;                     // u32[MAXPK]
+    static constexpr int S_OFF = MAXPK * 4;                // u32[SWORDS]
+    static constexpr int MAX_WARPS = 8;
 };
 
 struct WarpParams {
-    FrameParams f;   // pf_shift must be in [1, 62]
+    FrameParams f;            // pf_shift in [1, 62], 0.75 <= pitch_factor <= 64, overlaps <= 32
+    const float *window_out;  // [N] window * 1 / (2 N R): synthesis window with every scale folded in
 };
 
-// swizzled float4 slot of element [a][b][c] (each 0..7) of the exchange buffer
-__device__ __forceinline__ int zslot(int a, int b, int c) { return 64 * a + 8 * b + (c ^ b); }
+// swizzled slot of exchange element [a][b][c] (each 0..7)
+__device__ __forceinline__ int zslot(int a, int b, int c) { return 64 * a + 8 * (b ^ (a & 1)) + (c ^ b); }
 
 // padded index into the per-channel |X|^2 array: 4 floats of padding after every 16 bins and
 // 8 in front, so a lane's run of 24 floats is 6 aligned, conflict-free 16-byte loads
 __device__ __forceinline__ int mag_idx(int i) { return i + 4 * (i >> 4) + 8; }
 
-// swizzled float2 slot of spectrum bin k (keeps pairs (2i, 2i+1) adjacent)
-__device__ __forceinline__ int xs(int k) { return k ^ (((k >> 4) & 3) << 1); }
+// swizzled float2 slot of spectrum bin k (a bijection inside every aligned block of 64)
+__device__ __forceinline__ int xs(int k) { return k ^ ((k >> 3) & 6); }
 
 __device__ __forceinline__ cpx2 sel(bool c, cpx2 a, cpx2 b) {
     cpx2 o;
@@ -77,23 +84,26 @@ __device__ __forceinline__ void split_store(cpx2 za, cpx2 zb, int k, const float
     const float2 xr = add2(e_r, tt.re), xi = add2(e_i, tt.im);      // X[k]
     const float2 yr = sub2(e_r, tt.re), yi = sub2(tt.im, e_i);      // X[M-k]
     const int k2 = M - k;
-    X0[xs(k)] = make_float2(xr.x, xi.x);
-    X1[xs(k)] = make_float2(xr.y, xi.y);
-    X0[xs(k2)] = make_float2(yr.x, yi.x);
-    X1[xs(k2)] = make_float2(yr.y, yi.y);
+    const int s1 = xs(k), s2 = xs(k2);
+    X0[s1] = make_float2(xr.x, xi.x);
+    X1[s1] = make_float2(xr.y, xi.y);
+    X0[s2] = make_float2(yr.x, yi.x);
+    X1[s2] = make_float2(yr.y, yi.y);
     const float2 mk = fma2(xr, xr, mul2(xi, xi));
     const float2 mk2 = fma2(yr, yr, mul2(yi, yi));
-    mag0[mag_idx(k)] = mk.x;
-    mag1[mag_idx(k)] = mk.y;
-    mag0[mag_idx(k2)] = mk2.x;
-    mag1[mag_idx(k2)] = mk2.y;
+    const int m1 = mag_idx(k), m2 = mag_idx(k2);
+    mag0[m1] = mk.x;
+    mag1[m1] = mk.y;
+    mag0[m2] = mk2.x;
+    mag1[m2] = mk2.y;
 }
 
 // Hermitian C2R pre-pass of one (k, M-k) pair: Y -> Z'[k], Z'[M-k]
 __device__ __forceinline__ void unsplit_load(int k, const float2 *__restrict__ tw, const float2 *Y0,
                                              const float2 *Y1, cpx2 &zk, cpx2 &zmk) {
     constexpr int M = WarpGeo::M;
-    float2 a0 = Y0[k], a1 = Y1[k], b0 = Y0[M - k], b1 = Y1[M - k];
+    const int s1 = xs(k), s2 = xs(M - k);
+    float2 a0 = Y0[s1], a1 = Y1[s1], b0 = Y0[s2], b1 = Y1[s2];
     if (k == 0) { a0.y = 0.f; a1.y = 0.f; b0.y = 0.f; b1.y = 0.f; }
     const float2 ar = make_float2(a0.x, a1.x), ai = make_float2(a0.y, a1.y);
     const float2 br = make_float2(b0.x, b1.x), bi = make_float2(b0.y, b1.y);
@@ -115,33 +125,16 @@ __device__ __forceinline__ float2 stale_level1(const float2 *X, int q, const flo
     return make_float2(0.25f * (sr * w.x + si * w.y), 0.25f * (si * w.x - sr * w.y));
 }
 
-// generic stale slot on the swizzled spectrum (deeper levels; rare: pitch factors below 0.75)
-__device__ __noinline__ float2 stale_deep(const float2 *X, int pos, const float2 *__restrict__ tw) {
-    constexpr int N = WarpGeo::N;
-    int L = N, r = 1, s = 0, o = pos;
-    while (L > 4 && o > (L >> 1)) {
-        const int q = L >> 2;
-        const int sb = o / q;
-        o -= sb * q;
-        s += r * sb;
-        r <<= 2;
-        L = q;
-    }
-    float ar = 0.f, ai = 0.f;
-    for (int u = 0; u < r; u++) {
-        const int idx = o + u * L;
-        float2 xv;
-        if (idx <= N / 2) xv = X[xs(idx)];
-        else { xv = X[xs(N - idx)]; xv.y = -xv.y; }
-        const float2 w = __ldg(&tw[(s * idx) & (N - 1)]);
-        ar += xv.x * w.x + xv.y * w.y;
-        ai += xv.y * w.x - xv.x * w.y;
-    }
-    const float inv_r = 1.0f / float(r);
-    return make_float2(ar * inv_r, ai * inv_r);
+// store / load one packed complex (both channels) of the exchange planes
+__device__ __forceinline__ void zst(float2 *zre, float2 *zim, int slot, cpx2 v) {
+    zre[slot] = v.re;
+    zim[slot] = v.im;
+}
+__device__ __forceinline__ cpx2 zld(const float2 *zre, const float2 *zim, int slot) {
+    return cpx2{zre[slot], zim[slot]};
 }
 
-__global__ void __launch_bounds__(WarpGeo::THREADS)
+__global__ void __launch_bounds__(WarpGeo::MAX_WARPS * 32, 2)
 pv_process_warp_kernel(const WarpParams wp) {
     using W = WarpGeo;
     constexpr int N = W::N, M = W::M, NB = W::NB;
@@ -150,21 +143,15 @@ pv_process_warp_kernel(const WarpParams wp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int pair = blockIdx.x * W::WARPS + warp;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
     if (2 * pair >= p.num_channels) return;          // whole warp leaves; no CTA-wide barriers below
     unsigned char *mine = smem_raw + size_t(warp) * W::WARP_BYTES;
-    float4 *Zf = reinterpret_cast<float4 *>(mine + W::OFF_A);
-    float2 *X0 = reinterpret_cast<float2 *>(mine + W::OFF_A);
-    float2 *X1 = X0 + NB + 1;                                  // 514 slots each (swizzle stays inside 0..513)
-    float *mag0 = reinterpret_cast<float *>(mine + W::OFF_B);
+    float2 *zre = reinterpret_cast<float2 *>(mine + W::OFF_BUF);
+    float2 *zim = zre + W::PLANE;
+    float2 *X0 = reinterpret_cast<float2 *>(mine + W::OFF_BUF);      // X and (in place) Y, channel 0
+    float2 *X1 = X0 + W::XCH;
+    float *mag0 = reinterpret_cast<float *>(mine + W::OFF_MAG);
     float *mag1 = mag0 + W::MAG_FLOATS;
-    uint16_t *plist = reinterpret_cast<uint16_t *>(mine + W::OFF_LIST);   // [2][MAXPK]
-    float2 *Y0 = reinterpret_cast<float2 *>(mine + W::OFF_B);
-    float2 *Y1 = Y0 + NB + 1;
-    float4 *Zi = reinterpret_cast<float4 *>(mine + W::OFF_B);
-    uint32_t *desc = reinterpret_cast<uint32_t *>(mine + W::OFF_DESC);    // [2][MAXPK]
-    uint32_t *Sw = reinterpret_cast<uint32_t *>(mine + W::OFF_S);         // [2][SWORDS]
-    uint32_t *Ps = reinterpret_cast<uint32_t *>(mine + W::OFF_PS);        // [2][SWORDS]
 
     const int c0 = 2 * pair, c1 = c0 + 1;
     const bool has1 = c1 < p.num_channels;
@@ -173,6 +160,8 @@ pv_process_warp_kernel(const WarpParams wp) {
     const int keep = N - hop;
     const float2 *__restrict__ tw = p.tw;
     const unsigned FULL = 0xFFFFFFFFu;
+    const float *hist0 = p.hist + size_t(c0) * N;
+    const float *hist1 = p.hist + size_t(has1 ? c1 : c0) * N;
 
     // lane's two last-pass butterflies A = (k1a, k2a), B = (k1b, k2b); natural bins
     // kA + 64 j and kB + 64 j with kA + kB == 64 (lane 31 owns the two self-paired ones)
@@ -182,6 +171,15 @@ pv_process_warp_kernel(const WarpParams wp) {
     else { k1a = 0; k2a = 35 - lane; k1b = 0; k2b = (lane == 31) ? 0 : 8 - k2a; }
     const bool l31 = lane == 31;
     const int kA = k1a + 8 * k2a;
+    // pass-3 slots: zslot(k1, k2, j) == base ^ j
+    const int slotA = 64 * k1a + 8 * (k2a ^ (k1a & 1)) + k2a;
+    const int slotB = 64 * k1b + 8 * (k2b ^ (k1b & 1)) + k2b;
+    // pass-2 slots: butterflies (k1, m3) = (lane >> 3 [+4], lane & 7): zslot(k1, j, m3) == base2 ^ (9 j)
+    const int base2 = 64 * (lane >> 3) + 8 * ((lane >> 3) & 1) + (lane & 7);
+    // pass-1 slots: n = lane [+32] = (m2, m3): zslot(k1, m2, m3) == 64 k1 + (k1 odd ? base1o : base1e)
+    const int m2l = lane >> 3, m3l = lane & 7;
+    const int base1e = 8 * m2l + (m3l ^ m2l);
+    const int base1o = 8 * (m2l ^ 1) + (m3l ^ m2l);
 
     cpx2 a[8], b[8];
 
@@ -189,16 +187,15 @@ pv_process_warp_kernel(const WarpParams wp) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int n = lane + 32 * h;
-        const int m2 = n >> 3, m3 = n & 7;
         cpx2 x[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int s = 2 * (n + 64 * j);
+            const int s = 2 * n + 128 * j;
             float2 v0, v1 = make_float2(0.f, 0.f);
             if (s < keep) {
                 const int r = (s + rb + hop) & (N - 1);
-                v0 = *reinterpret_cast<const float2 *>(p.hist + size_t(c0) * N + r);
-                if (has1) v1 = *reinterpret_cast<const float2 *>(p.hist + size_t(c1) * N + r);
+                v0 = *reinterpret_cast<const float2 *>(hist0 + r);
+                if (has1) v1 = *reinterpret_cast<const float2 *>(hist1 + r);
             } else {
                 const int i = s - keep;
                 v0 = make_float2(0.f, 0.f);
@@ -220,34 +217,29 @@ pv_process_warp_kernel(const WarpParams wp) {
             x[k1] = cmul_s(x[k1], w.x, w.y);
         }
 #pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) {
-            const cpx2 v = x[k1];
-            Zf[zslot(k1, m2, m3)] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
-        }
+        for (int k1 = 0; k1 < 8; k1++)
+            zst(zre, zim, 64 * k1 + 32 * h + (((k1 & 1) ? base1o : base1e) ^ (4 * h)), x[k1]);
     }
     __syncwarp();
 
     // ---- forward pass 2: butterflies (k1, m3) over m2 ---------------------------------------
+    {
+        int s2[8];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int bf = lane + 32 * h;
-        const int k1 = bf >> 3, m3 = bf & 7;
-        cpx2 x[8];
+        for (int j = 0; j < 8; j++) s2[j] = base2 ^ (9 * j);
+        float2 w2[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float4 v = Zf[zslot(k1, j, m3)];
-            x[j] = cpx2{make_float2(v.x, v.y), make_float2(v.z, v.w)};
-        }
-        dft8<false>(x);
+        for (int k2 = 1; k2 < 8; k2++) w2[k2] = __ldg(&tw[16 * m3l * k2]);   // W_64^{m3 k2}
 #pragma unroll
-        for (int k2 = 1; k2 < 8; k2++) {
-            const float2 w = __ldg(&tw[16 * m3 * k2]);           // W_64^{m3 k2}
-            x[k2] = cmul_s(x[k2], w.x, w.y);
-        }
+        for (int h = 0; h < 2; h++) {
+            cpx2 x[8];
 #pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) {
-            const cpx2 v = x[k2];
-            Zf[zslot(k1, k2, m3)] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
+            for (int j = 0; j < 8; j++) x[j] = zld(zre, zim, s2[j] + 256 * h);
+            dft8<false>(x);
+#pragma unroll
+            for (int k2 = 1; k2 < 8; k2++) x[k2] = cmul_s(x[k2], w2[k2].x, w2[k2].y);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++) zst(zre, zim, s2[k2] + 256 * h, x[k2]);
         }
     }
     __syncwarp();
@@ -255,14 +247,12 @@ pv_process_warp_kernel(const WarpParams wp) {
     // ---- forward pass 3: butterflies A and B over m3; outputs stay in registers --------------
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const float4 va = Zf[zslot(k1a, k2a, j)];
-        const float4 vb = Zf[zslot(k1b, k2b, j)];
-        a[j] = cpx2{make_float2(va.x, va.y), make_float2(va.z, va.w)};
-        b[j] = cpx2{make_float2(vb.x, vb.y), make_float2(vb.z, vb.w)};
+        a[j] = zld(zre, zim, slotA ^ j);
+        b[j] = zld(zre, zim, slotB ^ j);
     }
     dft8<false>(a);      // a[j] = Z[kA + 64 j]
     dft8<false>(b);      // b[j] = Z[kB + 64 j]
-    __syncwarp();        // everyone has read Zf: X may overwrite it
+    __syncwarp();        // everyone has read the planes: X may overwrite them
 
     // ---- real split in registers -> X (2x scaled), |X|^2 ---------------------------------------
     // slots 0..3: (a[j], b[7-j]) at k = kA + 64 j          lane 31: (a[j], a[7-j]), kA == 32
@@ -283,41 +273,58 @@ pv_process_warp_kernel(const WarpParams wp) {
     if (l31) split_store(b[4], b[4], 256, tw, X0, X1, mag0, mag1);
     __syncwarp();
 
-    // ---- peaks, region descriptors (per channel) --------------------------------------------------
+    // ---- per channel: peaks -> region descriptors -> in-place shift --------------------------------
+    // rotation exp(+j 2 pi r / R) for r = lane (pv:155-157 with t = hop * calls, integer reduced)
+    float rot_c, rot_s;
+    {
+        const float2 w = __ldg(&tw[(lane & (p.overlaps - 1)) * (N / p.overlaps)]);
+        rot_c = w.x;
+        rot_s = -w.y;
+    }
     const long long pf_m = p.pf_mant;
     const int pf_s = p.pf_shift;
     const long long pf_half = 1ll << (pf_s - 1);
-    int npk[2];
-#pragma unroll
-    for (int ch = 0; ch < 2; ch++) {
-        const float *mg = ch ? mag1 : mag0;
-        uint16_t *pl = plist + ch * W::MAXPK;
-        uint32_t *dsc = desc + ch * W::MAXPK;
-        uint32_t *sw = Sw + ch * W::SWORDS;
-        uint32_t *ps = Ps + ch * W::SWORDS;
+    const int stepm = p.step_mod_r;
+    const int rmask = p.overlaps - 1;
+    const bool contract = p.pitch_factor < 1.0f;
+    const uint32_t le_mask = (2u << lane) - 1u;
+    const int sw_e = lane ^ ((lane >> 3) & 6);              // xs(32 s + lane) - 32 s, s even
+    const int sw_o = lane ^ (((lane >> 3) & 6) ^ 4);        // s odd
 
-        // 5-point strict maxima (pv:95-116) on this lane's run of 16 bins
-        float m[24];
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ch++) {
+        float *mg = ch ? mag1 : mag0;
+        float2 *Xc = ch ? X1 : X0;
+        uint32_t *dsc = reinterpret_cast<uint32_t *>(mg) + W::DESC_OFF / 4;
+        uint32_t *sw = reinterpret_cast<uint32_t *>(mg) + W::S_OFF / 4;
+
+        // 5-point strict maxima (pv:95-116) on this lane's run of 16 bins; squared magnitudes are
+        // non-negative floats, so they order like their bit patterns
+        uint32_t mask = 0;
         {
-            const float4 *mv = reinterpret_cast<const float4 *>(mg + 20 * lane);
-            const float4 q0 = mv[0], q1 = mv[2], q2 = mv[3], q3 = mv[4], q4 = mv[5], q5 = mv[7];
+            int m[24];
+            const int4 *mv = reinterpret_cast<const int4 *>(mg + 20 * lane);
+            const int4 q0 = mv[0], q1 = mv[2], q2 = mv[3], q3 = mv[4], q4 = mv[5], q5 = mv[7];
             m[0] = q0.x; m[1] = q0.y; m[2] = q0.z; m[3] = q0.w;
             m[4] = q1.x; m[5] = q1.y; m[6] = q1.z; m[7] = q1.w;
             m[8] = q2.x; m[9] = q2.y; m[10] = q2.z; m[11] = q2.w;
             m[12] = q3.x; m[13] = q3.y; m[14] = q3.z; m[15] = q3.w;
             m[16] = q4.x; m[17] = q4.y; m[18] = q4.z; m[19] = q4.w;
             m[20] = q5.x; m[21] = q5.y; m[22] = q5.z; m[23] = q5.w;
-        }
-        uint32_t mask = 0;
+            int q[22];
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-            const float v = m[e + 4];
-            const bool pk = (m[e + 2] < v) && (m[e + 3] < v) && (m[e + 5] < v) && (m[e + 6] < v);
-            mask |= pk ? (1u << e) : 0u;
+            for (int t = 2; t < 21; t++) q[t] = max(m[t], m[t + 1]);
+#pragma unroll
+            for (int e = 15; e >= 0; e--) {
+                const int nb_max = max(q[e + 2], q[e + 5]);        // bins e-2, e-1, e+1, e+2
+                mask = __funnelshift_l(uint32_t(nb_max - m[e + 4]), mask, 1);   // 1 iff m[e] > all four
+            }
         }
         if (lane == 0) mask &= ~3u;            // i >= 2
         if (lane == 31) mask &= ~(1u << 15);   // i <= nb - 3 == 510
-        // ordinals
+        __syncwarp();                          // all lanes have read mag: descriptors may overwrite it
+
+        // ordinals of this lane's peaks, position of the last peak before this lane's run
         const int cnt = __popc(mask);
         int incl = cnt;
 #pragma unroll
@@ -325,99 +332,138 @@ pv_process_warp_kernel(const WarpParams wp) {
             const int o = __shfl_up_sync(FULL, incl, d);
             if (lane >= d) incl += o;
         }
-        const int total = __shfl_sync(FULL, incl, 31);
-        npk[ch] = total;
+        const int npk = __shfl_sync(FULL, incl, 31);
+        const int own_last = mask ? (16 * lane + 31 - __clz(mask)) : -1;
+        const uint32_t nz_below = __ballot_sync(FULL, mask != 0) & (le_mask >> 1);
+        const int src = nz_below ? (31 - __clz(nz_below)) : 0;
+        int prev = __shfl_sync(FULL, own_last, src);
+        if (!nz_below) prev = -1;
+
         if (lane < W::SWORDS) sw[lane] = 0;
+        __syncwarp();
+        // one descriptor per region of influence (pv:124-141):  delta << 16 | rot index << 10 | peak
         {
             int ord = incl - cnt;
             uint32_t mm = mask;
             while (mm) {
                 const int bit = __ffs(mm) - 1;
                 mm &= mm - 1;
-                pl[ord++] = uint16_t(16 * lane + bit);
+                const int pk = 16 * lane + bit;
+                const int start = (prev < 0) ? 0 : pk - ((pk - prev) >> 1);
+                const long long psl = (pf_m * pk + pf_half) >> pf_s;       // Math.round(p * pitchFactor)
+                const bool valid = psl <= NB;                               // pv:127
+                const int delta = valid ? int(psl) - pk : 0x4000;           // 0x4000: lands outside [0, nb)
+                const int ri = (delta * stepm) & rmask;
+                dsc[ord] = (uint32_t(delta) << 16) | (uint32_t(ri) << 10) | uint32_t(pk);
+                atomicOr(&sw[start >> 5], 1u << (start & 31));
+                prev = pk;
+                ord++;
             }
         }
         __syncwarp();
-        // one descriptor per region of influence (pv:124-141): p | (delta + 1024) << 10 | valid << 22
-        for (int i = lane; i < total; i += 32) {
-            const int pk = pl[i];
-            int start = 0;
-            if (i > 0) { const int before = pl[i - 1]; start = pk - ((pk - before) >> 1); }
-            const long long psl = (pf_m * pk + pf_half) >> pf_s;          // Math.round(p * pitchFactor)
-            const bool valid = (psl <= NB) && (psl - pk > -1024);
-            const int delta = valid ? int(psl) - pk : 0;
-            dsc[i] = uint32_t(pk) | (uint32_t(delta + 1024) << 10) | (valid ? (1u << 22) : 0u);
-            atomicOr(&sw[start >> 5], 1u << (start & 31));
-        }
-        __syncwarp();
+        // lane w keeps word w of the region-start bitmap and (#starts in words < w) - 1
+        uint32_t s_reg = (lane < W::SWORDS) ? sw[lane] : 0u;
+        int ps_reg;
         {
-            const uint32_t wv = (lane < W::SWORDS) ? sw[lane] : 0u;
-            const int c = __popc(wv);
+            const int c = __popc(s_reg);
             int inc = c;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const int o = __shfl_up_sync(FULL, inc, d);
                 if (lane >= d) inc += o;
             }
-            if (lane < W::SWORDS) ps[lane] = uint32_t(inc - c);
+            ps_reg = inc - c - 1;
         }
-    }
-    __syncwarp();
 
-    // ---- clear Y (mag and the peak list are dead now) -------------------------------------------------
-    {
-        float4 *yz = reinterpret_cast<float4 *>(mine + W::OFF_B);
-        constexpr int NV = (2 * (NB + 1) * 8) / 16;      // 514 float4
-        for (int i = lane; i < NV; i += 32) yz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();
+        if (npk == 0) {
+            // no peaks (silence): the shifted spectrum is all zero (pv:121)
+            for (int i = lane; i < W::XCH; i += 32) Xc[i] = make_float2(0.f, 0.f);
+            continue;
+        }
 
-    // ---- shift every region of influence (pv:143-171) --------------------------------------------------
-    {
-        const int limit = p.src_limit;
-        const int nsteps = (limit + 31) >> 5;
-        const bool contract = p.pitch_factor < 1.0f;
-        const int rmask = p.overlaps - 1;
-        const int rstride = N / p.overlaps;
-        const int stepm = p.step_mod_r;
-        const uint32_t le_mask = (2u << lane) - 1u;
+        // region lookup + rotated value for source bin `bin` holding spectrum value v
+#define PVB_BIN_PREP(STEP, BIN, V)                                                       \
+        const uint32_t sw_w = __shfl_sync(FULL, s_reg, (STEP));                            \
+        const int ord = __shfl_sync(FULL, ps_reg, (STEP)) + __popc(sw_w & le_mask);        \
+        const uint32_t dv = dsc[ord];                                                      \
+        const int d = (BIN) + (int(dv) >> 16);                                             \
+        const bool okd = unsigned(d) < unsigned(NB);                                       \
+        const int ri = (dv >> 10) & 31;                                                    \
+        const float rc = __shfl_sync(FULL, rot_c, ri), rs = __shfl_sync(FULL, rot_s, ri);  \
+        const float2 y = make_float2((V).x * rc - (V).y * rs, (V).x * rs + (V).y * rc);    \
+        float2 *yp = Xc + xs(d);
+
+        if (contract) {
+            // values of the source bins 512 .. 671: X[512], then the stale slots 513 .. 640
+            float2 ext[5];
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-            if (npk[ch] == 0) continue;                  // silence: no peaks, spectrum stays zero
-            const float2 *Xc = ch ? X1 : X0;
-            float2 *Yc = ch ? Y1 : Y0;
-            const uint32_t *dsc = desc + ch * W::MAXPK;
-            const uint32_t *sw = Sw + ch * W::SWORDS;
-            const uint32_t *ps = Ps + ch * W::SWORDS;
-            for (int s = 0; s < nsteps; s++) {
+            for (int t = 0; t < 5; t++) {
+                const int q = 32 * t + lane;                 // bin 512 + q
+                float2 v = make_float2(0.f, 0.f);
+                if (q == 0) v = Xc[xs(M)];
+                else if (q <= N / 8) v = stale_level1(Xc, q, tw);
+                ext[t] = v;
+            }
+            __syncwarp();
+            // ascending sweep: every write lands at or below the bin just read (delta <= 0)
+#pragma unroll 2
+            for (int s = 0; s < 16; s++) {
                 const int bin = 32 * s + lane;
-                int ord;
-                if (s < W::SWORDS) ord = int(ps[s]) + __popc(sw[s] & le_mask) - 1;
-                else ord = npk[ch] - 1;
+                float2 *xp = Xc + 32 * s + ((s & 1) ? sw_o : sw_e);
+                const float2 v = *xp;
+                *xp = make_float2(0.f, 0.f);
+                PVB_BIN_PREP(s, bin, v)
+                const bool right = bin >= int(dv & 1023);
+                __syncwarp();
+                if (okd && right) *yp = y;                    // first writer of this bin
+                __syncwarp();
+                if (okd && !right) { float2 o = *yp; o.x += y.x; o.y += y.y; *yp = o; }
+            }
+            if (lane == 0) Xc[xs(M)] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 5; t++) {
+                const int s = 16 + t;
+                const int bin = 32 * s + lane;
+                const float2 v = ext[t];
+                const uint32_t sw_w = __shfl_sync(FULL, s_reg, s & 31);
+                int ord = __shfl_sync(FULL, ps_reg, s & 31) + __popc(sw_w & le_mask);
+                if (s >= W::SWORDS) ord = npk - 1;
                 const uint32_t dv = dsc[ord];
-                const int pk = dv & 1023;
-                const int delta = int((dv >> 10) & 4095) - 1024;
-                const int d = bin + delta;
-                const bool ok = (dv >> 22) && bin < limit && unsigned(d) < unsigned(NB);
-                float2 v;
-                if (bin <= M) v = Xc[xs(bin)];
-                else if (bin <= M + N / 8) v = stale_level1(Xc, bin - M, tw);
-                else v = ok ? stale_deep(Xc, bin, tw) : make_float2(0.f, 0.f);
-                const int ri = (delta * stepm) & rmask;
-                const float2 w = __ldg(&tw[ri * rstride]);          // (cos, -sin)
-                const float yr = v.x * w.x + v.y * w.y;
-                const float yi = v.y * w.x - v.x * w.y;
-                if (!contract) {
-                    if (ok) Yc[d] = make_float2(yr, yi);           // expansion: at most one source per bin
-                } else {
-                    const bool right = bin >= pk;
-                    if (ok && right) { float2 y = Yc[d]; y.x += yr; y.y += yi; Yc[d] = y; }
-                    __syncwarp();
-                    if (ok && !right) { float2 y = Yc[d]; y.x += yr; y.y += yi; Yc[d] = y; }
-                    __syncwarp();
-                }
+                const int d = bin + (int(dv) >> 16);
+                const bool okd = unsigned(d) < unsigned(NB);
+                const int ri = (dv >> 10) & 31;
+                const float rc = __shfl_sync(FULL, rot_c, ri), rs = __shfl_sync(FULL, rot_s, ri);
+                const float2 y = make_float2(v.x * rc - v.y * rs, v.x * rs + v.y * rc);
+                float2 *yp = Xc + xs(d);
+                const bool right = bin >= int(dv & 1023);
+                __syncwarp();
+                if (okd && right) *yp = y;
+                __syncwarp();
+                if (okd && !right) { float2 o = *yp; o.x += y.x; o.y += y.y; *yp = o; }
+            }
+        } else {
+            // descending sweep: every write lands at or above the bin just read (delta >= 0);
+            // expansion never maps two sources to one bin
+            {
+                const float2 v = (lane == 0) ? Xc[xs(M)] : make_float2(0.f, 0.f);
+                if (lane == 0) Xc[xs(M)] = make_float2(0.f, 0.f);
+                const int bin = M + lane;
+                PVB_BIN_PREP(16, bin, v)
+                __syncwarp();
+                if (okd && lane == 0) *yp = y;
+            }
+#pragma unroll 2
+            for (int s = 15; s >= 0; s--) {
+                const int bin = 32 * s + lane;
+                float2 *xp = Xc + 32 * s + ((s & 1) ? sw_o : sw_e);
+                const float2 v = *xp;
+                *xp = make_float2(0.f, 0.f);
+                PVB_BIN_PREP(s, bin, v)
+                __syncwarp();
+                if (okd) *yp = y;
             }
         }
+#undef PVB_BIN_PREP
     }
     __syncwarp();
 
@@ -427,10 +473,10 @@ pv_process_warp_kernel(const WarpParams wp) {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int k = (l31 && j >= 4) ? 64 * (7 - j) : kA + 64 * j;
-            unsplit_load(k, tw, Y0, Y1, zk[j], zmk[j]);
+            unsplit_load(k, tw, X0, X1, zk[j], zmk[j]);
         }
         z256 = zk[0];
-        if (l31) { cpx2 dummy; unsplit_load(256, tw, Y0, Y1, z256, dummy); }
+        if (l31) { cpx2 dummy; unsplit_load(256, tw, X0, X1, z256, dummy); }
 #pragma unroll
         for (int i = 0; i < 4; i++) a[i] = zk[i];
 #pragma unroll
@@ -444,7 +490,7 @@ pv_process_warp_kernel(const WarpParams wp) {
         b[6] = sel(l31, zmk[5], zmk[1]);
         b[7] = sel(l31, zmk[6], zmk[0]);
     }
-    __syncwarp();        // everyone has read Y: the inverse exchange buffer may overwrite it
+    __syncwarp();        // everyone has read Y: the inverse exchange planes may overwrite it
 
     // ---- inverse pass 1 (DIT): butterflies A and B over k3, twiddle conj(W_64^{k2 m3}) -------------------
     dft8<true>(a);
@@ -458,70 +504,67 @@ pv_process_warp_kernel(const WarpParams wp) {
             va = cmul_s(va, wa.x, -wa.y);
             vb = cmul_s(vb, wb.x, -wb.y);
         }
-        Zi[zslot(k1a, k2a, m3)] = make_float4(va.re.x, va.re.y, va.im.x, va.im.y);
-        Zi[zslot(k1b, k2b, m3)] = make_float4(vb.re.x, vb.re.y, vb.im.x, vb.im.y);
+        zst(zre, zim, slotA ^ m3, va);
+        zst(zre, zim, slotB ^ m3, vb);
     }
     __syncwarp();
 
     // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_512^{k1 (m3 + 8 m2)}) ---------------
+    {
+        int s2[8];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int bf = lane + 32 * h;
-        const int k1 = bf >> 3, m3 = bf & 7;
-        cpx2 x[8];
+        for (int j = 0; j < 8; j++) s2[j] = base2 ^ (9 * j);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float4 v = Zi[zslot(k1, j, m3)];
-            x[j] = cpx2{make_float2(v.x, v.y), make_float2(v.z, v.w)};
-        }
-        dft8<true>(x);
+        for (int h = 0; h < 2; h++) {
+            const int k1 = (lane >> 3) + 4 * h;
+            cpx2 x[8];
 #pragma unroll
-        for (int m2 = 0; m2 < 8; m2++) {
-            const float2 w = __ldg(&tw[2 * k1 * (m3 + 8 * m2)]);
-            const cpx2 v = cmul_s(x[m2], w.x, -w.y);
-            Zi[zslot(k1, m2, m3)] = make_float4(v.re.x, v.re.y, v.im.x, v.im.y);
+            for (int j = 0; j < 8; j++) x[j] = zld(zre, zim, s2[j] + 256 * h);
+            dft8<true>(x);
+#pragma unroll
+            for (int m2 = 0; m2 < 8; m2++) {
+                const float2 w = __ldg(&tw[2 * k1 * (m3l + 8 * m2)]);
+                zst(zre, zim, s2[m2] + 256 * h, cmul_s(x[m2], w.x, -w.y));
+            }
         }
     }
     __syncwarp();
 
     // ---- inverse pass 3: butterflies n over k1 -> z[n + 64 m1]; window, overlap-add, emit ------------------
     {
-        const float scale = 1.0f / float(2 * N);
-        const float inv_r = 1.0f / float(p.overlaps);
+        float *acc0 = p.acc + size_t(c0) * N;
+        float *acc1 = p.acc + size_t(has1 ? c1 : c0) * N;
+        float *out0 = p.out + size_t(c0) * hop;
+        float *out1 = p.out + size_t(has1 ? c1 : c0) * hop;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int n = lane + 32 * h;
-            const int m2 = n >> 3, m3 = n & 7;
             cpx2 x[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float4 v = Zi[zslot(j, m2, m3)];
-                x[j] = cpx2{make_float2(v.x, v.y), make_float2(v.z, v.w)};
-            }
+            for (int j = 0; j < 8; j++)
+                x[j] = zld(zre, zim, 64 * j + 32 * h + (((j & 1) ? base1o : base1e) ^ (4 * h)));
             dft8<true>(x);
 #pragma unroll
             for (int m1 = 0; m1 < 8; m1++) {
-                const int s = 2 * (n + 64 * m1);
-                const float2 w = __ldg(reinterpret_cast<const float2 *>(p.window + s));
-                const bool head = s < hop;
-                const bool tail = s >= keep;
+                const int s = 2 * n + 128 * m1;
+                // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the
+                // division by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of 2)
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(wp.window_out + s));
+                const float2 yr = mul2(x[m1].re, bc2(w.x));       // sample s   of (ch0, ch1)
+                const float2 yi = mul2(x[m1].im, bc2(w.y));       // sample s+1 of (ch0, ch1)
+                float2 y0 = make_float2(yr.x, yi.x), y1 = make_float2(yr.y, yi.y);
                 const int ring = (s + rb) & (N - 1);
-                // fromComplexArray -> f32, applyHannWindow, / nbOverlaps (pv:65-67, ola:153)
-                float2 y0 = make_float2(((x[m1].re.x * scale) * w.x) * inv_r, ((x[m1].im.x * scale) * w.y) * inv_r);
-                float2 y1 = make_float2(((x[m1].re.y * scale) * w.x) * inv_r, ((x[m1].im.y * scale) * w.y) * inv_r);
-                float2 *ap0 = reinterpret_cast<float2 *>(p.acc + size_t(c0) * N + ring);
-                float2 *ap1 = reinterpret_cast<float2 *>(p.acc + size_t(c1) * N + ring);
-                if (!tail) {
-                    const float2 q0 = *ap0;
+                if (s < keep) {                                   // not the tail: add what is there
+                    const float2 q0 = *reinterpret_cast<const float2 *>(acc0 + ring);
                     y0.x += q0.x; y0.y += q0.y;
-                    if (has1) { const float2 q1 = *ap1; y1.x += q1.x; y1.y += q1.y; }
+                    if (has1) { const float2 q1 = *reinterpret_cast<const float2 *>(acc1 + ring); y1.x += q1.x; y1.y += q1.y; }
                 }
-                if (head) {
-                    *reinterpret_cast<float2 *>(p.out + size_t(c0) * hop + s) = y0;
-                    if (has1) *reinterpret_cast<float2 *>(p.out + size_t(c1) * hop + s) = y1;
+                if (s < hop) {                                    // head: emit (ola:111-118)
+                    *reinterpret_cast<float2 *>(out0 + s) = y0;
+                    if (has1) *reinterpret_cast<float2 *>(out1 + s) = y1;
                 } else {
-                    *ap0 = y0;
-                    if (has1) *ap1 = y1;
+                    *reinterpret_cast<float2 *>(acc0 + ring) = y0;
+                    if (has1) *reinterpret_cast<float2 *>(acc1 + ring) = y1;
                 }
             }
         }
