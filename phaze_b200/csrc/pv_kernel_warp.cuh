@@ -47,7 +47,7 @@ struct WarpGeo {
     // descriptors / bitmap of channel c live in the (dead) mag space of channel c
     static constexpr int DESC_OFF = 0;                     // u32[MAXPK]
     static constexpr int S_OFF = MAXPK * 4;                // u32[SWORDS]
-    static constexpr int MAX_WARPS = 8;
+    static constexpr int MAX_WARPS = 7;          // 2 CTAs x 7 warps per SM leave 144 registers per thread
 };
 
 struct WarpParams {
@@ -183,42 +183,66 @@ pv_process_warp_kernel(const WarpParams wp) {
 
     cpx2 a[8], b[8];
 
+    // warm L2 with the overlap-add ring lines the tail of this kernel adds to (their loads
+    // would otherwise be a serial DRAM round trip at the very end); the slot that is only
+    // written ([rb - hop, rb)) is skipped
+    {
+        const int line = 32 * lane;                                     // floats [32 lane, 32 lane + 32)
+        if (((line - rb + hop) & (N - 1)) >= hop) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c0) * N + line));
+            if (has1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c1) * N + line));
+        }
+    }
+
     // ---- forward pass 1: butterflies n = lane, lane + 32 over m1 (stride 64), from global ----
+    {
+        // all 32 loads of the frame are issued before anything consumes them
+        float2 r0[16], r1[16];
+        const float *in0 = p.in ? p.in + size_t(c0) * hop : hist0;
+        const float *in1 = p.in ? p.in + size_t(has1 ? c1 : c0) * hop : hist0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int n = lane + 32 * h;
-        cpx2 x[8];
+        for (int e = 0; e < 16; e++) {
+            const int s = 2 * (lane + 32 * (e >> 3)) + 128 * (e & 7);
+            const bool old = s < keep;
+            const int r = (s + rb + hop) & (N - 1);
+            const int i = old ? 0 : s - keep;
+            const float *s0 = old ? hist0 + r : in0 + i;
+            const float *s1 = old ? hist1 + r : in1 + i;
+            r0[e] = *reinterpret_cast<const float2 *>(s0);
+            r1[e] = *reinterpret_cast<const float2 *>(s1);
+        }
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int s = 2 * n + 128 * j;
-            float2 v0, v1 = make_float2(0.f, 0.f);
-            if (s < keep) {
-                const int r = (s + rb + hop) & (N - 1);
-                v0 = *reinterpret_cast<const float2 *>(hist0 + r);
-                if (has1) v1 = *reinterpret_cast<const float2 *>(hist1 + r);
-            } else {
+        for (int e = 0; e < 16; e++) {
+            const int s = 2 * (lane + 32 * (e >> 3)) + 128 * (e & 7);
+            if (s >= keep) {                       // the new block: paused input is zeros (ola:93-100)
+                if (!p.in) { r0[e] = make_float2(0.f, 0.f); r1[e] = make_float2(0.f, 0.f); }
                 const int i = s - keep;
-                v0 = make_float2(0.f, 0.f);
-                if (p.in) {
-                    v0 = __ldg(reinterpret_cast<const float2 *>(p.in + size_t(c0) * hop + i));
-                    if (has1) v1 = __ldg(reinterpret_cast<const float2 *>(p.in + size_t(c1) * hop + i));
-                }
-                *reinterpret_cast<float2 *>(p.hist + size_t(c0) * N + rb + i) = v0;
-                if (has1) *reinterpret_cast<float2 *>(p.hist + size_t(c1) * N + rb + i) = v1;
+                *reinterpret_cast<float2 *>(p.hist + size_t(c0) * N + rb + i) = r0[e];
+                if (has1) *reinterpret_cast<float2 *>(p.hist + size_t(c1) * N + rb + i) = r1[e];
             }
-            const float2 w = __ldg(reinterpret_cast<const float2 *>(p.window + s));
-            x[j].re = mul2(make_float2(v0.x, v1.x), bc2(w.x));
-            x[j].im = mul2(make_float2(v0.y, v1.y), bc2(w.y));
-        }
-        dft8<false>(x);
-#pragma unroll
-        for (int k1 = 1; k1 < 8; k1++) {
-            const float2 w = __ldg(&tw[2 * n * k1]);             // W_512^{n k1}
-            x[k1] = cmul_s(x[k1], w.x, w.y);
+            if (!has1) r1[e] = make_float2(0.f, 0.f);
         }
 #pragma unroll
-        for (int k1 = 0; k1 < 8; k1++)
-            zst(zre, zim, 64 * k1 + 32 * h + (((k1 & 1) ? base1o : base1e) ^ (4 * h)), x[k1]);
+        for (int h = 0; h < 2; h++) {
+            const int n = lane + 32 * h;
+            cpx2 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int s = 2 * n + 128 * j;
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(p.window + s));
+                x[j].re = mul2(make_float2(r0[8 * h + j].x, r1[8 * h + j].x), bc2(w.x));
+                x[j].im = mul2(make_float2(r0[8 * h + j].y, r1[8 * h + j].y), bc2(w.y));
+            }
+            dft8<false>(x);
+#pragma unroll
+            for (int k1 = 1; k1 < 8; k1++) {
+                const float2 w = __ldg(&tw[2 * n * k1]);             // W_512^{n k1}
+                x[k1] = cmul_s(x[k1], w.x, w.y);
+            }
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++)
+                zst(zre, zim, 64 * k1 + 32 * h + (((k1 & 1) ? base1o : base1e) ^ (4 * h)), x[k1]);
+        }
     }
     __syncwarp();
 
@@ -539,6 +563,19 @@ pv_process_warp_kernel(const WarpParams wp) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int n = lane + 32 * h;
+            // accumulator values first (L2 hits thanks to the prefetch), then the butterflies
+            float2 q0[8], q1[8];
+#pragma unroll
+            for (int m1 = 0; m1 < 8; m1++) {
+                const int s = 2 * n + 128 * m1;
+                const int ring = (s + rb) & (N - 1);
+                q0[m1] = make_float2(0.f, 0.f);
+                q1[m1] = make_float2(0.f, 0.f);
+                if (s < keep) {                                   // the tail slot starts from zero (ola:134)
+                    q0[m1] = *reinterpret_cast<const float2 *>(acc0 + ring);
+                    q1[m1] = *reinterpret_cast<const float2 *>(acc1 + ring);
+                }
+            }
             cpx2 x[8];
 #pragma unroll
             for (int j = 0; j < 8; j++)
@@ -552,20 +589,13 @@ pv_process_warp_kernel(const WarpParams wp) {
                 const float2 w = __ldg(reinterpret_cast<const float2 *>(wp.window_out + s));
                 const float2 yr = mul2(x[m1].re, bc2(w.x));       // sample s   of (ch0, ch1)
                 const float2 yi = mul2(x[m1].im, bc2(w.y));       // sample s+1 of (ch0, ch1)
-                float2 y0 = make_float2(yr.x, yi.x), y1 = make_float2(yr.y, yi.y);
+                const float2 y0 = make_float2(yr.x + q0[m1].x, yi.x + q0[m1].y);
+                const float2 y1 = make_float2(yr.y + q1[m1].x, yi.y + q1[m1].y);
                 const int ring = (s + rb) & (N - 1);
-                if (s < keep) {                                   // not the tail: add what is there
-                    const float2 q0 = *reinterpret_cast<const float2 *>(acc0 + ring);
-                    y0.x += q0.x; y0.y += q0.y;
-                    if (has1) { const float2 q1 = *reinterpret_cast<const float2 *>(acc1 + ring); y1.x += q1.x; y1.y += q1.y; }
-                }
-                if (s < hop) {                                    // head: emit (ola:111-118)
-                    *reinterpret_cast<float2 *>(out0 + s) = y0;
-                    if (has1) *reinterpret_cast<float2 *>(out1 + s) = y1;
-                } else {
-                    *reinterpret_cast<float2 *>(acc0 + ring) = y0;
-                    if (has1) *reinterpret_cast<float2 *>(acc1 + ring) = y1;
-                }
+                float *d0 = (s < hop) ? out0 + s : acc0 + ring;   // head: emit (ola:111-118)
+                float *d1 = (s < hop) ? out1 + s : acc1 + ring;
+                *reinterpret_cast<float2 *>(d0) = y0;
+                if (has1) *reinterpret_cast<float2 *>(d1) = y1;
             }
         }
     }
