@@ -156,12 +156,15 @@ int source_limit(int n, float pitch_factor) {
     return int(lim);
 }
 
+size_t state_rows(int channels) { return size_t(channels > 0 ? ((channels + 1) & ~1) : 2); }
+
 int alloc_state(pvb_processor *p, int channels) {
     cudaFree(p->d_hist);
     cudaFree(p->d_acc);
     p->d_hist = p->d_acc = nullptr;
     p->channels = channels;
-    const size_t bytes = size_t(channels > 0 ? channels : 1) * size_t(p->n) * sizeof(float);
+    // rows are padded to an even channel count: the kernels process channels in pairs
+    const size_t bytes = state_rows(channels) * size_t(p->n) * sizeof(float);
     if (cudaMalloc(&p->d_hist, bytes) != cudaSuccess || cudaMalloc(&p->d_acc, bytes) != cudaSuccess) {
         cudaGetLastError();
         return fail(p, PVB_ERR_NOMEM, "cudaMalloc of %zu state bytes failed", 2 * bytes);
@@ -407,7 +410,7 @@ int32_t pvb_resize(pvb_processor *p, int32_t num_channels) {
 int32_t pvb_reset(pvb_processor *p) {
     if (!p) return PVB_ERR_BAD_ARG;
     DeviceGuard guard(p->device);
-    const size_t bytes = size_t(p->channels > 0 ? p->channels : 1) * size_t(p->n) * sizeof(float);
+    const size_t bytes = state_rows(p->channels) * size_t(p->n) * sizeof(float);
     PVB_CUDA(p, cudaMemsetAsync(p->d_hist, 0, bytes, p->stream));
     PVB_CUDA(p, cudaMemsetAsync(p->d_acc, 0, bytes, p->stream));
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));

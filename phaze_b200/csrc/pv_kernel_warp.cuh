@@ -160,8 +160,6 @@ pv_process_warp_kernel(const WarpParams wp) {
     const int keep = N - hop;
     const float2 *__restrict__ tw = p.tw;
     const unsigned FULL = 0xFFFFFFFFu;
-    const float *hist0 = p.hist + size_t(c0) * N;
-    const float *hist1 = p.hist + size_t(has1 ? c1 : c0) * N;
 
     // lane's two last-pass butterflies A = (k1a, k2a), B = (k1b, k2b); natural bins
     // kA + 64 j and kB + 64 j with kA + kB == 64 (lane 31 owns the two self-paired ones)
@@ -190,37 +188,42 @@ pv_process_warp_kernel(const WarpParams wp) {
         const int line = 32 * lane;                                     // floats [32 lane, 32 lane + 32)
         if (((line - rb + hop) & (N - 1)) >= hop) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c0) * N + line));
-            if (has1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c1) * N + line));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c1) * N + line));
         }
     }
 
     // ---- forward pass 1: butterflies n = lane, lane + 32 over m1 (stride 64), from global ----
     {
-        // all 32 loads of the frame are issued before anything consumes them
+        // all 32 loads of the frame are issued before anything consumes them.  Rows of hist /
+        // acc are padded to an even channel count by the host, so channel 1 is always +N floats.
         float2 r0[16], r1[16];
-        const float *in0 = p.in ? p.in + size_t(c0) * hop : hist0;
-        const float *in1 = p.in ? p.in + size_t(has1 ? c1 : c0) * hop : hist0;
+        char *histb = reinterpret_cast<char *>(p.hist + size_t(c0) * N);
+        const char *inb0 = reinterpret_cast<const char *>(p.in ? p.in + size_t(c0) * hop : p.hist);
+        const char *inb1 = inb0 + (has1 && p.in ? hop * 4 : 0);
+        const unsigned rbase = unsigned((2 * lane + rb + hop) & (N - 1)) * 4u;   // ring byte offset of sample 2*lane
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int s = 2 * (lane + 32 * (e >> 3)) + 128 * (e & 7);
-            const bool old = s < keep;
-            const int r = (s + rb + hop) & (N - 1);
-            const int i = old ? 0 : s - keep;
-            const float *s0 = old ? hist0 + r : in0 + i;
-            const float *s1 = old ? hist1 + r : in1 + i;
-            r0[e] = *reinterpret_cast<const float2 *>(s0);
-            r1[e] = *reinterpret_cast<const float2 *>(s1);
+            const int sd = 64 * (e >> 3) + 128 * (e & 7);         // sample index minus 2*lane
+            if (2 * lane + sd < keep) {
+                const unsigned off = (rbase + 4u * sd) & (N * 4 - 1);
+                r0[e] = *reinterpret_cast<const float2 *>(histb + off);
+                r1[e] = *reinterpret_cast<const float2 *>(histb + off + N * 4);
+            } else {
+                const int ib = (2 * lane + sd - keep) * 4;
+                r0[e] = *reinterpret_cast<const float2 *>(inb0 + ib);
+                r1[e] = *reinterpret_cast<const float2 *>(inb1 + ib);
+            }
         }
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int s = 2 * (lane + 32 * (e >> 3)) + 128 * (e & 7);
-            if (s >= keep) {                       // the new block: paused input is zeros (ola:93-100)
+            const int sd = 64 * (e >> 3) + 128 * (e & 7);
+            if (2 * lane + sd >= keep) {           // the new block: paused input is zeros (ola:93-100)
                 if (!p.in) { r0[e] = make_float2(0.f, 0.f); r1[e] = make_float2(0.f, 0.f); }
-                const int i = s - keep;
-                *reinterpret_cast<float2 *>(p.hist + size_t(c0) * N + rb + i) = r0[e];
-                if (has1) *reinterpret_cast<float2 *>(p.hist + size_t(c1) * N + rb + i) = r1[e];
+                if (!has1) r1[e] = make_float2(0.f, 0.f);
+                const unsigned off = unsigned(rb + 2 * lane + sd - keep) * 4u;
+                *reinterpret_cast<float2 *>(histb + off) = r0[e];
+                *reinterpret_cast<float2 *>(histb + off + N * 4) = r1[e];
             }
-            if (!has1) r1[e] = make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -254,7 +257,7 @@ pv_process_warp_kernel(const WarpParams wp) {
         float2 w2[8];
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = __ldg(&tw[16 * m3l * k2]);   // W_64^{m3 k2}
-#pragma unroll
+#pragma unroll 1
         for (int h = 0; h < 2; h++) {
             cpx2 x[8];
 #pragma unroll
@@ -405,21 +408,17 @@ pv_process_warp_kernel(const WarpParams wp) {
             continue;
         }
 
-        // region lookup + rotated value for source bin `bin` holding spectrum value v
-#define PVB_BIN_PREP(STEP, BIN, V)                                                       \
-        const uint32_t sw_w = __shfl_sync(FULL, s_reg, (STEP));                            \
-        const int ord = __shfl_sync(FULL, ps_reg, (STEP)) + __popc(sw_w & le_mask);        \
-        const uint32_t dv = dsc[ord];                                                      \
-        const int d = (BIN) + (int(dv) >> 16);                                             \
-        const bool okd = unsigned(d) < unsigned(NB);                                       \
-        const int ri = (dv >> 10) & 31;                                                    \
-        const float rc = __shfl_sync(FULL, rot_c, ri), rs = __shfl_sync(FULL, rot_s, ri);  \
-        const float2 y = make_float2((V).x * rc - (V).y * rs, (V).x * rs + (V).y * rc);    \
-        float2 *yp = Xc + xs(d);
-
+        // ---- in-place shift -------------------------------------------------------------------
+        // Source bins come in three chunks: bins 0..255, 256..511 (8 steps of 32 each) and the
+        // extension 512..671 (X[512] and the stale slots; 5 steps).  Per chunk:
+        //  A  region descriptor of every source bin this lane owns (bins 32 s + lane)
+        //  B  read those bins of X into registers, zero them in shared memory
+        //  C  right halves of the regions: plain stores (pairwise disjoint destinations)
+        //  D  left halves: read-add-store on top (pairwise disjoint among themselves)
+        // Contraction writes at or below the bin it read (chunks ascending), expansion at or
+        // above (chunks descending, and it never maps two sources to one bin: no pass D).
+        float2 ext[5];
         if (contract) {
-            // values of the source bins 512 .. 671: X[512], then the stale slots 513 .. 640
-            float2 ext[5];
 #pragma unroll
             for (int t = 0; t < 5; t++) {
                 const int q = 32 * t + lane;                 // bin 512 + q
@@ -428,66 +427,80 @@ pv_process_warp_kernel(const WarpParams wp) {
                 else if (q <= N / 8) v = stale_level1(Xc, q, tw);
                 ext[t] = v;
             }
-            __syncwarp();
-            // ascending sweep: every write lands at or below the bin just read (delta <= 0)
-#pragma unroll 2
-            for (int s = 0; s < 16; s++) {
-                const int bin = 32 * s + lane;
-                float2 *xp = Xc + 32 * s + ((s & 1) ? sw_o : sw_e);
-                const float2 v = *xp;
-                *xp = make_float2(0.f, 0.f);
-                PVB_BIN_PREP(s, bin, v)
-                const bool right = bin >= int(dv & 1023);
-                __syncwarp();
-                if (okd && right) *yp = y;                    // first writer of this bin
-                __syncwarp();
-                if (okd && !right) { float2 o = *yp; o.x += y.x; o.y += y.y; *yp = o; }
-            }
-            if (lane == 0) Xc[xs(M)] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int t = 0; t < 5; t++) {
-                const int s = 16 + t;
-                const int bin = 32 * s + lane;
-                const float2 v = ext[t];
-                const uint32_t sw_w = __shfl_sync(FULL, s_reg, s & 31);
-                int ord = __shfl_sync(FULL, ps_reg, s & 31) + __popc(sw_w & le_mask);
-                if (s >= W::SWORDS) ord = npk - 1;
-                const uint32_t dv = dsc[ord];
-                const int d = bin + (int(dv) >> 16);
-                const bool okd = unsigned(d) < unsigned(NB);
-                const int ri = (dv >> 10) & 31;
-                const float rc = __shfl_sync(FULL, rot_c, ri), rs = __shfl_sync(FULL, rot_s, ri);
-                const float2 y = make_float2(v.x * rc - v.y * rs, v.x * rs + v.y * rc);
-                float2 *yp = Xc + xs(d);
-                const bool right = bin >= int(dv & 1023);
-                __syncwarp();
-                if (okd && right) *yp = y;
-                __syncwarp();
-                if (okd && !right) { float2 o = *yp; o.x += y.x; o.y += y.y; *yp = o; }
-            }
         } else {
-            // descending sweep: every write lands at or above the bin just read (delta >= 0);
-            // expansion never maps two sources to one bin
-            {
-                const float2 v = (lane == 0) ? Xc[xs(M)] : make_float2(0.f, 0.f);
-                if (lane == 0) Xc[xs(M)] = make_float2(0.f, 0.f);
-                const int bin = M + lane;
-                PVB_BIN_PREP(16, bin, v)
-                __syncwarp();
-                if (okd && lane == 0) *yp = y;
-            }
-#pragma unroll 2
-            for (int s = 15; s >= 0; s--) {
-                const int bin = 32 * s + lane;
-                float2 *xp = Xc + 32 * s + ((s & 1) ? sw_o : sw_e);
-                const float2 v = *xp;
-                *xp = make_float2(0.f, 0.f);
-                PVB_BIN_PREP(s, bin, v)
-                __syncwarp();
-                if (okd) *yp = y;
-            }
+#pragma unroll
+            for (int t = 0; t < 5; t++) ext[t] = make_float2(0.f, 0.f);
+            if (lane == 0) ext[0] = Xc[xs(M)];
         }
-#undef PVB_BIN_PREP
+        __syncwarp();            // the stale slots were computed from an intact X
+        if (lane == 0) Xc[xs(M)] = make_float2(0.f, 0.f);
+
+        const bool quarter = p.overlaps == 4;    // R == 4: rotations are exact quarter turns
+        // rotate the value of source bin `bin` and store / accumulate it at bin + delta
+#define PVB_SHIFT_ONE(DV, BIN, V, PASS)                                                          \
+        {                                                                                          \
+            const int d = (BIN) + (int(DV) >> 16);                                                 \
+            const bool right = (BIN) >= int((DV) & 1023);                                          \
+            const bool mine = unsigned(d) < unsigned(NB) && (!contract || (right == ((PASS) == 0))); \
+            const int ri = ((DV) >> 10) & 31;                                                      \
+            float2 y;                                                                              \
+            if (quarter) {                                                                         \
+                const float ax = (ri & 1) ? -(V).y : (V).x, ay = (ri & 1) ? (V).x : (V).y;          \
+                y = make_float2((ri & 2) ? -ax : ax, (ri & 2) ? -ay : ay);                          \
+            } else {                                                                               \
+                const float rc = __shfl_sync(FULL, rot_c, ri), rs = __shfl_sync(FULL, rot_s, ri);  \
+                y = make_float2((V).x * rc - (V).y * rs, (V).x * rs + (V).y * rc);                  \
+            }                                                                                      \
+            float2 *yp = Xc + xs(d);                                                               \
+            if (mine) {                                                                            \
+                if ((PASS) == 1) { const float2 o = *yp; y.x += o.x; y.y += o.y; }                  \
+                *yp = y;                                                                           \
+            }                                                                                      \
+        }
+
+#pragma unroll 1
+        for (int it = 0; it < 3; it++) {
+            const int c = contract ? it : 2 - it;
+            if (c < 2) {
+                uint32_t dvs[8];
+                float2 xv[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int s = 8 * c + i;
+                    const uint32_t sw_w = __shfl_sync(FULL, s_reg, s);
+                    dvs[i] = dsc[__shfl_sync(FULL, ps_reg, s) + __popc(sw_w & le_mask)];
+                    float2 *xp = Xc + 256 * c + 32 * i + ((i & 1) ? sw_o : sw_e);
+                    xv[i] = *xp;
+                    *xp = make_float2(0.f, 0.f);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; i++) PVB_SHIFT_ONE(dvs[i], 256 * c + 32 * i + lane, xv[i], 0)
+                if (contract) {
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; i++) PVB_SHIFT_ONE(dvs[i], 256 * c + 32 * i + lane, xv[i], 1)
+                }
+            } else {
+                uint32_t dvs[5];
+#pragma unroll
+                for (int t = 0; t < 5; t++) {
+                    const int s = 16 + t;
+                    const uint32_t sw_w = __shfl_sync(FULL, s_reg, s);
+                    dvs[t] = dsc[__shfl_sync(FULL, ps_reg, s) + __popc(sw_w & le_mask)];
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 5; t++) PVB_SHIFT_ONE(dvs[t], 512 + 32 * t + lane, ext[t], 0)
+                if (contract) {
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < 5; t++) PVB_SHIFT_ONE(dvs[t], 512 + 32 * t + lane, ext[t], 1)
+                }
+            }
+            __syncwarp();
+        }
+#undef PVB_SHIFT_ONE
     }
     __syncwarp();
 
@@ -538,7 +551,7 @@ pv_process_warp_kernel(const WarpParams wp) {
         int s2[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) s2[j] = base2 ^ (9 * j);
-#pragma unroll
+#pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const int k1 = (lane >> 3) + 4 * h;
             cpx2 x[8];
@@ -556,24 +569,25 @@ pv_process_warp_kernel(const WarpParams wp) {
 
     // ---- inverse pass 3: butterflies n over k1 -> z[n + 64 m1]; window, overlap-add, emit ------------------
     {
-        float *acc0 = p.acc + size_t(c0) * N;
-        float *acc1 = p.acc + size_t(has1 ? c1 : c0) * N;
-        float *out0 = p.out + size_t(c0) * hop;
-        float *out1 = p.out + size_t(has1 ? c1 : c0) * hop;
-#pragma unroll
+        char *accb = reinterpret_cast<char *>(p.acc + size_t(c0) * N);
+        char *outb0 = reinterpret_cast<char *>(p.out + size_t(c0) * hop);
+        char *outb1 = outb0 + (has1 ? hop * 4 : 0);
+        const unsigned abase = unsigned((2 * lane + rb) & (N - 1)) * 4u;       // ring byte offset of sample 2*lane
+#pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const int n = lane + 32 * h;
             // accumulator values first (L2 hits thanks to the prefetch), then the butterflies
-            float2 q0[8], q1[8];
+            float2 q0[8], q1[8], wo[8];
 #pragma unroll
             for (int m1 = 0; m1 < 8; m1++) {
                 const int s = 2 * n + 128 * m1;
-                const int ring = (s + rb) & (N - 1);
+                const unsigned off = (abase + 4u * (64 * h + 128 * m1)) & (N * 4 - 1);
+                wo[m1] = __ldg(reinterpret_cast<const float2 *>(wp.window_out + s));
                 q0[m1] = make_float2(0.f, 0.f);
                 q1[m1] = make_float2(0.f, 0.f);
                 if (s < keep) {                                   // the tail slot starts from zero (ola:134)
-                    q0[m1] = *reinterpret_cast<const float2 *>(acc0 + ring);
-                    q1[m1] = *reinterpret_cast<const float2 *>(acc1 + ring);
+                    q0[m1] = *reinterpret_cast<const float2 *>(accb + off);
+                    q1[m1] = *reinterpret_cast<const float2 *>(accb + off + N * 4);
                 }
             }
             cpx2 x[8];
@@ -586,16 +600,19 @@ pv_process_warp_kernel(const WarpParams wp) {
                 const int s = 2 * n + 128 * m1;
                 // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the
                 // division by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of 2)
-                const float2 w = __ldg(reinterpret_cast<const float2 *>(wp.window_out + s));
+                const float2 w = wo[m1];
                 const float2 yr = mul2(x[m1].re, bc2(w.x));       // sample s   of (ch0, ch1)
                 const float2 yi = mul2(x[m1].im, bc2(w.y));       // sample s+1 of (ch0, ch1)
                 const float2 y0 = make_float2(yr.x + q0[m1].x, yi.x + q0[m1].y);
                 const float2 y1 = make_float2(yr.y + q1[m1].x, yi.y + q1[m1].y);
-                const int ring = (s + rb) & (N - 1);
-                float *d0 = (s < hop) ? out0 + s : acc0 + ring;   // head: emit (ola:111-118)
-                float *d1 = (s < hop) ? out1 + s : acc1 + ring;
-                *reinterpret_cast<float2 *>(d0) = y0;
-                if (has1) *reinterpret_cast<float2 *>(d1) = y1;
+                if (s < hop) {                                    // head: emit (ola:111-118)
+                    *reinterpret_cast<float2 *>(outb0 + 4 * s) = y0;
+                    if (has1) *reinterpret_cast<float2 *>(outb1 + 4 * s) = y1;
+                } else {
+                    const unsigned off = (abase + 4u * (64 * h + 128 * m1)) & (N * 4 - 1);
+                    *reinterpret_cast<float2 *>(accb + off) = y0;
+                    *reinterpret_cast<float2 *>(accb + off + N * 4) = y1;
+                }
             }
         }
     }
