@@ -1,0 +1,126 @@
+"""Channel sharding of one logical processor across the GPUs of a node (one process per GPU).
+
+Channels are fully independent on this path (src/phase-vocoder.js:49-53 loops over them
+serially; the only shared datum is timeCursor, phase-vocoder.js:71, which every shard
+advances identically), so the path shards with NO data-path collective: rank r owns a
+contiguous block of channels, its history / overlap-add rings live in its own HBM, and
+`process_local` touches nothing but local memory.
+
+`process_from_root` adds the exchange step the north-star names: rank 0 holds the full
+[C][hop] input block, scatters each rank's slab (grouped point-to-point sends ==
+ncclSend/ncclRecv over NVLink under the "nccl" backend), every rank processes its slab,
+and the output slabs are gathered back on rank 0.
+
+The per-shard engine is injected (`processor_factory`) so the partition / exchange logic is
+testable on CPU with the gloo backend; the default factory is the CUDA engine.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_channels: int, world_size: int) -> List[Tuple[int, int]]:
+    """[(first, last+1)] per rank: contiguous blocks, boundaries on even channels (the CUDA
+    kernels process channels in pairs; pairing must not depend on the number of shards)."""
+    pairs = (num_channels + 1) // 2
+    out = []
+    for r in range(world_size):
+        lo = min(2 * ((pairs * r) // world_size), num_channels)
+        hi = min(2 * ((pairs * (r + 1)) // world_size), num_channels)
+        out.append((lo, hi))
+    return out
+
+
+class _CudaShard:
+    """Default per-shard engine: the C-ABI handle on this rank's GPU, device tensors in/out."""
+
+    def __init__(self, num_channels: int, frame_size: int, hop_size: int, device: torch.device):
+        from .processor import BatchedPhaseVocoder
+        self.pv = BatchedPhaseVocoder(num_channels, frame_size, hop_size, device=device.index or 0)
+        self.device = device
+        self.hop = hop_size
+        self.num_channels = num_channels
+
+    def process(self, block: Optional[torch.Tensor], pitch_factor: float) -> torch.Tensor:
+        out = torch.empty((self.num_channels, self.hop), dtype=torch.float32, device=self.device)
+        if self.num_channels == 0:
+            self.pv.process_device(None, 0, pitch_factor)      # keeps timeCursor in step
+            return out
+        stream = torch.cuda.current_stream(self.device).cuda_stream or None
+        in_ptr = None
+        if block is not None:
+            assert block.is_cuda and block.dtype == torch.float32 and block.is_contiguous()
+            in_ptr = block.data_ptr()
+        self.pv.process_device(in_ptr, out.data_ptr(), pitch_factor, stream)
+        if stream is None:
+            self.pv.sync()
+        return out
+
+
+class ShardedPhaseVocoder:
+    def __init__(self, num_channels: int, frame_size: int = 2048, hop_size: int = 128,
+                 group: Optional[dist.ProcessGroup] = None,
+                 processor_factory: Optional[Callable[[int], object]] = None,
+                 device: Optional[torch.device] = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.num_channels, self.frame_size, self.hop_size = num_channels, frame_size, hop_size
+        self.bounds = shard_bounds(num_channels, self.world)
+        self.first, self.last = self.bounds[self.rank]
+        self.local_channels = self.last - self.first
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() \
+                else torch.device("cpu")
+        self.device = device
+        if processor_factory is None:
+            processor_factory = lambda n: _CudaShard(n, frame_size, hop_size, device)   # noqa: E731
+        self.engine = processor_factory(self.local_channels)
+
+    # -- shard-resident steady state: no collective --------------------------------------------
+    def process_local(self, local_block: Optional[torch.Tensor], pitch_factor: float) -> torch.Tensor:
+        """local_block: this rank's [local_channels][hop] slab (None == paused)."""
+        return self.engine.process(local_block, pitch_factor)
+
+    # -- single-root mode: scatter, process, gather ----------------------------------------------
+    def process_from_root(self, full_block: Optional[torch.Tensor], pitch_factor: float,
+                          root: int = 0) -> Optional[torch.Tensor]:
+        """full_block [C][hop] on `root` (ignored elsewhere).  Returns the [C][hop] output on root."""
+        hop = self.hop_size
+        local = torch.empty((self.local_channels, hop), dtype=torch.float32, device=self.device)
+        if self.world == 1:
+            local = full_block
+        else:
+            ops = []
+            if self.rank == root:
+                for r, (lo, hi) in enumerate(self.bounds):
+                    if r == root:
+                        local = full_block[lo:hi].contiguous()
+                    elif hi > lo:
+                        ops.append(dist.P2POp(dist.isend, full_block[lo:hi].contiguous(), r, self.group))
+            elif self.local_channels > 0:
+                ops.append(dist.P2POp(dist.irecv, local, root, self.group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+        out_local = self.engine.process(local, pitch_factor)
+        if self.world == 1:
+            return out_local
+        result = None
+        ops = []
+        if self.rank == root:
+            result = torch.empty((self.num_channels, hop), dtype=torch.float32, device=self.device)
+            for r, (lo, hi) in enumerate(self.bounds):
+                if r == root:
+                    result[lo:hi] = out_local
+                elif hi > lo:
+                    ops.append(dist.P2POp(dist.irecv, result[lo:hi], r, self.group))
+        elif self.local_channels > 0:
+            ops.append(dist.P2POp(dist.isend, out_local.contiguous(), root, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return result

@@ -1,0 +1,86 @@
+"""Known-answer properties of the oracle: independent of the golden vectors."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("n", [16, 64, 256, 512, 1024, 2048, 4096])
+def test_forward_fft_valid_half_is_rfft(oracle, n):
+    x = np.random.default_rng(n).uniform(-1, 1, n).astype(np.float32)
+    X = oracle.real_transform(x)
+    ref = np.fft.rfft(x.astype(np.float64))
+    assert np.abs(X[: n // 2 + 1] - ref).max() <= 1e-12 * n
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096])
+def test_stale_upper_bins_are_sub_transforms(oracle, n):
+    """bins N/2+1.. hold DFT_{N/4}(x[4m+2])[1..N/8]; 3N/4.. hold DFT_{N/4}(x[4m+3])[0..N/8];
+    N/2+N/8+1.. hold DFT_{N/16}(x[16m+10])[1..N/32]  (bundle:394-438 write pattern)."""
+    x = np.random.default_rng(7 * n).uniform(-1, 1, n).astype(np.float32)
+    X = oracle.real_transform(x)
+    xd = x.astype(np.float64)
+    f = np.fft.fft
+    assert np.abs(X[n // 2 + 1: n // 2 + n // 8 + 1] - f(xd[2::4])[1: n // 8 + 1]).max() < 1e-11
+    assert np.abs(X[3 * n // 4: 3 * n // 4 + n // 8 + 1] - f(xd[3::4])[: n // 8 + 1]).max() < 1e-11
+    a = n // 2 + n // 8 + 1
+    assert np.abs(X[a: a + n // 32] - f(xd[10::16])[1: n // 32 + 1]).max() < 1e-11
+
+
+def test_stale_bins_from_valid_half_identity(oracle):
+    """the identity the CUDA kernels use: slot N/2+q == 1/4 W^{-2q} (X[q] - X[N/4+q] + conj X[N/2-q] - conj X[N/4-q])"""
+    n = 1024
+    x = np.random.default_rng(3).uniform(-1, 1, n).astype(np.float32)
+    X = oracle.real_transform(x)
+    q = np.arange(1, n // 8 + 1)
+    w = np.exp(2j * np.pi * 2 * q / n)
+    rebuilt = 0.25 * w * (X[q] - X[n // 4 + q] + np.conj(X[n // 2 - q]) - np.conj(X[n // 4 - q]))
+    assert np.abs(rebuilt - X[n // 2 + q]).max() < 1e-11
+
+
+def test_inverse_round_trip(oracle):
+    n = 1024
+    x = np.random.default_rng(5).uniform(-1, 1, n)
+    spec = np.fft.fft(x)
+    assert np.abs(oracle.inverse_transform(spec).real - x).max() < 1e-12
+
+
+@pytest.mark.parametrize("n,hop", [(1024, 256), (2048, 128), (2048, 512), (256, 64)])
+def test_unity_pitch_is_a_scaled_delay(oracle, n, hop):
+    """pitchFactor 1: y[t] = (sum w^2 / R) x[t - (N - hop)] = 0.375 x[t - (N - hop)]"""
+    calls = 3 * n // hop
+    x = np.random.default_rng(11).uniform(-1, 1, (2, calls * hop)).astype(np.float32)
+    y = oracle.OracleProcessor(n, hop, 2).run(x, 1.0)
+    d = n - hop
+    err = y[:, d:] - 0.375 * x[:, :-d]
+    assert np.sqrt(np.mean(err ** 2)) < 5e-8
+
+
+def test_silence_gives_exact_zeros(oracle):
+    y = oracle.OracleProcessor(1024, 256, 2).run(np.zeros((2, 20 * 256), np.float32), 1.3)
+    assert not y.any()
+
+
+def test_bin_centred_sine_moves_to_scaled_bin(oracle):
+    n, hop, k, pf = 1024, 256, 40, 1.5
+    t = np.arange(40 * hop)
+    x = (0.5 * np.sin(2 * np.pi * k * t / n))[None].astype(np.float32)
+    y = oracle.OracleProcessor(n, hop, 1).run(x, pf)[0]
+    seg = y[20 * hop: 20 * hop + n] * np.hanning(n + 1)[:n]
+    assert np.argmax(np.abs(np.fft.rfft(seg))) == round(k * pf)
+
+
+def test_highest_source_bin_read(oracle):
+    """how far above N/2 shiftPeaks reads"""
+    x = np.random.default_rng(2).uniform(-1, 1, (1, 24 * 256)).astype(np.float32)
+    seen = {}
+    for pf in (0.8, 0.75, 0.5):
+        p = oracle.OracleProcessor(1024, 256, 1)
+        p.run(x, pf)
+        seen[pf] = p.max_source_bin
+    assert 600 <= seen[0.8] <= 616 and 630 <= seen[0.75] <= 640 and 740 <= seen[0.5] <= 768
+
+
+def test_bad_sizes_rejected(oracle):
+    with pytest.raises(ValueError):
+        oracle.OracleProcessor(1000, 250, 1)
+    with pytest.raises(ValueError):
+        oracle.real_transform(np.zeros(48, np.float32))
