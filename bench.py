@@ -33,6 +33,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "STFT frames/sec (1024-pt, hop 256) at 4096 ch; achieved HBM GB/s vs peak"
+
+
+def workload_name(channels, frame, hop, pitch):
+    return (f"{channels} mono channels per GPU, frame {frame} / hop {hop}, pitchFactor {pitch} "
+            f"(BASELINE configs[1])")
 UNIT = "frames/s"
 FRAME, HOP, CHANNELS, PITCH = 1024, 256, 4096, 0.8
 L2_BYTES = 126e6
@@ -215,10 +220,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.channels} mono channels, frame {frame} / hop {hop}, "
-                               f"pitchFactor {args.pitch} (BASELINE configs[1])",
+        "config": {"workload": workload_name(args.channels, frame, hop, args.pitch),
                    "frame": frame, "hop": hop, "pitch_factor": args.pitch,
-                   "channels_per_step": chans},
+                   "channels_per_gpu": args.channels, "channels_per_step": chans},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -310,7 +314,7 @@ def run_ours(args):
     frames_total = world * K * C
     value = frames_total / (ms_max * 1e-3)
 
-    # L2-resident variant (single instance, state stays in L2): reported for context only
+    # context only: (a) one instance, state stays in L2; (b) every instance on its own stream
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(min(W, 50)):
         procs[0].process_device(blocks[i % nblk].data_ptr(), outs[0].data_ptr(), pitch, sptr)
@@ -321,7 +325,24 @@ def run_ours(args):
     torch.cuda.synchronize()
     l2_value = K * C / (ev2.elapsed_time(ev3) * 1e-3)
 
-    # e2e: host buffers through pvb_process_many (pinned), H2D + D2H in the timed region
+    side = [torch.cuda.Stream() for _ in range(rotate)]
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev4.record(stream)
+    for st in side:
+        st.wait_event(ev4)
+    for i in range(K):
+        procs[i % rotate].process_device(blocks[i % nblk].data_ptr(), outs[i % rotate].data_ptr(),
+                                         pitch, side[i % rotate].cuda_stream)
+    for st in side:
+        e = torch.cuda.Event()
+        e.record(st)
+        stream.wait_event(e)
+    ev5.record(stream)
+    torch.cuda.synchronize()
+    streams_value = K * C / (ev4.elapsed_time(ev5) * 1e-3)
+
+    # e2e: host buffers through the C ABI (pinned), H2D + D2H in the timed region
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(procs, blocks_np, C, hop, pitch, K, dist)
@@ -331,7 +352,7 @@ def run_ours(args):
     achieved = 12.0 * frame * C / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
-                "peak_source": peak_src, "kernel": f"pvb::pv_process_kernel<{frame}>",
+                "peak_source": peak_src, "kernel": procs[0].kernel_name(pitch),
                 "algorithmic_bytes_per_launch": 12 * frame * C,
                 "avg_launch_us": kernel_ms * 1e3}
 
@@ -343,8 +364,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{C} mono channels per GPU, frame {frame} / hop {hop}, "
-                                   f"pitchFactor {args.pitch} (BASELINE configs[1])",
+            "config": {"workload": workload_name(C, frame, hop, args.pitch),
                        "frame": frame, "hop": hop, "pitch_factor": args.pitch,
                        "channels_per_gpu": C, "frames_per_step": C * world,
                        "l2_policy": f"inputs larger than L2: {rotate} processor instances "
@@ -355,6 +375,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "l2_resident_value": l2_value,
+            "concurrent_streams_value": streams_value,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -366,49 +387,61 @@ def run_ours(args):
 
 
 def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
-    """Same metric through the host-buffer entry point: every step copies its input block
-    from pinned host memory and reads its output block back."""
+    """Same metric through the host-buffer entry points: every step copies its input block from
+    pinned host memory to the device and its output block back (4 MiB each way at the default
+    workload).  `value` uses pvb_process_many (16 consecutive process() calls per submission,
+    copies and kernels pipelined on three streams, bit-identical to 16 single calls);
+    `single_call_value` uses the synchronous one-call-at-a-time pvb_process."""
     import ctypes as Ct
 
     import numpy as np
     import torch
 
     lib = phaze_b200_lib()
+    nblk = blocks_np.shape[0]
     nbytes = C * hop * 4
-    hin = lib.pvb_alloc_host(nbytes * blocks_np.shape[0])
-    hout = lib.pvb_alloc_host(nbytes)
-    Ct.memmove(hin, blocks_np.ctypes.data, nbytes * blocks_np.shape[0])
-    steps = int(min(K, 400))
-    p0 = procs[0]
+    batch = 16
+    hin = lib.pvb_alloc_host(nbytes * batch)
+    hout = lib.pvb_alloc_host(nbytes * batch)
+    for k in range(batch):
+        Ct.memmove(hin + k * nbytes, blocks_np[k % nblk].ctypes.data, nbytes)
 
-    def one(i):
-        rc = lib.pvb_process(procs[i % len(procs)]._h, hin + (i % blocks_np.shape[0]) * nbytes,
-                             hout, pitch)
+    def timed(fn, steps, per_call):
+        fn(0)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(steps // per_call):
+            fn(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        world = 1
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            world = dist.get_world_size()
+        return world * (steps // per_call) * per_call * C / float(t.item())
+
+    def many(i):
+        rc = lib.pvb_process_many(procs[i % len(procs)]._h, hin, hout, batch, pitch)
         assert rc == 0, rc
 
-    for i in range(5):
-        one(i)
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(steps):
-        one(i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    world = 1
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        world = dist.get_world_size()
-    dt = float(t.item())
+    def single(i):
+        rc = lib.pvb_process(procs[i % len(procs)]._h, hin + (i % batch) * nbytes, hout, pitch)
+        assert rc == 0, rc
+
+    steps = int(max(batch, min(K, 1600) // batch * batch))
+    value = timed(many, steps, batch)
+    single_value = timed(single, int(min(K, 400)), 1)
     check = float(np.ctypeslib.as_array(Ct.cast(hout, Ct.POINTER(Ct.c_float)), (C * hop,)).std())
     lib.pvb_free_host(hin)
     lib.pvb_free_host(hout)
-    return {"value": world * steps * C / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-            "d2h_bytes_per_step": nbytes, "steps": steps,
-            "api": "pvb_process(handle, in_host, out_host, pitch) - synchronous, pinned host buffers",
-            "out_std": check}
+    return {"value": value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "steps": steps, "calls_per_submission": batch,
+            "api": "pvb_process_many(handle, in_host, out_host, 16, pitch): pinned host buffers, "
+                   "H2D / kernel / D2H of consecutive calls overlapped, synchronous on return",
+            "single_call_value": single_value, "out_std": check}
 
 
 def phaze_b200_lib():
@@ -418,7 +451,7 @@ def phaze_b200_lib():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the
 # committed `ncu --set full` capture (profiles/), for the default workload; None until captured.
-NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_BYTES = 29.48e6   # profiles/r01_ncu_warp_kernel.txt: reads 29.45 MB + writes 0.03 MB (stores retire into L2)
 
 
 def main():

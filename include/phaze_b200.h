@@ -113,6 +113,9 @@ PVB_API int32_t pvb_num_channels(const pvb_processor *p);
 /* this.timeCursor (phase-vocoder.js:31,71): hop_size * (process calls so far) */
 PVB_API double pvb_time_cursor(const pvb_processor *p);
 PVB_API int32_t pvb_set_time_cursor(pvb_processor *p, double samples);
+/* name of the CUDA kernel a process() call with this pitch factor launches on this handle
+ * (two kernels exist: the warp-synchronous one for frame 1024 and the generic one) */
+PVB_API const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor);
 /* number of CUDA kernels this handle has launched since creation */
 PVB_API int64_t pvb_kernel_launches(const pvb_processor *p);
 

@@ -25,6 +25,8 @@ struct pvb_processor {
     float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
     size_t staging_floats = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;    // copy streams of the pipelined host path
+    std::vector<cudaEvent_t> ev_in, ev_done;
     int64_t launches = 0;
     char err[256] = "";
 };
@@ -201,10 +203,17 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// hooks of the pipelined host path: run before / after the launch of call k
+struct CallHooks {
+    virtual void before(int k, cudaStream_t s) = 0;
+    virtual void after(int k, cudaStream_t s) = 0;
+};
+
 int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls, float pf,
-           cudaStream_t s) {
+           cudaStream_t s, CallHooks *hooks = nullptr) {
     const size_t block = size_t(p->channels) * size_t(p->hop);
     for (int k = 0; k < num_calls; k++) {
+        if (hooks) hooks->before(k, s);
         pvb::FrameParams fp;
         fp.in = in_dev ? in_dev + size_t(k) * block : nullptr;
         fp.out = out_dev + size_t(k) * block;
@@ -226,6 +235,7 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         }
         p->ring_calls++;
         p->cursor_calls++;   // pv:71, once per call for all channels
+        if (hooks) hooks->after(k, s);
     }
     return PVB_OK;
 }
@@ -342,6 +352,10 @@ void pvb_destroy(pvb_processor *p) {
     cudaFree(p->d_tw);
     cudaFree(p->d_in);
     cudaFree(p->d_out);
+    for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->ev_done) cudaEventDestroy(e);
+    if (p->s_in) cudaStreamDestroy(p->s_in);
+    if (p->s_out) cudaStreamDestroy(p->s_out);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -365,7 +379,8 @@ int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t 
     if (!p) return PVB_ERR_BAD_ARG;
     if (!out || num_calls < 0) return fail(p, PVB_ERR_BAD_ARG, "pvb_process: bad argument");
     DeviceGuard guard(p->device);
-    const size_t floats = size_t(p->channels) * size_t(p->hop) * size_t(num_calls);
+    const size_t block = size_t(p->channels) * size_t(p->hop);
+    const size_t floats = block * size_t(num_calls);
     if (floats == 0) {
         p->ring_calls += num_calls;
         p->cursor_calls += num_calls;
@@ -373,10 +388,50 @@ int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t 
     }
     int rc = ensure_staging(p, floats);
     if (rc != PVB_OK) return rc;
-    if (in) PVB_CUDA(p, cudaMemcpyAsync(p->d_in, in, floats * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-    rc = submit(p, in ? p->d_in : nullptr, p->d_out, num_calls, pitch_factor, p->stream);
+    if (num_calls == 1) {
+        if (in) PVB_CUDA(p, cudaMemcpyAsync(p->d_in, in, floats * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+        rc = submit(p, in ? p->d_in : nullptr, p->d_out, 1, pitch_factor, p->stream);
+        if (rc != PVB_OK) return rc;
+        PVB_CUDA(p, cudaMemcpyAsync(out, p->d_out, floats * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+        PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+        return PVB_OK;
+    }
+    // several calls: the input copy of call k+1, the kernel of call k and the output copy of
+    // call k-1 overlap (three streams chained by events); results are those of K single calls
+    if (!p->s_in) {
+        PVB_CUDA(p, cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking));
+        PVB_CUDA(p, cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking));
+    }
+    while (int(p->ev_in.size()) < num_calls) {
+        cudaEvent_t a, b;
+        PVB_CUDA(p, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        PVB_CUDA(p, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        p->ev_in.push_back(a);
+        p->ev_done.push_back(b);
+    }
+    struct Pipe : CallHooks {
+        pvb_processor *p; const float *in; float *out; size_t block; cudaError_t err = cudaSuccess;
+        void note(cudaError_t e) { if (err == cudaSuccess) err = e; }
+        void before(int k, cudaStream_t s) override {
+            if (in) {
+                note(cudaMemcpyAsync(p->d_in + k * block, in + k * block, block * sizeof(float),
+                                     cudaMemcpyHostToDevice, p->s_in));
+                note(cudaEventRecord(p->ev_in[k], p->s_in));
+                note(cudaStreamWaitEvent(s, p->ev_in[k], 0));
+            }
+        }
+        void after(int k, cudaStream_t s) override {
+            note(cudaEventRecord(p->ev_done[k], s));
+            note(cudaStreamWaitEvent(p->s_out, p->ev_done[k], 0));
+            note(cudaMemcpyAsync(out + k * block, p->d_out + k * block, block * sizeof(float),
+                                 cudaMemcpyDeviceToHost, p->s_out));
+        }
+    } pipe;
+    pipe.p = p; pipe.in = in; pipe.out = out; pipe.block = block;
+    rc = submit(p, in ? p->d_in : nullptr, p->d_out, num_calls, pitch_factor, p->stream, &pipe);
     if (rc != PVB_OK) return rc;
-    PVB_CUDA(p, cudaMemcpyAsync(out, p->d_out, floats * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    PVB_CUDA(p, pipe.err);
+    PVB_CUDA(p, cudaStreamSynchronize(p->s_out));
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
     return PVB_OK;
 }
@@ -424,6 +479,22 @@ int32_t pvb_hop_size(const pvb_processor *p) { return p ? p->hop : PVB_ERR_BAD_A
 int32_t pvb_num_channels(const pvb_processor *p) { return p ? p->channels : PVB_ERR_BAD_ARG; }
 double pvb_time_cursor(const pvb_processor *p) { return p ? double(p->cursor_calls) * p->hop : 0.0; }
 int64_t pvb_kernel_launches(const pvb_processor *p) { return p ? p->launches : 0; }
+
+const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
+    if (!p) return "";
+    pvb::FrameParams fp{};
+    fp.pitch_factor = pitch_factor;
+    fp.overlaps = p->overlaps;
+    split_pitch_factor(pitch_factor, &fp.pf_mant, &fp.pf_shift);
+    if (warp_kernel_applies(p->n, fp) && !g_force_generic) return "pvb::pv_process_warp_kernel";
+    switch (p->n) {
+        case 256: return "pvb::pv_process_kernel<256>";
+        case 512: return "pvb::pv_process_kernel<512>";
+        case 1024: return "pvb::pv_process_kernel<1024>";
+        case 2048: return "pvb::pv_process_kernel<2048>";
+        default: return "pvb::pv_process_kernel<4096>";
+    }
+}
 
 int32_t pvb_set_time_cursor(pvb_processor *p, double samples) {
     if (!p) return PVB_ERR_BAD_ARG;

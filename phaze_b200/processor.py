@@ -79,6 +79,9 @@ class BatchedPhaseVocoder:
     def kernel_launches(self) -> int:
         return self._lib.pvb_kernel_launches(self._h)
 
+    def kernel_name(self, pitch_factor: float) -> str:
+        return self._lib.pvb_kernel_name(self._h, np.float32(pitch_factor)).decode()
+
     # -- process ----------------------------------------------------------------------
     def process(self, block: np.ndarray | None, pitch_factor: float,
                 out: np.ndarray | None = None) -> np.ndarray:
