@@ -436,12 +436,14 @@ pv_process_warp_kernel(const WarpParams wp) {
         if (lane == 0) Xc[xs(M)] = make_float2(0.f, 0.f);
 
         const bool quarter = p.overlaps == 4;    // R == 4: rotations are exact quarter turns
-        // rotate the value of source bin `bin` and store / accumulate it at bin + delta
-#define PVB_SHIFT_ONE(DV, BIN, V, PASS)                                                          \
+        // Pass C: rotate the value V of source bin BIN, store it at BIN + delta if this lane is the
+        // first writer of that bin (right half of its region, or any bin when expanding); otherwise
+        // keep the rotated value in V and the destination slot in DV for pass D.
+#define PVB_SHIFT_FIRST(DV, BIN, V)                                                               \
         {                                                                                          \
             const int d = (BIN) + (int(DV) >> 16);                                                 \
             const bool right = (BIN) >= int((DV) & 1023);                                          \
-            const bool mine = unsigned(d) < unsigned(NB) && (!contract || (right == ((PASS) == 0))); \
+            const bool okd = unsigned(d) < unsigned(NB);                                           \
             const int ri = ((DV) >> 10) & 31;                                                      \
             float2 y;                                                                              \
             if (quarter) {                                                                         \
@@ -451,12 +453,14 @@ pv_process_warp_kernel(const WarpParams wp) {
                 const float rc = __shfl_sync(FULL, rot_c, ri), rs = __shfl_sync(FULL, rot_s, ri);  \
                 y = make_float2((V).x * rc - (V).y * rs, (V).x * rs + (V).y * rc);                  \
             }                                                                                      \
-            float2 *yp = Xc + xs(d);                                                               \
-            if (mine) {                                                                            \
-                if ((PASS) == 1) { const float2 o = *yp; y.x += o.x; y.y += o.y; }                  \
-                *yp = y;                                                                           \
-            }                                                                                      \
+            const int slot = xs(d);                                                                \
+            (V) = y;                                                                               \
+            if (okd && (right || !contract)) Xc[slot] = y;                                         \
+            (DV) = (okd && !right && contract) ? uint32_t(slot) : 0xFFFFFFFFu;                     \
         }
+        // Pass D: left halves add on top of whatever pass C left in their bin
+#define PVB_SHIFT_SECOND(DV, V)                                                                   \
+        if ((DV) != 0xFFFFFFFFu) { float2 o = Xc[(DV)]; o.x += (V).x; o.y += (V).y; Xc[(DV)] = o; }
 
 #pragma unroll 1
         for (int it = 0; it < 3; it++) {
@@ -475,11 +479,11 @@ pv_process_warp_kernel(const WarpParams wp) {
                 }
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 8; i++) PVB_SHIFT_ONE(dvs[i], 256 * c + 32 * i + lane, xv[i], 0)
+                for (int i = 0; i < 8; i++) PVB_SHIFT_FIRST(dvs[i], 256 * c + 32 * i + lane, xv[i])
                 if (contract) {
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 8; i++) PVB_SHIFT_ONE(dvs[i], 256 * c + 32 * i + lane, xv[i], 1)
+                    for (int i = 0; i < 8; i++) PVB_SHIFT_SECOND(dvs[i], xv[i])
                 }
             } else {
                 uint32_t dvs[5];
@@ -491,16 +495,17 @@ pv_process_warp_kernel(const WarpParams wp) {
                 }
                 __syncwarp();
 #pragma unroll
-                for (int t = 0; t < 5; t++) PVB_SHIFT_ONE(dvs[t], 512 + 32 * t + lane, ext[t], 0)
+                for (int t = 0; t < 5; t++) PVB_SHIFT_FIRST(dvs[t], 512 + 32 * t + lane, ext[t])
                 if (contract) {
                     __syncwarp();
 #pragma unroll
-                    for (int t = 0; t < 5; t++) PVB_SHIFT_ONE(dvs[t], 512 + 32 * t + lane, ext[t], 1)
+                    for (int t = 0; t < 5; t++) PVB_SHIFT_SECOND(dvs[t], ext[t])
                 }
             }
             __syncwarp();
         }
-#undef PVB_SHIFT_ONE
+#undef PVB_SHIFT_FIRST
+#undef PVB_SHIFT_SECOND
     }
     __syncwarp();
 
