@@ -43,20 +43,23 @@ class _CudaShard:
         self.device = device
         self.hop = hop_size
         self.num_channels = num_channels
+        self.side = torch.cuda.Stream(device)      # the kernels run here, ordered after the caller's stream
 
     def process(self, block: Optional[torch.Tensor], pitch_factor: float) -> torch.Tensor:
         out = torch.empty((self.num_channels, self.hop), dtype=torch.float32, device=self.device)
         if self.num_channels == 0:
             self.pv.process_device(None, 0, pitch_factor)      # keeps timeCursor in step
             return out
-        stream = torch.cuda.current_stream(self.device).cuda_stream or None
+        cur = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(cur)                 # inputs (e.g. a finished NCCL recv) are ready
         in_ptr = None
         if block is not None:
             assert block.is_cuda and block.dtype == torch.float32 and block.is_contiguous()
             in_ptr = block.data_ptr()
-        self.pv.process_device(in_ptr, out.data_ptr(), pitch_factor, stream)
-        if stream is None:
-            self.pv.sync()
+            block.record_stream(self.side)
+        out.record_stream(self.side)
+        self.pv.process_device(in_ptr, out.data_ptr(), pitch_factor, self.side.cuda_stream)
+        cur.wait_stream(self.side)                 # whoever consumes `out` on the caller's stream waits
         return out
 
 
