@@ -6,6 +6,7 @@
 #include "../../include/phaze_b200.h"
 #include "pv_kernel.cuh"
 #include "pv_kernel_warp.cuh"
+#include "pv_kernel_pair.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -35,6 +36,8 @@ namespace {
 
 thread_local char g_create_err[256] = "";
 bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
+int g_kernel_1024 = 1;           // PVB_KERNEL_1024=1 (default): one warp per channel pair, 2: two warps per pair
+int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
 
 // pitch_factor == mant * 2^-shift exactly; shift outside [1, 62] -> 0 (kernel uses float64)
 void split_pitch_factor(float pf, int *mant, int *shift) {
@@ -129,14 +132,45 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
     pvb::WarpParams wp;
     wp.f = fp;
     wp.window_out = window_out;
+    wp.num_sms = num_sms;
+    wp.stagger_ns = (grid <= 2 * num_sms) ? g_stagger_ns : 0;
     pvb::pv_process_warp_kernel<<<grid, wpc * 32, size_t(wpc) * W::WARP_BYTES, s>>>(wp);
+    return cudaGetLastError();
+}
+
+// two warps per channel pair (pv_kernel_pair.cuh): same validity range as the warp kernel
+cudaError_t launch_pair(const pvb::FrameParams &fp, const float *window_out, int num_sms,
+                        cudaStream_t s) {
+    using G = pvb::PairGeo;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_pair_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(G::MAX_PAIRS * G::PAIR_BYTES));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int pairs = (fp.num_channels + 1) / 2;
+    if (pairs == 0) return cudaSuccess;
+    const int ppc = pick_warps_per_cta(pairs, num_sms);          // pairs per CTA, 4..7
+    const int grid = (pairs + ppc - 1) / ppc;
+    pvb::WarpParams wp;
+    wp.f = fp;
+    wp.window_out = window_out;
+    wp.num_sms = num_sms;
+    wp.stagger_ns = (grid <= 2 * num_sms) ? g_stagger_ns : 0;
+    pvb::pv_process_pair_kernel<<<grid, ppc * 64, size_t(ppc) * G::PAIR_BYTES, s>>>(wp);
     return cudaGetLastError();
 }
 
 cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
     const int n = h->n;
-    if (warp_kernel_applies(n, fp) && !g_force_generic)
+    if (warp_kernel_applies(n, fp) && !g_force_generic) {
+        if (g_kernel_1024 == 2) return launch_pair(fp, h->d_window_out, h->num_sms, s);
         return launch_warp(fp, h->d_window_out, h->num_sms, s);
+    }
     switch (n) {
         case 256: return launch_n<256>(fp, s);
         case 512: return launch_n<512>(fp, s);
@@ -271,6 +305,8 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
     if (cfg->num_channels < 0) return fail(nullptr, PVB_ERR_BAD_ARG, "negative channel count");
 
     if (const char *env = std::getenv("PVB_FORCE_GENERIC")) g_force_generic = env[0] == '1';
+    if (const char *env = std::getenv("PVB_KERNEL_1024")) g_kernel_1024 = (env[0] == '2') ? 2 : 1;
+    if (const char *env = std::getenv("PVB_STAGGER_NS")) g_stagger_ns = std::atoi(env);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -486,7 +522,8 @@ const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
     fp.pitch_factor = pitch_factor;
     fp.overlaps = p->overlaps;
     split_pitch_factor(pitch_factor, &fp.pf_mant, &fp.pf_shift);
-    if (warp_kernel_applies(p->n, fp) && !g_force_generic) return "pvb::pv_process_warp_kernel";
+    if (warp_kernel_applies(p->n, fp) && !g_force_generic)
+        return g_kernel_1024 == 2 ? "pvb::pv_process_pair_kernel" : "pvb::pv_process_warp_kernel";
     switch (p->n) {
         case 256: return "pvb::pv_process_kernel<256>";
         case 512: return "pvb::pv_process_kernel<512>";

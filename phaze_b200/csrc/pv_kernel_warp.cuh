@@ -53,6 +53,8 @@ struct WarpGeo {
 struct WarpParams {
     FrameParams f;            // pf_shift in [1, 62], 0.75 <= pitch_factor <= 64, overlaps <= 32
     const float *window_out;  // [N] window * 1 / (2 N R): synthesis window with every scale folded in
+    int stagger_ns;           // start-time offset between the warps that share an SM (0: none)
+    int num_sms;
 };
 
 // swizzled slot of exchange element [a][b][c] (each 0..7)
@@ -145,6 +147,13 @@ pv_process_warp_kernel(const WarpParams wp) {
     const int warp = threadIdx.x >> 5;
     const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
     if (2 * pair >= p.num_channels) return;          // whole warp leaves; no CTA-wide barriers below
+    // A launch that fits in one wave starts every warp in the same phase; they would then fight
+    // for the same pipe (FMA in the FFT passes, ALU in the shift, LSU in the exchanges) all the
+    // way through.  Spreading the start times lets the phases of different warps interleave.
+    if (wp.stagger_ns > 0) {
+        const int slot = 2 * warp + (int(blockIdx.x) >= wp.num_sms ? 1 : 0);
+        if (slot > 0) __nanosleep(unsigned(slot * wp.stagger_ns));
+    }
     unsigned char *mine = smem_raw + size_t(warp) * W::WARP_BYTES;
     float2 *zre = reinterpret_cast<float2 *>(mine + W::OFF_BUF);
     float2 *zim = zre + W::PLANE;

@@ -57,14 +57,15 @@ def test_parity_frame_size_sweep(oracle, N, pf):
 
 
 @pytest.mark.parametrize("pf", [0.8, 0.67, 0.7, 0.75, 0.9, 1.0, 1.2, 1.5, 2.0, 3.0])
-@pytest.mark.parametrize("force_generic", ["0", "1"])
-def test_parity_1024_both_kernels(oracle, monkeypatch, pf, force_generic):
-    """frame 1024 has two CUDA paths (warp-synchronous kernel for pf >= 2/3, generic kernel
-    otherwise); both must match the oracle."""
-    monkeypatch.setenv("PVB_FORCE_GENERIC", force_generic)
+@pytest.mark.parametrize("kernel", ["pair", "warp", "generic"])
+def test_parity_1024_all_kernels(oracle, monkeypatch, pf, kernel):
+    """frame 1024 has three CUDA paths: one warp per channel pair (default for pitch factors in
+    [0.75, 64]), two warps per pair (PVB_KERNEL_1024=2) and the generic kernel; all must match."""
+    monkeypatch.setenv("PVB_FORCE_GENERIC", "1" if kernel == "generic" else "0")
+    monkeypatch.setenv("PVB_KERNEL_1024", "1" if kernel == "warp" else "2")
     x, ref, got = _run_both(oracle, 1024, 256, 5, np.float32(pf), 17)
     err = _rms(got - ref)
-    print(f"pf={pf} generic={force_generic}: rms err {err:.3e}")
+    print(f"pf={pf} kernel={kernel}: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
 
 
