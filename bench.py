@@ -389,8 +389,8 @@ def run_ours(args):
 def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
     """Same metric through the host-buffer entry points: every step copies its input block from
     pinned host memory to the device and its output block back (4 MiB each way at the default
-    workload).  `value` uses pvb_process_many (16 consecutive process() calls per submission,
-    copies and kernels pipelined on three streams, bit-identical to 16 single calls);
+    workload).  `value` uses pvb_process_many (64 consecutive process() calls per submission,
+    copies and kernels pipelined on three streams, bit-identical to 64 single calls);
     `single_call_value` uses the synchronous one-call-at-a-time pvb_process."""
     import ctypes as Ct
 
@@ -400,7 +400,7 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
     lib = phaze_b200_lib()
     nblk = blocks_np.shape[0]
     nbytes = C * hop * 4
-    batch = 16
+    batch = 64
     hin = lib.pvb_alloc_host(nbytes * batch)
     hout = lib.pvb_alloc_host(nbytes * batch)
     for k in range(batch):
@@ -431,7 +431,7 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
         rc = lib.pvb_process(procs[i % len(procs)]._h, hin + (i % batch) * nbytes, hout, pitch)
         assert rc == 0, rc
 
-    steps = int(max(batch, min(K, 1600) // batch * batch))
+    steps = int(max(batch, min(K, 2048) // batch * batch))
     value = timed(many, steps, batch)
     single_value = timed(single, int(min(K, 400)), 1)
     check = float(np.ctypeslib.as_array(Ct.cast(hout, Ct.POINTER(Ct.c_float)), (C * hop,)).std())
@@ -439,7 +439,7 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
     lib.pvb_free_host(hout)
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
             "steps": steps, "calls_per_submission": batch,
-            "api": "pvb_process_many(handle, in_host, out_host, 16, pitch): pinned host buffers, "
+            "api": f"pvb_process_many(handle, in_host, out_host, {batch}, pitch): pinned host buffers, "
                    "H2D / kernel / D2H of consecutive calls overlapped, synchronous on return",
             "single_call_value": single_value, "out_std": check}
 
