@@ -7,6 +7,7 @@
 #include "pv_kernel.cuh"
 #include "pv_kernel_warp.cuh"
 #include "pv_kernel_pair.cuh"
+#include "pv_kernel_cta.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -91,10 +92,41 @@ cudaError_t launch_n(const pvb::FrameParams &fp, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// warp-synchronous kernel: frame 1024, pitch factors in [0.75, 64], R <= 32 (pv_kernel_warp.cuh)
-bool warp_kernel_applies(int n, const pvb::FrameParams &fp) {
-    return n == 1024 && fp.pf_shift >= 1 && fp.pitch_factor >= 0.75f && fp.pitch_factor <= 64.0f &&
-           fp.overlaps <= 32;
+// in-place shift kernels (pv_kernel_warp.cuh, pv_kernel_pair.cuh, pv_kernel_cta.cuh): pitch factors
+// in [0.75, 64] (first stale level only, at most two sources per bin), R <= 32
+bool fast_range(const pvb::FrameParams &fp) {
+    return fp.pf_shift >= 1 && fp.pitch_factor >= 0.75f && fp.pitch_factor <= 64.0f && fp.overlaps <= 32;
+}
+bool warp_kernel_applies(int n, const pvb::FrameParams &fp) { return n == 1024 && fast_range(fp); }
+
+template <int N>
+cudaError_t launch_cta_n(const pvb::FrameParams &fp, const float *window_out, cudaStream_t s) {
+    using G = pvb::CtaGeo<N>;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_cta_kernel<N>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, int(G::SMEM_BYTES));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int pairs = (fp.num_channels + 1) / 2;
+    const int grid = (pairs + G::G - 1) / G::G;
+    if (grid == 0) return cudaSuccess;
+    pvb::pv_process_cta_kernel<N><<<grid, G::THREADS, G::SMEM_BYTES, s>>>(fp, window_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cta(int n, const pvb::FrameParams &fp, const float *window_out, cudaStream_t s) {
+    switch (n) {
+        case 256: return launch_cta_n<256>(fp, window_out, s);
+        case 512: return launch_cta_n<512>(fp, window_out, s);
+        case 1024: return launch_cta_n<1024>(fp, window_out, s);
+        case 2048: return launch_cta_n<2048>(fp, window_out, s);
+        case 4096: return launch_cta_n<4096>(fp, window_out, s);
+    }
+    return cudaErrorInvalidValue;
 }
 
 // warps (channel pairs) per CTA: the choice that leaves the most even load per SM
@@ -167,10 +199,11 @@ cudaError_t launch_pair(const pvb::FrameParams &fp, const float *window_out, int
 
 cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
     const int n = h->n;
-    if (warp_kernel_applies(n, fp) && !g_force_generic) {
+    if (warp_kernel_applies(n, fp) && !g_force_generic && g_kernel_1024 != 3) {
         if (g_kernel_1024 == 2) return launch_pair(fp, h->d_window_out, h->num_sms, s);
         return launch_warp(fp, h->d_window_out, h->num_sms, s);
     }
+    if (fast_range(fp) && !g_force_generic) return launch_cta(n, fp, h->d_window_out, s);
     switch (n) {
         case 256: return launch_n<256>(fp, s);
         case 512: return launch_n<512>(fp, s);
@@ -305,7 +338,7 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
     if (cfg->num_channels < 0) return fail(nullptr, PVB_ERR_BAD_ARG, "negative channel count");
 
     if (const char *env = std::getenv("PVB_FORCE_GENERIC")) g_force_generic = env[0] == '1';
-    if (const char *env = std::getenv("PVB_KERNEL_1024")) g_kernel_1024 = (env[0] == '2') ? 2 : 1;
+    if (const char *env = std::getenv("PVB_KERNEL_1024")) g_kernel_1024 = (env[0] == '2') ? 2 : (env[0] == '3') ? 3 : 1;
     if (const char *env = std::getenv("PVB_STAGGER_NS")) g_stagger_ns = std::atoi(env);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -532,8 +565,17 @@ const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
     fp.pitch_factor = pitch_factor;
     fp.overlaps = p->overlaps;
     split_pitch_factor(pitch_factor, &fp.pf_mant, &fp.pf_shift);
-    if (warp_kernel_applies(p->n, fp) && !g_force_generic)
+    if (warp_kernel_applies(p->n, fp) && !g_force_generic && g_kernel_1024 != 3)
         return g_kernel_1024 == 2 ? "pvb::pv_process_pair_kernel" : "pvb::pv_process_warp_kernel";
+    if (fast_range(fp) && !g_force_generic) {
+        switch (p->n) {
+            case 256: return "pvb::pv_process_cta_kernel<256>";
+            case 512: return "pvb::pv_process_cta_kernel<512>";
+            case 1024: return "pvb::pv_process_cta_kernel<1024>";
+            case 2048: return "pvb::pv_process_cta_kernel<2048>";
+            default: return "pvb::pv_process_cta_kernel<4096>";
+        }
+    }
     switch (p->n) {
         case 256: return "pvb::pv_process_kernel<256>";
         case 512: return "pvb::pv_process_kernel<512>";

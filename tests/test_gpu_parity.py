@@ -57,12 +57,12 @@ def test_parity_frame_size_sweep(oracle, N, pf):
 
 
 @pytest.mark.parametrize("pf", [0.8, 0.67, 0.7, 0.75, 0.9, 1.0, 1.2, 1.5, 2.0, 3.0])
-@pytest.mark.parametrize("kernel", ["pair", "warp", "generic"])
+@pytest.mark.parametrize("kernel", ["pair", "warp", "cta", "generic"])
 def test_parity_1024_all_kernels(oracle, monkeypatch, pf, kernel):
     """frame 1024 has three CUDA paths: one warp per channel pair (default for pitch factors in
     [0.75, 64]), two warps per pair (PVB_KERNEL_1024=2) and the generic kernel; all must match."""
     monkeypatch.setenv("PVB_FORCE_GENERIC", "1" if kernel == "generic" else "0")
-    monkeypatch.setenv("PVB_KERNEL_1024", "1" if kernel == "warp" else "2")
+    monkeypatch.setenv("PVB_KERNEL_1024", {"warp": "1", "pair": "2", "cta": "3", "generic": "1"}[kernel])
     x, ref, got = _run_both(oracle, 1024, 256, 5, np.float32(pf), 17)
     err = _rms(got - ref)
     print(f"pf={pf} kernel={kernel}: rms err {err:.3e}")
@@ -81,3 +81,24 @@ def test_parity_deep_stale(oracle, pf):
 def test_parity_hop128_warp_kernel(oracle):
     x, ref, got = _run_both(oracle, 1024, 128, 3, np.float32(0.8), 30)
     assert _rms(got - ref) <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("N", [256, 512, 2048, 4096])
+@pytest.mark.parametrize("pf", [0.75, 0.9, 1.0, 1.3, 2.5])
+@pytest.mark.parametrize("force_generic", ["0", "1"])
+def test_parity_other_frame_sizes_both_kernels(oracle, monkeypatch, N, pf, force_generic):
+    """frame sizes other than 1024: the CTA kernel with the in-place shift (pitch factors in
+    [0.75, 64]) and the fully generic kernel must both match the oracle."""
+    monkeypatch.setenv("PVB_FORCE_GENERIC", force_generic)
+    hop = N // 4
+    x, ref, got = _run_both(oracle, N, hop, 5, np.float32(pf), 13)
+    err = _rms(got - ref)
+    print(f"N={N} pf={pf} generic={force_generic}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+def test_parity_native_2048_128_r16(oracle):
+    """the reference's own sizes: R = 16, rotations are not quarter turns"""
+    for pf in (0.8, 1.3):
+        x, ref, got = _run_both(oracle, 2048, 128, 3, np.float32(pf), 40)
+        assert _rms(got - ref) <= RMS_EXPECTED
