@@ -255,24 +255,36 @@ pv_process_cta_kernel(const FrameParams p, const float *__restrict__ window_out)
     const float2 *__restrict__ tw = p.tw;
 
     // ---- frame gather + analysis window (ola:91-146, pv:55) --------------------------------------
-    for (int m = t; m < M; m += T) {
-        const int n = 2 * m;
-        float2 v0 = make_float2(0.f, 0.f), v1 = v0;
-        if (n < keep) {
-            const int r = (n + rb + hop) & (N - 1);
-            if (has0) v0 = *reinterpret_cast<const float2 *>(p.hist + size_t(c0) * N + r);
-            if (has1) v1 = *reinterpret_cast<const float2 *>(p.hist + size_t(c1) * N + r);
-        } else {
-            const int i = n - keep;
-            if (p.in) {
-                if (has0) v0 = __ldg(reinterpret_cast<const float2 *>(p.in + size_t(c0) * hop + i));
-                if (has1) v1 = __ldg(reinterpret_cast<const float2 *>(p.in + size_t(c1) * hop + i));
+    // M / T == 8 elements per thread: all loads are issued before anything consumes them
+    {
+        float2 r0[8], r1[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int n = 2 * (t + T * j);
+            r0[j] = make_float2(0.f, 0.f);
+            r1[j] = make_float2(0.f, 0.f);
+            if (n < keep) {
+                const int r = (n + rb + hop) & (N - 1);
+                if (has0) r0[j] = *reinterpret_cast<const float2 *>(p.hist + size_t(c0) * N + r);
+                if (has1) r1[j] = *reinterpret_cast<const float2 *>(p.hist + size_t(c1) * N + r);
+            } else if (p.in) {
+                const int i = n - keep;
+                if (has0) r0[j] = __ldg(reinterpret_cast<const float2 *>(p.in + size_t(c0) * hop + i));
+                if (has1) r1[j] = __ldg(reinterpret_cast<const float2 *>(p.in + size_t(c1) * hop + i));
             }
-            if (has0) *reinterpret_cast<float2 *>(p.hist + size_t(c0) * N + rb + i) = v0;
-            if (has1) *reinterpret_cast<float2 *>(p.hist + size_t(c1) * N + rb + i) = v1;
         }
-        const float2 w = __ldg(reinterpret_cast<const float2 *>(p.window + n));
-        Z[zp(m)] = make_float4(v0.x * w.x, v1.x * w.x, v0.y * w.y, v1.y * w.y);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int m = t + T * j;
+            const int n = 2 * m;
+            if (n >= keep) {
+                const int i = n - keep;
+                if (has0) *reinterpret_cast<float2 *>(p.hist + size_t(c0) * N + rb + i) = r0[j];
+                if (has1) *reinterpret_cast<float2 *>(p.hist + size_t(c1) * N + rb + i) = r1[j];
+            }
+            const float2 w = __ldg(reinterpret_cast<const float2 *>(p.window + n));
+            Z[zp(m)] = make_float4(r0[j].x * w.x, r1[j].x * w.x, r0[j].y * w.y, r1[j].y * w.y);
+        }
     }
     // warm L2 with the overlap-add ring lines the tail adds to
     for (int line = 32 * t; line < N; line += 32 * T) {
@@ -336,30 +348,37 @@ pv_process_cta_kernel(const FrameParams p, const float *__restrict__ window_out)
     fft_inplace<N, true>(Z, t, tw);
 
     // ---- window (all scales folded in), overlap-add ring, emit (pv:65-67, ola:149-157,111-137) ------
-    for (int q = t; q < N / 4; q += T) {
-        const float4 za = Z[zp(dif_pos<N>(2 * q))];
-        const float4 zb = Z[zp(dif_pos<N>(2 * q + 1))];
-        const int k = 4 * q;
-        const float4 w = __ldg(reinterpret_cast<const float4 *>(window_out + k));
-        const bool head = k < hop;
-        const bool tail = k >= keep;
-        const int ring = (k + rb) & (N - 1);
+    // N / 4 / T == 4 float4 groups per thread and channel: accumulator loads first, then the math
+    {
+        float4 a0[4], a1[4];
 #pragma unroll
-        for (int ch = 0; ch < 2; ch++) {
-            if (!(ch ? has1 : has0)) continue;
-            const int c = ch ? c1 : c0;
-            float4 y;
-            y.x = (ch ? za.y : za.x) * w.x;
-            y.y = (ch ? za.w : za.z) * w.y;
-            y.z = (ch ? zb.y : zb.x) * w.z;
-            y.w = (ch ? zb.w : zb.z) * w.w;
-            float4 *ap = reinterpret_cast<float4 *>(p.acc + size_t(c) * N + ring);
-            if (!tail) {
-                const float4 a = *ap;
-                y.x += a.x; y.y += a.y; y.z += a.z; y.w += a.w;
+        for (int i = 0; i < 4; i++) {
+            const int k = 4 * (t + T * i);
+            const int ring = (k + rb) & (N - 1);
+            a0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a1[i] = a0[i];
+            if (k < keep) {                                   // the tail slot starts from zero (ola:134)
+                if (has0) a0[i] = *reinterpret_cast<const float4 *>(p.acc + size_t(c0) * N + ring);
+                if (has1) a1[i] = *reinterpret_cast<const float4 *>(p.acc + size_t(c1) * N + ring);
             }
-            if (head) *reinterpret_cast<float4 *>(p.out + size_t(c) * hop + k) = y;
-            else *ap = y;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int q = t + T * i;
+            const float4 za = Z[zp(dif_pos<N>(2 * q))];
+            const float4 zb = Z[zp(dif_pos<N>(2 * q + 1))];
+            const int k = 4 * q;
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(window_out + k));
+            const int ring = (k + rb) & (N - 1);
+            const float4 y0 = make_float4(za.x * w.x + a0[i].x, za.z * w.y + a0[i].y, zb.x * w.z + a0[i].z, zb.z * w.w + a0[i].w);
+            const float4 y1 = make_float4(za.y * w.x + a1[i].x, za.w * w.y + a1[i].y, zb.y * w.z + a1[i].z, zb.w * w.w + a1[i].w);
+            if (k < hop) {                                    // head: emit (ola:111-118)
+                if (has0) *reinterpret_cast<float4 *>(p.out + size_t(c0) * hop + k) = y0;
+                if (has1) *reinterpret_cast<float4 *>(p.out + size_t(c1) * hop + k) = y1;
+            } else {
+                if (has0) *reinterpret_cast<float4 *>(p.acc + size_t(c0) * N + ring) = y0;
+                if (has1) *reinterpret_cast<float4 *>(p.acc + size_t(c1) * N + ring) = y1;
+            }
         }
     }
 }
