@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--root-scatter", action="store_true",
+                    help="N>1: also time the single-root mode (NCCL scatter of input slabs, gather of outputs)")
     return ap.parse_args()
 
 
@@ -347,6 +349,10 @@ def run_ours(args):
     if not args.no_e2e:
         e2e = run_e2e(procs, blocks_np, C, hop, pitch, K, dist)
 
+    root_scatter = None
+    if dist and args.root_scatter:
+        root_scatter = run_root_scatter(C, frame, hop, pitch, world, rank, local, min(K, 300), host)
+
     peak, peak_src = measured_peak()
     kernel_ms = ms / max(launches, 1)                 # this rank's average launch duration
     achieved = 12.0 * frame * C / (kernel_ms * 1e-3) / 1e9
@@ -378,6 +384,8 @@ def run_ours(args):
             "concurrent_streams_value": streams_value,
             "cpu_baseline": cpu,
         }
+        if root_scatter:
+            line["root_scatter"] = root_scatter
         print(json.dumps(line))
     for p in procs:
         p.close()
@@ -442,6 +450,43 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
             "api": f"pvb_process_many(handle, in_host, out_host, {batch}, pitch): pinned host buffers, "
                    "H2D / kernel / D2H of consecutive calls overlapped, synchronous on return",
             "single_call_value": single_value, "out_std": check}
+
+
+def run_root_scatter(C, frame, hop, pitch, world, rank, local, steps, host_block_src):
+    """Single-root mode of the north-star: rank 0 holds the [world*C][hop] block in HBM, scatters the
+    slabs over NVLink (grouped ncclSend/ncclRecv), every rank runs its shard, outputs are gathered
+    back on rank 0.  Reports whole-job frames/s and the bytes that cross NVLink per second."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from phaze_b200.sharded import ShardedPhaseVocoder
+
+    total = world * C
+    sh = ShardedPhaseVocoder(total, frame, hop, device=torch.device("cuda", local))
+    blk = None
+    if rank == 0:
+        blk = torch.from_numpy(np.tile(host_block_src[:, :hop], (world, 1))).cuda().contiguous()
+    for _ in range(8):
+        sh.process_from_root(blk, pitch)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        sh.process_from_root(blk, pitch)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item()) * 1e-3
+    peer_bytes = 2 * (total - C) * hop * 4                     # slabs out + results back, per step
+    return {"value": steps * total / sec, "unit": UNIT, "steps": steps, "total_channels": total,
+            "nvlink_bytes_per_step": peer_bytes, "nvlink_gbs_at_root": steps * peer_bytes / sec / 1e9,
+            "nvlink_peer_copy_reference_gbs": 770.0,
+            "note": "root egress + ingress; shard-resident number is the main `value`"}
 
 
 def phaze_b200_lib():
