@@ -38,6 +38,7 @@ namespace {
 thread_local char g_create_err[256] = "";
 bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
 int g_kernel_1024 = 1;           // PVB_KERNEL_1024=1 (default): one warp per channel pair, 2: two warps per pair
+bool g_no_aligned = false;       // PVB_NO_ALIGNED=1: never use the hop %% 128 == 0 specialisation (tests)
 int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
 
 // pitch_factor == mant * 2^-shift exactly; shift outside [1, 62] -> 0 (kernel uses float64)
@@ -151,9 +152,13 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_warp_kernel,
+        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_warp_kernel<true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              int(W::MAX_WARPS * W::WARP_BYTES));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(pvb::pv_process_warp_kernel<false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(W::MAX_WARPS * W::WARP_BYTES));
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -166,7 +171,10 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
     wp.window_out = window_out;
     wp.num_sms = num_sms;
     wp.stagger_ns = (grid <= 2 * num_sms) ? g_stagger_ns : 0;
-    pvb::pv_process_warp_kernel<<<grid, wpc * 32, size_t(wpc) * W::WARP_BYTES, s>>>(wp);
+    if (fp.hop % 128 == 0 && !g_no_aligned)
+        pvb::pv_process_warp_kernel<true><<<grid, wpc * 32, size_t(wpc) * W::WARP_BYTES, s>>>(wp);
+    else
+        pvb::pv_process_warp_kernel<false><<<grid, wpc * 32, size_t(wpc) * W::WARP_BYTES, s>>>(wp);
     return cudaGetLastError();
 }
 
@@ -340,6 +348,7 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
     if (const char *env = std::getenv("PVB_FORCE_GENERIC")) g_force_generic = env[0] == '1';
     if (const char *env = std::getenv("PVB_KERNEL_1024")) g_kernel_1024 = (env[0] == '2') ? 2 : (env[0] == '3') ? 3 : 1;
     if (const char *env = std::getenv("PVB_STAGGER_NS")) g_stagger_ns = std::atoi(env);
+    if (const char *env = std::getenv("PVB_NO_ALIGNED")) g_no_aligned = env[0] == '1';
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {

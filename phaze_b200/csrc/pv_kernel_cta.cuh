@@ -286,6 +286,11 @@ pv_process_cta_kernel(const FrameParams p, const float *__restrict__ window_out)
             Z[zp(m)] = make_float4(r0[j].x * w.x, r1[j].x * w.x, r0[j].y * w.y, r1[j].y * w.y);
         }
     }
+    __syncthreads();
+
+    fft_inplace<N, false>(Z, t, tw);
+
+    // (after the frame has arrived, so that it does not compete with the frame loads)
     // warm L2 with the overlap-add ring lines the tail adds to
     for (int line = 32 * t; line < N; line += 32 * T) {
         if (((line - rb + hop) & (N - 1)) >= hop) {
@@ -293,9 +298,6 @@ pv_process_cta_kernel(const FrameParams p, const float *__restrict__ window_out)
             if (has1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c1) * N + line));
         }
     }
-    __syncthreads();
-
-    fft_inplace<N, false>(Z, t, tw);
 
     // ---- real split -> swizzled per-channel spectrum (2x scaled) -----------------------------------
     for (int k = t; k <= M / 2; k += T) {

@@ -136,6 +136,11 @@ __device__ __forceinline__ cpx2 zld(const float2 *zre, const float2 *zim, int sl
     return cpx2{zre[slot], zim[slot]};
 }
 
+// ALIGNED: hop is a multiple of 128.  Frame element j of a lane then sits in ring block
+// (j + rot) & 7 with a launch-uniform rot, so the rings are addressed as lane base + immediate,
+// old-vs-new-block and head / tail decisions are uniform branches, and the rotation between frame
+// order and ring order is folded into twiddle indices (shift theorem of the 8-point DFT).
+template <bool ALIGNED>
 __global__ void __launch_bounds__(WarpGeo::MAX_WARPS * 32, 2)
 pv_process_warp_kernel(const WarpParams wp) {
     using W = WarpGeo;
@@ -190,19 +195,62 @@ pv_process_warp_kernel(const WarpParams wp) {
 
     cpx2 a[8], b[8];
 
-    // warm L2 with the overlap-add ring lines the tail of this kernel adds to (their loads
-    // would otherwise be a serial DRAM round trip at the very end); the slot that is only
-    // written ([rb - hop, rb)) is skipped
-    {
-        const int line = 32 * lane;                                     // floats [32 lane, 32 lane + 32)
-        if (((line - rb + hop) & (N - 1)) >= hop) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c0) * N + line));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c1) * N + line));
-        }
-    }
-
     // ---- forward pass 1: butterflies n = lane, lane + 32 over m1 (stride 64), from global ----
-    {
+    if constexpr (ALIGNED) {
+        const int rot = ((rb + hop) >> 7) & 7;         // ring block of frame element j: (j + rot) & 7
+        const int jk = keep >> 7;                      // frame elements j >= jk are the new block
+        char *hl = reinterpret_cast<char *>(p.hist + size_t(c0) * N) + 8 * lane;
+        const char *il0 = reinterpret_cast<const char *>(p.in ? p.in + size_t(c0) * hop : p.hist) + 8 * lane;
+        const char *il1 = il0 + (has1 && p.in ? hop * 4 : 0);
+        const char *wl = reinterpret_cast<const char *>(p.window) + 8 * lane;
+        const bool paused = p.in == nullptr;
+        float2 r0[16], r1[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int h = e >> 3, b = e & 7;
+            const int j = (b - rot) & 7;               // uniform
+            if (j < jk) {
+                r0[e] = *reinterpret_cast<const float2 *>(hl + 256 * h + 512 * b);
+                r1[e] = *reinterpret_cast<const float2 *>(hl + 256 * h + 512 * b + N * 4);
+            } else {
+                r0[e] = *reinterpret_cast<const float2 *>(il0 + 256 * h + 512 * (j - jk));
+                r1[e] = *reinterpret_cast<const float2 *>(il1 + 256 * h + 512 * (j - jk));
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int h = e >> 3, b = e & 7;
+            const int j = (b - rot) & 7;
+            if (j >= jk) {                             // the new block: paused input is zeros (ola:93-100)
+                if (paused) { r0[e] = make_float2(0.f, 0.f); r1[e] = make_float2(0.f, 0.f); }
+                if (!has1) r1[e] = make_float2(0.f, 0.f);
+                *reinterpret_cast<float2 *>(hl + 256 * h + 512 * b) = r0[e];
+                *reinterpret_cast<float2 *>(hl + 256 * h + 512 * b + N * 4) = r1[e];
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int n = lane + 32 * h;
+            cpx2 x[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int j = (b - rot) & 7;
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(wl + 256 * h + 512 * j));
+                x[b].re = mul2(make_float2(r0[8 * h + b].x, r1[8 * h + b].x), bc2(w.x));
+                x[b].im = mul2(make_float2(r0[8 * h + b].y, r1[8 * h + b].y), bc2(w.y));
+            }
+            dft8<false>(x);                            // inputs in ring order: outputs carry W8^{rot k1}
+            const int tb = 2 * n - 128 * rot;
+#pragma unroll
+            for (int k1 = 1; k1 < 8; k1++) {
+                const float2 w = __ldg(&tw[(tb * k1) & (N - 1)]);    // W_512^{n k1} * W8^{-rot k1}
+                x[k1] = cmul_s(x[k1], w.x, w.y);
+            }
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++)
+                zst(zre, zim, 64 * k1 + 32 * h + (((k1 & 1) ? base1o : base1e) ^ (4 * h)), x[k1]);
+        }
+    } else {
         // all 32 loads of the frame are issued before anything consumes them.  Rows of hist /
         // acc are padded to an even channel count by the host, so channel 1 is always +N floats.
         float2 r0[16], r1[16];
@@ -257,6 +305,19 @@ pv_process_warp_kernel(const WarpParams wp) {
         }
     }
     __syncwarp();
+
+    // (issued only now, after the frame has arrived: at kernel start it would compete with the
+    // frame loads for DRAM bandwidth)
+    // warm L2 with the overlap-add ring lines the tail of this kernel adds to (their loads
+    // would otherwise be a serial DRAM round trip at the very end); the slot that is only
+    // written ([rb - hop, rb)) is skipped
+    {
+        const int line = 32 * lane;                                     // floats [32 lane, 32 lane + 32)
+        if (((line - rb + hop) & (N - 1)) >= hop) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c0) * N + line));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.acc + size_t(c1) * N + line));
+        }
+    }
 
     // ---- forward pass 2: butterflies (k1, m3) over m2 ---------------------------------------
     {
@@ -572,9 +633,12 @@ pv_process_warp_kernel(const WarpParams wp) {
 #pragma unroll
             for (int j = 0; j < 8; j++) x[j] = zld(zre, zim, s2[j] + 256 * h);
             dft8<true>(x);
+            // ALIGNED: the last pass must deliver its outputs in ring order, i.e. rotated by rotA
+            // blocks: pre-multiply its input k1 by W8^{k1 rotA}
+            const int rotk = ALIGNED ? 128 * k1 * ((rb >> 7) & 7) : 0;
 #pragma unroll
             for (int m2 = 0; m2 < 8; m2++) {
-                const float2 w = __ldg(&tw[2 * k1 * (m3l + 8 * m2)]);
+                const float2 w = __ldg(&tw[(2 * k1 * (m3l + 8 * m2) - rotk) & (N - 1)]);
                 zst(zre, zim, s2[m2] + 256 * h, cmul_s(x[m2], w.x, -w.y));
             }
         }
@@ -582,7 +646,49 @@ pv_process_warp_kernel(const WarpParams wp) {
     __syncwarp();
 
     // ---- inverse pass 3: butterflies n over k1 -> z[n + 64 m1]; window, overlap-add, emit ------------------
-    {
+    if constexpr (ALIGNED) {
+        const int rotA = (rb >> 7) & 7;                // ring block of output m1: (m1 + rotA) & 7
+        const int jk = keep >> 7, hq = hop >> 7;
+        char *al = reinterpret_cast<char *>(p.acc + size_t(c0) * N) + 8 * lane;
+        char *ol0 = reinterpret_cast<char *>(p.out + size_t(c0) * hop) + 8 * lane;
+        char *ol1 = ol0 + (has1 ? hop * 4 : 0);
+        const char *wol = reinterpret_cast<const char *>(wp.window_out) + 8 * lane;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            float2 q0[8], q1[8], wo[8];
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int j = (b - rotA) & 7;          // frame element held by ring block b (uniform)
+                wo[b] = __ldg(reinterpret_cast<const float2 *>(wol + 256 * h + 512 * j));
+                q0[b] = make_float2(0.f, 0.f);
+                q1[b] = make_float2(0.f, 0.f);
+                if (j < jk) {                          // the tail slot starts from zero (ola:134)
+                    q0[b] = *reinterpret_cast<const float2 *>(al + 256 * h + 512 * b);
+                    q1[b] = *reinterpret_cast<const float2 *>(al + 256 * h + 512 * b + N * 4);
+                }
+            }
+            cpx2 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                x[j] = zld(zre, zim, 64 * j + 32 * h + (((j & 1) ? base1o : base1e) ^ (4 * h)));
+            dft8<true>(x);                             // x[b]: output in ring block b
+#pragma unroll
+            for (int b = 0; b < 8; b++) {
+                const int j = (b - rotA) & 7;
+                const float2 yr = mul2(x[b].re, bc2(wo[b].x));
+                const float2 yi = mul2(x[b].im, bc2(wo[b].y));
+                const float2 y0 = make_float2(yr.x + q0[b].x, yi.x + q0[b].y);
+                const float2 y1 = make_float2(yr.y + q1[b].x, yi.y + q1[b].y);
+                if (j < hq) {                          // head: emit (ola:111-118)
+                    *reinterpret_cast<float2 *>(ol0 + 256 * h + 512 * j) = y0;
+                    if (has1) *reinterpret_cast<float2 *>(ol1 + 256 * h + 512 * j) = y1;
+                } else {
+                    *reinterpret_cast<float2 *>(al + 256 * h + 512 * b) = y0;
+                    *reinterpret_cast<float2 *>(al + 256 * h + 512 * b + N * 4) = y1;
+                }
+            }
+        }
+    } else {
         char *accb = reinterpret_cast<char *>(p.acc + size_t(c0) * N);
         char *outb0 = reinterpret_cast<char *>(p.out + size_t(c0) * hop);
         char *outb1 = outb0 + (has1 ? hop * 4 : 0);

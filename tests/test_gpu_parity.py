@@ -102,3 +102,18 @@ def test_parity_native_2048_128_r16(oracle):
     for pf in (0.8, 1.3):
         x, ref, got = _run_both(oracle, 2048, 128, 3, np.float32(pf), 40)
         assert _rms(got - ref) <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("hop", [32, 64, 128, 256, 512, 1024])
+@pytest.mark.parametrize("pf", [0.8, 1.3])
+@pytest.mark.parametrize("no_aligned", ["0", "1"])
+def test_parity_1024_hop_sweep(oracle, monkeypatch, hop, pf, no_aligned):
+    """warp kernel at every hop (R = 32 ... 1): hop % 128 == 0 takes the ring-order specialisation
+    (rotation folded into the twiddles), the others the general addressing; PVB_NO_ALIGNED=1
+    forces the general one everywhere."""
+    monkeypatch.setenv("PVB_NO_ALIGNED", no_aligned)
+    calls = 2 * (1024 // hop) + 7
+    x, ref, got = _run_both(oracle, 1024, hop, 3, np.float32(pf), calls)
+    err = _rms(got - ref)
+    print(f"hop={hop} pf={pf} no_aligned={no_aligned}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
