@@ -136,7 +136,7 @@ struct Geo {
     static constexpr int M = N / 2;            // complex FFT length
     static constexpr int NB = M + 1;           // magnitudes.length (pv:40)
     static constexpr int T = M / 8;            // threads per channel pair
-    static constexpr int ZSLOTS = M + M / 8;   // padded float4 slots of the FFT buffer
+    static constexpr int ZSLOTS = M + M / 8 + M / 128 + 1;   // padded float4 slots of the FFT buffer
     static constexpr int NWORDS = (NB + 31) / 32;
     static constexpr int NBP = (NB + 1) & ~1;  // nb rounded up to keep 16-byte alignment
     static constexpr size_t Z_BYTES = size_t(ZSLOTS) * 16;
@@ -153,8 +153,9 @@ struct Geo {
     static constexpr int L0 = (log2n() % 2 == 0) ? 4 : 2;
 };
 
-// padded slot of logical complex index i (conflict-free 16-byte accesses for strides 1, 8, 64, ...)
-__device__ __forceinline__ int zp(int i) { return i + (i >> 3); }
+// padded slot of logical complex index i: conflict-free 16-byte accesses for the strides of the
+// radix-8 passes (1, 8, 64) and, thanks to the second term, for the digit-reversed reads (stride M/8)
+__device__ __forceinline__ int zp(int i) { return i + (i >> 3) + (i >> 7); }
 
 // position (before padding) of natural-order output k after the in-place DIF passes
 template <int N>

@@ -23,7 +23,7 @@ struct CtaGeo {
     static constexpr int M = N / 2;
     static constexpr int NB = M + 1;
     static constexpr int T = M / 8;                        // threads per channel pair
-    static constexpr int ZSLOTS = M + M / 8;
+    static constexpr int ZSLOTS = M + M / 8 + M / 128 + 1;
     static constexpr size_t Z_BYTES = size_t(ZSLOTS) * 16;
     static constexpr int XSLOTS = ((M + 1 + N / 8 + 1) + 127) & ~127;     // spectrum + stale extension, swizzle-block aligned
     static constexpr size_t X_BYTES = size_t(2) * XSLOTS * 8;
@@ -38,13 +38,20 @@ struct CtaGeo {
     static constexpr int SRB = (BPL < 16) ? BPL : 16;      // bins per sub-run
 };
 
-// swizzled float2 slot of spectrum bin k (a bijection inside every aligned block of 128)
-__device__ __forceinline__ int xsw(int k) { return k ^ ((k >> 3) & 6) ^ ((k >> 6) & 1); }
+// swizzled float2 slot of spectrum bin k: the low 4 bits are XORed with the index of the peak-scan
+// run the bin belongs to (bins per lane = M/32), so that both 32 consecutive bins (split, sweep)
+// and one bin per run (peak scan: lanes BPL bins apart) hit 16 different 8-byte banks
+template <int N>
+__device__ __forceinline__ int xsw(int k) {
+    constexpr int BPL = N / 64;
+    constexpr int SH = (BPL >= 32) ? 5 : (BPL >= 16) ? 4 : (BPL >= 8) ? 3 : 2;
+    return k ^ ((k >> SH) & 15);
+}
 
 // value fft.js leaves in slot N/2 + q, 1 <= q <= N/8 (first stale level; see stale_bin())
 template <int N>
 __device__ __forceinline__ float2 stale_first_level(const float2 *X, int q, const float2 *__restrict__ tw) {
-    const float2 a = X[xsw(q)], b = X[xsw(N / 4 + q)], c = X[xsw(N / 2 - q)], d = X[xsw(N / 4 - q)];
+    const float2 a = X[xsw<N>(q)], b = X[xsw<N>(N / 4 + q)], c = X[xsw<N>(N / 2 - q)], d = X[xsw<N>(N / 4 - q)];
     const float sr = (a.x - b.x) + (c.x - d.x);
     const float si = (a.y - b.y) - (c.y - d.y);
     const float2 w = __ldg(&tw[2 * q]);                  // conj(w) = W_N^{-2q}
@@ -73,7 +80,7 @@ __device__ __forceinline__ void shift_channel(float2 *Xc, uint32_t *dsc, uint32_
         for (int e = 0; e < SRB + 4; e++) {
             int k = base - 2 + e;
             k = k < 0 ? 0 : (k > M ? M : k);
-            const float2 v = Xc[xsw(k)];
+            const float2 v = Xc[xsw<N>(k)];
             m[e] = __float_as_int(fmaf(v.x, v.x, v.y * v.y));
         }
         int q[SRB + 3];
@@ -156,14 +163,14 @@ __device__ __forceinline__ void shift_channel(float2 *Xc, uint32_t *dsc, uint32_
     __syncwarp();
 
     if (npk == 0) {                                        // silence: the shifted spectrum is zero (pv:121)
-        for (int i = lane; i <= M + 1; i += 32) Xc[xsw(i)] = make_float2(0.f, 0.f);
+        for (int i = lane; i <= M + 1; i += 32) Xc[xsw<N>(i)] = make_float2(0.f, 0.f);
         __syncwarp();
         return;
     }
 
     // ---- stale slots N/2+1 .. N/2+N/8 into the extension of X (only read when contracting) ----
     if (contract) {
-        for (int q = lane + 1; q <= N / 8; q += 32) Xc[xsw(M + q)] = stale_first_level<N>(Xc, q, tw);
+        for (int q = lane + 1; q <= N / 8; q += 32) Xc[xsw<N>(M + q)] = stale_first_level<N>(Xc, q, tw);
     }
     __syncwarp();
 
@@ -195,7 +202,7 @@ __device__ __forceinline__ void shift_channel(float2 *Xc, uint32_t *dsc, uint32_
             dvs[i] = (bin < src_bins) ? dsc[ord] : 0x40000000u;
             xv[i] = make_float2(0.f, 0.f);
             if (bin < src_bins) {
-                float2 *xp = Xc + xsw(bin);
+                float2 *xp = Xc + xsw<N>(bin);
                 xv[i] = *xp;
                 *xp = make_float2(0.f, 0.f);
             }
@@ -217,7 +224,7 @@ __device__ __forceinline__ void shift_channel(float2 *Xc, uint32_t *dsc, uint32_
                 const float rc = __shfl_sync(FULL, rot_c, ri), rs = __shfl_sync(FULL, rot_s, ri);
                 y = make_float2(xv[i].x * rc - xv[i].y * rs, xv[i].x * rs + xv[i].y * rc);
             }
-            const int slot = xsw(d);
+            const int slot = xsw<N>(d);
             xv[i] = y;
             if (okd && (right || !contract)) Xc[slot] = y;                 // first writer of that bin
             dvs[i] = (okd && !right && contract) ? uint32_t(slot) : 0xFFFFFFFFu;
@@ -309,7 +316,7 @@ pv_process_cta_kernel(const FrameParams p, const float *__restrict__ window_out)
         const cpx2 tt = cmul_s(cpx2{o_r, o_i}, w.x, w.y);
         const float2 xr = add2(e_r, tt.re), xi = add2(e_i, tt.im);          // X[k]
         const float2 yr = sub2(e_r, tt.re), yi = sub2(tt.im, e_i);          // X[M-k]
-        const int s1 = xsw(k), s2 = xsw(M - k);
+        const int s1 = xsw<N>(k), s2 = xsw<N>(M - k);
         X[s1] = make_float2(xr.x, xi.x);
         X[XS + s1] = make_float2(xr.y, xi.y);
         X[s2] = make_float2(yr.x, yi.x);
@@ -333,7 +340,7 @@ pv_process_cta_kernel(const FrameParams p, const float *__restrict__ window_out)
 
     // ---- Hermitian C2R pre-pass: Y[0..M] -> Z'[0..M) (natural order) ---------------------------------
     for (int k = t; k <= M / 2; k += T) {
-        const int s1 = xsw(k), s2 = xsw(M - k);
+        const int s1 = xsw<N>(k), s2 = xsw<N>(M - k);
         float2 a0 = X[s1], a1 = X[XS + s1], b0 = X[s2], b1 = X[XS + s2];
         if (k == 0) { a0.y = 0.f; a1.y = 0.f; b0.y = 0.f; b1.y = 0.f; }
         const float2 ar = make_float2(a0.x, a1.x), ai = make_float2(a0.y, a1.y);
