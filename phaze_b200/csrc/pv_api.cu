@@ -8,6 +8,7 @@
 #include "pv_kernel_warp.cuh"
 #include "pv_kernel_pair.cuh"
 #include "pv_kernel_cta.cuh"
+#include "pv_kernel_ring.cuh"
 
 #include <cmath>
 #include <cstdarg>
@@ -21,6 +22,10 @@ struct pvb_processor {
     int n = 0, hop = 0, overlaps = 0, channels = 0, device = 0;
     uint64_t ring_calls = 0;     // process() calls since the rings were last zeroed / set
     uint64_t cursor_calls = 0;   // timeCursor / hop (pv:31,71)
+    // layout of d_hist / d_acc: planar rows (pv_kernel.cuh), pairs of channels interleaved and
+    // aligned to the time cursor (pv_kernel_ring.cuh), or all zero (either reading is valid)
+    enum Layout { ZERO, PLANAR, PAIRED };
+    Layout layout = ZERO;
     float *d_hist = nullptr, *d_acc = nullptr, *d_window = nullptr, *d_window_out = nullptr;
     int num_sms = 148;
     float2 *d_tw = nullptr;
@@ -37,7 +42,7 @@ namespace {
 
 thread_local char g_create_err[256] = "";
 bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
-int g_kernel_1024 = 1;           // PVB_KERNEL_1024=1 (default): one warp per channel pair, 2: two warps per pair
+int g_kernel_1024 = 0;           // PVB_KERNEL_1024: 0 (default) ring-order kernel, 1 warp kernel, 2 two warps per pair, 3 CTA kernel
 bool g_no_aligned = false;       // PVB_NO_ALIGNED=1: never use the hop %% 128 == 0 specialisation (tests)
 int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
 
@@ -178,6 +183,46 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
     return cudaGetLastError();
 }
 
+// ring-order kernel (pv_kernel_ring.cuh): paired state layout aligned to the time cursor
+bool ring_kernel_applies(const pvb_processor *h, const pvb::FrameParams &fp) {
+    return h->n == 1024 && fast_range(fp) && h->hop % 128 == 0 && h->hop <= 512 && g_kernel_1024 == 0 &&
+           !g_force_generic;
+}
+
+cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+    using G = pvb::RingGeo;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(G::DTAB_BYTES + G::MAX_WARPS * G::WARP_BYTES));
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int pairs = (fp.num_channels + 1) / 2;
+    if (pairs == 0) return cudaSuccess;
+    const int wpc = pick_warps_per_cta(pairs, h->num_sms);
+    const int grid = (pairs + wpc - 1) / wpc;
+    pvb::RingParams rp;
+    rp.in = fp.in;
+    rp.out = fp.out;
+    rp.hist2 = reinterpret_cast<float4 *>(fp.hist);
+    rp.acc2 = reinterpret_cast<float4 *>(fp.acc);
+    rp.window2 = h->d_window;
+    rp.window_out2 = h->d_window_out;
+    rp.tw = fp.tw;
+    rp.num_channels = fp.num_channels;
+    rp.hop = fp.hop;
+    rp.tmod = fp.step_mod_r * fp.hop;
+    rp.pitch_factor = fp.pitch_factor;
+    rp.pf_mant = fp.pf_mant;
+    rp.pf_shift = fp.pf_shift;
+    pvb::pv_process_ring_kernel<<<grid, wpc * 32, G::DTAB_BYTES + size_t(wpc) * G::WARP_BYTES, s>>>(rp);
+    return cudaGetLastError();
+}
+
 // two warps per channel pair (pv_kernel_pair.cuh): same validity range as the warp kernel
 cudaError_t launch_pair(const pvb::FrameParams &fp, const float *window_out, int num_sms,
                         cudaStream_t s) {
@@ -207,6 +252,7 @@ cudaError_t launch_pair(const pvb::FrameParams &fp, const float *window_out, int
 
 cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
     const int n = h->n;
+    if (ring_kernel_applies(h, fp)) return launch_ring(h, fp, s);
     if (warp_kernel_applies(n, fp) && !g_force_generic && g_kernel_1024 != 3) {
         if (g_kernel_1024 == 2) return launch_pair(fp, h->d_window_out, h->num_sms, s);
         return launch_warp(fp, h->d_window_out, h->num_sms, s);
@@ -249,6 +295,42 @@ int alloc_state(pvb_processor *p, int channels) {
     PVB_CUDA(p, cudaMemsetAsync(p->d_hist, 0, bytes, p->stream));
     PVB_CUDA(p, cudaMemsetAsync(p->d_acc, 0, bytes, p->stream));
     p->ring_calls = 0;
+    p->layout = pvb_processor::ZERO;
+    return PVB_OK;
+}
+
+// Re-lay the state for the other kernel family (rare: the pitch factor left / entered the range
+// of the ring-order kernel, or the host touches the state).  Out of place, on stream s.
+int ensure_layout(pvb_processor *p, pvb_processor::Layout want, cudaStream_t s) {
+    if (p->layout == want || p->channels == 0) return PVB_OK;
+    if (p->layout == pvb_processor::ZERO) {
+        p->layout = want;
+        return PVB_OK;
+    }
+    const size_t rows = state_rows(p->channels);
+    const size_t bytes = rows * size_t(p->n) * sizeof(float);
+    float *nh = nullptr, *na = nullptr;
+    if (cudaMalloc(&nh, bytes) != cudaSuccess || cudaMalloc(&na, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(nh);
+        return fail(p, PVB_ERR_NOMEM, "cudaMalloc of %zu bytes for the state re-layout failed", 2 * bytes);
+    }
+    const int rb = int(p->ring_calls % uint64_t(p->overlaps)) * p->hop;
+    const int tmod = int(p->cursor_calls % uint64_t(p->overlaps)) * p->hop;
+    const int pairs = int(rows / 2);
+    const bool to_paired = want == pvb_processor::PAIRED;
+    float *planar_h = to_paired ? p->d_hist : nh, *planar_a = to_paired ? p->d_acc : na;
+    float *paired_h = to_paired ? nh : p->d_hist, *paired_a = to_paired ? na : p->d_acc;
+    pvb::pv_ring_convert_kernel<<<p->num_sms * 8, 256, 0, s>>>(
+        planar_h, planar_a, reinterpret_cast<float2 *>(paired_h), reinterpret_cast<float2 *>(paired_a),
+        pairs, p->n, p->hop, rb, tmod, to_paired ? 1 : 0);
+    PVB_CUDA(p, cudaGetLastError());
+    PVB_CUDA(p, cudaStreamSynchronize(s));
+    cudaFree(p->d_hist);
+    cudaFree(p->d_acc);
+    p->d_hist = nh;
+    p->d_acc = na;
+    p->layout = want;
     return PVB_OK;
 }
 
@@ -305,6 +387,11 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         fp.pitch_factor = pf;
         split_pitch_factor(pf, &fp.pf_mant, &fp.pf_shift);
         if (p->channels > 0) {
+            const int rc = ensure_layout(p, ring_kernel_applies(p, fp) ? pvb_processor::PAIRED
+                                                                       : pvb_processor::PLANAR, s);
+            if (rc != PVB_OK) return rc;
+            fp.hist = p->d_hist;
+            fp.acc = p->d_acc;
             PVB_CUDA(p, launch(p, fp, s));
             p->launches++;
         }
@@ -345,10 +432,21 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         return fail(nullptr, PVB_ERR_BAD_SIZE, "hop %d must divide frame %d and be a multiple of 4", hop, n);
     if (cfg->num_channels < 0) return fail(nullptr, PVB_ERR_BAD_ARG, "negative channel count");
 
-    if (const char *env = std::getenv("PVB_FORCE_GENERIC")) g_force_generic = env[0] == '1';
-    if (const char *env = std::getenv("PVB_KERNEL_1024")) g_kernel_1024 = (env[0] == '2') ? 2 : (env[0] == '3') ? 3 : 1;
-    if (const char *env = std::getenv("PVB_STAGGER_NS")) g_stagger_ns = std::atoi(env);
-    if (const char *env = std::getenv("PVB_NO_ALIGNED")) g_no_aligned = env[0] == '1';
+    // test / experiment switches, re-read at every create (unset == default)
+    {
+        const char *env = std::getenv("PVB_FORCE_GENERIC");
+        g_force_generic = env && env[0] == '1';
+    }
+    if (const char *env = std::getenv("PVB_KERNEL_1024"))
+        g_kernel_1024 = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 0;
+    else
+        g_kernel_1024 = 0;
+    {
+        const char *env = std::getenv("PVB_STAGGER_NS");
+        g_stagger_ns = env ? std::atoi(env) : 0;
+        env = std::getenv("PVB_NO_ALIGNED");
+        g_no_aligned = env && env[0] == '1';
+    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -378,7 +476,7 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
     }
 
     // tables, computed in double like the JS and rounded once to float32
-    std::vector<float> win(n), win_out(n);
+    std::vector<float> win(2 * n), win_out(2 * n);    // stored twice: the ring-order kernel reads them rotated
     std::vector<float2> tw(n);
     const double pi = 3.14159265358979323846;
     for (int i = 0; i < n; i++) {
@@ -386,6 +484,10 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         // synthesis window with 1/N (inverseTransform), the two folded 1/2 of the real-split and
         // 1/nbOverlaps (ola:153) folded in; all powers of two, so the product is exact
         win_out[i] = win[i] * (1.0f / float(2 * n)) * (1.0f / float(p->overlaps));
+    }
+    for (int i = 0; i < n; i++) {
+        win[n + i] = win[i];
+        win_out[n + i] = win_out[i];
     }
     for (int j = 0; j < n; j++) {
         double c = std::cos(2 * pi * j / n), s = -std::sin(2 * pi * j / n);
@@ -397,14 +499,14 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         tw[j] = make_float2(float(c), float(s));
     }
     cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaMalloc(&p->d_window, n * sizeof(float)) != cudaSuccess ||
-        cudaMalloc(&p->d_window_out, n * sizeof(float)) != cudaSuccess ||
+    if (cudaMalloc(&p->d_window, 2 * n * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&p->d_window_out, 2 * n * sizeof(float)) != cudaSuccess ||
         cudaMalloc(&p->d_tw, n * sizeof(float2)) != cudaSuccess) {
         fail(p, PVB_ERR_NOMEM, "cudaMalloc of tables failed");
         return bail(PVB_ERR_NOMEM);
     }
-    if (cudaMemcpy(p->d_window, win.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(p->d_window_out, win_out.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+    if (cudaMemcpy(p->d_window, win.data(), 2 * n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(p->d_window_out, win_out.data(), 2 * n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(p->d_tw, tw.data(), n * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
         fail(p, PVB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(PVB_ERR_CUDA);
@@ -559,6 +661,7 @@ int32_t pvb_reset(pvb_processor *p) {
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
     p->ring_calls = 0;
     p->cursor_calls = 0;
+    p->layout = pvb_processor::ZERO;
     return PVB_OK;
 }
 
@@ -574,6 +677,7 @@ const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
     fp.pitch_factor = pitch_factor;
     fp.overlaps = p->overlaps;
     split_pitch_factor(pitch_factor, &fp.pf_mant, &fp.pf_shift);
+    if (ring_kernel_applies(p, fp)) return "pvb::pv_process_ring_kernel";
     if (warp_kernel_applies(p->n, fp) && !g_force_generic && g_kernel_1024 != 3)
         return g_kernel_1024 == 2 ? "pvb::pv_process_pair_kernel" : "pvb::pv_process_warp_kernel";
     if (fast_range(fp) && !g_force_generic) {
@@ -600,6 +704,11 @@ int32_t pvb_set_time_cursor(pvb_processor *p, double samples) {
     const double calls = samples / p->hop;
     if (!(samples >= 0) || calls != std::floor(calls) || calls > 9.0e15)
         return fail(p, PVB_ERR_BAD_ARG, "timeCursor must be a non-negative multiple of the hop size");
+    if (p->layout == pvb_processor::PAIRED) {       // the paired rings are aligned to the cursor
+        DeviceGuard guard(p->device);
+        const int rc = ensure_layout(p, pvb_processor::PLANAR, p->stream);
+        if (rc != PVB_OK) return rc;
+    }
     p->cursor_calls = uint64_t(calls);
     return PVB_OK;
 }
@@ -616,6 +725,10 @@ int32_t pvb_get_state(pvb_processor *p, float *blob) {
     if (cn == 0) return PVB_OK;
     std::vector<float> ring(2 * cn);
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    {
+        const int rc = ensure_layout(p, pvb_processor::PLANAR, p->stream);
+        if (rc != PVB_OK) return rc;
+    }
     PVB_CUDA(p, cudaMemcpy(ring.data(), p->d_hist, cn * sizeof(float), cudaMemcpyDeviceToHost));
     PVB_CUDA(p, cudaMemcpy(ring.data() + cn, p->d_acc, cn * sizeof(float), cudaMemcpyDeviceToHost));
     const int n = p->n, hop = p->hop;
@@ -649,6 +762,7 @@ int32_t pvb_set_state(pvb_processor *p, const float *blob) {
         }
     }
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    p->layout = pvb_processor::PLANAR;      // whatever was there is replaced
     PVB_CUDA(p, cudaMemcpy(p->d_hist, ring.data(), cn * sizeof(float), cudaMemcpyHostToDevice));
     PVB_CUDA(p, cudaMemcpy(p->d_acc, ring.data() + cn, cn * sizeof(float), cudaMemcpyHostToDevice));
     return PVB_OK;

@@ -1,0 +1,549 @@
+// pv_kernel_ring.cuh — ring-order fused kernel for frame size 1024 (sm_100a), one warp per
+// channel pair.  Same reference arithmetic as pv_kernel.cuh (one launch == one process() call,
+// ola-processor.js:159-171 + phase-vocoder.js:45-72), reorganised around one identity:
+//
+//   Both state rings are kept ALIGNED TO THE TIME CURSOR t (frame sample n lives at ring index
+//   (n + t) mod N).  The FFT of the ring-ordered windowed frame is U[k] = X[k] e^{-j 2 pi k t / N},
+//   so shiftPeaks' rotation e^{j 2 pi (bs - b) t / N} (phase-vocoder.js:155-170) turns into the
+//   identity  V[b + delta] += U[b],  and the inverse FFT of V is the output frame in ring order
+//   again.  No rotation, no cos/sin, no re-ordering between ring and frame order; only the two
+//   window tables are read at a rotated offset (doubled tables, base + immediate).
+//
+// Further differences from pv_kernel_warp.cuh:
+//   * state layout "paired": hist2 / acc2 hold float2 (ch0, ch1) per sample, so 16-byte global
+//     accesses deliver packed f32x2 operands for both channels (no pack / unpack moves);
+//   * exchange buffer = 16-byte slots (re0, re1, im0, im1) at 65 k1 + 8 r + c: every 128-bit
+//     access pattern of the three radix-8 passes is conflict free and is lane base + immediate;
+//   * the spectrum is stored as one float4 per bin for both channels (bin k at k + (k >> 4));
+//     every lane owns a RUN of 16 consecutive bins: |X|^2 is recomputed from the run (packed),
+//     peaks are a 16-bit mask per lane, and the region of influence of every bin (nearest peak,
+//     ties to the higher one, pv:132-141) comes from one forward and one backward scan in
+//     registers; delta = round(p * pitchFactor) - p is a 513-entry table built once per CTA;
+//   * no peak list, no descriptors, no prefix sums, no atomics.
+//
+// Valid for hop % 128 == 0, hop <= 512 and pitch factors in [0.75, 64] (first stale level only,
+// right halves and left halves of regions stay pairwise disjoint after the shift).  tests/
+// ring_kernel_model.py restates this file lane by lane in numpy and is checked against the oracle.
+#pragma once
+
+#include "pv_kernel.cuh"
+#include "pv_kernel_warp.cuh"
+
+namespace pvb {
+
+struct RingGeo {
+    static constexpr int N = 1024, M = 512, NB = 513;
+    static constexpr int EX_SLOTS = 65 * 7 + 64;            // 519 exchange slots of 16 bytes
+    static constexpr int XQ_SLOTS = 546;                    // bin k at k + (k >> 4); 545 = halo dummy
+    static constexpr int WARP_BYTES = XQ_SLOTS * 16;        // 8736 (>= 519 * 16)
+    static constexpr int DTAB_BYTES = 1040;                 // int16 delta table, 514 entries
+    static constexpr int MAX_WARPS = 7;
+    static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin
+};
+
+struct RingParams {
+    const float *in;            // [C][hop] or nullptr (paused input: zeros, ola:93-100)
+    float *out;                 // [C][hop]
+    float4 *hist2;              // [pairs][N/2] : (ch0[i], ch1[i], ch0[i+1], ch1[i+1]), ring aligned to t
+    float4 *acc2;               // [pairs][N/2] : overlap-add ring, same alignment
+    const float *window2;       // [2N] Hann window, twice
+    const float *window_out2;   // [2N] window / (2 N R), twice
+    const float2 *tw;           // [N]  W_N^j
+    int num_channels;
+    int hop;
+    int tmod;                   // timeCursor mod N (multiple of hop)
+    float pitch_factor;
+    int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
+};
+
+__device__ __forceinline__ float4 pack4(cpx2 v) { return make_float4(v.re.x, v.re.y, v.im.x, v.im.y); }
+__device__ __forceinline__ cpx2 unpack4(float4 v) { return cpx2{make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
+
+// forward real-split of one (k, M-k) pair: 2 X[k] -> *dk, 2 X[M-k] -> *dm (both channels)
+__device__ __forceinline__ void ring_split(cpx2 za, cpx2 zb, float2 w, float4 *dk, float4 *dm) {
+    const float2 e_r = add2(za.re, zb.re), e_i = sub2(za.im, zb.im);
+    const float2 o_r = add2(za.im, zb.im), o_i = sub2(zb.re, za.re);
+    const cpx2 tt = cmul_s(cpx2{o_r, o_i}, w.x, w.y);
+    *dk = pack4(cpx2{add2(e_r, tt.re), add2(e_i, tt.im)});
+    *dm = pack4(cpx2{sub2(e_r, tt.re), sub2(tt.im, e_i)});
+}
+
+// Hermitian C2R pre-pass of one (k, M-k) pair
+__device__ __forceinline__ void ring_unsplit(cpx2 yk, cpx2 ym, float2 w, cpx2 &zk, cpx2 &zmk) {
+    const float2 e_r = add2(yk.re, ym.re), e_i = sub2(yk.im, ym.im);
+    const float2 d_r = sub2(yk.re, ym.re), d_i = add2(yk.im, ym.im);
+    const cpx2 pp = cmul_s(cpx2{d_r, d_i}, w.x, -w.y);
+    zk = cpx2{sub2(e_r, pp.im), add2(e_i, pp.re)};
+    zmk = cpx2{add2(e_r, pp.im), sub2(pp.re, e_i)};
+}
+
+// 5-point strict maxima (pv:95-116) of bins b0 .. b0+15 from squared magnitudes m[0..19] of bins
+// b0-2 .. b0+17 (non-negative floats order like their bit patterns)
+__device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
+    int q[19];
+#pragma unroll
+    for (int t = 0; t < 19; t++) q[t] = max(m[t], m[t + 1]);
+    uint32_t mask = 0;
+#pragma unroll
+    for (int e = 15; e >= 0; e--) {
+        const int nb_max = max(q[e], q[e + 3]);                      // bins e-2, e-1, e+1, e+2
+        mask = __funnelshift_l(uint32_t(nb_max - m[e + 2]), mask, 1);
+    }
+    return mask;
+}
+
+// Region of influence of every bin of the run (channel CH), shifted destinations, pass C.
+//   dst[e] : byte offset (inside the warp's XQ buffer) of the re component the bin adds to in
+//            pass D, or -1 when it was already stored / falls outside [0, nb)
+template <int CH>
+__device__ __forceinline__ void ring_shift_first(const float4 (&xv)[16], uint32_t mask, int lane,
+                                                 uint32_t nz, const unsigned char *dtab,
+                                                 unsigned char *xq, bool contract, int (&dst)[16],
+                                                 int &d_last) {
+    constexpr int NB = RingGeo::NB;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int b0 = 16 * lane;
+    // positions are carried scaled by 2 (they double as byte offsets into the int16 table)
+    const int own_last2 = 2 * (b0 + 31 - __clz(mask));
+    const int own_first2 = 2 * (b0 + __ffs(mask) - 1);
+    const uint32_t below = nz & ((1u << lane) - 1u);
+    const uint32_t above = nz & ~((2u << lane) - 1u);
+    int prev2 = __shfl_sync(FULL, own_last2, (31 - __clz(below)) & 31);
+    int next2 = __shfl_sync(FULL, own_first2, (__ffs(above) - 1) & 31);
+    if (!below) prev2 = -60000;
+    if (!above) next2 = 60000;
+    const int p_last2 = __shfl_sync(FULL, own_last2, 31 - __clz(nz));
+    d_last = *reinterpret_cast<const short *>(dtab + p_last2);
+
+    int nx[16];
+#pragma unroll
+    for (int e = 15; e >= 0; e--) {
+        nx[e] = next2;                                               // first peak above bin e
+        if ((mask >> e) & 1u) next2 = 2 * (b0 + e);
+    }
+    float *yf = reinterpret_cast<float *>(xq);
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        if ((mask >> e) & 1u) prev2 = 2 * (b0 + e);                  // last peak at or below bin e
+        // nearest peak, ties to the higher one:  next - b <= b - prev
+        const bool take_next = (nx[e] + prev2 - 4 * b0) <= 4 * e;
+        const int owner2 = take_next ? nx[e] : prev2;
+        const int delta = *reinterpret_cast<const short *>(dtab + owner2);
+        const int d = b0 + e + delta;
+        const bool ok = unsigned(d) < unsigned(NB);
+        const int off = (d + (d >> 4)) * 16 + 4 * CH;                // re component of bin d
+        const float re = CH ? xv[e].y : xv[e].x, im = CH ? xv[e].w : xv[e].z;
+        const bool first = !take_next || !contract;                  // right half (or expanding): plain store
+        if (ok && first) {
+            *reinterpret_cast<float *>(xq + off) = re;
+            *reinterpret_cast<float *>(xq + off + 8) = im;
+        }
+        dst[e] = (ok && !first) ? off : -1;
+    }
+    (void)yf;
+}
+
+template <int CH>
+__device__ __forceinline__ void ring_shift_second(const float4 (&xv)[16], const int (&dst)[16],
+                                                  unsigned char *xq) {
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        if (dst[e] >= 0) {
+            float *pr = reinterpret_cast<float *>(xq + dst[e]);
+            const float re = CH ? xv[e].y : xv[e].x, im = CH ? xv[e].w : xv[e].z;
+            pr[0] += re;
+            pr[2] += im;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RingGeo::MAX_WARPS * 32, 2)
+pv_process_ring_kernel(const RingParams p) {
+    using G = RingGeo;
+    constexpr int N = G::N, NB = G::NB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool live = 2 * pair < p.num_channels;
+    const unsigned FULL = 0xFFFFFFFFu;
+    unsigned char *dtab = smem_raw;
+    unsigned char *mine = smem_raw + G::DTAB_BYTES + size_t(warp) * G::WARP_BYTES;
+    float4 *ex = reinterpret_cast<float4 *>(mine);
+    float4 *XQ = reinterpret_cast<float4 *>(mine);
+
+    const int c0 = 2 * pair;
+    const bool has1 = c0 + 1 < p.num_channels;
+    const int hop = p.hop;
+    const int t = p.tmod;
+    const int nblk = hop >> 7;
+    const int jb = ((t - hop + N) >> 7) & 7;      // ring 128-block that receives the new input block
+    const int je = (t >> 7) & 7;                  // ring 128-block of frame sample 0 (emitted)
+    const float2 *__restrict__ tw = p.tw;
+
+    // ---- frame loads: all 16 issued before anything consumes them ------------------------------
+    float4 r[16];
+    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + lane;
+    if (live) {
+        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * lane : nullptr;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int h = e >> 3, j = e & 7;
+            const int jj = (j - jb) & 7;                              // uniform
+            if (jj < nblk) {
+                float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
+                if (i0) {
+                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * jj));
+                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * jj));
+                }
+                r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
+            } else {
+                r[e] = hl[32 * h + 64 * j];
+            }
+        }
+    }
+    // ---- delta table: round(p * pitchFactor) - p, exact integer arithmetic (pv:125-127) ----------
+    {
+        const long long pf_m = p.pf_mant;
+        const int pf_s = p.pf_shift;
+        const long long half = 1ll << (pf_s - 1);
+        for (int pk = threadIdx.x; pk <= NB; pk += blockDim.x) {
+            const long long ps = (pf_m * pk + half) >> pf_s;
+            const int delta = (ps <= NB) ? int(ps) - pk : G::INVALID_DELTA;
+            reinterpret_cast<short *>(dtab)[pk] = short(delta);
+        }
+    }
+    __syncthreads();
+    if (!live) return;          // no CTA-wide barriers below
+
+    // the new block joins the history ring (ola:105)
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int h = e >> 3, j = e & 7;
+        if (((j - jb) & 7) < nblk) hl[32 * h + 64 * j] = r[e];
+    }
+
+    // ---- Hann window (pv:55) + forward pass 1: butterflies n = lane + 32 h over j (stride 64) ---
+    {
+        const float *wl = p.window2 + ((N - t) & (N - 1)) + 2 * lane;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int nl = lane + 32 * h;
+            cpx2 x[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float2 w = __ldg(reinterpret_cast<const float2 *>(wl + 64 * h + 128 * j));
+                const float4 v = r[8 * h + j];
+                x[j].re = mul2(make_float2(v.x, v.y), bc2(w.x));
+                x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
+            }
+            dft8<false>(x);
+#pragma unroll
+            for (int k1 = 1; k1 < 8; k1++) {
+                const float2 w = __ldg(&tw[2 * nl * k1]);             // W_512^{n k1}
+                x[k1] = cmul_s(x[k1], w.x, w.y);
+            }
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++) ex[65 * k1 + nl] = pack4(x[k1]);
+        }
+    }
+    __syncwarp();
+
+    // warm L2 with the overlap-add ring lines the tail of this kernel adds to (the slot that is
+    // only written, ring [t - hop, t), is skipped)
+    {
+        const int line = 16 * lane;                                   // float4 index: 256 bytes per lane
+        if ((((line >> 6) - jb) & 7) >= nblk) {
+            const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
+        }
+    }
+
+    // ---- forward pass 2: butterflies (k1, m3) over m2, in place -----------------------------------
+    const int m3l = lane & 7;
+    {
+        float2 w2[8];
+#pragma unroll
+        for (int k2 = 1; k2 < 8; k2++) w2[k2] = __ldg(&tw[16 * m3l * k2]);      // W_64^{m3 k2}
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            float4 *bp = ex + 65 * ((lane >> 3) + 4 * h) + m3l;
+            cpx2 x[8];
+#pragma unroll
+            for (int m2 = 0; m2 < 8; m2++) x[m2] = unpack4(bp[8 * m2]);
+            dft8<false>(x);
+#pragma unroll
+            for (int k2 = 1; k2 < 8; k2++) x[k2] = cmul_s(x[k2], w2[k2].x, w2[k2].y);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++) bp[8 * k2] = pack4(x[k2]);
+        }
+    }
+    __syncwarp();
+
+    // ---- forward pass 3: butterflies A (bins lane + 64 j) and B (bins 64 - lane + 64 j) ------------
+    // lane 0 owns the two self-paired butterflies: A = bins 64 j, B = bins 32 + 64 j
+    const bool l0 = lane == 0;
+    const int kB = l0 ? 32 : 64 - lane;
+    const int exA = 65 * (lane & 7) + 8 * (lane >> 3);
+    const int exB = 65 * (kB & 7) + 8 * (kB >> 3);
+    cpx2 a[8], b[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        a[c] = unpack4(ex[exA + c]);
+        b[c] = unpack4(ex[exB + c]);
+    }
+    dft8<false>(a);      // a[j] = Z[lane + 64 j]
+    dft8<false>(b);      // b[j] = Z[kB + 64 j]
+    __syncwarp();        // everyone has read the exchange slots: X may overwrite them
+
+    // ---- real split in registers -> XQ (2x scaled) --------------------------------------------------
+    // slot j pairs (a[j], b[7-j]) at k = lane + 64 j.  lane 0: j < 4: (b[j], b[7-j]) at k = 32 + 64 j;
+    // j >= 4: (a[j-4], a[(12-j)&7]) at k = 64 (j-4); plus the self pair k = 256 (a[4]).
+    const int gA = lane + (lane >> 4);                                // slot of bin lane
+    const int gB = 544 - lane - ((lane + 15) >> 4);                   // slot of bin 512 - lane
+    const int sAlo = l0 ? 34 : gA, sAhi = l0 ? -272 : gA;
+    const int sBlo = l0 ? 510 : gB, sBhi = l0 ? 816 : gB;
+    const int tlo = l0 ? 32 : lane, thi = l0 ? -256 : lane;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const cpx2 za = sel(l0, b[j], a[j]);
+        ring_split(za, b[7 - j], __ldg(&tw[tlo + 64 * j]), XQ + sAlo + 68 * j, XQ + sBlo - 68 * j);
+    }
+#pragma unroll
+    for (int j = 4; j < 8; j++) {
+        const cpx2 za = sel(l0, a[j - 4], a[j]);
+        const cpx2 zb = sel(l0, a[(12 - j) & 7], b[7 - j]);
+        ring_split(za, zb, __ldg(&tw[thi + 64 * j]), XQ + sAhi + 68 * j, XQ + sBhi - 68 * j);
+    }
+    if (l0) ring_split(a[4], a[4], __ldg(&tw[256]), XQ + 272, XQ + 272);
+    __syncwarp();
+
+    // ---- peaks, regions of influence, in-place shift (pv:95-173) ----------------------------------------
+    {
+        const bool contract = p.pitch_factor < 1.0f;
+        const float4 *runp = XQ + 17 * lane;                          // slot of bin 16 lane
+        float4 xv[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) xv[e] = runp[e];
+        uint32_t mask0, mask1;
+        {
+            const float4 *hlo = lane ? runp - 3 : XQ;                 // bins 16 lane - 2, - 1 (lane 0: unused)
+            float4 hv[4];
+            hv[0] = hlo[0]; hv[1] = hlo[1]; hv[2] = runp[17]; hv[3] = runp[18];
+            int m0[20], m1[20];
+#pragma unroll
+            for (int i = 0; i < 20; i++) {
+                const float4 v = (i < 2) ? hv[i] : (i < 18) ? xv[i - 2] : hv[i - 16];
+                const float2 re = make_float2(v.x, v.y), im = make_float2(v.z, v.w);
+                const float2 mg = fma2(re, re, mul2(im, im));         // pv:82-92, float32
+                m0[i] = __float_as_int(mg.x);
+                m1[i] = __float_as_int(mg.y);
+            }
+            mask0 = ring_peak_mask(m0);
+            mask1 = ring_peak_mask(m1);
+            if (lane == 0) { mask0 &= ~3u; mask1 &= ~3u; }            // i >= 2
+            if (lane == 31) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); }     // i <= nb - 3
+        }
+        const uint32_t nz0 = __ballot_sync(FULL, mask0 != 0);
+        const uint32_t nz1 = __ballot_sync(FULL, mask1 != 0);
+
+        // extension: bin 512 and the first stale level (what _realTransform4 leaves in slots
+        // N/2 + q, bundle:394-438), rebuilt from the valid half; bins 512 + lane + 32 i
+        float4 ext[4];
+        ext[0] = ext[1] = ext[2] = ext[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l0) ext[0] = XQ[544];
+        if (contract) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int q = lane + 32 * i;
+                const int qq = q ? q : 1;
+                const int sq = qq + (qq >> 4);                        // slot of bin q
+                const int sm = 544 - qq - ((qq + 15) >> 4);           // slot of bin 512 - q
+                const cpx2 A = unpack4(XQ[sq]), Bv = unpack4(XQ[sq + 272]);        // bins q, 256 + q
+                const cpx2 Cv = unpack4(XQ[sm]), D = unpack4(XQ[sm - 272]);        // bins 512 - q, 256 - q
+                const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, D.re));
+                const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, D.im));
+                const float2 w = __ldg(&tw[2 * qq]);
+                const cpx2 s = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
+                if (q) ext[i] = pack4(s);
+            }
+        }
+        __syncwarp();            // every lane holds its sources: the buffer becomes Y
+#pragma unroll
+        for (int i = 0; i < 17; i++) XQ[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < 2) XQ[544 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+
+        int dst0[16], dst1[16];
+        if (nz0) {
+            int d_last;
+            ring_shift_first<0>(xv, mask0, lane, nz0, dtab, mine, contract, dst0, d_last);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int d = 512 + lane + 32 * i + d_last;
+                if (unsigned(d) < unsigned(NB)) {
+                    float *pr = reinterpret_cast<float *>(mine + (d + (d >> 4)) * 16);
+                    pr[0] = ext[i].x;
+                    pr[2] = ext[i].z;
+                }
+            }
+        }
+        if (nz1) {
+            int d_last;
+            ring_shift_first<1>(xv, mask1, lane, nz1, dtab, mine, contract, dst1, d_last);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int d = 512 + lane + 32 * i + d_last;
+                if (unsigned(d) < unsigned(NB)) {
+                    float *pr = reinterpret_cast<float *>(mine + (d + (d >> 4)) * 16);
+                    pr[1] = ext[i].y;
+                    pr[3] = ext[i].w;
+                }
+            }
+        }
+        if (contract) {
+            __syncwarp();
+            if (nz0) ring_shift_second<0>(xv, dst0, mine);
+            if (nz1) ring_shift_second<1>(xv, dst1, mine);
+        }
+    }
+    __syncwarp();
+
+    // ---- Hermitian C2R pre-pass in registers (mirror of the split) -------------------------------------
+    {
+        cpx2 zk[8], zmk[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int sa = (j < 4 ? sAlo : sAhi) + 68 * j, sb = (j < 4 ? sBlo : sBhi) - 68 * j;
+            cpx2 yk = unpack4(XQ[sa]), ym = unpack4(XQ[sb]);
+            if (j == 4) {                        // lane 0: k == 0, bins 0 and N/2 enter with their real part only
+                yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
+                ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
+            }
+            const float2 w = __ldg(&tw[(j < 4 ? tlo : thi) + 64 * j]);
+            ring_unsplit(yk, ym, w, zk[j], zmk[j]);
+        }
+        cpx2 z256, dummy;
+        {
+            const cpx2 y = unpack4(XQ[272]);
+            ring_unsplit(y, y, __ldg(&tw[256]), z256, dummy);
+        }
+        a[0] = sel(l0, zk[4], zk[0]);
+        a[1] = sel(l0, zk[5], zk[1]);
+        a[2] = sel(l0, zk[6], zk[2]);
+        a[3] = sel(l0, zk[7], zk[3]);
+        a[4] = sel(l0, z256, zk[4]);
+        a[5] = sel(l0, zmk[7], zk[5]);
+        a[6] = sel(l0, zmk[6], zk[6]);
+        a[7] = sel(l0, zmk[5], zk[7]);
+        b[0] = sel(l0, zk[0], zmk[7]);
+        b[1] = sel(l0, zk[1], zmk[6]);
+        b[2] = sel(l0, zk[2], zmk[5]);
+        b[3] = sel(l0, zk[3], zmk[4]);
+        b[4] = zmk[3];
+        b[5] = zmk[2];
+        b[6] = zmk[1];
+        b[7] = zmk[0];
+    }
+    __syncwarp();        // everyone has read Y: the exchange slots may overwrite it
+
+    // ---- inverse pass 1 (DIT): butterflies A and B over k3, twiddle conj(W_64^{k2 m3}) -------------------
+    dft8<true>(a);
+    dft8<true>(b);
+    {
+        const int k2a = lane >> 3, k2b = kB >> 3;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            cpx2 va = a[c], vb = b[c];
+            if (c > 0) {
+                const float2 wa = __ldg(&tw[16 * k2a * c]);
+                const float2 wb = __ldg(&tw[16 * k2b * c]);
+                va = cmul_s(va, wa.x, -wa.y);
+                vb = cmul_s(vb, wb.x, -wb.y);
+            }
+            ex[exA + c] = pack4(va);
+            ex[exB + c] = pack4(vb);
+        }
+    }
+    __syncwarp();
+
+    // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_512^{k1 (m3 + 8 m2)}) ---------------
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+        const int k1 = (lane >> 3) + 4 * h;
+        float4 *bp = ex + 65 * k1 + m3l;
+        cpx2 x[8];
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) x[k2] = unpack4(bp[8 * k2]);
+        dft8<true>(x);
+#pragma unroll
+        for (int m2 = 0; m2 < 8; m2++) {
+            const float2 w = __ldg(&tw[2 * k1 * (m3l + 8 * m2)]);
+            bp[8 * m2] = pack4(cmul_s(x[m2], w.x, -w.y));
+        }
+    }
+    __syncwarp();
+
+    // ---- inverse pass 3: butterflies n over k1 -> ring samples; window, overlap-add, emit ------------------
+    {
+        float4 *al = p.acc2 + size_t(pair) * (N / 2) + lane;
+        float *o0 = p.out + size_t(c0) * hop + 2 * lane;
+        const float *wol = p.window_out2 + ((N - t) & (N - 1)) + 2 * lane;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int nl = lane + 32 * h;
+            float4 q[8];
+            float2 wo[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                wo[j] = __ldg(reinterpret_cast<const float2 *>(wol + 64 * h + 128 * j));
+                q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (((j - jb) & 7) >= nblk) q[j] = al[32 * h + 64 * j];     // the tail slot starts from zero (ola:134)
+            }
+            cpx2 x[8];
+#pragma unroll
+            for (int k1 = 0; k1 < 8; k1++) x[k1] = unpack4(ex[65 * k1 + nl]);
+            dft8<true>(x);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the division
+                // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
+                const float2 y0 = fma2(x[j].re, bc2(wo[j].x), make_float2(q[j].x, q[j].y));
+                const float2 y1 = fma2(x[j].im, bc2(wo[j].y), make_float2(q[j].z, q[j].w));
+                const int jj = (j - je) & 7;
+                if (jj < nblk) {                                      // head: emit (ola:111-118)
+                    *reinterpret_cast<float2 *>(o0 + 64 * h + 128 * jj) = make_float2(y0.x, y1.x);
+                    if (has1) *reinterpret_cast<float2 *>(o0 + hop + 64 * h + 128 * jj) = make_float2(y0.y, y1.y);
+                } else {
+                    al[32 * h + 64 * j] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                }
+            }
+        }
+    }
+}
+
+// planar [C'][N] rings (pv_kernel.cuh conventions: frame sample n at hist[(n + rb + hop) mod N],
+// accumulator sample k at acc[(k + rb) mod N]) <-> paired rings aligned to t
+__global__ void pv_ring_convert_kernel(float *hist_planar, float *acc_planar, float2 *hist2, float2 *acc2,
+                                       int pairs, int n, int hop, int rb, int tmod, int to_paired) {
+    const long long total = (long long)pairs * n;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int pr = int(idx / n), s = int(idx % n);               // frame-order sample s of pair pr
+        const int ih = (s + rb + hop) & (n - 1), ia = (s + rb) & (n - 1), i2 = (s + tmod) & (n - 1);
+        float *h0 = hist_planar + (size_t(2 * pr) * n), *h1 = h0 + n;
+        float *a0 = acc_planar + (size_t(2 * pr) * n), *a1 = a0 + n;
+        if (to_paired) {
+            hist2[size_t(pr) * n + i2] = make_float2(h0[ih], h1[ih]);
+            acc2[size_t(pr) * n + i2] = (s < n - hop) ? make_float2(a0[ia], a1[ia]) : make_float2(0.f, 0.f);
+        } else {
+            const float2 hv = hist2[size_t(pr) * n + i2], av = acc2[size_t(pr) * n + i2];
+            h0[ih] = hv.x; h1[ih] = hv.y;
+            a0[ia] = (s < n - hop) ? av.x : 0.f;
+            a1[ia] = (s < n - hop) ? av.y : 0.f;
+        }
+    }
+}
+
+}  // namespace pvb

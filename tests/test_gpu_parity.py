@@ -57,12 +57,14 @@ def test_parity_frame_size_sweep(oracle, N, pf):
 
 
 @pytest.mark.parametrize("pf", [0.8, 0.67, 0.7, 0.75, 0.9, 1.0, 1.2, 1.5, 2.0, 3.0])
-@pytest.mark.parametrize("kernel", ["pair", "warp", "cta", "generic"])
+@pytest.mark.parametrize("kernel", ["ring", "pair", "warp", "cta", "generic"])
 def test_parity_1024_all_kernels(oracle, monkeypatch, pf, kernel):
-    """frame 1024 has three CUDA paths: one warp per channel pair (default for pitch factors in
-    [0.75, 64]), two warps per pair (PVB_KERNEL_1024=2) and the generic kernel; all must match."""
+    """frame 1024 has five CUDA paths: the ring-order kernel (default for pitch factors in
+    [0.75, 64] and hop % 128 == 0), one warp per channel pair (PVB_KERNEL_1024=1), two warps per
+    pair (=2), the CTA kernel (=3) and the generic kernel; all must match."""
     monkeypatch.setenv("PVB_FORCE_GENERIC", "1" if kernel == "generic" else "0")
-    monkeypatch.setenv("PVB_KERNEL_1024", {"warp": "1", "pair": "2", "cta": "3", "generic": "1"}[kernel])
+    monkeypatch.setenv("PVB_KERNEL_1024",
+                       {"ring": "0", "warp": "1", "pair": "2", "cta": "3", "generic": "1"}[kernel])
     x, ref, got = _run_both(oracle, 1024, 256, 5, np.float32(pf), 17)
     err = _rms(got - ref)
     print(f"pf={pf} kernel={kernel}: rms err {err:.3e}")
@@ -111,9 +113,65 @@ def test_parity_1024_hop_sweep(oracle, monkeypatch, hop, pf, no_aligned):
     """warp kernel at every hop (R = 32 ... 1): hop % 128 == 0 takes the ring-order specialisation
     (rotation folded into the twiddles), the others the general addressing; PVB_NO_ALIGNED=1
     forces the general one everywhere."""
+    monkeypatch.setenv("PVB_KERNEL_1024", "1")
     monkeypatch.setenv("PVB_NO_ALIGNED", no_aligned)
     calls = 2 * (1024 // hop) + 7
     x, ref, got = _run_both(oracle, 1024, hop, 3, np.float32(pf), calls)
     err = _rms(got - ref)
     print(f"hop={hop} pf={pf} no_aligned={no_aligned}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("hop", [128, 256, 512])
+@pytest.mark.parametrize("pf", [0.75, 0.8, 0.97, 1.0, 1.3, 2.0, 7.5])
+def test_parity_ring_kernel_hops(oracle, hop, pf):
+    """the ring-order kernel (default at frame 1024) at every hop it accepts, odd channel count"""
+    from phaze_b200 import BatchedPhaseVocoder
+    with BatchedPhaseVocoder(3, 1024, hop) as pv:
+        assert "ring" in pv.kernel_name(np.float32(pf))
+    calls = 3 * (1024 // hop) + 5
+    x, ref, got = _run_both(oracle, 1024, hop, 3, np.float32(pf), calls)
+    err = _rms(got - ref)
+    print(f"hop={hop} pf={pf}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+def test_parity_ring_kernel_many_channels(oracle):
+    """more pairs than one CTA holds, last pair half empty, several CTAs per SM slot"""
+    x, ref, got = _run_both(oracle, 1024, 256, 45, np.float32(0.8), 11)
+    assert _rms(got - ref) <= RMS_EXPECTED
+    per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
+    assert per_channel.max() <= RMS_EXPECTED
+
+
+def test_layout_changes_mid_stream(oracle):
+    """the pitch factor moves between the ring-order kernel (paired state, aligned to the time
+    cursor) and the generic kernel (planar state): the state is re-laid on the device each time;
+    a paused block, a checkpoint round trip and a time-cursor jump happen in between."""
+    from phaze_b200 import BatchedPhaseVocoder
+    N, hop, C = 1024, 256, 5
+    plan = [(0.8, 5), (0.5, 3), (1.2, 4), (0.6, 2), (0.9, 6)]
+    total = sum(n for _, n in plan)
+    x = signals.channels(3, C, total * hop)
+    ref_p = oracle.OracleProcessor(N, hop, C)
+    ref = np.empty_like(x)
+    got = np.empty_like(x)
+    with BatchedPhaseVocoder(C, N, hop) as pv:
+        k = 0
+        for pf, n in plan:
+            for _ in range(n):
+                s = slice(k * hop, (k + 1) * hop)
+                blk = None if k == 7 else x[:, s]
+                ref[:, s] = ref_p.process_packed(blk, np.float32(pf))
+                got[:, s] = pv.process(blk, np.float32(pf))
+                k += 1
+                if k == 9:
+                    st = pv.get_state()
+                    pv.reset()
+                    pv.set_state(st)
+                if k == 12:
+                    ref_p.time_cursor = 40 * hop
+                    pv.time_cursor = 40 * hop
+    err = _rms(got - ref)
+    print(f"layout changes: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
