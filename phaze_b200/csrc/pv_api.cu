@@ -29,6 +29,7 @@ struct pvb_processor {
     float *d_hist = nullptr, *d_acc = nullptr, *d_window = nullptr, *d_window_out = nullptr;
     int num_sms = 148;
     float2 *d_tw = nullptr;
+    float4 *d_ring_tab = nullptr;    // tables of the ring-order kernel (frame 1024 only)
     float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
     size_t staging_floats = 0;
     cudaStream_t stream = nullptr;
@@ -195,9 +196,14 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(G::DTAB_BYTES + G::MAX_WARPS * G::WARP_BYTES));
+        const int smem = int(G::TAB_BYTES + G::MAX_WARPS * G::WARP_BYTES);
+        cudaError_t e = cudaSuccess;
+#define PVB_RING_ATTR(NBLK, JB)                                                                   \
+        if (e == cudaSuccess)                                                                     \
+            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<NBLK, JB>,                       \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        PVB_RING_ATTR(0, 0) PVB_RING_ATTR(2, 0) PVB_RING_ATTR(2, 2) PVB_RING_ATTR(2, 4) PVB_RING_ATTR(2, 6)
+#undef PVB_RING_ATTR
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -212,14 +218,25 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     rp.acc2 = reinterpret_cast<float4 *>(fp.acc);
     rp.window2 = h->d_window;
     rp.window_out2 = h->d_window_out;
-    rp.tw = fp.tw;
+    rp.gtab = h->d_ring_tab;
     rp.num_channels = fp.num_channels;
     rp.hop = fp.hop;
     rp.tmod = fp.step_mod_r * fp.hop;
     rp.pitch_factor = fp.pitch_factor;
     rp.pf_mant = fp.pf_mant;
     rp.pf_shift = fp.pf_shift;
-    pvb::pv_process_ring_kernel<<<grid, wpc * 32, G::DTAB_BYTES + size_t(wpc) * G::WARP_BYTES, s>>>(rp);
+    const size_t smem = G::TAB_BYTES + size_t(wpc) * G::WARP_BYTES;
+    const int jb = ((rp.tmod - rp.hop + 1024) >> 7) & 7;
+    if (rp.hop == 256) {        // the headline geometry: ring-block roles fixed at compile time
+        switch (jb) {
+            case 0: pvb::pv_process_ring_kernel<2, 0><<<grid, wpc * 32, smem, s>>>(rp); break;
+            case 2: pvb::pv_process_ring_kernel<2, 2><<<grid, wpc * 32, smem, s>>>(rp); break;
+            case 4: pvb::pv_process_ring_kernel<2, 4><<<grid, wpc * 32, smem, s>>>(rp); break;
+            default: pvb::pv_process_ring_kernel<2, 6><<<grid, wpc * 32, smem, s>>>(rp); break;
+        }
+    } else {
+        pvb::pv_process_ring_kernel<0, 0><<<grid, wpc * 32, smem, s>>>(rp);
+    }
     return cudaGetLastError();
 }
 
@@ -511,6 +528,15 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         fail(p, PVB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(PVB_ERR_CUDA);
     }
+    if (n == 1024) {
+        std::vector<float2> rt(pvb::RingGeo::GTAB_BYTES / sizeof(float2));
+        pvb::ring_host_tables(tw.data(), rt.data());
+        if (cudaMalloc(&p->d_ring_tab, pvb::RingGeo::GTAB_BYTES) != cudaSuccess ||
+            cudaMemcpy(p->d_ring_tab, rt.data(), pvb::RingGeo::GTAB_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) {
+            fail(p, PVB_ERR_CUDA, "ring table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return bail(PVB_ERR_CUDA);
+        }
+    }
     int rc = alloc_state(p, cfg->num_channels);
     if (rc != PVB_OK) return bail(rc);
     if (cudaStreamSynchronize(p->stream) != cudaSuccess) {
@@ -530,6 +556,7 @@ void pvb_destroy(pvb_processor *p) {
     cudaFree(p->d_window);
     cudaFree(p->d_window_out);
     cudaFree(p->d_tw);
+    cudaFree(p->d_ring_tab);
     cudaFree(p->d_in);
     cudaFree(p->d_out);
     for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);

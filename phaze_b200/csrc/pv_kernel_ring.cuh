@@ -36,7 +36,20 @@ struct RingGeo {
     static constexpr int EX_SLOTS = 65 * 7 + 64;            // 519 exchange slots of 16 bytes
     static constexpr int XQ_SLOTS = 546;                    // bin k at k + (k >> 4); 545 = halo dummy
     static constexpr int WARP_BYTES = XQ_SLOTS * 16;        // 8736 (>= 519 * 16)
+    // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
     static constexpr int DTAB_BYTES = 1040;                 // int16 delta table, 514 entries
+    static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
+    static constexpr int TW1_BYTES = 8 * TW1_ROW * 8;       // tw1[k1][n] = W_512^{n k1}, n < 64
+    static constexpr int W64_BYTES = 64 * 8;                // w64[a][b] = W_64^{a b}
+    static constexpr int TWH_BYTES = 520 * 8;               // twh[k] = W_1024^k, k <= 512
+    static constexpr int GTAB_BYTES = TW1_BYTES + W64_BYTES + TWH_BYTES;    // copied verbatim from global
+    static constexpr int WIN_BYTES = 1024 * 4;              // window / synthesis window, rotated by t
+    static constexpr int OFF_TW1 = DTAB_BYTES;
+    static constexpr int OFF_W64 = OFF_TW1 + TW1_BYTES;
+    static constexpr int OFF_TWH = OFF_W64 + W64_BYTES;
+    static constexpr int OFF_WIN = OFF_TWH + TWH_BYTES;
+    static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
+    static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;  // 18512
     static constexpr int MAX_WARPS = 7;
     static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin
 };
@@ -48,7 +61,7 @@ struct RingParams {
     float4 *acc2;               // [pairs][N/2] : overlap-add ring, same alignment
     const float *window2;       // [2N] Hann window, twice
     const float *window_out2;   // [2N] window / (2 N R), twice
-    const float2 *tw;           // [N]  W_N^j
+    const float4 *gtab;         // [GTAB_BYTES / 16] tw1 | w64 | twh, built by the host (ring_host_tables)
     int num_channels;
     int hop;
     int tmod;                   // timeCursor mod N (multiple of hop)
@@ -157,6 +170,11 @@ __device__ __forceinline__ void ring_shift_second(const float4 (&xv)[16], const 
     }
 }
 
+// NBLK = hop / 128 and JB = ring 128-block that receives the new input block, as template
+// parameters (NBLK > 0), make the role of every ring block (history / new input / emitted head /
+// zero tail) a compile-time fact: no predicated duplicates of the global accesses.  NBLK == 0 is
+// the same kernel with both read from the parameters (launch-uniform branches).
+template <int NBLK, int JB>
 __global__ void __launch_bounds__(RingGeo::MAX_WARPS * 32, 2)
 pv_process_ring_kernel(const RingParams p) {
     using G = RingGeo;
@@ -168,7 +186,12 @@ pv_process_ring_kernel(const RingParams p) {
     const bool live = 2 * pair < p.num_channels;
     const unsigned FULL = 0xFFFFFFFFu;
     unsigned char *dtab = smem_raw;
-    unsigned char *mine = smem_raw + G::DTAB_BYTES + size_t(warp) * G::WARP_BYTES;
+    const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
+    const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
+    const float2 *twh = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
+    const float *swin = reinterpret_cast<const float *>(smem_raw + G::OFF_WIN);
+    const float *swout = reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
+    unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(warp) * G::WARP_BYTES;
     float4 *ex = reinterpret_cast<float4 *>(mine);
     float4 *XQ = reinterpret_cast<float4 *>(mine);
 
@@ -176,34 +199,51 @@ pv_process_ring_kernel(const RingParams p) {
     const bool has1 = c0 + 1 < p.num_channels;
     const int hop = p.hop;
     const int t = p.tmod;
-    const int nblk = hop >> 7;
-    const int jb = ((t - hop + N) >> 7) & 7;      // ring 128-block that receives the new input block
-    const int je = (t >> 7) & 7;                  // ring 128-block of frame sample 0 (emitted)
-    const float2 *__restrict__ tw = p.tw;
+    const int nblk = NBLK ? NBLK : (hop >> 7);
+    const int jb = NBLK ? JB : (((t - hop + N) >> 7) & 7);    // ring 128-block that receives the new input block
+    const int je = (jb + nblk) & 7;                           // ring 128-block of frame sample 0 (emitted)
 
-    // ---- frame loads: all 16 issued before anything consumes them ------------------------------
+    // ---- frame loads: all issued before anything consumes them ---------------------------------
     float4 r[16];
+    float2 un0[NBLK ? 2 * NBLK : 1], un1[NBLK ? 2 * NBLK : 1];
     float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + lane;
     if (live) {
         const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * lane : nullptr;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             const int h = e >> 3, j = e & 7;
-            const int jj = (j - jb) & 7;                              // uniform
+            const int jj = (j - jb) & 7;                              // launch-uniform
             if (jj < nblk) {
                 float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
                 if (i0) {
                     u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * jj));
                     if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * jj));
                 }
-                r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
+                if constexpr (NBLK > 0) {
+                    un0[h * NBLK + jj] = u0;                          // packed after the barrier: the moves
+                    un1[h * NBLK + jj] = u1;                          // must not sit between the loads
+                } else {
+                    r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
+                }
             } else {
                 r[e] = hl[32 * h + 64 * j];
             }
         }
     }
-    // ---- delta table: round(p * pitchFactor) - p, exact integer arithmetic (pv:125-127) ----------
+    // ---- CTA-shared tables (while the frame is in flight) -----------------------------------------
     {
+        float4 *dg = reinterpret_cast<float4 *>(smem_raw + G::OFF_TW1);
+        for (int i = threadIdx.x; i < G::GTAB_BYTES / 16; i += blockDim.x) dg[i] = __ldg(p.gtab + i);
+        const int rot = (N - t) & (N - 1);
+        const float4 *w1 = reinterpret_cast<const float4 *>(p.window2 + rot);
+        const float4 *w2 = reinterpret_cast<const float4 *>(p.window_out2 + rot);
+        float4 *d1 = reinterpret_cast<float4 *>(smem_raw + G::OFF_WIN);
+        float4 *d2 = reinterpret_cast<float4 *>(smem_raw + G::OFF_WOUT);
+        for (int i = threadIdx.x; i < N / 4; i += blockDim.x) {
+            d1[i] = __ldg(w1 + i);
+            d2[i] = __ldg(w2 + i);
+        }
+        // delta table: round(p * pitchFactor) - p, exact integer arithmetic (pv:125-127)
         const long long pf_m = p.pf_mant;
         const int pf_s = p.pf_shift;
         const long long half = 1ll << (pf_s - 1);
@@ -220,19 +260,26 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         const int h = e >> 3, j = e & 7;
-        if (((j - jb) & 7) < nblk) hl[32 * h + 64 * j] = r[e];
+        const int jj = (j - jb) & 7;
+        if (jj < nblk) {
+            if constexpr (NBLK > 0) {
+                const float2 u0 = un0[h * NBLK + jj], u1 = un1[h * NBLK + jj];
+                r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
+            }
+            hl[32 * h + 64 * j] = r[e];
+        }
     }
 
     // ---- Hann window (pv:55) + forward pass 1: butterflies n = lane + 32 h over j (stride 64) ---
     {
-        const float *wl = p.window2 + ((N - t) & (N - 1)) + 2 * lane;
+        const float *wl = swin + 2 * lane;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int nl = lane + 32 * h;
             cpx2 x[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const float2 w = __ldg(reinterpret_cast<const float2 *>(wl + 64 * h + 128 * j));
+                const float2 w = *reinterpret_cast<const float2 *>(wl + 64 * h + 128 * j);
                 const float4 v = r[8 * h + j];
                 x[j].re = mul2(make_float2(v.x, v.y), bc2(w.x));
                 x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
@@ -240,7 +287,7 @@ pv_process_ring_kernel(const RingParams p) {
             dft8<false>(x);
 #pragma unroll
             for (int k1 = 1; k1 < 8; k1++) {
-                const float2 w = __ldg(&tw[2 * nl * k1]);             // W_512^{n k1}
+                const float2 w = tw1[G::TW1_ROW * k1 + nl];           // W_512^{n k1}
                 x[k1] = cmul_s(x[k1], w.x, w.y);
             }
 #pragma unroll
@@ -265,7 +312,7 @@ pv_process_ring_kernel(const RingParams p) {
     {
         float2 w2[8];
 #pragma unroll
-        for (int k2 = 1; k2 < 8; k2++) w2[k2] = __ldg(&tw[16 * m3l * k2]);      // W_64^{m3 k2}
+        for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             float4 *bp = ex + 65 * ((lane >> 3) + 4 * h) + m3l;
@@ -308,15 +355,15 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const cpx2 za = sel(l0, b[j], a[j]);
-        ring_split(za, b[7 - j], __ldg(&tw[tlo + 64 * j]), XQ + sAlo + 68 * j, XQ + sBlo - 68 * j);
+        ring_split(za, b[7 - j], twh[tlo + 64 * j], XQ + sAlo + 68 * j, XQ + sBlo - 68 * j);
     }
 #pragma unroll
     for (int j = 4; j < 8; j++) {
         const cpx2 za = sel(l0, a[j - 4], a[j]);
         const cpx2 zb = sel(l0, a[(12 - j) & 7], b[7 - j]);
-        ring_split(za, zb, __ldg(&tw[thi + 64 * j]), XQ + sAhi + 68 * j, XQ + sBhi - 68 * j);
+        ring_split(za, zb, twh[thi + 64 * j], XQ + sAhi + 68 * j, XQ + sBhi - 68 * j);
     }
-    if (l0) ring_split(a[4], a[4], __ldg(&tw[256]), XQ + 272, XQ + 272);
+    if (l0) ring_split(a[4], a[4], twh[256], XQ + 272, XQ + 272);
     __syncwarp();
 
     // ---- peaks, regions of influence, in-place shift (pv:95-173) ----------------------------------------
@@ -364,7 +411,7 @@ pv_process_ring_kernel(const RingParams p) {
                 const cpx2 Cv = unpack4(XQ[sm]), D = unpack4(XQ[sm - 272]);        // bins 512 - q, 256 - q
                 const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, D.re));
                 const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, D.im));
-                const float2 w = __ldg(&tw[2 * qq]);
+                const float2 w = twh[2 * qq];
                 const cpx2 s = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
                 if (q) ext[i] = pack4(s);
             }
@@ -421,13 +468,13 @@ pv_process_ring_kernel(const RingParams p) {
                 yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
                 ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
             }
-            const float2 w = __ldg(&tw[(j < 4 ? tlo : thi) + 64 * j]);
+            const float2 w = twh[(j < 4 ? tlo : thi) + 64 * j];
             ring_unsplit(yk, ym, w, zk[j], zmk[j]);
         }
         cpx2 z256, dummy;
         {
             const cpx2 y = unpack4(XQ[272]);
-            ring_unsplit(y, y, __ldg(&tw[256]), z256, dummy);
+            ring_unsplit(y, y, twh[256], z256, dummy);
         }
         a[0] = sel(l0, zk[4], zk[0]);
         a[1] = sel(l0, zk[5], zk[1]);
@@ -457,8 +504,8 @@ pv_process_ring_kernel(const RingParams p) {
         for (int c = 0; c < 8; c++) {
             cpx2 va = a[c], vb = b[c];
             if (c > 0) {
-                const float2 wa = __ldg(&tw[16 * k2a * c]);
-                const float2 wb = __ldg(&tw[16 * k2b * c]);
+                const float2 wa = w64[8 * c + k2a];
+                const float2 wb = w64[8 * c + k2b];
                 va = cmul_s(va, wa.x, -wa.y);
                 vb = cmul_s(vb, wb.x, -wb.y);
             }
@@ -468,18 +515,30 @@ pv_process_ring_kernel(const RingParams p) {
     }
     __syncwarp();
 
+    // accumulator values (L2 hits thanks to the prefetch) are requested before the last exchange so
+    // that their latency hides behind inverse pass 2; the tail slot starts from zero (ola:134)
+    float4 *al = p.acc2 + size_t(pair) * (N / 2) + lane;
+    float4 q[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int h = e >> 3, j = e & 7;
+        q[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (((j - jb) & 7) >= nblk) q[e] = al[32 * h + 64 * j];
+    }
+
     // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_512^{k1 (m3 + 8 m2)}) ---------------
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
         const int k1 = (lane >> 3) + 4 * h;
         float4 *bp = ex + 65 * k1 + m3l;
+        const float2 *twp = tw1 + G::TW1_ROW * k1 + m3l;
         cpx2 x[8];
 #pragma unroll
         for (int k2 = 0; k2 < 8; k2++) x[k2] = unpack4(bp[8 * k2]);
         dft8<true>(x);
 #pragma unroll
         for (int m2 = 0; m2 < 8; m2++) {
-            const float2 w = __ldg(&tw[2 * k1 * (m3l + 8 * m2)]);
+            const float2 w = twp[8 * m2];
             bp[8 * m2] = pack4(cmul_s(x[m2], w.x, -w.y));
         }
     }
@@ -487,20 +546,11 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- inverse pass 3: butterflies n over k1 -> ring samples; window, overlap-add, emit ------------------
     {
-        float4 *al = p.acc2 + size_t(pair) * (N / 2) + lane;
         float *o0 = p.out + size_t(c0) * hop + 2 * lane;
-        const float *wol = p.window_out2 + ((N - t) & (N - 1)) + 2 * lane;
-#pragma unroll 1
+        const float *wol = swout + 2 * lane;
+#pragma unroll
         for (int h = 0; h < 2; h++) {
             const int nl = lane + 32 * h;
-            float4 q[8];
-            float2 wo[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                wo[j] = __ldg(reinterpret_cast<const float2 *>(wol + 64 * h + 128 * j));
-                q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (((j - jb) & 7) >= nblk) q[j] = al[32 * h + 64 * j];     // the tail slot starts from zero (ola:134)
-            }
             cpx2 x[8];
 #pragma unroll
             for (int k1 = 0; k1 < 8; k1++) x[k1] = unpack4(ex[65 * k1 + nl]);
@@ -509,8 +559,10 @@ pv_process_ring_kernel(const RingParams p) {
             for (int j = 0; j < 8; j++) {
                 // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the division
                 // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
-                const float2 y0 = fma2(x[j].re, bc2(wo[j].x), make_float2(q[j].x, q[j].y));
-                const float2 y1 = fma2(x[j].im, bc2(wo[j].y), make_float2(q[j].z, q[j].w));
+                const float2 wo = *reinterpret_cast<const float2 *>(wol + 64 * h + 128 * j);
+                const float4 qv = q[8 * h + j];
+                const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
+                const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
                 const int jj = (j - je) & 7;
                 if (jj < nblk) {                                      // head: emit (ola:111-118)
                     *reinterpret_cast<float2 *>(o0 + 64 * h + 128 * jj) = make_float2(y0.x, y1.x);
@@ -521,6 +573,18 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
+}
+
+// tables the ring-order kernel copies into shared memory: tw1[k1][n] (rows of TW1_ROW), w64[a][b], twh[k]
+inline void ring_host_tables(const float2 *tw /* [1024] W_1024^j */, float2 *out /* GTAB_BYTES / 8 */) {
+    using G = RingGeo;
+    float2 *tw1 = out, *w64 = out + G::TW1_BYTES / 8, *twh = w64 + G::W64_BYTES / 8;
+    for (int i = 0; i < G::GTAB_BYTES / 8; i++) out[i] = make_float2(0.f, 0.f);
+    for (int k1 = 0; k1 < 8; k1++)
+        for (int n = 0; n < 64; n++) tw1[G::TW1_ROW * k1 + n] = tw[(2 * n * k1) & 1023];
+    for (int a = 0; a < 8; a++)
+        for (int b = 0; b < 8; b++) w64[8 * a + b] = tw[(16 * a * b) & 1023];
+    for (int k = 0; k <= 512; k++) twh[k] = tw[k];
 }
 
 // planar [C'][N] rings (pv_kernel.cuh conventions: frame sample n at hist[(n + rb + hop) mod N],
