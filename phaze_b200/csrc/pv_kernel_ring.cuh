@@ -37,7 +37,7 @@ struct RingGeo {
     static constexpr int XQ_SLOTS = 546;                    // bin k at k + (k >> 4); 545 = halo dummy
     static constexpr int WARP_BYTES = XQ_SLOTS * 16;        // 8736 (>= 519 * 16)
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
-    static constexpr int DTAB_BYTES = 1040;                 // int16 delta table, 514 entries
+    static constexpr int DTAB_BYTES = 2592;                 // key table: int32, bin p at p + 4 (p >> 4), p <= 513
     static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
     static constexpr int TW1_BYTES = 8 * TW1_ROW * 8;       // tw1[k1][n] = W_512^{n k1}, n < 64
     static constexpr int W64_BYTES = 64 * 8;                // w64[a][b] = W_64^{a b}
@@ -90,6 +90,13 @@ __device__ __forceinline__ void ring_unsplit(cpx2 yk, cpx2 ym, float2 w, cpx2 &z
     zmk = cpx2{add2(e_r, pp.im), sub2(pp.re, e_i)};
 }
 
+// one bin of the shifted spectrum (both channels) from the four planes of Y
+__device__ __forceinline__ cpx2 ring_load_planes(const unsigned char *mine, int slot) {
+    constexpr int PLW = RingGeo::XQ_SLOTS;                             // words per plane
+    const float *y = reinterpret_cast<const float *>(mine) + slot;
+    return cpx2{make_float2(y[0], y[PLW]), make_float2(y[2 * PLW], y[3 * PLW])};
+}
+
 // 5-point strict maxima (pv:95-116) of bins b0 .. b0+15 from squared magnitudes m[0..19] of bins
 // b0-2 .. b0+17 (non-negative floats order like their bit patterns)
 __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
@@ -105,69 +112,49 @@ __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
     return mask;
 }
 
-// Region of influence of every bin of the run (channel CH), shifted destinations, pass C.
-//   dst[e] : byte offset (inside the warp's XQ buffer) of the re component the bin adds to in
-//            pass D, or -1 when it was already stored / falls outside [0, nb)
-template <int CH>
-__device__ __forceinline__ void ring_shift_first(const float4 (&xv)[16], uint32_t mask, int lane,
-                                                 uint32_t nz, const unsigned char *dtab,
-                                                 unsigned char *xq, bool contract, int (&dst)[16],
-                                                 int &d_last) {
+// Region of influence of every bin of the run, for one channel (pv:124-141): the owner of a bin
+// is the nearest peak, ties go to the higher one.  Peaks travel as KEYS (see the key table in
+// the kernel): high half = 2 * (peak + 2048), low half = delta + 32768.  Returns per bin the byte
+// offset of its destination word inside plane 0 of Y (dump slot when it falls outside [0, nb))
+// and a 16-bit mask of the bins that are stored first (right half of their region, or any bin
+// when expanding); the others are added on top in the second sub-step.
+__device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_t nz, const int (&rk)[16],
+                                                const int *krun, bool contract, int (&dst)[16],
+                                                uint32_t &first, int &d_last) {
     constexpr int NB = RingGeo::NB;
     const unsigned FULL = 0xFFFFFFFFu;
     const int b0 = 16 * lane;
-    // positions are carried scaled by 2 (they double as byte offsets into the int16 table)
-    const int own_last2 = 2 * (b0 + 31 - __clz(mask));
-    const int own_first2 = 2 * (b0 + __ffs(mask) - 1);
+    const int own_last = krun[(31 - __clz(mask)) & 15];              // keys of this lane's last / first peak
+    const int own_first = krun[(__ffs(mask) - 1) & 15];
     const uint32_t below = nz & ((1u << lane) - 1u);
     const uint32_t above = nz & ~((2u << lane) - 1u);
-    int prev2 = __shfl_sync(FULL, own_last2, (31 - __clz(below)) & 31);
-    int next2 = __shfl_sync(FULL, own_first2, (__ffs(above) - 1) & 31);
-    if (!below) prev2 = -60000;
-    if (!above) next2 = 60000;
-    const int p_last2 = __shfl_sync(FULL, own_last2, 31 - __clz(nz));
-    d_last = *reinterpret_cast<const short *>(dtab + p_last2);
+    int pkey = __shfl_sync(FULL, own_last, (31 - __clz(below)) & 31);
+    int nkey = __shfl_sync(FULL, own_first, (__ffs(above) - 1) & 31);
+    if (!below) pkey = 0;                                            // "peak" at -2048: never the nearest
+    if (!above) nkey = (2 * 8190) << 16;                             // "peak" at +6142
+    const int lkey = __shfl_sync(FULL, own_last, 31 - __clz(nz));
+    d_last = (lkey & 0xFFFF) - 32768;
 
     int nx[16];
 #pragma unroll
     for (int e = 15; e >= 0; e--) {
-        nx[e] = next2;                                               // first peak above bin e
-        if ((mask >> e) & 1u) next2 = 2 * (b0 + e);
+        nx[e] = nkey;                                                // first peak above bin e
+        if ((mask >> e) & 1u) nkey = rk[e];
     }
-    float *yf = reinterpret_cast<float *>(xq);
+    const int thr0 = (4 * (b0 + 2048) + 2) << 16;
+    uint32_t fm = 0;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        if ((mask >> e) & 1u) prev2 = 2 * (b0 + e);                  // last peak at or below bin e
-        // nearest peak, ties to the higher one:  next - b <= b - prev
-        const bool take_next = (nx[e] + prev2 - 4 * b0) <= 4 * e;
-        const int owner2 = take_next ? nx[e] : prev2;
-        const int delta = *reinterpret_cast<const short *>(dtab + owner2);
-        const int d = b0 + e + delta;
-        const bool ok = unsigned(d) < unsigned(NB);
-        const int off = (d + (d >> 4)) * 16 + 4 * CH;                // re component of bin d
-        const float re = CH ? xv[e].y : xv[e].x, im = CH ? xv[e].w : xv[e].z;
-        const bool first = !take_next || !contract;                  // right half (or expanding): plain store
-        if (ok && first) {
-            *reinterpret_cast<float *>(xq + off) = re;
-            *reinterpret_cast<float *>(xq + off + 8) = im;
-        }
-        dst[e] = (ok && !first) ? off : -1;
+        if ((mask >> e) & 1u) pkey = rk[e];                          // last peak at or below bin e
+        // next - b <= b - prev  <=>  2 next' + 2 prev' (+ carry of the low halves) < 4 b' + 2
+        const bool take_next = (nx[e] + pkey - thr0) < ((4 * e) << 16);
+        const int okey = take_next ? nx[e] : pkey;
+        const int d = (okey & 0xFFFF) + (b0 + e - 32768);
+        const int slot = (unsigned(d) < unsigned(NB)) ? d + (d >> 4) : 545;
+        dst[e] = 4 * slot;
+        if (!take_next) fm |= 1u << e;
     }
-    (void)yf;
-}
-
-template <int CH>
-__device__ __forceinline__ void ring_shift_second(const float4 (&xv)[16], const int (&dst)[16],
-                                                  unsigned char *xq) {
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-        if (dst[e] >= 0) {
-            float *pr = reinterpret_cast<float *>(xq + dst[e]);
-            const float re = CH ? xv[e].y : xv[e].x, im = CH ? xv[e].w : xv[e].z;
-            pr[0] += re;
-            pr[2] += im;
-        }
-    }
+    first = contract ? fm : 0xFFFFu;
 }
 
 // NBLK = hop / 128 and JB = ring 128-block that receives the new input block, as template
@@ -185,7 +172,7 @@ pv_process_ring_kernel(const RingParams p) {
     const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
     const bool live = 2 * pair < p.num_channels;
     const unsigned FULL = 0xFFFFFFFFu;
-    unsigned char *dtab = smem_raw;
+    int *ktab = reinterpret_cast<int *>(smem_raw);
     const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
     const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
     const float2 *twh = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
@@ -243,14 +230,15 @@ pv_process_ring_kernel(const RingParams p) {
             d1[i] = __ldg(w1 + i);
             d2[i] = __ldg(w2 + i);
         }
-        // delta table: round(p * pitchFactor) - p, exact integer arithmetic (pv:125-127)
+        // key table: what a peak at bin pk contributes to the region scan: its position and
+        // delta = round(pk * pitchFactor) - pk in exact integer arithmetic (pv:125-127)
         const long long pf_m = p.pf_mant;
         const int pf_s = p.pf_shift;
         const long long half = 1ll << (pf_s - 1);
         for (int pk = threadIdx.x; pk <= NB; pk += blockDim.x) {
             const long long ps = (pf_m * pk + half) >> pf_s;
             const int delta = (ps <= NB) ? int(ps) - pk : G::INVALID_DELTA;
-            reinterpret_cast<short *>(dtab)[pk] = short(delta);
+            ktab[pk + 4 * (pk >> 4)] = ((2 * (pk + 2048)) << 16) | (delta + 32768);
         }
     }
     __syncthreads();
@@ -366,22 +354,20 @@ pv_process_ring_kernel(const RingParams p) {
     if (l0) ring_split(a[4], a[4], twh[256], XQ + 272, XQ + 272);
     __syncwarp();
 
-    // ---- peaks, regions of influence, in-place shift (pv:95-173) ----------------------------------------
+    // ---- peaks, regions of influence, shift (pv:95-173) -------------------------------------------------
+    // X lives in float4 slots (both channels per bin); the shifted spectrum Y is written over it as
+    // four planes of floats (re0 | re1 | im0 | im1, bin d at word d + (d >> 4)): the 32-bit scatter of
+    // lanes that own runs 16 bins apart then spreads over all banks.
     {
         const bool contract = p.pitch_factor < 1.0f;
         const float4 *runp = XQ + 17 * lane;                          // slot of bin 16 lane
-        float4 xv[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) xv[e] = runp[e];
         uint32_t mask0, mask1;
         {
             const float4 *hlo = lane ? runp - 3 : XQ;                 // bins 16 lane - 2, - 1 (lane 0: unused)
-            float4 hv[4];
-            hv[0] = hlo[0]; hv[1] = hlo[1]; hv[2] = runp[17]; hv[3] = runp[18];
             int m0[20], m1[20];
 #pragma unroll
             for (int i = 0; i < 20; i++) {
-                const float4 v = (i < 2) ? hv[i] : (i < 18) ? xv[i - 2] : hv[i - 16];
+                const float4 v = (i < 2) ? hlo[i] : (i < 18) ? runp[i - 2] : runp[i - 1];   // i >= 18: bins 16 lane + 16, + 17 (slot 16 is padding)
                 const float2 re = make_float2(v.x, v.y), im = make_float2(v.z, v.w);
                 const float2 mg = fma2(re, re, mul2(im, im));         // pv:82-92, float32
                 m0[i] = __float_as_int(mg.x);
@@ -395,8 +381,26 @@ pv_process_ring_kernel(const RingParams p) {
         const uint32_t nz0 = __ballot_sync(FULL, mask0 != 0);
         const uint32_t nz1 = __ballot_sync(FULL, mask1 != 0);
 
-        // extension: bin 512 and the first stale level (what _realTransform4 leaves in slots
-        // N/2 + q, bundle:394-438), rebuilt from the valid half; bins 512 + lane + 32 i
+        int dst0[16], dst1[16];
+        uint32_t first0 = 0, first1 = 0;
+        int dl0 = 0, dl1 = 0;
+        {
+            const int *krun = ktab + 20 * lane;                       // keys of bins 16 lane .. + 15
+            int rk[16];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int4 kv = *reinterpret_cast<const int4 *>(krun + 4 * i);
+                rk[4 * i] = kv.x; rk[4 * i + 1] = kv.y; rk[4 * i + 2] = kv.z; rk[4 * i + 3] = kv.w;
+            }
+            if (nz0) ring_owner_scan(mask0, lane, nz0, rk, krun, contract, dst0, first0, dl0);
+            if (nz1) ring_owner_scan(mask1, lane, nz1, rk, krun, contract, dst1, first1, dl1);
+        }
+
+        // sources into registers: own run, bin 512 and the first stale level (what _realTransform4
+        // leaves in slots N/2 + q, bundle:394-438, rebuilt from the valid half); bins 512 + lane + 32 i
+        float4 xv[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) xv[e] = runp[e];
         float4 ext[4];
         ext[0] = ext[1] = ext[2] = ext[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (l0) ext[0] = XQ[544];
@@ -412,8 +416,8 @@ pv_process_ring_kernel(const RingParams p) {
                 const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, D.re));
                 const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, D.im));
                 const float2 w = twh[2 * qq];
-                const cpx2 s = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
-                if (q) ext[i] = pack4(s);
+                const cpx2 sv = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
+                if (q) ext[i] = pack4(sv);
             }
         }
         __syncwarp();            // every lane holds its sources: the buffer becomes Y
@@ -422,37 +426,69 @@ pv_process_ring_kernel(const RingParams p) {
         if (lane < 2) XQ[544 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
 
-        int dst0[16], dst1[16];
+        constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane (546 words)
+        // first sub-step: plain stores (pairwise disjoint destinations)
         if (nz0) {
-            int d_last;
-            ring_shift_first<0>(xv, mask0, lane, nz0, dtab, mine, contract, dst0, d_last);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                if ((first0 >> e) & 1u) {
+                    *reinterpret_cast<float *>(mine + dst0[e]) = xv[e].x;
+                    *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL) = xv[e].z;
+                }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int d = 512 + lane + 32 * i + d_last;
+                const int d = 512 + lane + 32 * i + dl0;
                 if (unsigned(d) < unsigned(NB)) {
-                    float *pr = reinterpret_cast<float *>(mine + (d + (d >> 4)) * 16);
-                    pr[0] = ext[i].x;
-                    pr[2] = ext[i].z;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4))) = ext[i].x;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + 2 * PL) = ext[i].z;
                 }
             }
         }
         if (nz1) {
-            int d_last;
-            ring_shift_first<1>(xv, mask1, lane, nz1, dtab, mine, contract, dst1, d_last);
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                if ((first1 >> e) & 1u) {
+                    *reinterpret_cast<float *>(mine + dst1[e] + PL) = xv[e].y;
+                    *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = xv[e].w;
+                }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int d = 512 + lane + 32 * i + d_last;
+                const int d = 512 + lane + 32 * i + dl1;
                 if (unsigned(d) < unsigned(NB)) {
-                    float *pr = reinterpret_cast<float *>(mine + (d + (d >> 4)) * 16);
-                    pr[1] = ext[i].y;
-                    pr[3] = ext[i].w;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + PL) = ext[i].y;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + 3 * PL) = ext[i].w;
                 }
             }
         }
         if (contract) {
+            // second sub-step: left halves add on top (pairwise disjoint among themselves, so the
+            // loads of a batch can all be issued before the first store)
             __syncwarp();
-            if (nz0) ring_shift_second<0>(xv, dst0, mine);
-            if (nz1) ring_shift_second<1>(xv, dst1, mine);
+#pragma unroll
+            for (int g = 0; g < 2; g++) {
+                float o0r[8], o0i[8], o1r[8], o1i[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int e = 8 * g + i;
+                    const bool s0 = nz0 && !((first0 >> e) & 1u), s1 = nz1 && !((first1 >> e) & 1u);
+                    o0r[i] = o0i[i] = o1r[i] = o1i[i] = 0.f;
+                    if (s0) { o0r[i] = *reinterpret_cast<float *>(mine + dst0[e]); o0i[i] = *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL); }
+                    if (s1) { o1r[i] = *reinterpret_cast<float *>(mine + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL); }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int e = 8 * g + i;
+                    const bool s0 = nz0 && !((first0 >> e) & 1u), s1 = nz1 && !((first1 >> e) & 1u);
+                    if (s0) {
+                        *reinterpret_cast<float *>(mine + dst0[e]) = o0r[i] + xv[e].x;
+                        *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL) = o0i[i] + xv[e].z;
+                    }
+                    if (s1) {
+                        *reinterpret_cast<float *>(mine + dst1[e] + PL) = o1r[i] + xv[e].y;
+                        *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = o1i[i] + xv[e].w;
+                    }
+                }
+            }
         }
     }
     __syncwarp();
@@ -463,7 +499,7 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int sa = (j < 4 ? sAlo : sAhi) + 68 * j, sb = (j < 4 ? sBlo : sBhi) - 68 * j;
-            cpx2 yk = unpack4(XQ[sa]), ym = unpack4(XQ[sb]);
+            cpx2 yk = ring_load_planes(mine, sa), ym = ring_load_planes(mine, sb);
             if (j == 4) {                        // lane 0: k == 0, bins 0 and N/2 enter with their real part only
                 yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
                 ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
@@ -473,7 +509,7 @@ pv_process_ring_kernel(const RingParams p) {
         }
         cpx2 z256, dummy;
         {
-            const cpx2 y = unpack4(XQ[272]);
+            const cpx2 y = ring_load_planes(mine, 272);
             ring_unsplit(y, y, twh[256], z256, dummy);
         }
         a[0] = sel(l0, zk[4], zk[0]);
