@@ -132,7 +132,7 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_
     int nkey = __shfl_sync(FULL, own_first, (__ffs(above) - 1) & 31);
     if (!below) pkey = 0;                                            // "peak" at -2048: never the nearest
     if (!above) nkey = (2 * 8190) << 16;                             // "peak" at +6142
-    const int lkey = __shfl_sync(FULL, own_last, 31 - __clz(nz));
+    const int lkey = __shfl_sync(FULL, own_last, (31 - __clz(nz)) & 31);
     d_last = (lkey & 0xFFFF) - 32768;
 
     int nx[16];
@@ -217,29 +217,44 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
-    // ---- CTA-shared tables (while the frame is in flight) -----------------------------------------
+    // ---- CTA-shared tables (while the frame is in flight): asynchronous 16-byte copies, fixed trip
+    // counts (CTAs have 4..7 warps; no division by blockDim, nothing waits on the frame loads) ---------
     {
-        float4 *dg = reinterpret_cast<float4 *>(smem_raw + G::OFF_TW1);
-        for (int i = threadIdx.x; i < G::GTAB_BYTES / 16; i += blockDim.x) dg[i] = __ldg(p.gtab + i);
         const int rot = (N - t) & (N - 1);
         const float4 *w1 = reinterpret_cast<const float4 *>(p.window2 + rot);
         const float4 *w2 = reinterpret_cast<const float4 *>(p.window_out2 + rot);
-        float4 *d1 = reinterpret_cast<float4 *>(smem_raw + G::OFF_WIN);
-        float4 *d2 = reinterpret_cast<float4 *>(smem_raw + G::OFF_WOUT);
-        for (int i = threadIdx.x; i < N / 4; i += blockDim.x) {
-            d1[i] = __ldg(w1 + i);
-            d2[i] = __ldg(w2 + i);
+        const unsigned s_tab = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_TW1));
+        const unsigned s_win = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WIN));
+        const unsigned s_wout = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WOUT));
+#pragma unroll
+        for (int k = 0; k < (G::GTAB_BYTES / 16 + 127) / 128; k++) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < G::GTAB_BYTES / 16)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_tab + 16 * i), "l"(p.gtab + i));
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < N / 4) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_win + 16 * i), "l"(w1 + i));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_wout + 16 * i), "l"(w2 + i));
+            }
         }
         // key table: what a peak at bin pk contributes to the region scan: its position and
         // delta = round(pk * pitchFactor) - pk in exact integer arithmetic (pv:125-127)
         const long long pf_m = p.pf_mant;
         const int pf_s = p.pf_shift;
         const long long half = 1ll << (pf_s - 1);
-        for (int pk = threadIdx.x; pk <= NB; pk += blockDim.x) {
-            const long long ps = (pf_m * pk + half) >> pf_s;
-            const int delta = (ps <= NB) ? int(ps) - pk : G::INVALID_DELTA;
-            ktab[pk + 4 * (pk >> 4)] = ((2 * (pk + 2048)) << 16) | (delta + 32768);
+#pragma unroll
+        for (int k = 0; k < (NB + 1 + 127) / 128; k++) {
+            const int pk = threadIdx.x + k * blockDim.x;
+            if (pk <= NB) {
+                const long long ps = (pf_m * pk + half) >> pf_s;
+                const int delta = (ps <= NB) ? int(ps) - pk : G::INVALID_DELTA;
+                ktab[pk + 4 * (pk >> 4)] = ((2 * (pk + 2048)) << 16) | (delta + 32768);
+            }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
     if (!live) return;          // no CTA-wide barriers below
@@ -301,7 +316,7 @@ pv_process_ring_kernel(const RingParams p) {
         float2 w2[8];
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
-#pragma unroll 1
+#pragma unroll
         for (int h = 0; h < 2; h++) {
             float4 *bp = ex + 65 * ((lane >> 3) + 4 * h) + m3l;
             cpx2 x[8];
@@ -392,8 +407,10 @@ pv_process_ring_kernel(const RingParams p) {
                 const int4 kv = *reinterpret_cast<const int4 *>(krun + 4 * i);
                 rk[4 * i] = kv.x; rk[4 * i + 1] = kv.y; rk[4 * i + 2] = kv.z; rk[4 * i + 3] = kv.w;
             }
-            if (nz0) ring_owner_scan(mask0, lane, nz0, rk, krun, contract, dst0, first0, dl0);
-            if (nz1) ring_owner_scan(mask1, lane, nz1, rk, krun, contract, dst1, first1, dl1);
+            // both scans run unconditionally (a channel without peaks ends up with every bin on the
+            // dump slot): two independent instruction streams the scheduler can interleave
+            ring_owner_scan(mask0, lane, nz0, rk, krun, contract, dst0, first0, dl0);
+            ring_owner_scan(mask1, lane, nz1, rk, krun, contract, dst1, first1, dl1);
         }
 
         // sources into registers: own run, bin 512 and the first stale level (what _realTransform4
@@ -563,7 +580,7 @@ pv_process_ring_kernel(const RingParams p) {
     }
 
     // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_512^{k1 (m3 + 8 m2)}) ---------------
-#pragma unroll 1
+#pragma unroll
     for (int h = 0; h < 2; h++) {
         const int k1 = (lane >> 3) + 4 * h;
         float4 *bp = ex + 65 * k1 + m3l;
