@@ -45,6 +45,7 @@ thread_local char g_create_err[256] = "";
 bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
 int g_kernel_1024 = 0;           // PVB_KERNEL_1024: 0 (default) ring-order kernel, 1 warp kernel, 2 two warps per pair, 3 CTA kernel
 bool g_no_aligned = false;       // PVB_NO_ALIGNED=1: never use the hop %% 128 == 0 specialisation (tests)
+bool g_no_pdl = false;           // PVB_NO_PDL=1: ring kernel without programmatic dependent launch (experiments)
 int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
 
 // pitch_factor == mant * 2^-shift exactly; shift outside [1, 62] -> 0 (kernel uses float64)
@@ -227,17 +228,28 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     rp.pf_shift = fp.pf_shift;
     const size_t smem = G::TAB_BYTES + size_t(wpc) * G::WARP_BYTES;
     const int jb = ((rp.tmod - rp.hop + 1024) >> 7) & 7;
+    // programmatic dependent launch: CTAs of this launch may become resident (and stage their
+    // tables) while the previous kernel on the stream drains; the kernel itself waits
+    // (griddepcontrol.wait) before it touches anything an earlier launch may have written
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(wpc * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (rp.hop == 256) {        // the headline geometry: ring-block roles fixed at compile time
         switch (jb) {
-            case 0: pvb::pv_process_ring_kernel<2, 0><<<grid, wpc * 32, smem, s>>>(rp); break;
-            case 2: pvb::pv_process_ring_kernel<2, 2><<<grid, wpc * 32, smem, s>>>(rp); break;
-            case 4: pvb::pv_process_ring_kernel<2, 4><<<grid, wpc * 32, smem, s>>>(rp); break;
-            default: pvb::pv_process_ring_kernel<2, 6><<<grid, wpc * 32, smem, s>>>(rp); break;
+            case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 0>, rp);
+            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 2>, rp);
+            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 4>, rp);
+            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 6>, rp);
         }
-    } else {
-        pvb::pv_process_ring_kernel<0, 0><<<grid, wpc * 32, smem, s>>>(rp);
     }
-    return cudaGetLastError();
+    return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<0, 0>, rp);
 }
 
 // two warps per channel pair (pv_kernel_pair.cuh): same validity range as the warp kernel
@@ -463,6 +475,8 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         g_stagger_ns = env ? std::atoi(env) : 0;
         env = std::getenv("PVB_NO_ALIGNED");
         g_no_aligned = env && env[0] == '1';
+        env = std::getenv("PVB_NO_PDL");
+        g_no_pdl = env && env[0] == '1';
     }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

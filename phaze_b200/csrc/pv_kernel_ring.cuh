@@ -190,35 +190,12 @@ pv_process_ring_kernel(const RingParams p) {
     const int jb = NBLK ? JB : (((t - hop + N) >> 7) & 7);    // ring 128-block that receives the new input block
     const int je = (jb + nblk) & 7;                           // ring 128-block of frame sample 0 (emitted)
 
-    // ---- frame loads: all issued before anything consumes them ---------------------------------
-    float4 r[16];
-    float2 un0[NBLK ? 2 * NBLK : 1], un1[NBLK ? 2 * NBLK : 1];
-    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + lane;
-    if (live) {
-        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * lane : nullptr;
-#pragma unroll
-        for (int e = 0; e < 16; e++) {
-            const int h = e >> 3, j = e & 7;
-            const int jj = (j - jb) & 7;                              // launch-uniform
-            if (jj < nblk) {
-                float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
-                if (i0) {
-                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * jj));
-                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * jj));
-                }
-                if constexpr (NBLK > 0) {
-                    un0[h * NBLK + jj] = u0;                          // packed after the barrier: the moves
-                    un1[h * NBLK + jj] = u1;                          // must not sit between the loads
-                } else {
-                    r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
-                }
-            } else {
-                r[e] = hl[32 * h + 64 * j];
-            }
-        }
-    }
-    // ---- CTA-shared tables (while the frame is in flight): asynchronous 16-byte copies, fixed trip
-    // counts (CTAs have 4..7 warps; no division by blockDim, nothing waits on the frame loads) ---------
+    // Programmatic dependent launch: the next launch on the stream may place its CTAs as soon as
+    // ours leave; everything up to griddepcontrol.wait touches only constant tables, so it overlaps
+    // the tail of the previous launch.
+    asm volatile("griddepcontrol.launch_dependents;");
+    // ---- CTA-shared tables: asynchronous 16-byte copies, fixed trip counts (CTAs have 4..7 warps;
+    // no division by blockDim) --------------------------------------------------------------------------
     {
         const int rot = (N - t) & (N - 1);
         const float4 *w1 = reinterpret_cast<const float4 *>(p.window2 + rot);
@@ -254,8 +231,36 @@ pv_process_ring_kernel(const RingParams p) {
                 ktab[pk + 4 * (pk >> 4)] = ((2 * (pk + 2048)) << 16) | (delta + 32768);
             }
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // state / input written by earlier launches is visible
+    // ---- frame loads: all issued before anything consumes them ---------------------------------
+    float4 r[16];
+    float2 un0[NBLK ? 2 * NBLK : 1], un1[NBLK ? 2 * NBLK : 1];
+    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + lane;
+    if (live) {
+        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * lane : nullptr;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int h = e >> 3, j = e & 7;
+            const int jj = (j - jb) & 7;                              // launch-uniform
+            if (jj < nblk) {
+                float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
+                if (i0) {
+                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * jj));
+                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * jj));
+                }
+                if constexpr (NBLK > 0) {
+                    un0[h * NBLK + jj] = u0;                          // packed after the barrier: the moves
+                    un1[h * NBLK + jj] = u1;                          // must not sit between the loads
+                } else {
+                    r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
+                }
+            } else {
+                r[e] = hl[32 * h + 64 * j];
+            }
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
     if (!live) return;          // no CTA-wide barriers below
 
