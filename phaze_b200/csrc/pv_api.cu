@@ -15,7 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 struct pvb_processor {
@@ -45,6 +47,12 @@ thread_local char g_create_err[256] = "";
 bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
 int g_kernel_1024 = 0;           // PVB_KERNEL_1024: 0 (default) ring-order kernel, 1 warp kernel, 2 two warps per pair, 3 CTA kernel
 bool g_no_aligned = false;       // PVB_NO_ALIGNED=1: never use the hop %% 128 == 0 specialisation (tests)
+int g_early = -1;                // PVB_EARLY=0/1/2: cap on the ring kernel's pre-wait state loads (experiments)
+// Which handle launched the library's most recent kernel on each stream.  The ring-order kernel uses
+// it to decide how much of its state is provably older than the kernel in front of it (see
+// RingParams::early); every launch path records itself here.
+std::mutex g_stream_mu;
+std::unordered_map<cudaStream_t, const void *> g_last_on_stream;
 bool g_no_pdl = false;           // PVB_NO_PDL=1: ring kernel without programmatic dependent launch (experiments)
 int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
 
@@ -226,6 +234,15 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     rp.pitch_factor = fp.pitch_factor;
     rp.pf_mant = fp.pf_mant;
     rp.pf_shift = fp.pf_shift;
+    {
+        // early state loads: 2 when another handle's kernel (which passed its own wait before it let
+        // us launch) sits between this handle's previous call and this one, else 1
+        std::lock_guard<std::mutex> lk(g_stream_mu);
+        auto it = g_last_on_stream.find(s);
+        rp.early = (it != g_last_on_stream.end() && it->second != h) ? 2 : 1;
+        if (g_no_pdl) rp.early = 0;
+        if (g_early >= 0 && rp.early > g_early) rp.early = g_early;
+    }
     const size_t smem = G::TAB_BYTES + size_t(wpc) * G::WARP_BYTES;
     const int jb = ((rp.tmod - rp.hop + 1024) >> 7) & 7;
     // programmatic dependent launch: CTAs of this launch may become resident (and stage their
@@ -279,7 +296,17 @@ cudaError_t launch_pair(const pvb::FrameParams &fp, const float *window_out, int
     return cudaGetLastError();
 }
 
+cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s);
+
 cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+    const cudaError_t e = launch_any(h, fp, s);
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    if (g_last_on_stream.size() > 4096) g_last_on_stream.clear();     // streams come and go; unknown == conservative
+    g_last_on_stream[s] = h;
+    return e;
+}
+
+cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
     const int n = h->n;
     if (ring_kernel_applies(h, fp)) return launch_ring(h, fp, s);
     if (warp_kernel_applies(n, fp) && !g_force_generic && g_kernel_1024 != 3) {
@@ -477,6 +504,8 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         g_no_aligned = env && env[0] == '1';
         env = std::getenv("PVB_NO_PDL");
         g_no_pdl = env && env[0] == '1';
+        env = std::getenv("PVB_EARLY");
+        g_early = env ? std::atoi(env) : -1;
     }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);

@@ -65,6 +65,7 @@ struct RingParams {
     int num_channels;
     int hop;
     int tmod;                   // timeCursor mod N (multiple of hop)
+    int early;                  // which state loads may precede griddepcontrol.wait (0, 1, 2; see the kernel)
     float pitch_factor;
     int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
 };
@@ -190,10 +191,9 @@ pv_process_ring_kernel(const RingParams p) {
     const int jb = NBLK ? JB : (((t - hop + N) >> 7) & 7);    // ring 128-block that receives the new input block
     const int je = (jb + nblk) & 7;                           // ring 128-block of frame sample 0 (emitted)
 
-    // Programmatic dependent launch: the next launch on the stream may place its CTAs as soon as
-    // ours leave; everything up to griddepcontrol.wait touches only constant tables, so it overlaps
-    // the tail of the previous launch.
-    asm volatile("griddepcontrol.launch_dependents;");
+    // Programmatic dependent launch: our CTAs may become resident while the previous kernel on the
+    // stream drains; everything up to griddepcontrol.wait touches only constant tables (and state
+    // that is provably older than that kernel), so it overlaps the previous launch's tail.
     // ---- CTA-shared tables: asynchronous 16-byte copies, fixed trip counts (CTAs have 4..7 warps;
     // no division by blockDim) --------------------------------------------------------------------------
     {
@@ -232,11 +232,40 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // state / input written by earlier launches is visible
     // ---- frame loads: all issued before anything consumes them ---------------------------------
+    // History written by launches OLDER than the kernel in front of us on the stream is already
+    // complete when our CTAs start (that kernel passed its own griddepcontrol.wait before it let us
+    // launch), so those loads are issued before our wait and overlap the previous launch's tail:
+    //   p.early == 2: none of this handle's state was written by the previous kernel -> all of hist
+    //   p.early == 1: the previous kernel may be this handle's last call -> all but its newest block
+    //   p.early == 0: everything after the wait
+    // The input block always waits (it belongs to the caller's stream order).
     float4 r[16];
     float2 un0[NBLK ? 2 * NBLK : 1], un1[NBLK ? 2 * NBLK : 1];
     float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + lane;
+    const int early = p.early;
+    if (live && early) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const int h = e >> 3, j = e & 7;
+            const int jj = (j - jb) & 7;                              // launch-uniform
+            // jj < nblk: new input; jj >= 8 - nblk: the block the previous call wrote
+            if (jj >= nblk && (jj < 8 - nblk || early == 2)) r[e] = hl[32 * h + 64 * j];
+        }
+        if (early == 2) {
+            // warm L2 with the overlap-add ring lines the tail of this kernel adds to
+            const int line = 16 * lane;                               // float4 index: 256 bytes per lane
+            if ((((line >> 6) - jb) & 7) >= nblk) {
+                const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
+            }
+        }
+    }
+    // our dependents may launch only now: whoever starts behind us can rely on everything older
+    // than us being complete
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     if (live) {
         const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * lane : nullptr;
 #pragma unroll
@@ -255,7 +284,7 @@ pv_process_ring_kernel(const RingParams p) {
                 } else {
                     r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
                 }
-            } else {
+            } else if (!(early && (jj < 8 - nblk || early == 2))) {
                 r[e] = hl[32 * h + 64 * j];
             }
         }
@@ -308,7 +337,7 @@ pv_process_ring_kernel(const RingParams p) {
     // only written, ring [t - hop, t), is skipped)
     {
         const int line = 16 * lane;                                   // float4 index: 256 bytes per lane
-        if ((((line >> 6) - jb) & 7) >= nblk) {
+        if (early != 2 && (((line >> 6) - jb) & 7) >= nblk) {
             const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
