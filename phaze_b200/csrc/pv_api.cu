@@ -234,6 +234,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     rp.pitch_factor = fp.pitch_factor;
     rp.pf_mant = fp.pf_mant;
     rp.pf_shift = fp.pf_shift;
+    rp.stagger_ns = g_stagger_ns;
     {
         // early state loads: 2 when another handle's kernel (which passed its own wait before it let
         // us launch) sits between this handle's previous call and this one, else 1

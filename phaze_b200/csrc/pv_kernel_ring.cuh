@@ -65,6 +65,7 @@ struct RingParams {
     int num_channels;
     int hop;
     int tmod;                   // timeCursor mod N (multiple of hop)
+    int stagger_ns;             // experiment: delay odd warps by this much before the first pass
     int early;                  // which state loads may precede griddepcontrol.wait (0, 1, 2; see the kernel)
     float pitch_factor;
     int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
@@ -117,8 +118,10 @@ __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
 // is the nearest peak, ties go to the higher one.  Peaks travel as KEYS (see the key table in
 // the kernel): high half = 2 * (peak + 2048), low half = delta + 32768.  Returns per bin the byte
 // offset of its destination word inside plane 0 of Y (dump slot when it falls outside [0, nb))
-// and a 16-bit mask of the bins that are stored first (right half of their region, or any bin
-// when expanding); the others are added on top in the second sub-step.
+// and a 16-bit mask of the bins that are stored first (every bin that is the first writer of its
+// destination: right halves, left-half bins that do not land on the previous region, any bin when
+// expanding); the others are added on top in the second sub-step.  When contracting the first
+// writers cover [0, nb) completely, so the destination buffer needs no zero fill.
 __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_t nz, const int (&rk)[16],
                                                 const int *krun, bool contract, int (&dst)[16],
                                                 uint32_t &first, int &d_last) {
@@ -148,12 +151,22 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_
     for (int e = 0; e < 16; e++) {
         if ((mask >> e) & 1u) pkey = rk[e];                          // last peak at or below bin e
         // next - b <= b - prev  <=>  2 next' + 2 prev' (+ carry of the low halves) < 4 b' + 2
-        const bool take_next = (nx[e] + pkey - thr0) < ((4 * e) << 16);
+        const int tt = nx[e] + pkey - thr0 - ((4 * e) << 16);
+        const bool take_next = tt < 0;
         const int okey = take_next ? nx[e] : pkey;
         const int d = (okey & 0xFFFF) + (b0 + e - 32768);
         const int slot = (unsigned(d) < unsigned(NB)) ? d + (d >> 4) : 545;
         dst[e] = 4 * slot;
-        if (!take_next) fm |= 1u << e;
+        // A bin of a left half (owner = next peak Q, previous peak P) lands on top of the right half of
+        // region P iff it is one of the first delta_P - delta_Q bins of its region (pv:132-141, 169-170):
+        //   b - start_Q < delta_P - delta_Q,  b - start_Q = (2b - P - Q) >> 1 = s >> 2 with s = 4b' - 2P' - 2Q'.
+        // tt >> 16 = -s - 2 + c, c = carry of the two low halves (0 or 1), s even:
+        // floor(s / 4) = (~(tt >> 16)) >> 2 for either carry.  delta_P - delta_Q is the signed low half
+        // of the key difference (negative for the "no previous peak" key when contracting).
+        const int s4 = ~(tt >> 16);
+        const int cdiff = short(pkey - nx[e]);
+        const bool collide = take_next && (s4 >> 2) < cdiff;
+        if (!collide) fm |= 1u << e;
     }
     first = contract ? fm : 0xFFFFu;
 }
@@ -293,6 +306,7 @@ pv_process_ring_kernel(const RingParams p) {
     __syncthreads();
     if (!live) return;          // no CTA-wide barriers below
 
+    if (p.stagger_ns > 0 && (warp & 1)) __nanosleep(unsigned(p.stagger_ns));
     // the new block joins the history ring (ola:105)
 #pragma unroll
     for (int e = 0; e < 16; e++) {
@@ -472,10 +486,14 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
         __syncwarp();            // every lane holds its sources: the buffer becomes Y
+        // Expansion leaves gaps between the shifted regions, a channel without peaks leaves everything
+        // empty: zero fill.  Contraction with peaks in both channels writes every bin of [0, nb).
+        if (!contract || !nz0 || !nz1) {
 #pragma unroll
-        for (int i = 0; i < 17; i++) XQ[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < 2) XQ[544 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
+            for (int i = 0; i < 17; i++) XQ[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < 2) XQ[544 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+        }
 
         constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane (546 words)
         // first sub-step: plain stores (pairwise disjoint destinations)

@@ -235,27 +235,35 @@ def step(hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 if cf and contract:
                     cf.note("stale_ld", xslot(qq) * XW, 16); cf.note("stale_ld_m", xslot(512 - qq) * XW, 16)
 
-        # owner of every bin of the run: nearest peak, ties to the higher one (pv:132-141)
+        # owner of every bin of the run: nearest peak, ties to the higher one (pv:132-141).  A bin is
+        # a FIRST writer of its destination unless it belongs to a left half and is one of the first
+        # delta_P - delta_Q bins of its region (those land on the right half of the previous region).
         nextv = np.zeros((16, 32), np.int64)
         Q = next_after.copy()
         for e in range(15, -1, -1):
             nextv[e] = Q
             Q = np.where((mask >> e) & 1, b0 + e, Q)
         P = prev_before.copy()
-        dest = np.zeros((16, 32), np.int64); right = np.zeros((16, 32), bool)
+        dest = np.zeros((16, 32), np.int64); first = np.zeros((16, 32), bool)
         for e in range(16):
             bb = b0 + e
             P = np.where((mask >> e) & 1, bb, P)
             take_next = (nextv[e] - bb) <= (bb - P)
             owner = np.where(take_next, nextv[e], P)
             dest[e] = bb + dtab[owner]
-            right[e] = ~take_next
+            has_prev = P > -30000
+            dP = np.where(has_prev, dtab[np.maximum(P, 0)], -10 ** 6)
+            dQ = dtab[np.clip(nextv[e], 0, NB)]
+            collide = take_next & (((2 * bb - P - nextv[e]) >> 1) < (dP - dQ))
+            first[e] = ~collide | (not contract)
 
-        # in place: every lane holds its sources in registers; zero, then two ordered sub-steps
-        X[ch, :] = 0
-        for e in range(16):                           # pass C: right halves (all bins when expanding)
-            ok = (dest[e] >= 0) & (dest[e] < NB) & (right[e] | (not contract))
+        # in place: every lane holds its sources in registers.  Contraction covers [0, nb) with first
+        # writers (NaN fill proves it); expansion leaves gaps and needs the zero fill.
+        X[ch, :] = np.nan if contract else 0
+        for e in range(16):                           # first sub-step: plain stores
+            ok = (dest[e] >= 0) & (dest[e] < NB) & first[e]
             for L in np.nonzero(ok)[0]:
+                assert not contract or np.isnan(X[ch, xslot(dest[e][L])].real), "two first writers"
                 X[ch, xslot(dest[e][L])] = xv[e][L]
         for i in range(4):
             d = 512 + LANES + 32 * i + d_last
@@ -263,10 +271,12 @@ def step(hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
             for L in np.nonzero(ok)[0]:
                 X[ch, xslot(d[L])] = ext[i][L]
         if contract:
-            for e in range(16):                       # pass D: left halves add on top
-                ok = (dest[e] >= 0) & (dest[e] < NB) & ~right[e]
+            assert not np.isnan(X[ch, xslot(np.arange(NB))].real).any(), "first writers must cover [0, nb)"
+            for e in range(16):                       # second sub-step: the rest adds on top
+                ok = (dest[e] >= 0) & (dest[e] < NB) & ~first[e]
                 for L in np.nonzero(ok)[0]:
                     X[ch, xslot(dest[e][L])] += xv[e][L]
+            X[ch, np.isnan(X[ch].real)] = 0          # padding slots
 
     # ---- Hermitian C2R pre-pass (mirror of the split) -------------------------------------------
     def unsplit(k):
