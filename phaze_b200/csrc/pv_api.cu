@@ -47,6 +47,7 @@ thread_local char g_create_err[256] = "";
 bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
 int g_kernel_1024 = 0;           // PVB_KERNEL_1024: 0 (default) ring-order kernel, 1 warp kernel, 2 two warps per pair, 3 CTA kernel
 bool g_no_aligned = false;       // PVB_NO_ALIGNED=1: never use the hop %% 128 == 0 specialisation (tests)
+int g_skip = 0;                  // PVB_SKIP: phase-skipping timing experiments of the ring kernel (wrong results)
 int g_early = -1;                // PVB_EARLY=0/1/2: cap on the ring kernel's pre-wait state loads (experiments)
 // Which handle launched the library's most recent kernel on each stream.  The ring-order kernel uses
 // it to decide how much of its state is provably older than the kernel in front of it (see
@@ -235,6 +236,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     rp.pf_mant = fp.pf_mant;
     rp.pf_shift = fp.pf_shift;
     rp.stagger_ns = g_stagger_ns;
+    rp.skip = g_skip;
     {
         // early state loads: 2 when another handle's kernel (which passed its own wait before it let
         // us launch) sits between this handle's previous call and this one, else 1
@@ -505,6 +507,8 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         g_no_aligned = env && env[0] == '1';
         env = std::getenv("PVB_NO_PDL");
         g_no_pdl = env && env[0] == '1';
+        env = std::getenv("PVB_SKIP");
+        g_skip = env ? std::atoi(env) : 0;
         env = std::getenv("PVB_EARLY");
         g_early = env ? std::atoi(env) : -1;
     }

@@ -66,6 +66,8 @@ struct RingParams {
     int hop;
     int tmod;                   // timeCursor mod N (multiple of hop)
     int stagger_ns;             // experiment: delay odd warps by this much before the first pass
+    int skip;                   // experiment (PVB_SKIP, results become wrong): bit 0 the whole middle, bit 1 forward
+                                // and inverse pass 2, bit 2 split + unsplit stores / loads of the spectrum
     int early;                  // which state loads may precede griddepcontrol.wait (0, 1, 2; see the kernel)
     float pitch_factor;
     int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
@@ -117,15 +119,14 @@ __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
 // Region of influence of every bin of the run, for one channel (pv:124-141): the owner of a bin
 // is the nearest peak, ties go to the higher one.  Peaks travel as KEYS (see the key table in
 // the kernel): high half = 2 * (peak + 2048), low half = delta + 32768.  Returns per bin the byte
-// offset of its destination word inside plane 0 of Y (dump slot when it falls outside [0, nb))
-// and a 16-bit mask of the bins that are stored first (every bin that is the first writer of its
-// destination: right halves, left-half bins that do not land on the previous region, any bin when
-// expanding); the others are added on top in the second sub-step.  When contracting the first
-// writers cover [0, nb) completely, so the destination buffer needs no zero fill.
+// offset of its destination word inside plane 0 of Y (dump slot when it falls outside [0, nb)),
+// with the sign bit set when the bin belongs to the LEFT half of its region while contracting:
+// those are added on top in the second sub-step, everything else is stored first (right halves are
+// pairwise disjoint after the shift, and so are left halves, for pitch factors >= 0.75).
+// The integer pipe runs at half rate, so this loop is written for the fewest ALU operations.
 __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_t nz, const int (&rk)[16],
-                                                const int *krun, bool contract, int (&dst)[16],
-                                                uint32_t &first, int &d_last) {
-    constexpr int NB = RingGeo::NB;
+                                                const int *krun, int second_flag, int (&dst)[16],
+                                                int &d_last) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int b0 = 16 * lane;
     const int own_last = krun[(31 - __clz(mask)) & 15];              // keys of this lane's last / first peak
@@ -146,29 +147,18 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_
         if ((mask >> e) & 1u) nkey = rk[e];
     }
     const int thr0 = (4 * (b0 + 2048) + 2) << 16;
-    uint32_t fm = 0;
+    const int cb = b0 - 32768;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         if ((mask >> e) & 1u) pkey = rk[e];                          // last peak at or below bin e
         // next - b <= b - prev  <=>  2 next' + 2 prev' (+ carry of the low halves) < 4 b' + 2
-        const int tt = nx[e] + pkey - thr0 - ((4 * e) << 16);
-        const bool take_next = tt < 0;
+        const int tt = nx[e] + pkey - thr0;
+        const bool take_next = tt < ((4 * e) << 16);
         const int okey = take_next ? nx[e] : pkey;
-        const int d = (okey & 0xFFFF) + (b0 + e - 32768);
-        const int slot = (unsigned(d) < unsigned(NB)) ? d + (d >> 4) : 545;
-        dst[e] = 4 * slot;
-        // A bin of a left half (owner = next peak Q, previous peak P) lands on top of the right half of
-        // region P iff it is one of the first delta_P - delta_Q bins of its region (pv:132-141, 169-170):
-        //   b - start_Q < delta_P - delta_Q,  b - start_Q = (2b - P - Q) >> 1 = s >> 2 with s = 4b' - 2P' - 2Q'.
-        // tt >> 16 = -s - 2 + c, c = carry of the two low halves (0 or 1), s even:
-        // floor(s / 4) = (~(tt >> 16)) >> 2 for either carry.  delta_P - delta_Q is the signed low half
-        // of the key difference (negative for the "no previous peak" key when contracting).
-        const int s4 = ~(tt >> 16);
-        const int cdiff = short(pkey - nx[e]);
-        const bool collide = take_next && (s4 >> 2) < cdiff;
-        if (!collide) fm |= 1u << e;
+        const int d = (okey & 0xFFFF) + cb + e;
+        const unsigned slot = min(unsigned(d + (d >> 4)), 545u);     // d < 0 or d >= nb: dump slot
+        dst[e] = int(4u * slot) | ((tt - ((4 * e) << 16)) & second_flag);
     }
-    first = contract ? fm : 0xFFFFu;
 }
 
 // NBLK = hop / 128 and JB = ring 128-block that receives the new input block, as template
@@ -360,7 +350,7 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- forward pass 2: butterflies (k1, m3) over m2, in place -----------------------------------
     const int m3l = lane & 7;
-    {
+    if (!(p.skip & 2)) {
         float2 w2[8];
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
@@ -418,6 +408,7 @@ pv_process_ring_kernel(const RingParams p) {
     __syncwarp();
 
     // ---- peaks, regions of influence, shift (pv:95-173) -------------------------------------------------
+    if (!(p.skip & 1))
     // X lives in float4 slots (both channels per bin); the shifted spectrum Y is written over it as
     // four planes of floats (re0 | re1 | im0 | im1, bin d at word d + (d >> 4)): the 32-bit scatter of
     // lanes that own runs 16 bins apart then spreads over all banks.
@@ -445,7 +436,6 @@ pv_process_ring_kernel(const RingParams p) {
         const uint32_t nz1 = __ballot_sync(FULL, mask1 != 0);
 
         int dst0[16], dst1[16];
-        uint32_t first0 = 0, first1 = 0;
         int dl0 = 0, dl1 = 0;
         {
             const int *krun = ktab + 20 * lane;                       // keys of bins 16 lane .. + 15
@@ -457,8 +447,9 @@ pv_process_ring_kernel(const RingParams p) {
             }
             // both scans run unconditionally (a channel without peaks ends up with every bin on the
             // dump slot): two independent instruction streams the scheduler can interleave
-            ring_owner_scan(mask0, lane, nz0, rk, krun, contract, dst0, first0, dl0);
-            ring_owner_scan(mask1, lane, nz1, rk, krun, contract, dst1, first1, dl1);
+            const int second_flag = contract ? int(0x80000000u) : 0;
+            ring_owner_scan(mask0, lane, nz0, rk, krun, second_flag, dst0, dl0);
+            ring_owner_scan(mask1, lane, nz1, rk, krun, second_flag, dst1, dl1);
         }
 
         // sources into registers: own run, bin 512 and the first stale level (what _realTransform4
@@ -486,24 +477,25 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
         __syncwarp();            // every lane holds its sources: the buffer becomes Y
-        // Expansion leaves gaps between the shifted regions, a channel without peaks leaves everything
-        // empty: zero fill.  Contraction with peaks in both channels writes every bin of [0, nb).
-        if (!contract || !nz0 || !nz1) {
 #pragma unroll
-            for (int i = 0; i < 17; i++) XQ[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < 2) XQ[544 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncwarp();
-        }
+        for (int i = 0; i < 17; i++) XQ[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < 2) XQ[544 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
 
         constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane (546 words)
         // first sub-step: plain stores (pairwise disjoint destinations)
-        if (nz0) {
 #pragma unroll
-            for (int e = 0; e < 16; e++)
-                if ((first0 >> e) & 1u) {
-                    *reinterpret_cast<float *>(mine + dst0[e]) = xv[e].x;
-                    *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL) = xv[e].z;
-                }
+        for (int e = 0; e < 16; e++) {
+            if (dst0[e] >= 0) {
+                *reinterpret_cast<float *>(mine + dst0[e]) = xv[e].x;
+                *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL) = xv[e].z;
+            }
+            if (dst1[e] >= 0) {
+                *reinterpret_cast<float *>(mine + dst1[e] + PL) = xv[e].y;
+                *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = xv[e].w;
+            }
+        }
+        if (nz0) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int d = 512 + lane + 32 * i + dl0;
@@ -514,12 +506,6 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
         if (nz1) {
-#pragma unroll
-            for (int e = 0; e < 16; e++)
-                if ((first1 >> e) & 1u) {
-                    *reinterpret_cast<float *>(mine + dst1[e] + PL) = xv[e].y;
-                    *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = xv[e].w;
-                }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int d = 512 + lane + 32 * i + dl1;
@@ -533,28 +519,27 @@ pv_process_ring_kernel(const RingParams p) {
             // second sub-step: left halves add on top (pairwise disjoint among themselves, so the
             // loads of a batch can all be issued before the first store)
             __syncwarp();
+            unsigned char *mine2 = mine + 0x80000000u;                // cancels the flag bit of dst
 #pragma unroll
             for (int g = 0; g < 2; g++) {
                 float o0r[8], o0i[8], o1r[8], o1i[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int e = 8 * g + i;
-                    const bool s0 = nz0 && !((first0 >> e) & 1u), s1 = nz1 && !((first1 >> e) & 1u);
                     o0r[i] = o0i[i] = o1r[i] = o1i[i] = 0.f;
-                    if (s0) { o0r[i] = *reinterpret_cast<float *>(mine + dst0[e]); o0i[i] = *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL); }
-                    if (s1) { o1r[i] = *reinterpret_cast<float *>(mine + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL); }
+                    if (dst0[e] < 0) { o0r[i] = *reinterpret_cast<float *>(mine2 + dst0[e]); o0i[i] = *reinterpret_cast<float *>(mine2 + dst0[e] + 2 * PL); }
+                    if (dst1[e] < 0) { o1r[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + 3 * PL); }
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int e = 8 * g + i;
-                    const bool s0 = nz0 && !((first0 >> e) & 1u), s1 = nz1 && !((first1 >> e) & 1u);
-                    if (s0) {
-                        *reinterpret_cast<float *>(mine + dst0[e]) = o0r[i] + xv[e].x;
-                        *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL) = o0i[i] + xv[e].z;
+                    if (dst0[e] < 0) {
+                        *reinterpret_cast<float *>(mine2 + dst0[e]) = o0r[i] + xv[e].x;
+                        *reinterpret_cast<float *>(mine2 + dst0[e] + 2 * PL) = o0i[i] + xv[e].z;
                     }
-                    if (s1) {
-                        *reinterpret_cast<float *>(mine + dst1[e] + PL) = o1r[i] + xv[e].y;
-                        *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = o1i[i] + xv[e].w;
+                    if (dst1[e] < 0) {
+                        *reinterpret_cast<float *>(mine2 + dst1[e] + PL) = o1r[i] + xv[e].y;
+                        *reinterpret_cast<float *>(mine2 + dst1[e] + 3 * PL) = o1i[i] + xv[e].w;
                     }
                 }
             }
@@ -632,6 +617,7 @@ pv_process_ring_kernel(const RingParams p) {
     }
 
     // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_512^{k1 (m3 + 8 m2)}) ---------------
+    if (!(p.skip & 2))
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int k1 = (lane >> 3) + 4 * h;

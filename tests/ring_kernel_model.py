@@ -235,9 +235,7 @@ def step(hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 if cf and contract:
                     cf.note("stale_ld", xslot(qq) * XW, 16); cf.note("stale_ld_m", xslot(512 - qq) * XW, 16)
 
-        # owner of every bin of the run: nearest peak, ties to the higher one (pv:132-141).  A bin is
-        # a FIRST writer of its destination unless it belongs to a left half and is one of the first
-        # delta_P - delta_Q bins of its region (those land on the right half of the previous region).
+        # owner of every bin of the run: nearest peak, ties to the higher one (pv:132-141)
         nextv = np.zeros((16, 32), np.int64)
         Q = next_after.copy()
         for e in range(15, -1, -1):
@@ -251,32 +249,32 @@ def step(hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
             take_next = (nextv[e] - bb) <= (bb - P)
             owner = np.where(take_next, nextv[e], P)
             dest[e] = bb + dtab[owner]
-            has_prev = P > -30000
-            dP = np.where(has_prev, dtab[np.maximum(P, 0)], -10 ** 6)
-            dQ = dtab[np.clip(nextv[e], 0, NB)]
-            collide = take_next & (((2 * bb - P - nextv[e]) >> 1) < (dP - dQ))
-            first[e] = ~collide | (not contract)
+            first[e] = ~take_next | (not contract)    # right half of its region, or expanding
 
-        # in place: every lane holds its sources in registers.  Contraction covers [0, nb) with first
-        # writers (NaN fill proves it); expansion leaves gaps and needs the zero fill.
-        X[ch, :] = np.nan if contract else 0
+        # in place: every lane holds its sources in registers; zero fill, then two ordered sub-steps
+        # (right halves are pairwise disjoint after the shift, and so are left halves: checked here)
+        X[ch, :] = 0
+        written = np.zeros(XSLOTS, np.int64)
         for e in range(16):                           # first sub-step: plain stores
             ok = (dest[e] >= 0) & (dest[e] < NB) & first[e]
             for L in np.nonzero(ok)[0]:
-                assert not contract or np.isnan(X[ch, xslot(dest[e][L])].real), "two first writers"
+                written[xslot(dest[e][L])] += 1
                 X[ch, xslot(dest[e][L])] = xv[e][L]
         for i in range(4):
             d = 512 + LANES + 32 * i + d_last
             ok = (d >= 0) & (d < NB)
             for L in np.nonzero(ok)[0]:
+                written[xslot(d[L])] += 1
                 X[ch, xslot(d[L])] = ext[i][L]
+        assert written.max() <= 1, "two first writers for one bin"
+        written[:] = 0
         if contract:
-            assert not np.isnan(X[ch, xslot(np.arange(NB))].real).any(), "first writers must cover [0, nb)"
-            for e in range(16):                       # second sub-step: the rest adds on top
+            for e in range(16):                       # second sub-step: left halves add on top
                 ok = (dest[e] >= 0) & (dest[e] < NB) & ~first[e]
                 for L in np.nonzero(ok)[0]:
+                    written[xslot(dest[e][L])] += 1
                     X[ch, xslot(dest[e][L])] += xv[e][L]
-            X[ch, np.isnan(X[ch].real)] = 0          # padding slots
+            assert written.max() <= 1, "two second writers for one bin"
 
     # ---- Hermitian C2R pre-pass (mirror of the split) -------------------------------------------
     def unsplit(k):
