@@ -375,7 +375,9 @@ def run_ours(args):
                        "channels_per_gpu": C, "frames_per_step": C * world,
                        "l2_policy": f"inputs larger than L2: {rotate} processor instances "
                                     f"({rotate * state_bytes / 2**20:.0f} MiB of state+io) rotated per step",
-                       "parallelism": f"channel-sharded x{world}, no data-path collective"},
+                       "parallelism": f"channel-sharded x{world}, no data-path collective",
+                       "launch": "one stream; consecutive launches chained by programmatic dependent launch "
+                                 "(state older than the preceding kernel is loaded before griddepcontrol.wait)"},
             "roofline": roofline,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -496,7 +498,7 @@ def phaze_b200_lib():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the
 # committed `ncu --set full` capture (profiles/), for the default workload; None until captured.
-NCU_TRAFFIC_BYTES = 29.48e6   # profiles/r01_ncu_warp_kernel.txt: reads 29.45 MB + writes 0.03 MB (stores retire into L2)
+NCU_TRAFFIC_BYTES = 29.51e6   # profiles/r01_ncu_ring_kernel.txt: reads 29.44 MB + writes 0.06 MB (stores retire into L2)
 
 
 def main():
