@@ -23,7 +23,7 @@
 //
 // Valid for hop % 128 == 0, hop <= 512 and pitch factors in [0.75, 64] (first stale level only,
 // right halves and left halves of regions stay pairwise disjoint after the shift).  tests/
-// ring_kernel_model.py restates this file lane by lane in numpy and is checked against the oracle.
+// ring_kernel_model.py restates this file lane by lane in numpy (CPU test of the design).
 #pragma once
 
 #include "pv_kernel.cuh"
