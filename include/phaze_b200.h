@@ -118,6 +118,10 @@ PVB_API int32_t pvb_set_time_cursor(pvb_processor *p, double samples);
 PVB_API const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor);
 /* number of CUDA kernels this handle has launched since creation */
 PVB_API int64_t pvb_kernel_launches(const pvb_processor *p);
+/* Diagnostics: consecutive launches of the frame-1024 kernel synchronise per channel pair through
+   completion flags in device memory (bounded spin); this counts flags that never arrived.  Must
+   stay 0.  Synchronises the handle's stream; -1 on CUDA error. */
+PVB_API int64_t pvb_ring_stuck_count(pvb_processor *p);
 
 /* checkpoint / resume of the per-channel state.  Blob layout (float32):
  * [num_channels][frame_size] input history in time order (oldest first),

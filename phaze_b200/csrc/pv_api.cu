@@ -32,6 +32,8 @@ struct pvb_processor {
     int num_sms = 148;
     float2 *d_tw = nullptr;
     float4 *d_ring_tab = nullptr;    // tables of the ring-order kernel (frame 1024 only)
+    unsigned *d_done = nullptr;      // [pairs] + 1: per-pair completion flags of the ring-order kernel, stuck counter
+    unsigned ring_seq = 0;           // sequence number of this handle's last ring-order launch
     float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
     size_t staging_floats = 0;
     cudaStream_t stream = nullptr;
@@ -54,6 +56,12 @@ int g_early = -1;                // PVB_EARLY=0/1/2: cap on the ring kernel's pr
 // RingParams::early); every launch path records itself here.
 std::mutex g_stream_mu;
 std::unordered_map<cudaStream_t, const void *> g_last_on_stream;
+// caller buffers of the library's most recent launches per stream: flag mode lets launches overlap
+// beyond their immediate predecessor, so a new call whose input aliases a recent output (handles
+// chained through a buffer) or whose output aliases a recent input falls back to grid mode
+struct RecentIo { const char *in_lo, *in_hi, *out_lo, *out_hi; };
+std::unordered_map<cudaStream_t, std::vector<RecentIo>> g_recent_io;
+bool g_no_flags = false;         // PVB_NO_FLAGS=1: ring kernel always in grid mode (experiments)
 bool g_no_pdl = false;           // PVB_NO_PDL=1: ring kernel without programmatic dependent launch (experiments)
 int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
 
@@ -200,6 +208,8 @@ bool ring_kernel_applies(const pvb_processor *h, const pvb::FrameParams &fp) {
            !g_force_generic;
 }
 
+size_t state_rows(int channels);
+
 cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
     using G = pvb::RingGeo;
     static bool configured[64] = {};
@@ -245,7 +255,28 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
         rp.early = (it != g_last_on_stream.end() && it->second != h) ? 2 : 1;
         if (g_no_pdl) rp.early = 0;
         if (g_early >= 0 && rp.early > g_early) rp.early = g_early;
+        // flag mode needs the caller's buffers to be disjoint from those of the recent launches
+        const size_t io_bytes = size_t(fp.num_channels) * size_t(fp.hop) * sizeof(float);
+        RecentIo io;
+        io.in_lo = reinterpret_cast<const char *>(fp.in);
+        io.in_hi = fp.in ? io.in_lo + io_bytes : io.in_lo;
+        io.out_lo = reinterpret_cast<const char *>(fp.out);
+        io.out_hi = io.out_lo + io_bytes;
+        auto &recent = g_recent_io[s];
+        bool safe = !g_no_pdl && !g_no_flags;
+        for (const RecentIo &r : recent) {
+            if (io.in_lo < r.out_hi && r.out_lo < io.in_hi) safe = false;      // reads what a recent call writes
+            if (io.out_lo < r.in_hi && r.in_lo < io.out_hi) safe = false;      // writes what a recent call reads
+        }
+        if (!safe) recent.clear();          // a grid-mode launch waits for everything before it
+        recent.push_back(io);
+        if (recent.size() > 8) recent.erase(recent.begin());
+        rp.flag_mode = safe ? 1 : 0;
     }
+    rp.done = h->d_done;
+    rp.stuck = h->d_done + (state_rows(h->channels) / 2);
+    rp.wait_seq = h->ring_seq;
+    rp.my_seq = h->ring_seq + 1;
     const size_t smem = G::TAB_BYTES + size_t(wpc) * G::WARP_BYTES;
     const int jb = ((rp.tmod - rp.hop + 1024) >> 7) & 7;
     // programmatic dependent launch: CTAs of this launch may become resident (and stage their
@@ -261,6 +292,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
     if (rp.hop == 256) {        // the headline geometry: ring-block roles fixed at compile time
         switch (jb) {
             case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 0>, rp);
@@ -343,7 +375,10 @@ size_t state_rows(int channels) { return size_t(channels > 0 ? ((channels + 1) &
 int alloc_state(pvb_processor *p, int channels) {
     cudaFree(p->d_hist);
     cudaFree(p->d_acc);
+    cudaFree(p->d_done);
     p->d_hist = p->d_acc = nullptr;
+    p->d_done = nullptr;
+    p->ring_seq = 0;
     p->channels = channels;
     // rows are padded to an even channel count: the kernels process channels in pairs
     const size_t bytes = state_rows(channels) * size_t(p->n) * sizeof(float);
@@ -351,8 +386,14 @@ int alloc_state(pvb_processor *p, int channels) {
         cudaGetLastError();
         return fail(p, PVB_ERR_NOMEM, "cudaMalloc of %zu state bytes failed", 2 * bytes);
     }
+    const size_t flag_bytes = (state_rows(channels) / 2 + 1) * sizeof(unsigned);
+    if (cudaMalloc(&p->d_done, flag_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(p, PVB_ERR_NOMEM, "cudaMalloc of the completion flags failed");
+    }
     PVB_CUDA(p, cudaMemsetAsync(p->d_hist, 0, bytes, p->stream));
     PVB_CUDA(p, cudaMemsetAsync(p->d_acc, 0, bytes, p->stream));
+    PVB_CUDA(p, cudaMemsetAsync(p->d_done, 0, flag_bytes, p->stream));
     p->ring_calls = 0;
     p->layout = pvb_processor::ZERO;
     return PVB_OK;
@@ -507,6 +548,8 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         g_no_aligned = env && env[0] == '1';
         env = std::getenv("PVB_NO_PDL");
         g_no_pdl = env && env[0] == '1';
+        env = std::getenv("PVB_NO_FLAGS");
+        g_no_flags = env && env[0] == '1';
         env = std::getenv("PVB_SKIP");
         g_skip = env ? std::atoi(env) : 0;
         env = std::getenv("PVB_EARLY");
@@ -605,6 +648,7 @@ void pvb_destroy(pvb_processor *p) {
     cudaFree(p->d_window_out);
     cudaFree(p->d_tw);
     cudaFree(p->d_ring_tab);
+    cudaFree(p->d_done);
     cudaFree(p->d_in);
     cudaFree(p->d_out);
     for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
@@ -745,6 +789,16 @@ int32_t pvb_hop_size(const pvb_processor *p) { return p ? p->hop : PVB_ERR_BAD_A
 int32_t pvb_num_channels(const pvb_processor *p) { return p ? p->channels : PVB_ERR_BAD_ARG; }
 double pvb_time_cursor(const pvb_processor *p) { return p ? double(p->cursor_calls) * p->hop : 0.0; }
 int64_t pvb_kernel_launches(const pvb_processor *p) { return p ? p->launches : 0; }
+
+int64_t pvb_ring_stuck_count(pvb_processor *p) {
+    if (!p || !p->d_done) return 0;
+    DeviceGuard guard(p->device);
+    unsigned v = 0;
+    if (cudaStreamSynchronize(p->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, p->d_done + state_rows(p->channels) / 2, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    return int64_t(v);
+}
 
 const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
     if (!p) return "";

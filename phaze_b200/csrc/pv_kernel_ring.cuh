@@ -69,6 +69,12 @@ struct RingParams {
     int skip;                   // experiment (PVB_SKIP, results become wrong): bit 0 the whole middle, bit 1 forward
                                 // and inverse pass 2, bit 2 split + unsplit stores / loads of the spectrum
     int early;                  // which state loads may precede griddepcontrol.wait (0, 1, 2; see the kernel)
+    // per-pair completion flags: done[pair] holds the sequence number of the last call of this handle
+    // whose state / output for that pair is complete (release store at the end of every launch)
+    unsigned *done;
+    unsigned wait_seq, my_seq;  // this call may touch a pair once done[pair] >= wait_seq; it stores my_seq
+    int flag_mode;              // 1: synchronise on done[] per pair instead of waiting for the whole previous grid
+    unsigned *stuck;            // incremented if a flag never arrives (bounded spin; see pvb_ring_stuck_count)
     float pitch_factor;
     int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
 };
@@ -195,8 +201,16 @@ pv_process_ring_kernel(const RingParams p) {
     const int je = (jb + nblk) & 7;                           // ring 128-block of frame sample 0 (emitted)
 
     // Programmatic dependent launch: our CTAs may become resident while the previous kernel on the
-    // stream drains; everything up to griddepcontrol.wait touches only constant tables (and state
-    // that is provably older than that kernel), so it overlaps the previous launch's tail.
+    // stream drains.  Two ways to respect what earlier launches wrote:
+    //  * flag mode (the host has checked that the caller's buffers do not alias those of recent
+    //    launches): dependents are released at once, every warp waits for ITS pair's completion
+    //    flag only, and the CTA waits for the previous grid at its very end, so that "this grid is
+    //    complete" still implies "everything before it is complete".  Calls of different handles, and
+    //    different pairs of one handle, then overlap freely: the load phase of one CTA runs under
+    //    the compute phase of its SM neighbour.
+    //  * grid mode: griddepcontrol.wait before the first dependent access; everything up to it
+    //    touches only constant tables (and state that is provably older than the previous kernel).
+    if (p.flag_mode) asm volatile("griddepcontrol.launch_dependents;");
     // ---- CTA-shared tables: asynchronous 16-byte copies, fixed trip counts (CTAs have 4..7 warps;
     // no division by blockDim) --------------------------------------------------------------------------
     {
@@ -246,8 +260,25 @@ pv_process_ring_kernel(const RingParams p) {
     float4 r[16];
     float2 un0[NBLK ? 2 * NBLK : 1], un1[NBLK ? 2 * NBLK : 1];
     float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + lane;
-    const int early = p.early;
-    if (live && early) {
+    const int early = p.flag_mode ? 0 : p.early;
+    if (p.flag_mode) {
+        if (live) {
+            // acquire: the previous call of this handle has finished with this pair (bounded spin: a
+            // lost flag must not hang the device; the host can read the stuck counter)
+            unsigned v;
+            int it = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done + pair) : "memory");
+                if (int(v - p.wait_seq) >= 0) break;
+                if (++it > 200000) {
+                    if (lane == 0) atomicAdd(p.stuck, 1u);
+                    break;
+                }
+                __nanosleep(200);
+            }
+            __syncwarp();
+        }
+    } else if (live && early) {
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             const int h = e >> 3, j = e & 7;
@@ -265,10 +296,12 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
-    // our dependents may launch only now: whoever starts behind us can rely on everything older
-    // than us being complete
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;");
+    if (!p.flag_mode) {
+        // our dependents may launch only now: whoever starts behind us can rely on everything older
+        // than us being complete
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+    }
     if (live) {
         const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * lane : nullptr;
 #pragma unroll
@@ -664,6 +697,14 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
+    // release: state and output of this pair are complete for call my_seq
+    __threadfence();
+    __syncwarp();
+    if (lane == 0)
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done + pair), "r"(p.my_seq) : "memory");
+    // flag mode skipped the wait at the top: take it here, where the previous grid is long gone, so
+    // that completion stays transitive along the stream
+    if (p.flag_mode) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // tables the ring-order kernel copies into shared memory: tw1[k1][n] (rows of TW1_ROW), w64[a][b], twh[k]

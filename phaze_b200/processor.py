@@ -79,6 +79,11 @@ class BatchedPhaseVocoder:
     def kernel_launches(self) -> int:
         return self._lib.pvb_kernel_launches(self._h)
 
+    @property
+    def ring_stuck_count(self) -> int:
+        """completion flags of the frame-1024 kernel that never arrived (must stay 0)"""
+        return self._lib.pvb_ring_stuck_count(self._h)
+
     def kernel_name(self, pitch_factor: float) -> str:
         return self._lib.pvb_kernel_name(self._h, np.float32(pitch_factor)).decode()
 

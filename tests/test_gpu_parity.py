@@ -175,3 +175,42 @@ def test_layout_changes_mid_stream(oracle):
     err = _rms(got - ref)
     print(f"layout changes: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
+
+
+def test_flag_mode_chained_handles_and_back_to_back(oracle):
+    """Consecutive launches of the frame-1024 kernel overlap (per-pair completion flags instead of
+    a grid-wide wait).  (a) one handle called back to back on a stream with device buffers: each
+    pair waits for its own previous call; (b) two handles chained through ONE device buffer
+    (A's output is B's input, and is overwritten by A's next call): the library must notice the
+    aliasing and order those launches; (c) no flag was ever lost."""
+    import torch
+    from phaze_b200 import BatchedPhaseVocoder
+    N, hop, C, calls = 1024, 256, 37, 24
+    pfa, pfb = np.float32(0.8), np.float32(1.25)
+    x = signals.channels(7, C, calls * hop)
+    oa, ob = oracle.OracleProcessor(N, hop, C), oracle.OracleProcessor(N, hop, C)
+    ref_a = np.empty_like(x)
+    ref_b = np.empty_like(x)
+    for k in range(calls):
+        s = slice(k * hop, (k + 1) * hop)
+        ref_a[:, s] = oa.process_packed(x[:, s], pfa)
+        ref_b[:, s] = ob.process_packed(ref_a[:, s], pfb)
+    stream = torch.cuda.Stream()
+    xin = torch.from_numpy(np.ascontiguousarray(x.reshape(C, calls, hop).transpose(1, 0, 2))).cuda()
+    mid = torch.empty((C, hop), dtype=torch.float32, device="cuda")        # shared by both handles
+    out_a = torch.empty((calls, C, hop), dtype=torch.float32, device="cuda")
+    out_b = torch.empty((calls, C, hop), dtype=torch.float32, device="cuda")
+    with BatchedPhaseVocoder(C, N, hop) as a, BatchedPhaseVocoder(C, N, hop) as b, \
+            BatchedPhaseVocoder(C, N, hop) as solo:
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            for k in range(calls):
+                a.process_device(xin[k].data_ptr(), mid.data_ptr(), pfa, stream.cuda_stream)
+                b.process_device(mid.data_ptr(), out_b[k].data_ptr(), pfb, stream.cuda_stream)
+                solo.process_device(xin[k].data_ptr(), out_a[k].data_ptr(), pfa, stream.cuda_stream)
+        stream.synchronize()
+        assert a.ring_stuck_count == 0 and b.ring_stuck_count == 0 and solo.ring_stuck_count == 0
+    got_a = out_a.cpu().numpy().transpose(1, 0, 2).reshape(C, calls * hop)
+    got_b = out_b.cpu().numpy().transpose(1, 0, 2).reshape(C, calls * hop)
+    assert _rms(got_a - ref_a) <= RMS_EXPECTED
+    assert _rms(got_b - ref_b) <= RMS_EXPECTED
