@@ -61,6 +61,8 @@ std::unordered_map<cudaStream_t, const void *> g_last_on_stream;
 // chained through a buffer) or whose output aliases a recent input falls back to grid mode
 struct RecentIo { const char *in_lo, *in_hi, *out_lo, *out_hi; };
 std::unordered_map<cudaStream_t, std::vector<RecentIo>> g_recent_io;
+int g_ring_pad_kb = 0;
+int g_ring_wpc = 0;              // PVB_RING_WPC: warps (pairs) per CTA of the ring kernel (0: balance one wave)
 bool g_no_flags = false;         // PVB_NO_FLAGS=1: ring kernel always in grid mode (experiments)
 bool g_no_pdl = false;           // PVB_NO_PDL=1: ring kernel without programmatic dependent launch (experiments)
 int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
@@ -216,7 +218,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        const int smem = int(G::TAB_BYTES + G::MAX_WARPS * G::WARP_BYTES);
+        const int smem = 227 * 1024;
         cudaError_t e = cudaSuccess;
 #define PVB_RING_ATTR(NBLK, JB)                                                                   \
         if (e == cudaSuccess)                                                                     \
@@ -229,7 +231,8 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     }
     const int pairs = (fp.num_channels + 1) / 2;
     if (pairs == 0) return cudaSuccess;
-    const int wpc = pick_warps_per_cta(pairs, h->num_sms);
+    int wpc = pick_warps_per_cta(pairs, h->num_sms);
+    if (g_ring_wpc >= 1 && g_ring_wpc <= G::MAX_WARPS) wpc = g_ring_wpc;
     const int grid = (pairs + wpc - 1) / wpc;
     pvb::RingParams rp;
     rp.in = fp.in;
@@ -277,7 +280,8 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     rp.stuck = h->d_done + (state_rows(h->channels) / 2);
     rp.wait_seq = h->ring_seq;
     rp.my_seq = h->ring_seq + 1;
-    const size_t smem = G::TAB_BYTES + size_t(wpc) * G::WARP_BYTES;
+    // PVB_RING_PAD_KB: occupancy experiment (extra dynamic shared memory per CTA)
+    const size_t smem = G::TAB_BYTES + size_t(wpc) * G::WARP_BYTES + size_t(g_ring_pad_kb) * 1024;
     const int jb = ((rp.tmod - rp.hop + 1024) >> 7) & 7;
     // programmatic dependent launch: CTAs of this launch may become resident (and stage their
     // tables) while the previous kernel on the stream drains; the kernel itself waits
@@ -548,6 +552,10 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         g_no_aligned = env && env[0] == '1';
         env = std::getenv("PVB_NO_PDL");
         g_no_pdl = env && env[0] == '1';
+        env = std::getenv("PVB_RING_PAD_KB");
+        g_ring_pad_kb = env ? std::atoi(env) : 0;
+        env = std::getenv("PVB_RING_WPC");
+        g_ring_wpc = env ? std::atoi(env) : 0;
         env = std::getenv("PVB_NO_FLAGS");
         g_no_flags = env && env[0] == '1';
         env = std::getenv("PVB_SKIP");
