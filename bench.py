@@ -376,8 +376,8 @@ def run_ours(args):
                        "l2_policy": f"inputs larger than L2: {rotate} processor instances "
                                     f"({rotate * state_bytes / 2**20:.0f} MiB of state+io) rotated per step",
                        "parallelism": f"channel-sharded x{world}, no data-path collective",
-                       "launch": "one stream; consecutive launches chained by programmatic dependent launch "
-                                 "(state older than the preceding kernel is loaded before griddepcontrol.wait)"},
+                       "launch": "one stream; consecutive launches chained by programmatic dependent launch, "
+                                 "each channel pair waits for its own previous call (completion flags)"},
             "roofline": roofline,
             "e2e": e2e,
             "gpu_launches": int(launches),
