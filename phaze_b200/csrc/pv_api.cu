@@ -31,7 +31,7 @@ struct pvb_processor {
     float *d_hist = nullptr, *d_acc = nullptr, *d_window = nullptr, *d_window_out = nullptr;
     int num_sms = 148;
     float2 *d_tw = nullptr;
-    float4 *d_ring_tab = nullptr;    // tables of the ring-order kernel (frame 1024 only)
+    float4 *d_ring_tab = nullptr;    // tables of the ring-order kernel (frames 1024 and 2048)
     unsigned *d_done = nullptr;      // [pairs] + 1: per-pair completion flags of the ring-order kernel, stuck counter
     unsigned ring_seq = 0;           // sequence number of this handle's last ring-order launch
     float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
@@ -61,6 +61,10 @@ std::unordered_map<cudaStream_t, const void *> g_last_on_stream;
 // chained through a buffer) or whose output aliases a recent input falls back to grid mode
 struct RecentIo { const char *in_lo, *in_hi, *out_lo, *out_hi; };
 std::unordered_map<cudaStream_t, std::vector<RecentIo>> g_recent_io;
+// whether the library's previous launch on the stream ran in flag mode: such a kernel releases its
+// dependents without waiting, so "older than the kernel in front of us" no longer means "complete"
+// and a grid-mode launch behind it must not load anything before its griddepcontrol.wait
+std::unordered_map<cudaStream_t, bool> g_last_flag_mode;
 int g_ring_pad_kb = 0;
 int g_ring_wpc = 0;              // PVB_RING_WPC: warps (pairs) per CTA of the ring kernel (0: balance one wave)
 bool g_no_flags = false;         // PVB_NO_FLAGS=1: ring kernel always in grid mode (experiments)
@@ -206,34 +210,38 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
 
 // ring-order kernel (pv_kernel_ring.cuh): paired state layout aligned to the time cursor
 bool ring_kernel_applies(const pvb_processor *h, const pvb::FrameParams &fp) {
-    return h->n == 1024 && fast_range(fp) && h->hop % 128 == 0 && h->hop <= 512 && g_kernel_1024 == 0 &&
-           !g_force_generic;
+    return (h->n == 1024 || h->n == 2048) && fast_range(fp) && h->hop % 128 == 0 && h->hop <= h->n / 2 &&
+           g_kernel_1024 == 0 && !g_force_generic;
 }
 
 size_t state_rows(int channels);
 
 cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
-    using G = pvb::RingGeo;
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         const int smem = 227 * 1024;
         cudaError_t e = cudaSuccess;
-#define PVB_RING_ATTR(NBLK, JB)                                                                   \
+#define PVB_RING_ATTR(N, NBLK, JB)                                                                \
         if (e == cudaSuccess)                                                                     \
-            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<NBLK, JB>,                       \
+            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLK, JB>,                    \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        PVB_RING_ATTR(0, 0) PVB_RING_ATTR(2, 0) PVB_RING_ATTR(2, 2) PVB_RING_ATTR(2, 4) PVB_RING_ATTR(2, 6)
+        PVB_RING_ATTR(1024, 0, 0) PVB_RING_ATTR(1024, 2, 0) PVB_RING_ATTR(1024, 2, 2)
+        PVB_RING_ATTR(1024, 2, 4) PVB_RING_ATTR(1024, 2, 6) PVB_RING_ATTR(2048, 0, 0)
 #undef PVB_RING_ATTR
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     const int pairs = (fp.num_channels + 1) / 2;
     if (pairs == 0) return cudaSuccess;
-    int wpc = pick_warps_per_cta(pairs, h->num_sms);
-    if (g_ring_wpc >= 1 && g_ring_wpc <= G::MAX_WARPS) wpc = g_ring_wpc;
-    const int grid = (pairs + wpc - 1) / wpc;
+    const bool big = h->n == 2048;
+    // pairs per CTA: frame 1024 balances one wave (4..7 warps); frame 2048 uses 2..3 pairs of two warps
+    int ppc = big ? 3 : pick_warps_per_cta(pairs, h->num_sms);
+    const int max_ppc = big ? pvb::RingGeoT<2048>::MAX_PAIRS : pvb::RingGeoT<1024>::MAX_PAIRS;
+    if (g_ring_wpc >= (big ? 2 : 4) && g_ring_wpc <= max_ppc) ppc = g_ring_wpc;
+    const int grid = (pairs + ppc - 1) / ppc;
+    const int threads = ppc * (big ? pvb::RingGeoT<2048>::TP : pvb::RingGeoT<1024>::TP);
     pvb::RingParams rp;
     rp.in = fp.in;
     rp.out = fp.out;
@@ -275,20 +283,25 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
         recent.push_back(io);
         if (recent.size() > 8) recent.erase(recent.begin());
         rp.flag_mode = safe ? 1 : 0;
+        bool &last_flag = g_last_flag_mode[s];
+        if (last_flag) rp.early = 0;
+        last_flag = safe;
     }
     rp.done = h->d_done;
     rp.stuck = h->d_done + (state_rows(h->channels) / 2);
     rp.wait_seq = h->ring_seq;
     rp.my_seq = h->ring_seq + 1;
     // PVB_RING_PAD_KB: occupancy experiment (extra dynamic shared memory per CTA)
-    const size_t smem = G::TAB_BYTES + size_t(wpc) * G::WARP_BYTES + size_t(g_ring_pad_kb) * 1024;
+    const size_t smem = (big ? pvb::RingGeoT<2048>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<2048>::PAIR_BYTES
+                             : pvb::RingGeoT<1024>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<1024>::PAIR_BYTES) +
+                        size_t(g_ring_pad_kb) * 1024;
     const int jb = ((rp.tmod - rp.hop + 1024) >> 7) & 7;
     // programmatic dependent launch: CTAs of this launch may become resident (and stage their
     // tables) while the previous kernel on the stream drains; the kernel itself waits
     // (griddepcontrol.wait) before it touches anything an earlier launch may have written
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(wpc * 32);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -297,15 +310,16 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
+    if (big) return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 0, 0>, rp);
     if (rp.hop == 256) {        // the headline geometry: ring-block roles fixed at compile time
         switch (jb) {
-            case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 0>, rp);
-            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 2>, rp);
-            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 4>, rp);
-            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2, 6>, rp);
+            case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 0>, rp);
+            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 2>, rp);
+            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 4>, rp);
+            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 6>, rp);
         }
     }
-    return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<0, 0>, rp);
+    return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 0, 0>, rp);
 }
 
 // two warps per channel pair (pv_kernel_pair.cuh): same validity range as the warp kernel
@@ -340,6 +354,7 @@ cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaS
 cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
     const cudaError_t e = launch_any(h, fp, s);
     std::lock_guard<std::mutex> lk(g_stream_mu);
+    if (!ring_kernel_applies(h, fp)) g_last_flag_mode[s] = false;     // the other kernels are plain launches
     if (g_last_on_stream.size() > 4096) g_last_on_stream.clear();     // streams come and go; unknown == conservative
     g_last_on_stream[s] = h;
     return e;
@@ -627,11 +642,13 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         fail(p, PVB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(PVB_ERR_CUDA);
     }
-    if (n == 1024) {
-        std::vector<float2> rt(pvb::RingGeo::GTAB_BYTES / sizeof(float2));
-        pvb::ring_host_tables(tw.data(), rt.data());
-        if (cudaMalloc(&p->d_ring_tab, pvb::RingGeo::GTAB_BYTES) != cudaSuccess ||
-            cudaMemcpy(p->d_ring_tab, rt.data(), pvb::RingGeo::GTAB_BYTES, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (n == 1024 || n == 2048) {
+        const size_t tab_bytes = n == 1024 ? pvb::RingGeoT<1024>::GTAB_BYTES : pvb::RingGeoT<2048>::GTAB_BYTES;
+        std::vector<float2> rt(tab_bytes / sizeof(float2));
+        if (n == 1024) pvb::ring_host_tables<1024>(tw.data(), rt.data());
+        else pvb::ring_host_tables<2048>(tw.data(), rt.data());
+        if (cudaMalloc(&p->d_ring_tab, tab_bytes) != cudaSuccess ||
+            cudaMemcpy(p->d_ring_tab, rt.data(), tab_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
             fail(p, PVB_ERR_CUDA, "ring table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
             return bail(PVB_ERR_CUDA);
         }

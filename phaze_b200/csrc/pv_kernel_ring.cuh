@@ -1,5 +1,5 @@
-// pv_kernel_ring.cuh — ring-order fused kernel for frame size 1024 (sm_100a), one warp per
-// channel pair.  Same reference arithmetic as pv_kernel.cuh (one launch == one process() call,
+// pv_kernel_ring.cuh — ring-order fused kernel for frame sizes 1024 (one warp per channel pair)
+// and 2048 (two warps per pair; every thread owns 16 complex points of the half-size FFT), sm_100a.  Same reference arithmetic as pv_kernel.cuh (one launch == one process() call,
 // ola-processor.js:159-171 + phase-vocoder.js:45-72), reorganised around one identity:
 //
 //   Both state rings are kept ALIGNED TO THE TIME CURSOR t (frame sample n lives at ring index
@@ -31,28 +31,42 @@
 
 namespace pvb {
 
-struct RingGeo {
-    static constexpr int N = 1024, M = 512, NB = 513;
-    static constexpr int EX_SLOTS = 65 * 7 + 64;            // 519 exchange slots of 16 bytes
-    static constexpr int XQ_SLOTS = 546;                    // bin k at k + (k >> 4); 545 = halo dummy
-    static constexpr int WARP_BYTES = XQ_SLOTS * 16;        // 8736 (>= 519 * 16)
+template <int N_>
+struct RingGeoT {
+    static constexpr int N = N_, M = N / 2, NB = M + 1;
+    static constexpr int TP = N / 32;                       // threads per channel pair (16 complex points each)
+    static constexpr int WPP = TP / 32;                     // warps per pair
+    static constexpr int R1 = M / 64;                       // radix of the first pass: 8 or 16
+    static constexpr int LR1 = (R1 == 8) ? 3 : 4;
+    static constexpr int NB1 = 16 / R1;                     // first-pass butterflies per thread
+    static constexpr int KS = M / 8;                        // stride between the outputs of a last-pass butterfly
+    static constexpr int SS = KS + KS / 16;                 // the same in spectrum slots
+    static constexpr int NJ = N / 128;                      // ring blocks of 128 samples
+    static constexpr int SM = M + M / 16;                   // slot of bin M
+    static constexpr int EX_SLOTS = 65 * (R1 - 1) + 64;     // exchange slots of 16 bytes: 65 k1 + 8 r + c
+    static constexpr int XQ_SLOTS = SM + 2;                 // bin k at k + (k >> 4); last slot = dump / halo dummy
+    static constexpr int SCR_BYTES = (WPP > 1) ? 4 * TP * 4 + 32 : 0;   // cross-warp key exchange of the region scan
+    static constexpr int PAIR_BYTES = XQ_SLOTS * 16 + SCR_BYTES;
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
-    static constexpr int DTAB_BYTES = 2592;                 // key table: int32, bin p at p + 4 (p >> 4), p <= 513
+    static constexpr int DTAB_BYTES = ((NB + 1 + 4 * ((NB >> 4) + 1)) * 4 + 15) & ~15;   // key table: bin p at p + 4 (p >> 4)
     static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
-    static constexpr int TW1_BYTES = 8 * TW1_ROW * 8;       // tw1[k1][n] = W_512^{n k1}, n < 64
+    static constexpr int TW1_BYTES = R1 * TW1_ROW * 8;      // tw1[k1][n] = W_M^{n k1}, n < 64
     static constexpr int W64_BYTES = 64 * 8;                // w64[a][b] = W_64^{a b}
-    static constexpr int TWH_BYTES = 520 * 8;               // twh[k] = W_1024^k, k <= 512
+    static constexpr int TWH_BYTES = (M + 8) * 8;           // twh[k] = W_N^k, k <= M
     static constexpr int GTAB_BYTES = TW1_BYTES + W64_BYTES + TWH_BYTES;    // copied verbatim from global
-    static constexpr int WIN_BYTES = 1024 * 4;              // window / synthesis window, rotated by t
+    static constexpr int WIN_BYTES = N * 4;                 // window / synthesis window, rotated by t
     static constexpr int OFF_TW1 = DTAB_BYTES;
     static constexpr int OFF_W64 = OFF_TW1 + TW1_BYTES;
     static constexpr int OFF_TWH = OFF_W64 + W64_BYTES;
     static constexpr int OFF_WIN = OFF_TWH + TWH_BYTES;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
-    static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;  // 18512
-    static constexpr int MAX_WARPS = 7;
+    static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;
+    static constexpr int MAX_PAIRS = (N == 1024) ? 7 : 3;   // pairs per CTA; two CTAs per SM
+    static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
+    static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
     static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin
 };
+using RingGeo = RingGeoT<1024>;
 
 struct RingParams {
     const float *in;            // [C][hop] or nullptr (paused input: zeros, ola:93-100)
@@ -67,7 +81,7 @@ struct RingParams {
     int tmod;                   // timeCursor mod N (multiple of hop)
     int stagger_ns;             // experiment: delay odd warps by this much before the first pass
     int skip;                   // experiment (PVB_SKIP, results become wrong): bit 0 the whole middle, bit 1 forward
-                                // and inverse pass 2, bit 2 split + unsplit stores / loads of the spectrum
+                                // and inverse pass 2
     int early;                  // which state loads may precede griddepcontrol.wait (0, 1, 2; see the kernel)
     // per-pair completion flags: done[pair] holds the sequence number of the last call of this handle
     // whose state / output for that pair is complete (release store at the end of every launch)
@@ -81,6 +95,52 @@ struct RingParams {
 
 __device__ __forceinline__ float4 pack4(cpx2 v) { return make_float4(v.re.x, v.re.y, v.im.x, v.im.y); }
 __device__ __forceinline__ cpx2 unpack4(float4 v) { return cpx2{make_float2(v.x, v.y), make_float2(v.z, v.w)}; }
+
+// barrier among the threads of one channel pair (a warp, or two warps on a named barrier)
+template <int TP>
+__device__ __forceinline__ void pair_sync(int pair_in_cta) {
+    if constexpr (TP == 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(pair_in_cta + 1), "n"(TP) : "memory");
+    }
+}
+
+#define PVB_COS_PI_8 0.92387953251128673848f
+#define PVB_SIN_PI_8 0.38268343236508978178f
+
+// in-register 16-point DFT, natural order in and out: one radix-2 DIF step with W16^n, two dft8
+template <bool INV>
+__device__ __forceinline__ void dft16(cpx2 (&x)[16]) {
+    constexpr float sg = INV ? 1.f : -1.f;                  // sign of the imaginary part of W16^n
+    cpx2 a[8], b[8];
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+        a[n] = cadd(x[n], x[n + 8]);
+        b[n] = csub(x[n], x[n + 8]);
+    }
+    b[1] = cmul_s(b[1], PVB_COS_PI_8, sg * PVB_SIN_PI_8);
+    b[2] = mul_w8_1<INV>(b[2]);
+    b[3] = cmul_s(b[3], PVB_SIN_PI_8, sg * PVB_COS_PI_8);
+    b[4] = mul_mj<INV>(b[4]);
+    b[5] = cmul_s(b[5], -PVB_SIN_PI_8, sg * PVB_COS_PI_8);
+    b[6] = mul_w8_3<INV>(b[6]);
+    b[7] = cmul_s(b[7], -PVB_COS_PI_8, sg * PVB_SIN_PI_8);
+    dft8<INV>(a);
+    dft8<INV>(b);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        x[2 * k] = a[k];
+        x[2 * k + 1] = b[k];
+    }
+}
+
+// R-point DFT of x[0..R) (R = 8 or 16)
+template <int R, bool INV>
+__device__ __forceinline__ void dft_r(cpx2 *x) {
+    if constexpr (R == 8) dft8<INV>(*reinterpret_cast<cpx2(*)[8]>(x));
+    else dft16<INV>(*reinterpret_cast<cpx2(*)[16]>(x));
+}
 
 // forward real-split of one (k, M-k) pair: 2 X[k] -> *dk, 2 X[M-k] -> *dm (both channels)
 __device__ __forceinline__ void ring_split(cpx2 za, cpx2 zb, float2 w, float4 *dk, float4 *dm) {
@@ -100,9 +160,9 @@ __device__ __forceinline__ void ring_unsplit(cpx2 yk, cpx2 ym, float2 w, cpx2 &z
     zmk = cpx2{add2(e_r, pp.im), sub2(pp.re, e_i)};
 }
 
-// one bin of the shifted spectrum (both channels) from the four planes of Y
+// one bin of the shifted spectrum (both channels) from the four planes of Y (PLW words per plane)
+template <int PLW>
 __device__ __forceinline__ cpx2 ring_load_planes(const unsigned char *mine, int slot) {
-    constexpr int PLW = RingGeo::XQ_SLOTS;                             // words per plane
     const float *y = reinterpret_cast<const float *>(mine) + slot;
     return cpx2{make_float2(y[0], y[PLW]), make_float2(y[2 * PLW], y[3 * PLW])};
 }
@@ -124,28 +184,16 @@ __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
 
 // Region of influence of every bin of the run, for one channel (pv:124-141): the owner of a bin
 // is the nearest peak, ties go to the higher one.  Peaks travel as KEYS (see the key table in
-// the kernel): high half = 2 * (peak + 2048), low half = delta + 32768.  Returns per bin the byte
-// offset of its destination word inside plane 0 of Y (dump slot when it falls outside [0, nb)),
-// with the sign bit set when the bin belongs to the LEFT half of its region while contracting:
-// those are added on top in the second sub-step, everything else is stored first (right halves are
-// pairwise disjoint after the shift, and so are left halves, for pitch factors >= 0.75).
+// the kernel): high half = 2 * (peak + 2048), low half = delta + 32768.  pkey / nkey: the nearest
+// peak below / above this thread's run.  Returns per bin the byte offset of its destination word
+// inside plane 0 of Y (dump slot when it falls outside [0, nb)), with the sign bit set when the bin
+// belongs to the LEFT half of its region while contracting: those are added on top in the second
+// sub-step, everything else is stored first (right halves are pairwise disjoint after the shift,
+// and so are left halves, for pitch factors >= 0.75).
 // The integer pipe runs at half rate, so this loop is written for the fewest ALU operations.
-__device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_t nz, const int (&rk)[16],
-                                                const int *krun, int second_flag, int (&dst)[16],
-                                                int &d_last) {
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int b0 = 16 * lane;
-    const int own_last = krun[(31 - __clz(mask)) & 15];              // keys of this lane's last / first peak
-    const int own_first = krun[(__ffs(mask) - 1) & 15];
-    const uint32_t below = nz & ((1u << lane) - 1u);
-    const uint32_t above = nz & ~((2u << lane) - 1u);
-    int pkey = __shfl_sync(FULL, own_last, (31 - __clz(below)) & 31);
-    int nkey = __shfl_sync(FULL, own_first, (__ffs(above) - 1) & 31);
-    if (!below) pkey = 0;                                            // "peak" at -2048: never the nearest
-    if (!above) nkey = (2 * 8190) << 16;                             // "peak" at +6142
-    const int lkey = __shfl_sync(FULL, own_last, (31 - __clz(nz)) & 31);
-    d_last = (lkey & 0xFFFF) - 32768;
-
+template <int DUMP>
+__device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey, int nkey, const int (&rk)[16],
+                                                int second_flag, int (&dst)[16]) {
     int nx[16];
 #pragma unroll
     for (int e = 15; e >= 0; e--) {
@@ -162,24 +210,26 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int lane, uint32_
         const bool take_next = tt < ((4 * e) << 16);
         const int okey = take_next ? nx[e] : pkey;
         const int d = (okey & 0xFFFF) + cb + e;
-        const unsigned slot = min(unsigned(d + (d >> 4)), 545u);     // d < 0 or d >= nb: dump slot
+        const unsigned slot = min(unsigned(d + (d >> 4)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
         dst[e] = int(4u * slot) | ((tt - ((4 * e) << 16)) & second_flag);
     }
 }
 
+// N = frame size (1024: one warp per pair, 2048: two warps per pair).
 // NBLK = hop / 128 and JB = ring 128-block that receives the new input block, as template
 // parameters (NBLK > 0), make the role of every ring block (history / new input / emitted head /
 // zero tail) a compile-time fact: no predicated duplicates of the global accesses.  NBLK == 0 is
 // the same kernel with both read from the parameters (launch-uniform branches).
-template <int NBLK, int JB>
-__global__ void __launch_bounds__(RingGeo::MAX_WARPS * 32, 2)
+template <int N, int NBLK, int JB>
+__global__ void __launch_bounds__(RingGeoT<N>::MAX_PAIRS * RingGeoT<N>::TP, 2)
 pv_process_ring_kernel(const RingParams p) {
-    using G = RingGeo;
-    constexpr int N = G::N, NB = G::NB;
+    using G = RingGeoT<N>;
+    constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int pair = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int tp = threadIdx.x % TP;                // thread within the pair
+    const int pin = threadIdx.x / TP;               // pair within the CTA
+    const int pair = blockIdx.x * (blockDim.x / TP) + pin;
     const bool live = 2 * pair < p.num_channels;
     const unsigned FULL = 0xFFFFFFFFu;
     int *ktab = reinterpret_cast<int *>(smem_raw);
@@ -188,7 +238,7 @@ pv_process_ring_kernel(const RingParams p) {
     const float2 *twh = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
     const float *swin = reinterpret_cast<const float *>(smem_raw + G::OFF_WIN);
     const float *swout = reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
-    unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(warp) * G::WARP_BYTES;
+    unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(pin) * G::PAIR_BYTES;
     float4 *ex = reinterpret_cast<float4 *>(mine);
     float4 *XQ = reinterpret_cast<float4 *>(mine);
 
@@ -197,22 +247,22 @@ pv_process_ring_kernel(const RingParams p) {
     const int hop = p.hop;
     const int t = p.tmod;
     const int nblk = NBLK ? NBLK : (hop >> 7);
-    const int jb = NBLK ? JB : (((t - hop + N) >> 7) & 7);    // ring 128-block that receives the new input block
-    const int je = (jb + nblk) & 7;                           // ring 128-block of frame sample 0 (emitted)
+    const int jb = NBLK ? JB : (((t - hop + N) >> 7) & (NJ - 1));   // ring 128-block that receives the new input block
+    const int je = (jb + nblk) & (NJ - 1);                          // ring 128-block of frame sample 0 (emitted)
 
     // Programmatic dependent launch: our CTAs may become resident while the previous kernel on the
     // stream drains.  Two ways to respect what earlier launches wrote:
     //  * flag mode (the host has checked that the caller's buffers do not alias those of recent
-    //    launches): dependents are released at once, every warp waits for ITS pair's completion
-    //    flag only, and the CTA waits for the previous grid at its very end, so that "this grid is
-    //    complete" still implies "everything before it is complete".  Calls of different handles, and
+    //    launches): dependents are released at once, every pair waits for ITS completion flag only,
+    //    and the CTA waits for the previous grid at its very end, so that "this grid is complete"
+    //    still implies "everything before it is complete".  Calls of different handles, and
     //    different pairs of one handle, then overlap freely: the load phase of one CTA runs under
     //    the compute phase of its SM neighbour.
     //  * grid mode: griddepcontrol.wait before the first dependent access; everything up to it
     //    touches only constant tables (and state that is provably older than the previous kernel).
     if (p.flag_mode) asm volatile("griddepcontrol.launch_dependents;");
-    // ---- CTA-shared tables: asynchronous 16-byte copies, fixed trip counts (CTAs have 4..7 warps;
-    // no division by blockDim) --------------------------------------------------------------------------
+    // ---- CTA-shared tables: asynchronous 16-byte copies, fixed trip counts (CTAs have at least
+    // MIN_THREADS threads; no division by blockDim) --------------------------------------------------
     {
         const int rot = (N - t) & (N - 1);
         const float4 *w1 = reinterpret_cast<const float4 *>(p.window2 + rot);
@@ -221,13 +271,13 @@ pv_process_ring_kernel(const RingParams p) {
         const unsigned s_win = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WIN));
         const unsigned s_wout = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WOUT));
 #pragma unroll
-        for (int k = 0; k < (G::GTAB_BYTES / 16 + 127) / 128; k++) {
+        for (int k = 0; k < (G::GTAB_BYTES / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
             if (i < G::GTAB_BYTES / 16)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_tab + 16 * i), "l"(p.gtab + i));
         }
 #pragma unroll
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < (N / 4 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
             if (i < N / 4) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_win + 16 * i), "l"(w1 + i));
@@ -240,7 +290,7 @@ pv_process_ring_kernel(const RingParams p) {
         const int pf_s = p.pf_shift;
         const long long half = 1ll << (pf_s - 1);
 #pragma unroll
-        for (int k = 0; k < (NB + 1 + 127) / 128; k++) {
+        for (int k = 0; k < (NB + 1 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int pk = threadIdx.x + k * blockDim.x;
             if (pk <= NB) {
                 const long long ps = (pf_m * pk + half) >> pf_s;
@@ -250,16 +300,17 @@ pv_process_ring_kernel(const RingParams p) {
         }
     }
     // ---- frame loads: all issued before anything consumes them ---------------------------------
-    // History written by launches OLDER than the kernel in front of us on the stream is already
-    // complete when our CTAs start (that kernel passed its own griddepcontrol.wait before it let us
-    // launch), so those loads are issued before our wait and overlap the previous launch's tail:
+    // Element e of a thread: first-pass butterfly h = e / R1, input j = e % R1, ring float4 index
+    // tp + 32 h + 64 j; it lies in ring 128-block j.  The new block is loaded as (ch0 pair, ch1 pair)
+    // and interleaved after the wait (moves must not sit between the loads).
+    // Grid mode only: history written by launches OLDER than the kernel in front of us on the stream
+    // is already complete when our CTAs start (that kernel passed its own griddepcontrol.wait before
+    // it let us launch), so those loads are issued before our wait:
     //   p.early == 2: none of this handle's state was written by the previous kernel -> all of hist
     //   p.early == 1: the previous kernel may be this handle's last call -> all but its newest block
-    //   p.early == 0: everything after the wait
     // The input block always waits (it belongs to the caller's stream order).
     float4 r[16];
-    float2 un0[NBLK ? 2 * NBLK : 1], un1[NBLK ? 2 * NBLK : 1];
-    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + lane;
+    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + tp;
     const int early = p.flag_mode ? 0 : p.early;
     if (p.flag_mode) {
         if (live) {
@@ -271,7 +322,7 @@ pv_process_ring_kernel(const RingParams p) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done + pair) : "memory");
                 if (int(v - p.wait_seq) >= 0) break;
                 if (++it > 200000) {
-                    if (lane == 0) atomicAdd(p.stuck, 1u);
+                    if (tp == 0) atomicAdd(p.stuck, 1u);
                     break;
                 }
                 __nanosleep(200);
@@ -281,15 +332,15 @@ pv_process_ring_kernel(const RingParams p) {
     } else if (live && early) {
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int h = e >> 3, j = e & 7;
-            const int jj = (j - jb) & 7;                              // launch-uniform
-            // jj < nblk: new input; jj >= 8 - nblk: the block the previous call wrote
-            if (jj >= nblk && (jj < 8 - nblk || early == 2)) r[e] = hl[32 * h + 64 * j];
+            const int h = e / R1, j = e % R1;
+            const int jj = (j - jb) & (NJ - 1);                       // launch-uniform
+            // jj < nblk: new input; jj >= NJ - nblk: the block the previous call wrote
+            if (jj >= nblk && (jj < NJ - nblk || early == 2)) r[e] = hl[32 * h + 64 * j];
         }
         if (early == 2) {
             // warm L2 with the overlap-add ring lines the tail of this kernel adds to
-            const int line = 16 * lane;                               // float4 index: 256 bytes per lane
-            if ((((line >> 6) - jb) & 7) >= nblk) {
+            const int line = 16 * tp;                                 // float4 index: 256 bytes per thread
+            if ((((line >> 6) - jb) & (NJ - 1)) >= nblk) {
                 const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
@@ -303,24 +354,19 @@ pv_process_ring_kernel(const RingParams p) {
         asm volatile("griddepcontrol.launch_dependents;");
     }
     if (live) {
-        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * lane : nullptr;
+        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * tp : nullptr;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int h = e >> 3, j = e & 7;
-            const int jj = (j - jb) & 7;                              // launch-uniform
+            const int h = e / R1, j = e % R1;
+            const int jj = (j - jb) & (NJ - 1);                       // launch-uniform
             if (jj < nblk) {
                 float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
                 if (i0) {
                     u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * jj));
                     if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * jj));
                 }
-                if constexpr (NBLK > 0) {
-                    un0[h * NBLK + jj] = u0;                          // packed after the barrier: the moves
-                    un1[h * NBLK + jj] = u1;                          // must not sit between the loads
-                } else {
-                    r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
-                }
-            } else if (!(early && (jj < 8 - nblk || early == 2))) {
+                r[e] = make_float4(u0.x, u0.y, u1.x, u1.y);           // interleaved below
+            } else if (!(early && (jj < NJ - nblk || early == 2))) {
                 r[e] = hl[32 * h + 64 * j];
             }
         }
@@ -329,52 +375,48 @@ pv_process_ring_kernel(const RingParams p) {
     __syncthreads();
     if (!live) return;          // no CTA-wide barriers below
 
-    if (p.stagger_ns > 0 && (warp & 1)) __nanosleep(unsigned(p.stagger_ns));
+    if (p.stagger_ns > 0 && (pin & 1)) __nanosleep(unsigned(p.stagger_ns));
     // the new block joins the history ring (ola:105)
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int h = e >> 3, j = e & 7;
-        const int jj = (j - jb) & 7;
-        if (jj < nblk) {
-            if constexpr (NBLK > 0) {
-                const float2 u0 = un0[h * NBLK + jj], u1 = un1[h * NBLK + jj];
-                r[e] = make_float4(u0.x, u1.x, u0.y, u1.y);
-            }
+        const int h = e / R1, j = e % R1;
+        if (((j - jb) & (NJ - 1)) < nblk) {
+            r[e] = make_float4(r[e].x, r[e].z, r[e].y, r[e].w);       // (ch0[i], ch1[i], ch0[i+1], ch1[i+1])
             hl[32 * h + 64 * j] = r[e];
         }
     }
 
-    // ---- Hann window (pv:55) + forward pass 1: butterflies n = lane + 32 h over j (stride 64) ---
+    // ---- Hann window (pv:55) + forward pass 1: butterflies n = tp (+ 32) over j (stride 64) -----
     {
-        const float *wl = swin + 2 * lane;
+        const float *wl = swin + 2 * tp;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int nl = lane + 32 * h;
-            cpx2 x[8];
+        for (int h = 0; h < G::NB1; h++) {
+            const int nl = tp + 32 * h;
+            cpx2 x[R1];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < R1; j++) {
                 const float2 w = *reinterpret_cast<const float2 *>(wl + 64 * h + 128 * j);
-                const float4 v = r[8 * h + j];
+                const float4 v = r[R1 * h + j];
                 x[j].re = mul2(make_float2(v.x, v.y), bc2(w.x));
                 x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
             }
-            dft8<false>(x);
+            dft_r<R1, false>(x);
 #pragma unroll
-            for (int k1 = 1; k1 < 8; k1++) {
-                const float2 w = tw1[G::TW1_ROW * k1 + nl];           // W_512^{n k1}
+            for (int k1 = 1; k1 < R1; k1++) {
+                const float2 w = tw1[G::TW1_ROW * k1 + nl];           // W_M^{n k1}
                 x[k1] = cmul_s(x[k1], w.x, w.y);
             }
 #pragma unroll
-            for (int k1 = 0; k1 < 8; k1++) ex[65 * k1 + nl] = pack4(x[k1]);
+            for (int k1 = 0; k1 < R1; k1++) ex[65 * k1 + nl] = pack4(x[k1]);
         }
     }
-    __syncwarp();
+    pair_sync<TP>(pin);
 
     // warm L2 with the overlap-add ring lines the tail of this kernel adds to (the slot that is
     // only written, ring [t - hop, t), is skipped)
     {
-        const int line = 16 * lane;                                   // float4 index: 256 bytes per lane
-        if (early != 2 && (((line >> 6) - jb) & 7) >= nblk) {
+        const int line = 16 * tp;                                     // float4 index: 256 bytes per thread
+        if (early != 2 && (((line >> 6) - jb) & (NJ - 1)) >= nblk) {
             const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
@@ -382,14 +424,14 @@ pv_process_ring_kernel(const RingParams p) {
     }
 
     // ---- forward pass 2: butterflies (k1, m3) over m2, in place -----------------------------------
-    const int m3l = lane & 7;
+    const int m3l = tp & 7;
     if (!(p.skip & 2)) {
         float2 w2[8];
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            float4 *bp = ex + 65 * ((lane >> 3) + 4 * h) + m3l;
+            float4 *bp = ex + 65 * ((tp >> 3) + (R1 / 2) * h) + m3l;
             cpx2 x[8];
 #pragma unroll
             for (int m2 = 0; m2 < 8; m2++) x[m2] = unpack4(bp[8 * m2]);
@@ -400,61 +442,61 @@ pv_process_ring_kernel(const RingParams p) {
             for (int k2 = 0; k2 < 8; k2++) bp[8 * k2] = pack4(x[k2]);
         }
     }
-    __syncwarp();
+    pair_sync<TP>(pin);
 
-    // ---- forward pass 3: butterflies A (bins lane + 64 j) and B (bins 64 - lane + 64 j) ------------
-    // lane 0 owns the two self-paired butterflies: A = bins 64 j, B = bins 32 + 64 j
-    const bool l0 = lane == 0;
-    const int kB = l0 ? 32 : 64 - lane;
-    const int exA = 65 * (lane & 7) + 8 * (lane >> 3);
-    const int exB = 65 * (kB & 7) + 8 * (kB >> 3);
+    // ---- forward pass 3: butterflies A (bins tp + KS j) and B (bins KS - tp + KS j) ----------------
+    // thread 0 owns the two self-paired butterflies: A = bins KS j, B = bins KS/2 + KS j
+    const bool l0 = tp == 0;
+    const int kB = l0 ? KS / 2 : KS - tp;
+    const int exA = 65 * (tp & (R1 - 1)) + 8 * (tp >> G::LR1);
+    const int exB = 65 * (kB & (R1 - 1)) + 8 * (kB >> G::LR1);
     cpx2 a[8], b[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         a[c] = unpack4(ex[exA + c]);
         b[c] = unpack4(ex[exB + c]);
     }
-    dft8<false>(a);      // a[j] = Z[lane + 64 j]
-    dft8<false>(b);      // b[j] = Z[kB + 64 j]
-    __syncwarp();        // everyone has read the exchange slots: X may overwrite them
+    dft8<false>(a);      // a[j] = Z[tp + KS j]
+    dft8<false>(b);      // b[j] = Z[kB + KS j]
+    pair_sync<TP>(pin);  // everyone has read the exchange slots: X may overwrite them
 
     // ---- real split in registers -> XQ (2x scaled) --------------------------------------------------
-    // slot j pairs (a[j], b[7-j]) at k = lane + 64 j.  lane 0: j < 4: (b[j], b[7-j]) at k = 32 + 64 j;
-    // j >= 4: (a[j-4], a[(12-j)&7]) at k = 64 (j-4); plus the self pair k = 256 (a[4]).
-    const int gA = lane + (lane >> 4);                                // slot of bin lane
-    const int gB = 544 - lane - ((lane + 15) >> 4);                   // slot of bin 512 - lane
-    const int sAlo = l0 ? 34 : gA, sAhi = l0 ? -272 : gA;
-    const int sBlo = l0 ? 510 : gB, sBhi = l0 ? 816 : gB;
-    const int tlo = l0 ? 32 : lane, thi = l0 ? -256 : lane;
+    // slot j pairs (a[j], b[7-j]) at k = tp + KS j.  thread 0: j < 4: (b[j], b[7-j]) at k = KS/2 + KS j;
+    // j >= 4: (a[j-4], a[(12-j)&7]) at k = KS (j-4); plus the self pair k = M/2 (a[4]).
+    const int gA = tp + (tp >> 4);                                    // slot of bin tp
+    const int gB = G::SM - tp - ((tp + 15) >> 4);                     // slot of bin M - tp
+    const int sAlo = l0 ? KS / 2 + KS / 32 : gA, sAhi = l0 ? -4 * SS : gA;
+    const int sBlo = l0 ? G::SM - KS / 2 - KS / 32 : gB, sBhi = l0 ? G::SM + 4 * SS : gB;
+    const int tlo = l0 ? KS / 2 : tp, thi = l0 ? -4 * KS : tp;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const cpx2 za = sel(l0, b[j], a[j]);
-        ring_split(za, b[7 - j], twh[tlo + 64 * j], XQ + sAlo + 68 * j, XQ + sBlo - 68 * j);
+        ring_split(za, b[7 - j], twh[tlo + KS * j], XQ + sAlo + SS * j, XQ + sBlo - SS * j);
     }
 #pragma unroll
     for (int j = 4; j < 8; j++) {
         const cpx2 za = sel(l0, a[j - 4], a[j]);
         const cpx2 zb = sel(l0, a[(12 - j) & 7], b[7 - j]);
-        ring_split(za, zb, twh[thi + 64 * j], XQ + sAhi + 68 * j, XQ + sBhi - 68 * j);
+        ring_split(za, zb, twh[thi + KS * j], XQ + sAhi + SS * j, XQ + sBhi - SS * j);
     }
-    if (l0) ring_split(a[4], a[4], twh[256], XQ + 272, XQ + 272);
-    __syncwarp();
+    if (l0) ring_split(a[4], a[4], twh[M / 2], XQ + M / 2 + M / 32, XQ + M / 2 + M / 32);
+    pair_sync<TP>(pin);
 
     // ---- peaks, regions of influence, shift (pv:95-173) -------------------------------------------------
-    if (!(p.skip & 1))
     // X lives in float4 slots (both channels per bin); the shifted spectrum Y is written over it as
     // four planes of floats (re0 | re1 | im0 | im1, bin d at word d + (d >> 4)): the 32-bit scatter of
-    // lanes that own runs 16 bins apart then spreads over all banks.
+    // threads that own runs 16 bins apart then spreads over all banks.
+    if (!(p.skip & 1))
     {
         const bool contract = p.pitch_factor < 1.0f;
-        const float4 *runp = XQ + 17 * lane;                          // slot of bin 16 lane
+        const float4 *runp = XQ + 17 * tp;                            // slot of bin 16 tp
         uint32_t mask0, mask1;
         {
-            const float4 *hlo = lane ? runp - 3 : XQ;                 // bins 16 lane - 2, - 1 (lane 0: unused)
+            const float4 *hlo = tp ? runp - 3 : XQ;                   // bins 16 tp - 2, - 1 (thread 0: unused)
             int m0[20], m1[20];
 #pragma unroll
             for (int i = 0; i < 20; i++) {
-                const float4 v = (i < 2) ? hlo[i] : (i < 18) ? runp[i - 2] : runp[i - 1];   // i >= 18: bins 16 lane + 16, + 17 (slot 16 is padding)
+                const float4 v = (i < 2) ? hlo[i] : (i < 18) ? runp[i - 2] : runp[i - 1];   // i >= 18: bins 16 tp + 16, + 17 (slot 16 is padding)
                 const float2 re = make_float2(v.x, v.y), im = make_float2(v.z, v.w);
                 const float2 mg = fma2(re, re, mul2(im, im));         // pv:82-92, float32
                 m0[i] = __float_as_int(mg.x);
@@ -462,46 +504,87 @@ pv_process_ring_kernel(const RingParams p) {
             }
             mask0 = ring_peak_mask(m0);
             mask1 = ring_peak_mask(m1);
-            if (lane == 0) { mask0 &= ~3u; mask1 &= ~3u; }            // i >= 2
-            if (lane == 31) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); }     // i <= nb - 3
+            if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; }              // i >= 2
+            if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); }       // i <= nb - 3
         }
-        const uint32_t nz0 = __ballot_sync(FULL, mask0 != 0);
-        const uint32_t nz1 = __ballot_sync(FULL, mask1 != 0);
 
         int dst0[16], dst1[16];
         int dl0 = 0, dl1 = 0;
+        bool any0, any1;
         {
-            const int *krun = ktab + 20 * lane;                       // keys of bins 16 lane .. + 15
+            const int *krun = ktab + 20 * tp;                         // keys of bins 16 tp .. + 15
             int rk[16];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int4 kv = *reinterpret_cast<const int4 *>(krun + 4 * i);
                 rk[4 * i] = kv.x; rk[4 * i + 1] = kv.y; rk[4 * i + 2] = kv.z; rk[4 * i + 3] = kv.w;
             }
+            // keys of the nearest peaks below / above this thread's run, and of the last peak
+            const int ol0 = krun[(31 - __clz(mask0)) & 15], of0 = krun[(__ffs(mask0) - 1) & 15];
+            const int ol1 = krun[(31 - __clz(mask1)) & 15], of1 = krun[(__ffs(mask1) - 1) & 15];
+            int pk0, nk0, lk0, pk1, nk1, lk1;
+            const int none_above = (2 * 8190) << 16;                  // "peak" at +6142; below: key 0 = "peak" at -2048
+            if constexpr (TP == 32) {
+                const uint32_t nz0 = __ballot_sync(FULL, mask0 != 0), nz1 = __ballot_sync(FULL, mask1 != 0);
+                const uint32_t lt = (1u << tp) - 1u, gt = ~((2u << tp) - 1u);
+                pk0 = __shfl_sync(FULL, ol0, (31 - __clz(nz0 & lt)) & 31);
+                nk0 = __shfl_sync(FULL, of0, (__ffs(nz0 & gt) - 1) & 31);
+                lk0 = __shfl_sync(FULL, ol0, (31 - __clz(nz0)) & 31);
+                pk1 = __shfl_sync(FULL, ol1, (31 - __clz(nz1 & lt)) & 31);
+                nk1 = __shfl_sync(FULL, of1, (__ffs(nz1 & gt) - 1) & 31);
+                lk1 = __shfl_sync(FULL, ol1, (31 - __clz(nz1)) & 31);
+                if (!(nz0 & lt)) pk0 = 0;
+                if (!(nz0 & gt)) nk0 = none_above;
+                if (!(nz1 & lt)) pk1 = 0;
+                if (!(nz1 & gt)) nk1 = none_above;
+                any0 = nz0 != 0;
+                any1 = nz1 != 0;
+            } else {
+                // two warps per pair: exchange through the pair's scratch area
+                int *scr = reinterpret_cast<int *>(mine + G::XQ_SLOTS * 16);      // [4][TP] keys, [4] ballots
+                scr[tp] = ol0; scr[TP + tp] = of0; scr[2 * TP + tp] = ol1; scr[3 * TP + tp] = of1;
+                const uint32_t bl0 = __ballot_sync(FULL, mask0 != 0), bl1 = __ballot_sync(FULL, mask1 != 0);
+                if (lane == 0) { scr[4 * TP + (tp >> 5)] = int(bl0); scr[4 * TP + 2 + (tp >> 5)] = int(bl1); }
+                pair_sync<TP>(pin);
+                const unsigned long long nz0 = (unsigned long long)uint32_t(scr[4 * TP]) | ((unsigned long long)uint32_t(scr[4 * TP + 1]) << 32);
+                const unsigned long long nz1 = (unsigned long long)uint32_t(scr[4 * TP + 2]) | ((unsigned long long)uint32_t(scr[4 * TP + 3]) << 32);
+                const unsigned long long lt = (1ull << tp) - 1ull, gt = ~((2ull << tp) - 1ull);
+                pk0 = (nz0 & lt) ? scr[63 - __clzll((long long)(nz0 & lt))] : 0;
+                nk0 = (nz0 & gt) ? scr[TP + __ffsll((long long)(nz0 & gt)) - 1] : none_above;
+                lk0 = scr[(63 - __clzll((long long)nz0)) & 63];
+                pk1 = (nz1 & lt) ? scr[2 * TP + 63 - __clzll((long long)(nz1 & lt))] : 0;
+                nk1 = (nz1 & gt) ? scr[3 * TP + __ffsll((long long)(nz1 & gt)) - 1] : none_above;
+                lk1 = scr[2 * TP + ((63 - __clzll((long long)nz1)) & 63)];
+                any0 = nz0 != 0;
+                any1 = nz1 != 0;
+            }
+            dl0 = (lk0 & 0xFFFF) - 32768;
+            dl1 = (lk1 & 0xFFFF) - 32768;
             // both scans run unconditionally (a channel without peaks ends up with every bin on the
             // dump slot): two independent instruction streams the scheduler can interleave
             const int second_flag = contract ? int(0x80000000u) : 0;
-            ring_owner_scan(mask0, lane, nz0, rk, krun, second_flag, dst0, dl0);
-            ring_owner_scan(mask1, lane, nz1, rk, krun, second_flag, dst1, dl1);
+            ring_owner_scan<G::XQ_SLOTS - 1>(mask0, 16 * tp, pk0, nk0, rk, second_flag, dst0);
+            ring_owner_scan<G::XQ_SLOTS - 1>(mask1, 16 * tp, pk1, nk1, rk, second_flag, dst1);
         }
 
-        // sources into registers: own run, bin 512 and the first stale level (what _realTransform4
-        // leaves in slots N/2 + q, bundle:394-438, rebuilt from the valid half); bins 512 + lane + 32 i
+        // sources into registers: own run, bin M and the first stale level (what _realTransform4
+        // leaves in slots N/2 + q, bundle:394-438, rebuilt from the valid half); bins M + tp + TP i
         float4 xv[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) xv[e] = runp[e];
         float4 ext[4];
         ext[0] = ext[1] = ext[2] = ext[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (l0) ext[0] = XQ[544];
+        if (l0) ext[0] = XQ[G::SM];
         if (contract) {
+            constexpr int QO = N / 4 + N / 64;                        // slots between bins k and k + N/4
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int q = lane + 32 * i;
+                const int q = tp + TP * i;
                 const int qq = q ? q : 1;
                 const int sq = qq + (qq >> 4);                        // slot of bin q
-                const int sm = 544 - qq - ((qq + 15) >> 4);           // slot of bin 512 - q
-                const cpx2 A = unpack4(XQ[sq]), Bv = unpack4(XQ[sq + 272]);        // bins q, 256 + q
-                const cpx2 Cv = unpack4(XQ[sm]), D = unpack4(XQ[sm - 272]);        // bins 512 - q, 256 - q
+                const int sm = G::SM - qq - ((qq + 15) >> 4);         // slot of bin M - q
+                const cpx2 A = unpack4(XQ[sq]), Bv = unpack4(XQ[sq + QO]);         // bins q, N/4 + q
+                const cpx2 Cv = unpack4(XQ[sm]), D = unpack4(XQ[sm - QO]);         // bins M - q, N/4 - q
                 const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, D.re));
                 const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, D.im));
                 const float2 w = twh[2 * qq];
@@ -509,13 +592,13 @@ pv_process_ring_kernel(const RingParams p) {
                 if (q) ext[i] = pack4(sv);
             }
         }
-        __syncwarp();            // every lane holds its sources: the buffer becomes Y
+        pair_sync<TP>(pin);      // every thread holds its sources: the buffer becomes Y
 #pragma unroll
-        for (int i = 0; i < 17; i++) XQ[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < 2) XQ[544 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
+        for (int i = 0; i < 17; i++) XQ[tp + TP * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tp < 2) XQ[17 * TP + tp] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pair_sync<TP>(pin);
 
-        constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane (546 words)
+        constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane
         // first sub-step: plain stores (pairwise disjoint destinations)
 #pragma unroll
         for (int e = 0; e < 16; e++) {
@@ -528,20 +611,20 @@ pv_process_ring_kernel(const RingParams p) {
                 *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = xv[e].w;
             }
         }
-        if (nz0) {
+        if (any0) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int d = 512 + lane + 32 * i + dl0;
+                const int d = M + tp + TP * i + dl0;
                 if (unsigned(d) < unsigned(NB)) {
                     *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4))) = ext[i].x;
                     *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + 2 * PL) = ext[i].z;
                 }
             }
         }
-        if (nz1) {
+        if (any1) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int d = 512 + lane + 32 * i + dl1;
+                const int d = M + tp + TP * i + dl1;
                 if (unsigned(d) < unsigned(NB)) {
                     *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + PL) = ext[i].y;
                     *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + 3 * PL) = ext[i].w;
@@ -551,7 +634,7 @@ pv_process_ring_kernel(const RingParams p) {
         if (contract) {
             // second sub-step: left halves add on top (pairwise disjoint among themselves, so the
             // loads of a batch can all be issued before the first store)
-            __syncwarp();
+            pair_sync<TP>(pin);
             unsigned char *mine2 = mine + 0x80000000u;                // cancels the flag bit of dst
 #pragma unroll
             for (int g = 0; g < 2; g++) {
@@ -578,32 +661,32 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
-    __syncwarp();
+    pair_sync<TP>(pin);
 
     // ---- Hermitian C2R pre-pass in registers (mirror of the split) -------------------------------------
     {
         cpx2 zk[8], zmk[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int sa = (j < 4 ? sAlo : sAhi) + 68 * j, sb = (j < 4 ? sBlo : sBhi) - 68 * j;
-            cpx2 yk = ring_load_planes(mine, sa), ym = ring_load_planes(mine, sb);
-            if (j == 4) {                        // lane 0: k == 0, bins 0 and N/2 enter with their real part only
+            const int sa = (j < 4 ? sAlo : sAhi) + SS * j, sb = (j < 4 ? sBlo : sBhi) - SS * j;
+            cpx2 yk = ring_load_planes<G::XQ_SLOTS>(mine, sa), ym = ring_load_planes<G::XQ_SLOTS>(mine, sb);
+            if (j == 4) {                        // thread 0: k == 0, bins 0 and N/2 enter with their real part only
                 yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
                 ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
             }
-            const float2 w = twh[(j < 4 ? tlo : thi) + 64 * j];
+            const float2 w = twh[(j < 4 ? tlo : thi) + KS * j];
             ring_unsplit(yk, ym, w, zk[j], zmk[j]);
         }
-        cpx2 z256, dummy;
+        cpx2 zh, dummy;
         {
-            const cpx2 y = ring_load_planes(mine, 272);
-            ring_unsplit(y, y, twh[256], z256, dummy);
+            const cpx2 y = ring_load_planes<G::XQ_SLOTS>(mine, M / 2 + M / 32);
+            ring_unsplit(y, y, twh[M / 2], zh, dummy);
         }
         a[0] = sel(l0, zk[4], zk[0]);
         a[1] = sel(l0, zk[5], zk[1]);
         a[2] = sel(l0, zk[6], zk[2]);
         a[3] = sel(l0, zk[7], zk[3]);
-        a[4] = sel(l0, z256, zk[4]);
+        a[4] = sel(l0, zh, zk[4]);
         a[5] = sel(l0, zmk[7], zk[5]);
         a[6] = sel(l0, zmk[6], zk[6]);
         a[7] = sel(l0, zmk[5], zk[7]);
@@ -616,13 +699,13 @@ pv_process_ring_kernel(const RingParams p) {
         b[6] = zmk[1];
         b[7] = zmk[0];
     }
-    __syncwarp();        // everyone has read Y: the exchange slots may overwrite it
+    pair_sync<TP>(pin);  // everyone has read Y: the exchange slots may overwrite it
 
     // ---- inverse pass 1 (DIT): butterflies A and B over k3, twiddle conj(W_64^{k2 m3}) -------------------
     dft8<true>(a);
     dft8<true>(b);
     {
-        const int k2a = lane >> 3, k2b = kB >> 3;
+        const int k2a = tp >> G::LR1, k2b = kB >> G::LR1;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             cpx2 va = a[c], vb = b[c];
@@ -636,24 +719,24 @@ pv_process_ring_kernel(const RingParams p) {
             ex[exB + c] = pack4(vb);
         }
     }
-    __syncwarp();
+    pair_sync<TP>(pin);
 
     // accumulator values (L2 hits thanks to the prefetch) are requested before the last exchange so
     // that their latency hides behind inverse pass 2; the tail slot starts from zero (ola:134)
-    float4 *al = p.acc2 + size_t(pair) * (N / 2) + lane;
+    float4 *al = p.acc2 + size_t(pair) * (N / 2) + tp;
     float4 q[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int h = e >> 3, j = e & 7;
+        const int h = e / R1, j = e % R1;
         q[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (((j - jb) & 7) >= nblk) q[e] = al[32 * h + 64 * j];
+        if (((j - jb) & (NJ - 1)) >= nblk) q[e] = al[32 * h + 64 * j];
     }
 
-    // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_512^{k1 (m3 + 8 m2)}) ---------------
+    // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_M^{k1 (m3 + 8 m2)}) -----------------
     if (!(p.skip & 2))
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        const int k1 = (lane >> 3) + 4 * h;
+        const int k1 = (tp >> 3) + (R1 / 2) * h;
         float4 *bp = ex + 65 * k1 + m3l;
         const float2 *twp = tw1 + G::TW1_ROW * k1 + m3l;
         cpx2 x[8];
@@ -666,28 +749,28 @@ pv_process_ring_kernel(const RingParams p) {
             bp[8 * m2] = pack4(cmul_s(x[m2], w.x, -w.y));
         }
     }
-    __syncwarp();
+    pair_sync<TP>(pin);
 
     // ---- inverse pass 3: butterflies n over k1 -> ring samples; window, overlap-add, emit ------------------
     {
-        float *o0 = p.out + size_t(c0) * hop + 2 * lane;
-        const float *wol = swout + 2 * lane;
+        float *o0 = p.out + size_t(c0) * hop + 2 * tp;
+        const float *wol = swout + 2 * tp;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int nl = lane + 32 * h;
-            cpx2 x[8];
+        for (int h = 0; h < G::NB1; h++) {
+            const int nl = tp + 32 * h;
+            cpx2 x[R1];
 #pragma unroll
-            for (int k1 = 0; k1 < 8; k1++) x[k1] = unpack4(ex[65 * k1 + nl]);
-            dft8<true>(x);
+            for (int k1 = 0; k1 < R1; k1++) x[k1] = unpack4(ex[65 * k1 + nl]);
+            dft_r<R1, true>(x);
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < R1; j++) {
                 // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the division
                 // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
                 const float2 wo = *reinterpret_cast<const float2 *>(wol + 64 * h + 128 * j);
-                const float4 qv = q[8 * h + j];
+                const float4 qv = q[R1 * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
-                const int jj = (j - je) & 7;
+                const int jj = (j - je) & (NJ - 1);
                 if (jj < nblk) {                                      // head: emit (ola:111-118)
                     *reinterpret_cast<float2 *>(o0 + 64 * h + 128 * jj) = make_float2(y0.x, y1.x);
                     if (has1) *reinterpret_cast<float2 *>(o0 + hop + 64 * h + 128 * jj) = make_float2(y0.y, y1.y);
@@ -699,8 +782,8 @@ pv_process_ring_kernel(const RingParams p) {
     }
     // release: state and output of this pair are complete for call my_seq
     __threadfence();
-    __syncwarp();
-    if (lane == 0)
+    pair_sync<TP>(pin);
+    if (tp == 0)
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done + pair), "r"(p.my_seq) : "memory");
     // flag mode skipped the wait at the top: take it here, where the previous grid is long gone, so
     // that completion stays transitive along the stream
@@ -708,15 +791,16 @@ pv_process_ring_kernel(const RingParams p) {
 }
 
 // tables the ring-order kernel copies into shared memory: tw1[k1][n] (rows of TW1_ROW), w64[a][b], twh[k]
-inline void ring_host_tables(const float2 *tw /* [1024] W_1024^j */, float2 *out /* GTAB_BYTES / 8 */) {
-    using G = RingGeo;
+template <int N>
+inline void ring_host_tables(const float2 *tw /* [N] W_N^j */, float2 *out /* GTAB_BYTES / 8 */) {
+    using G = RingGeoT<N>;
     float2 *tw1 = out, *w64 = out + G::TW1_BYTES / 8, *twh = w64 + G::W64_BYTES / 8;
     for (int i = 0; i < G::GTAB_BYTES / 8; i++) out[i] = make_float2(0.f, 0.f);
-    for (int k1 = 0; k1 < 8; k1++)
-        for (int n = 0; n < 64; n++) tw1[G::TW1_ROW * k1 + n] = tw[(2 * n * k1) & 1023];
+    for (int k1 = 0; k1 < G::R1; k1++)
+        for (int n = 0; n < 64; n++) tw1[G::TW1_ROW * k1 + n] = tw[(2 * n * k1) & (N - 1)];    // W_M^{n k1}
     for (int a = 0; a < 8; a++)
-        for (int b = 0; b < 8; b++) w64[8 * a + b] = tw[(16 * a * b) & 1023];
-    for (int k = 0; k <= 512; k++) twh[k] = tw[k];
+        for (int b = 0; b < 8; b++) w64[8 * a + b] = tw[((N / 64) * a * b) & (N - 1)];
+    for (int k = 0; k <= G::M; k++) twh[k] = tw[k];
 }
 
 // planar [C'][N] rings (pv_kernel.cuh conventions: frame sample n at hist[(n + rb + hop) mod N],

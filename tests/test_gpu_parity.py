@@ -87,11 +87,14 @@ def test_parity_hop128_warp_kernel(oracle):
 
 @pytest.mark.parametrize("N", [256, 512, 2048, 4096])
 @pytest.mark.parametrize("pf", [0.75, 0.9, 1.0, 1.3, 2.5])
-@pytest.mark.parametrize("force_generic", ["0", "1"])
+@pytest.mark.parametrize("force_generic", ["0", "1", "cta"])
 def test_parity_other_frame_sizes_both_kernels(oracle, monkeypatch, N, pf, force_generic):
-    """frame sizes other than 1024: the CTA kernel with the in-place shift (pitch factors in
-    [0.75, 64]) and the fully generic kernel must both match the oracle."""
-    monkeypatch.setenv("PVB_FORCE_GENERIC", force_generic)
+    """frame sizes other than 1024: the default kernel (ring-order at 2048, CTA kernel with the
+    in-place shift elsewhere; pitch factors in [0.75, 64]), the CTA kernel everywhere
+    (PVB_KERNEL_1024=3) and the fully generic kernel must all match the oracle."""
+    monkeypatch.setenv("PVB_FORCE_GENERIC", "1" if force_generic == "1" else "0")
+    if force_generic == "cta":
+        monkeypatch.setenv("PVB_KERNEL_1024", "3")
     hop = N // 4
     x, ref, got = _run_both(oracle, N, hop, 5, np.float32(pf), 13)
     err = _rms(got - ref)
@@ -134,6 +137,26 @@ def test_parity_ring_kernel_hops(oracle, hop, pf):
     err = _rms(got - ref)
     print(f"hop={hop} pf={pf}: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("hop", [128, 256, 512, 1024])
+@pytest.mark.parametrize("pf", [0.75, 0.8, 1.0, 1.3, 2.0])
+def test_parity_ring_kernel_2048(oracle, hop, pf):
+    """frame 2048 (the reference's own size): two warps per pair, radix-16 first pass"""
+    from phaze_b200 import BatchedPhaseVocoder
+    with BatchedPhaseVocoder(5, 2048, hop) as pv:
+        assert "ring" in pv.kernel_name(np.float32(pf))
+    calls = 2 * (2048 // hop) + 5
+    x, ref, got = _run_both(oracle, 2048, hop, 5, np.float32(pf), calls)
+    err = _rms(got - ref)
+    print(f"N=2048 hop={hop} pf={pf}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+def test_parity_ring_kernel_2048_many_channels(oracle):
+    x, ref, got = _run_both(oracle, 2048, 512, 23, np.float32(0.8), 9)
+    per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
+    assert per_channel.max() <= RMS_EXPECTED
 
 
 def test_parity_ring_kernel_many_channels(oracle):

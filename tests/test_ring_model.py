@@ -14,16 +14,18 @@ def _rms(a):
     return float(np.sqrt(np.mean(np.square(a.astype(np.float64)))))
 
 
-@pytest.mark.parametrize("hop,pf,calls,start", [
-    (256, 0.8, 10, 0), (256, 1.2, 9, 0), (256, 1.25, 9, 3), (128, 0.75, 20, 5),
-    (512, 1.5, 6, 1), (256, 1.0, 9, 0), (256, 3.0, 8, 2),
+@pytest.mark.parametrize("frame,hop,pf,calls,start", [
+    (1024, 256, 0.8, 10, 0), (1024, 256, 1.2, 9, 0), (1024, 256, 1.25, 9, 3), (1024, 128, 0.75, 20, 5),
+    (1024, 512, 1.5, 6, 1), (1024, 256, 1.0, 9, 0), (1024, 256, 3.0, 8, 2),
+    (2048, 512, 1.5, 7, 0), (2048, 512, 0.8, 7, 2), (2048, 128, 0.8, 20, 3), (2048, 128, 1.2, 18, 0),
+    (2048, 1024, 2.0, 4, 1),
 ])
-def test_model_matches_oracle(oracle, hop, pf, calls, start):
+def test_model_matches_oracle(oracle, frame, hop, pf, calls, start):
     x = signals.channels(11, 2, calls * hop)
-    ref_p = oracle.OracleProcessor(1024, hop, 2)
+    ref_p = oracle.OracleProcessor(frame, hop, 2)
     ref_p.time_cursor = start * hop
     ref = ref_p.run(x, np.float32(pf))
-    got = model.run(x, pf, hop, start_calls=start)
+    got = model.run(x, pf, hop, start_calls=start, frame=frame)
     assert _rms(ref) > 1e-2
     assert _rms(got - ref) <= 2e-8
 
@@ -34,6 +36,7 @@ def test_model_shared_memory_patterns_are_conflict_free(oracle):
     cf = model.Conflicts()
     x = signals.channels(0, 2, 6 * 256)
     model.run(x, 0.8, 256, cf)
+    model.run(signals.channels(0, 2, 5 * 512), 0.8, 512, cf, frame=2048)
     for name in ("p1_st", "p2_ld", "p3_ldA", "p3_ldB", "run_ld", "stale_ld"):
         assert cf.worst[name] == 1.0, (name, cf.worst)
     assert max(cf.worst.values()) <= 2.0, cf.worst
