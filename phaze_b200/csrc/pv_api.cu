@@ -229,6 +229,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         PVB_RING_ATTR(1024, 0, 0) PVB_RING_ATTR(1024, 2, 0) PVB_RING_ATTR(1024, 2, 2)
         PVB_RING_ATTR(1024, 2, 4) PVB_RING_ATTR(1024, 2, 6) PVB_RING_ATTR(2048, 0, 0)
+        PVB_RING_ATTR(2048, 4, 0) PVB_RING_ATTR(2048, 4, 4) PVB_RING_ATTR(2048, 4, 8) PVB_RING_ATTR(2048, 4, 12)
 #undef PVB_RING_ATTR
         if (e != cudaSuccess) return e;
         configured[dev] = true;
@@ -237,7 +238,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     if (pairs == 0) return cudaSuccess;
     const bool big = h->n == 2048;
     // pairs per CTA: frame 1024 balances one wave (4..7 warps); frame 2048 uses 2..3 pairs of two warps
-    int ppc = big ? 3 : pick_warps_per_cta(pairs, h->num_sms);
+    int ppc = big ? 4 : pick_warps_per_cta(pairs, h->num_sms);
     const int max_ppc = big ? pvb::RingGeoT<2048>::MAX_PAIRS : pvb::RingGeoT<1024>::MAX_PAIRS;
     if (g_ring_wpc >= (big ? 2 : 4) && g_ring_wpc <= max_ppc) ppc = g_ring_wpc;
     const int grid = (pairs + ppc - 1) / ppc;
@@ -310,7 +311,17 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
-    if (big) return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 0, 0>, rp);
+    if (big) {
+        if (rp.hop == 512) {    // config 3: ring-block roles fixed at compile time
+            switch (((rp.tmod - rp.hop + 2048) >> 7) & 15) {
+                case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 0>, rp);
+                case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 4>, rp);
+                case 8: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 8>, rp);
+                default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 12>, rp);
+            }
+        }
+        return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 0, 0>, rp);
+    }
     if (rp.hop == 256) {        // the headline geometry: ring-block roles fixed at compile time
         switch (jb) {
             case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 0>, rp);

@@ -61,7 +61,7 @@ struct RingGeoT {
     static constexpr int OFF_WIN = OFF_TWH + TWH_BYTES;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;
-    static constexpr int MAX_PAIRS = (N == 1024) ? 7 : 3;   // pairs per CTA; two CTAs per SM
+    static constexpr int MAX_PAIRS = (N == 1024) ? 7 : 4;   // pairs per CTA; two CTAs per SM
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
     static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin
