@@ -223,13 +223,12 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         const int smem = 227 * 1024;
         cudaError_t e = cudaSuccess;
-#define PVB_RING_ATTR(N, NBLK, JB)                                                                \
+#define PVB_RING_ATTR(N, NBLK)                                                                    \
         if (e == cudaSuccess)                                                                     \
-            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLK, JB>,                    \
+            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLK>,                        \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        PVB_RING_ATTR(1024, 0, 0) PVB_RING_ATTR(1024, 2, 0) PVB_RING_ATTR(1024, 2, 2)
-        PVB_RING_ATTR(1024, 2, 4) PVB_RING_ATTR(1024, 2, 6) PVB_RING_ATTR(2048, 0, 0)
-        PVB_RING_ATTR(2048, 4, 0) PVB_RING_ATTR(2048, 4, 4) PVB_RING_ATTR(2048, 4, 8) PVB_RING_ATTR(2048, 4, 12)
+        PVB_RING_ATTR(1024, 1) PVB_RING_ATTR(1024, 2) PVB_RING_ATTR(1024, 4)
+        PVB_RING_ATTR(2048, 1) PVB_RING_ATTR(2048, 2) PVB_RING_ATTR(2048, 4) PVB_RING_ATTR(2048, 8)
 #undef PVB_RING_ATTR
         if (e != cudaSuccess) return e;
         configured[dev] = true;
@@ -296,7 +295,6 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     const size_t smem = (big ? pvb::RingGeoT<2048>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<2048>::PAIR_BYTES
                              : pvb::RingGeoT<1024>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<1024>::PAIR_BYTES) +
                         size_t(g_ring_pad_kb) * 1024;
-    const int jb = ((rp.tmod - rp.hop + 1024) >> 7) & 7;
     // programmatic dependent launch: CTAs of this launch may become resident (and stage their
     // tables) while the previous kernel on the stream drains; the kernel itself waits
     // (griddepcontrol.wait) before it touches anything an earlier launch may have written
@@ -311,26 +309,20 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
+    const int nblk = rp.hop >> 7;
     if (big) {
-        if (rp.hop == 512) {    // config 3: ring-block roles fixed at compile time
-            switch (((rp.tmod - rp.hop + 2048) >> 7) & 15) {
-                case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 0>, rp);
-                case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 4>, rp);
-                case 8: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 8>, rp);
-                default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4, 12>, rp);
-            }
-        }
-        return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 0, 0>, rp);
-    }
-    if (rp.hop == 256) {        // the headline geometry: ring-block roles fixed at compile time
-        switch (jb) {
-            case 0: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 0>, rp);
-            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 2>, rp);
-            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 4>, rp);
-            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2, 6>, rp);
+        switch (nblk) {
+            case 1: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 1>, rp);
+            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 2>, rp);
+            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4>, rp);
+            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 8>, rp);
         }
     }
-    return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 0, 0>, rp);
+    switch (nblk) {
+        case 1: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 1>, rp);
+        case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2>, rp);
+        default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 4>, rp);
+    }
 }
 
 // two warps per channel pair (pv_kernel_pair.cuh): same validity range as the warp kernel
@@ -654,7 +646,7 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         return bail(PVB_ERR_CUDA);
     }
     if (n == 1024 || n == 2048) {
-        const size_t tab_bytes = n == 1024 ? pvb::RingGeoT<1024>::GTAB_BYTES : pvb::RingGeoT<2048>::GTAB_BYTES;
+        const size_t tab_bytes = n == 1024 ? pvb::ring_host_table_bytes<1024>() : pvb::ring_host_table_bytes<2048>();
         std::vector<float2> rt(tab_bytes / sizeof(float2));
         if (n == 1024) pvb::ring_host_tables<1024>(tw.data(), rt.data());
         else pvb::ring_host_tables<2048>(tw.data(), rt.data());

@@ -75,7 +75,7 @@ struct RingParams {
     float4 *acc2;               // [pairs][N/2] : overlap-add ring, same alignment
     const float *window2;       // [2N] Hann window, twice
     const float *window_out2;   // [2N] window / (2 N R), twice
-    const float4 *gtab;         // [GTAB_BYTES / 16] tw1 | w64 | twh, built by the host (ring_host_tables)
+    const float4 *gtab;         // NJ x tw1 | w64 | twh, built by the host (ring_host_tables)
     int num_channels;
     int hop;
     int tmod;                   // timeCursor mod N (multiple of hop)
@@ -215,12 +215,15 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
     }
 }
 
-// N = frame size (1024: one warp per pair, 2048: two warps per pair).
-// NBLK = hop / 128 and JB = ring 128-block that receives the new input block, as template
-// parameters (NBLK > 0), make the role of every ring block (history / new input / emitted head /
-// zero tail) a compile-time fact: no predicated duplicates of the global accesses.  NBLK == 0 is
-// the same kernel with both read from the parameters (launch-uniform branches).
-template <int N, int NBLK, int JB>
+// N = frame size (1024: one warp per pair, 2048: two warps per pair), NBLK = hop / 128.
+// Registers of the first / last FFT pass are indexed by FRAME block f (128 samples), so the role
+// of every register (history / new input / emitted head / zero tail) is a compile-time fact: no
+// predicated duplicates of the global accesses.  Frame block f sits in ring block (f + toff) mod
+// NJ, toff = (timeCursor / 128) mod NJ; only the global addresses depend on toff.  The DFT over
+// ring blocks of the rotated register array is the DFT over f times W_R1^{toff k1} (shift
+// theorem); that factor is folded into the first-pass twiddles, W_M^{(n + 64 toff) k1}: the host
+// keeps one such table per toff and the CTA stages the one it needs.
+template <int N, int NBLK>
 __global__ void __launch_bounds__(RingGeoT<N>::MAX_PAIRS * RingGeoT<N>::TP, 2)
 pv_process_ring_kernel(const RingParams p) {
     using G = RingGeoT<N>;
@@ -246,9 +249,11 @@ pv_process_ring_kernel(const RingParams p) {
     const bool has1 = c0 + 1 < p.num_channels;
     const int hop = p.hop;
     const int t = p.tmod;
-    const int nblk = NBLK ? NBLK : (hop >> 7);
-    const int jb = NBLK ? JB : (((t - hop + N) >> 7) & (NJ - 1));   // ring 128-block that receives the new input block
-    const int je = (jb + nblk) & (NJ - 1);                          // ring 128-block of frame sample 0 (emitted)
+    constexpr int nblk = NBLK;
+    const int toff = (t >> 7) & (NJ - 1);           // ring 128-block of frame block 0
+    // ring float4 offset of frame block f: 64 ((f + toff) mod NJ) == 64 f + (wraps ? ro_wrap : ro_lin)
+    const int ro_lin = 64 * toff, ro_wrap = 64 * toff - 64 * NJ;
+#define PVB_RING_OFF(f) (64 * (f) + (((f) + toff >= NJ) ? ro_wrap : ro_lin))
 
     // Programmatic dependent launch: our CTAs may become resident while the previous kernel on the
     // stream drains.  Two ways to respect what earlier launches wrote:
@@ -264,17 +269,25 @@ pv_process_ring_kernel(const RingParams p) {
     // ---- CTA-shared tables: asynchronous 16-byte copies, fixed trip counts (CTAs have at least
     // MIN_THREADS threads; no division by blockDim) --------------------------------------------------
     {
-        const int rot = (N - t) & (N - 1);
-        const float4 *w1 = reinterpret_cast<const float4 *>(p.window2 + rot);
-        const float4 *w2 = reinterpret_cast<const float4 *>(p.window_out2 + rot);
+        const float4 *w1 = reinterpret_cast<const float4 *>(p.window2);
+        const float4 *w2 = reinterpret_cast<const float4 *>(p.window_out2);
         const unsigned s_tab = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_TW1));
+        const unsigned s_rest = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_W64));
         const unsigned s_win = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WIN));
         const unsigned s_wout = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WOUT));
+        const float4 *g_tw1 = p.gtab + toff * (G::TW1_BYTES / 16);            // the table of this toff
+        const float4 *g_rest = p.gtab + NJ * (G::TW1_BYTES / 16);             // w64 | twh
 #pragma unroll
-        for (int k = 0; k < (G::GTAB_BYTES / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
+        for (int k = 0; k < (G::TW1_BYTES / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
-            if (i < G::GTAB_BYTES / 16)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_tab + 16 * i), "l"(p.gtab + i));
+            if (i < G::TW1_BYTES / 16)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_tab + 16 * i), "l"(g_tw1 + i));
+        }
+#pragma unroll
+        for (int k = 0; k < ((G::W64_BYTES + G::TWH_BYTES) / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
+            const int i = threadIdx.x + k * blockDim.x;
+            if (i < (G::W64_BYTES + G::TWH_BYTES) / 16)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_rest + 16 * i), "l"(g_rest + i));
         }
 #pragma unroll
         for (int k = 0; k < (N / 4 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
@@ -300,9 +313,9 @@ pv_process_ring_kernel(const RingParams p) {
         }
     }
     // ---- frame loads: all issued before anything consumes them ---------------------------------
-    // Element e of a thread: first-pass butterfly h = e / R1, input j = e % R1, ring float4 index
-    // tp + 32 h + 64 j; it lies in ring 128-block j.  The new block is loaded as (ch0 pair, ch1 pair)
-    // and interleaved after the wait (moves must not sit between the loads).
+    // Element e of a thread: first-pass butterfly h = e / R1, frame block f = e % R1, ring float4
+    // index tp + 32 h + PVB_RING_OFF(f).  The new block (f >= NJ - NBLK) is loaded as (ch0 pair, ch1
+    // pair) and interleaved after the wait (moves must not sit between the loads).
     // Grid mode only: history written by launches OLDER than the kernel in front of us on the stream
     // is already complete when our CTAs start (that kernel passed its own griddepcontrol.wait before
     // it let us launch), so those loads are issued before our wait:
@@ -332,15 +345,14 @@ pv_process_ring_kernel(const RingParams p) {
     } else if (live && early) {
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int h = e / R1, j = e % R1;
-            const int jj = (j - jb) & (NJ - 1);                       // launch-uniform
-            // jj < nblk: new input; jj >= NJ - nblk: the block the previous call wrote
-            if (jj >= nblk && (jj < NJ - nblk || early == 2)) r[e] = hl[32 * h + 64 * j];
+            const int h = e / R1, f = e % R1;
+            // f >= NJ - nblk: new input; the nblk blocks below: what the previous call wrote
+            if (f < NJ - nblk && (f < NJ - 2 * nblk || early == 2)) r[e] = hl[32 * h + PVB_RING_OFF(f)];
         }
         if (early == 2) {
             // warm L2 with the overlap-add ring lines the tail of this kernel adds to
             const int line = 16 * tp;                                 // float4 index: 256 bytes per thread
-            if ((((line >> 6) - jb) & (NJ - 1)) >= nblk) {
+            if ((((line >> 6) - toff) & (NJ - 1)) < NJ - nblk) {
                 const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
@@ -357,17 +369,16 @@ pv_process_ring_kernel(const RingParams p) {
         const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * tp : nullptr;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int h = e / R1, j = e % R1;
-            const int jj = (j - jb) & (NJ - 1);                       // launch-uniform
-            if (jj < nblk) {
+            const int h = e / R1, f = e % R1;
+            if (f >= NJ - nblk) {
                 float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
                 if (i0) {
-                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * jj));
-                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * jj));
+                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * (f - (NJ - nblk))));
+                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * (f - (NJ - nblk))));
                 }
                 r[e] = make_float4(u0.x, u0.y, u1.x, u1.y);           // interleaved below
-            } else if (!(early && (jj < NJ - nblk || early == 2))) {
-                r[e] = hl[32 * h + 64 * j];
+            } else if (!(early && (f < NJ - 2 * nblk || early == 2))) {
+                r[e] = hl[32 * h + PVB_RING_OFF(f)];
             }
         }
     }
@@ -379,14 +390,14 @@ pv_process_ring_kernel(const RingParams p) {
     // the new block joins the history ring (ola:105)
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int h = e / R1, j = e % R1;
-        if (((j - jb) & (NJ - 1)) < nblk) {
+        const int h = e / R1, f = e % R1;
+        if (f >= NJ - nblk) {
             r[e] = make_float4(r[e].x, r[e].z, r[e].y, r[e].w);       // (ch0[i], ch1[i], ch0[i+1], ch1[i+1])
-            hl[32 * h + 64 * j] = r[e];
+            hl[32 * h + PVB_RING_OFF(f)] = r[e];
         }
     }
 
-    // ---- Hann window (pv:55) + forward pass 1: butterflies n = tp (+ 32) over j (stride 64) -----
+    // ---- Hann window (pv:55) + forward pass 1: butterflies n = tp (+ 32) over the frame blocks ---
     {
         const float *wl = swin + 2 * tp;
 #pragma unroll
@@ -403,7 +414,7 @@ pv_process_ring_kernel(const RingParams p) {
             dft_r<R1, false>(x);
 #pragma unroll
             for (int k1 = 1; k1 < R1; k1++) {
-                const float2 w = tw1[G::TW1_ROW * k1 + nl];           // W_M^{n k1}
+                const float2 w = tw1[G::TW1_ROW * k1 + nl];           // W_M^{(n + 64 toff) k1}
                 x[k1] = cmul_s(x[k1], w.x, w.y);
             }
 #pragma unroll
@@ -416,7 +427,7 @@ pv_process_ring_kernel(const RingParams p) {
     // only written, ring [t - hop, t), is skipped)
     {
         const int line = 16 * tp;                                     // float4 index: 256 bytes per thread
-        if (early != 2 && (((line >> 6) - jb) & (NJ - 1)) >= nblk) {
+        if (early != 2 && (((line >> 6) - toff) & (NJ - 1)) < NJ - nblk) {
             const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
@@ -727,12 +738,12 @@ pv_process_ring_kernel(const RingParams p) {
     float4 q[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int h = e / R1, j = e % R1;
+        const int h = e / R1, f = e % R1;
         q[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (((j - jb) & (NJ - 1)) >= nblk) q[e] = al[32 * h + 64 * j];
+        if (f < NJ - nblk) q[e] = al[32 * h + PVB_RING_OFF(f)];
     }
 
-    // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_M^{k1 (m3 + 8 m2)}) -----------------
+    // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_M^{k1 (m3 + 8 m2 + 64 toff)}) -------
     if (!(p.skip & 2))
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -770,12 +781,11 @@ pv_process_ring_kernel(const RingParams p) {
                 const float4 qv = q[R1 * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
-                const int jj = (j - je) & (NJ - 1);
-                if (jj < nblk) {                                      // head: emit (ola:111-118)
-                    *reinterpret_cast<float2 *>(o0 + 64 * h + 128 * jj) = make_float2(y0.x, y1.x);
-                    if (has1) *reinterpret_cast<float2 *>(o0 + hop + 64 * h + 128 * jj) = make_float2(y0.y, y1.y);
+                if (j < nblk) {                                       // head: emit (ola:111-118)
+                    *reinterpret_cast<float2 *>(o0 + 64 * h + 128 * j) = make_float2(y0.x, y1.x);
+                    if (has1) *reinterpret_cast<float2 *>(o0 + hop + 64 * h + 128 * j) = make_float2(y0.y, y1.y);
                 } else {
-                    al[32 * h + 64 * j] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    al[32 * h + PVB_RING_OFF(j)] = make_float4(y0.x, y0.y, y1.x, y1.y);
                 }
             }
         }
@@ -788,16 +798,23 @@ pv_process_ring_kernel(const RingParams p) {
     // flag mode skipped the wait at the top: take it here, where the previous grid is long gone, so
     // that completion stays transitive along the stream
     if (p.flag_mode) asm volatile("griddepcontrol.wait;" ::: "memory");
+#undef PVB_RING_OFF
 }
 
-// tables the ring-order kernel copies into shared memory: tw1[k1][n] (rows of TW1_ROW), w64[a][b], twh[k]
+// tables the ring-order kernel copies into shared memory: NJ first-pass twiddle tables
+// tw1[toff][k1][n] = W_M^{(n + 64 toff) k1} (rows of TW1_ROW), then w64[a][b] = W_64^{ab}, twh[k] = W_N^k
 template <int N>
-inline void ring_host_tables(const float2 *tw /* [N] W_N^j */, float2 *out /* GTAB_BYTES / 8 */) {
+constexpr int ring_host_table_bytes() { return RingGeoT<N>::NJ * RingGeoT<N>::TW1_BYTES + RingGeoT<N>::W64_BYTES + RingGeoT<N>::TWH_BYTES; }
+
+template <int N>
+inline void ring_host_tables(const float2 *tw /* [N] W_N^j */, float2 *out /* ring_host_table_bytes / 8 */) {
     using G = RingGeoT<N>;
-    float2 *tw1 = out, *w64 = out + G::TW1_BYTES / 8, *twh = w64 + G::W64_BYTES / 8;
-    for (int i = 0; i < G::GTAB_BYTES / 8; i++) out[i] = make_float2(0.f, 0.f);
-    for (int k1 = 0; k1 < G::R1; k1++)
-        for (int n = 0; n < 64; n++) tw1[G::TW1_ROW * k1 + n] = tw[(2 * n * k1) & (N - 1)];    // W_M^{n k1}
+    float2 *w64 = out + G::NJ * (G::TW1_BYTES / 8), *twh = w64 + G::W64_BYTES / 8;
+    for (int i = 0; i < ring_host_table_bytes<N>() / 8; i++) out[i] = make_float2(0.f, 0.f);
+    for (int toff = 0; toff < G::NJ; toff++)
+        for (int k1 = 0; k1 < G::R1; k1++)
+            for (int n = 0; n < 64; n++)
+                out[toff * (G::TW1_BYTES / 8) + G::TW1_ROW * k1 + n] = tw[(2 * (n + 64 * toff) * k1) & (N - 1)];
     for (int a = 0; a < 8; a++)
         for (int b = 0; b < 8; b++) w64[8 * a + b] = tw[((N / 64) * a * b) & (N - 1)];
     for (int k = 0; k <= G::M; k++) twh[k] = tw[k];

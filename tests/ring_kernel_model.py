@@ -111,20 +111,23 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     dtab = delta_table(g, pf32)
     contract = bool(pf32 < 1.0)
     t = int(t) % N
-    jb = ((t - hop) // 128) % NJ
-    je = (t // 128) % NJ
     nblk = hop // 128
     ex = np.zeros((g.EX_SLOTS, 2), C64)            # exchange: slot -> (ch0, ch1) complex
     nls = [T, T + 32] if TP == 32 else [T]         # pass-1 butterflies of a thread (n mod 64)
 
-    # ---- load, window, forward pass 1 (DFT over j, stride 64) ----------------------------------
+    # ---- load, window, forward pass 1 (DFT over the 128-sample blocks, stride 64) ---------------
+    # Registers are indexed by FRAME block f (so the role of every register -- history, new input,
+    # emitted head, zero tail -- is static); it sits in ring block j = (f + toff) mod NJ.  The DFT over
+    # ring blocks of the rotated register array is the DFT over f times W_R1^{toff k1} (shift theorem),
+    # which is folded into the pass-1 twiddle: W_M^{(n + 64 toff) k1}.
+    toff = (t // 128) % NJ
     for nl in nls:
         z = np.zeros((R1, TP, 2), C64)
-        for j in range(R1):
-            i = 2 * nl + 128 * j                    # ring index of sample pair (i, i + 1); block j
-            jj = (j - jb) % NJ
-            if jj < nblk:                           # new block (ola:91-108)
-                s = 2 * nl + 128 * jj
+        for f in range(R1):
+            j = (f + toff) % NJ
+            i = 2 * nl + 128 * j                    # ring index of sample pair (i, i + 1)
+            if f >= NJ - nblk:                      # new block (ola:91-108)
+                s = 2 * nl + 128 * (f - (NJ - nblk))
                 if inblk is None:
                     x0 = np.zeros((TP, 2), F32); x1 = np.zeros((TP, 2), F32)
                 else:
@@ -132,11 +135,12 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 hist2[i] = x0; hist2[i + 1] = x1
             else:
                 x0 = hist2[i]; x1 = hist2[i + 1]
-            w0 = win[(i - t) % N][:, None]; w1 = win[(i + 1 - t) % N][:, None]
-            z[j] = (x0 * w0).astype(F32) + 1j * (x1 * w1).astype(F32)
+            fi = 2 * nl + 128 * f                   # frame position of the sample pair
+            w0 = win[fi][:, None]; w1 = win[fi + 1][:, None]
+            z[f] = (x0 * w0).astype(F32) + 1j * (x1 * w1).astype(F32)
         z = dft(z)
         for k1 in range(R1):
-            v = z[k1] * tw[(2 * nl * k1) % N][:, None]          # W_M^{n k1}
+            v = z[k1] * tw[(2 * (nl + 64 * toff) * k1) % N][:, None]      # W_M^{(n + 64 toff) k1}
             slot = 65 * k1 + nl
             ex[slot] = v
             if cf: cf.note("p1_st", slot * 16, 16)
@@ -315,28 +319,29 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     for c in range(8):
         ex[sA + c] = a[c] * np.conj(tw[(w64s * (kA // R1) * c) % N])[:, None]
         ex[sB + c] = b[c] * np.conj(tw[(w64s * (kB // R1) * c) % N])[:, None]
-    # ---- inverse pass 2 (DFT over k2 -> m2), twiddle conj(W_M^{k1 (m3 + 8 m2)}) -----------------
+    # ---- inverse pass 2 (DFT over k2 -> m2), twiddle conj(W_M^{k1 (m3 + 8 m2 + 64 toff)}) -------
     for h in range(2):
         k1 = (T >> 3) + (R1 // 2) * h
         base = 65 * k1 + m3
         x = dft(np.stack([ex[base + 8 * k2] for k2 in range(8)]), inv=True)
         for m2 in range(8):
-            ex[base + 8 * m2] = x[m2] * np.conj(tw[(2 * k1 * (m3 + 8 * m2)) % N])[:, None]
-    # ---- inverse pass 3 (DFT over k1 -> j); window, overlap-add, emit ---------------------------
+            ex[base + 8 * m2] = x[m2] * np.conj(tw[(2 * k1 * (m3 + 8 * m2 + 64 * toff)) % N])[:, None]
+    # ---- inverse pass 3 (DFT over k1 -> frame block f); window, overlap-add, emit ---------------
     out = np.zeros((2, hop), F32)
     for nl in nls:
         x = dft(np.stack([ex[65 * k1 + nl] for k1 in range(R1)]), inv=True)
-        for j in range(R1):
+        for f in range(R1):
+            j = (f + toff) % NJ
             i = 2 * nl + 128 * j
-            w0 = win_out[(i - t) % N][:, None]; w1 = win_out[(i + 1 - t) % N][:, None]
-            y0 = (x[j].real.astype(F32) * w0).astype(F32); y1 = (x[j].imag.astype(F32) * w1).astype(F32)
-            tail = ((j - jb) % NJ) < nblk               # starts from zero (ola:134)
+            fi = 2 * nl + 128 * f
+            w0 = win_out[fi][:, None]; w1 = win_out[fi + 1][:, None]
+            y0 = (x[f].real.astype(F32) * w0).astype(F32); y1 = (x[f].imag.astype(F32) * w1).astype(F32)
+            tail = f >= NJ - nblk                       # starts from zero (ola:134)
             q0 = np.zeros((TP, 2), F32) if tail else acc2[i]
             q1 = np.zeros((TP, 2), F32) if tail else acc2[i + 1]
             y0 = y0 + q0; y1 = y1 + q1
-            jj = (j - je) % NJ
-            if jj < nblk:                               # head: emit (ola:111-118)
-                s = 2 * nl + 128 * jj
+            if f < nblk:                                # head: emit (ola:111-118)
+                s = 2 * nl + 128 * f
                 out[:, s] = y0.T; out[:, s + 1] = y1.T
             else:
                 acc2[i] = y0; acc2[i + 1] = y1
