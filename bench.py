@@ -485,10 +485,36 @@ def run_root_scatter(C, frame, hop, pitch, world, rank, local, steps, host_block
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sec = float(t.item()) * 1e-3
     peer_bytes = 2 * (total - C) * hop * 4                     # slabs out + results back, per step
-    return {"value": steps * total / sec, "unit": UNIT, "steps": steps, "total_channels": total,
-            "nvlink_bytes_per_step": peer_bytes, "nvlink_gbs_at_root": steps * peer_bytes / sec / 1e9,
-            "nvlink_peer_copy_reference_gbs": 770.0,
-            "note": "root egress + ingress; shard-resident number is the main `value`"}
+    res = {"value": steps * total / sec, "unit": UNIT, "steps": steps, "total_channels": total,
+           "nvlink_bytes_per_step": peer_bytes, "nvlink_gbs_at_root": steps * peer_bytes / sec / 1e9,
+           "nvlink_peer_copy_reference_gbs": 770.0,
+           "note": "root egress + ingress; shard-resident number is the main `value`"}
+    del sh
+    # streamed root mode: audio buffers of Kc calls per message ([C][Kc*hop]), scatter of buffer i+1
+    # and gather of buffer i-1 under the kernels of buffer i
+    Kc, nbuf = 16, 12
+    sh = ShardedPhaseVocoder(total, frame, hop, device=torch.device("cuda", local))
+    bufs = None
+    if rank == 0:
+        one = torch.from_numpy(np.tile(host_block_src[:, :hop], (world, Kc))).cuda().contiguous()
+        bufs = [one.clone() for _ in range(nbuf)]
+    sh.process_stream_from_root(bufs, pitch, Kc, 4)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    sh.process_stream_from_root(bufs, pitch, Kc, nbuf)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item()) * 1e-3
+    res["streamed"] = {"value": nbuf * Kc * total / sec, "unit": UNIT, "calls_per_message": Kc, "buffers": nbuf,
+                       "message_bytes_per_peer": C * Kc * hop * 4,
+                       "nvlink_gbs_at_root": nbuf * Kc * peer_bytes / sec / 1e9,
+                       "api": "ShardedPhaseVocoder.process_stream_from_root"}
+    return res
 
 
 def phaze_b200_lib():

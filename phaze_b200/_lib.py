@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphaze_b200.so")
+# PVB_LIBRARY: another build of the same library (kernel experiments: profiles/*.sh)
+LIB_PATH = os.environ.get("PVB_LIBRARY") or os.path.join(_HERE, "libphaze_b200.so")
 
 PVB_OK, PVB_ERR_BAD_SIZE, PVB_ERR_BAD_ARG, PVB_ERR_CUDA, PVB_ERR_NOMEM = 0, -1, -2, -3, -4
 

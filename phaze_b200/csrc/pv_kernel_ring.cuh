@@ -31,6 +31,12 @@
 
 namespace pvb {
 
+// channel pairs (warps) per CTA at frame 1024; two CTAs per SM at 128 registers.  7 fills one wave
+// of 4096 channels on 148 SMs exactly; 8 uses the whole register file (16 warps per SM).
+#ifndef PVB_RING_PAIRS_1024
+#define PVB_RING_PAIRS_1024 7
+#endif
+
 template <int N_>
 struct RingGeoT {
     static constexpr int N = N_, M = N / 2, NB = M + 1;
@@ -61,7 +67,7 @@ struct RingGeoT {
     static constexpr int OFF_WIN = OFF_TWH + TWH_BYTES;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;
-    static constexpr int MAX_PAIRS = (N == 1024) ? 7 : 4;   // pairs per CTA; two CTAs per SM
+    static constexpr int MAX_PAIRS = (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA; two CTAs per SM
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
     static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin

@@ -9,7 +9,10 @@ contiguous block of channels, its history / overlap-add rings live in its own HB
 `process_from_root` adds the exchange step the north-star names: rank 0 holds the full
 [C][hop] input block, scatters each rank's slab (grouped point-to-point sends ==
 ncclSend/ncclRecv over NVLink under the "nccl" backend), every rank processes its slab,
-and the output slabs are gathered back on rank 0.
+and the output slabs are gathered back on rank 0.  `process_stream_from_root` is the same
+exchange for a stream of audio buffers ([C][K*hop], K process() calls per message): slabs are
+sent without a staging copy, and the scatter of buffer i+1 and the gather of buffer i-1 run
+under the kernels of buffer i.
 
 The per-shard engine is injected (`processor_factory`) so the partition / exchange logic is
 testable on CPU with the gloo backend; the default factory is the CUDA engine.
@@ -60,6 +63,25 @@ class _CudaShard:
         out.record_stream(self.side)
         self.pv.process_device(in_ptr, out.data_ptr(), pitch_factor, self.side.cuda_stream)
         cur.wait_stream(self.side)                 # whoever consumes `out` on the caller's stream waits
+        return out
+
+
+    def process_many(self, blocks: torch.Tensor, pitch_factor: float) -> torch.Tensor:
+        """blocks [K][num_channels][hop] on the device: K consecutive process() calls in one
+        submission (pvb_process_many_device); returns [K][num_channels][hop]."""
+        K = blocks.shape[0]
+        out = torch.empty((K, self.num_channels, self.hop), dtype=torch.float32, device=self.device)
+        if self.num_channels == 0:
+            self.pv.process_device(None, 0, pitch_factor, num_calls=K)
+            return out
+        assert blocks.is_cuda and blocks.dtype == torch.float32 and blocks.is_contiguous()
+        cur = torch.cuda.current_stream(self.device)
+        self.side.wait_stream(cur)
+        blocks.record_stream(self.side)
+        out.record_stream(self.side)
+        self.pv.process_device(blocks.data_ptr(), out.data_ptr(), pitch_factor, self.side.cuda_stream,
+                               num_calls=K)
+        cur.wait_stream(self.side)
         return out
 
 
@@ -127,3 +149,86 @@ class ShardedPhaseVocoder:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         return result
+
+    # -- single-root mode for a stream of audio buffers: K calls per message, pipelined -------------
+    def _engine_many(self, blocks: torch.Tensor, pitch_factor: float) -> torch.Tensor:
+        if hasattr(self.engine, "process_many"):
+            return self.engine.process_many(blocks, pitch_factor)
+        return torch.stack([self.engine.process(blocks[k], pitch_factor) for k in range(blocks.shape[0])])
+
+    def process_stream_from_root(self, buffers, pitch_factor: float, calls_per_buffer: int,
+                                 num_buffers: int, root: int = 0) -> list:
+        """`buffers`: on `root`, a sequence of `num_buffers` tensors [C][K*hop] (channel-major audio,
+        K = calls_per_buffer consecutive process() calls per channel); ignored elsewhere.  Returns
+        the [C][K*hop] outputs on root (an empty list elsewhere).
+
+        A rank's slab of a buffer is contiguous, so it is sent and received in place (one message
+        of K hops per peer and direction); the [channel][call] <-> [call][channel] re-ordering the
+        kernels need happens on the owning rank.  Messages are posted one buffer ahead: the scatter
+        of buffer i+1 and the gather of buffer i-1 overlap the kernels of buffer i.  The result is
+        bit-identical to `num_buffers * K` process_from_root calls."""
+        hop, K = self.hop_size, calls_per_buffer
+        Cl, lo, hi = self.local_channels, self.first, self.last
+        is_root = self.rank == root
+        results: list = []
+        if self.world == 1:
+            for i in range(num_buffers):
+                blocks = buffers[i].view(Cl, K, hop).transpose(0, 1).contiguous()
+                out = self._engine_many(blocks, pitch_factor)
+                results.append(out.transpose(0, 1).contiguous().view(Cl, K * hop))
+            return results
+
+        def post_scatter(i):
+            """-> (works, this rank's [Cl][K*hop] slab of buffer i)"""
+            ops = []
+            if is_root:
+                buf = buffers[i]
+                assert buf.shape == (self.num_channels, K * hop) and buf.is_contiguous()
+                for r, (a, b) in enumerate(self.bounds):
+                    if r != root and b > a:
+                        ops.append(dist.P2POp(dist.isend, buf[a:b], r, self.group))
+                slab = buf[lo:hi]
+            else:
+                slab = torch.empty((Cl, K * hop), dtype=torch.float32, device=self.device)
+                if Cl > 0:
+                    ops.append(dist.P2POp(dist.irecv, slab, root, self.group))
+            return (dist.batch_isend_irecv(ops) if ops else []), slab
+
+        def post_gather(out_slab):
+            """-> (works, the [C][K*hop] result on root / None)"""
+            ops, res = [], None
+            if is_root:
+                res = torch.empty((self.num_channels, K * hop), dtype=torch.float32, device=self.device)
+                res[lo:hi] = out_slab
+                for r, (a, b) in enumerate(self.bounds):
+                    if r != root and b > a:
+                        ops.append(dist.P2POp(dist.irecv, res[a:b], r, self.group))
+            elif Cl > 0:
+                ops.append(dist.P2POp(dist.isend, out_slab, root, self.group))
+            return (dist.batch_isend_irecv(ops) if ops else []), res
+
+        pending_in = post_scatter(0) if num_buffers > 0 else None
+        pending_out = []                                   # [(works, result, keep-alive)]
+        for i in range(num_buffers):
+            works, slab = pending_in
+            for w in works:
+                w.wait()                                   # buffer i has arrived
+            if i + 1 < num_buffers:
+                pending_in = post_scatter(i + 1)           # travels under the kernels of buffer i
+            blocks = slab.view(Cl, K, hop).transpose(0, 1).contiguous()
+            out = self._engine_many(blocks, pitch_factor)
+            out_slab = out.transpose(0, 1).contiguous().view(Cl, K * hop)
+            gw, res = post_gather(out_slab)                # travels under the kernels of buffer i+1
+            pending_out.append((gw, res, out_slab))
+            while len(pending_out) > 2:                    # bound the buffers in flight
+                gw0, res0, _ = pending_out.pop(0)
+                for w in gw0:
+                    w.wait()
+                if is_root:
+                    results.append(res0)
+        for gw0, res0, _ in pending_out:
+            for w in gw0:
+                w.wait()
+            if is_root:
+                results.append(res0)
+        return results

@@ -31,13 +31,22 @@ def main():
         res = sh.process_from_root(blk, pf)
         if rank == 0:
             outs.append(res.cpu().numpy())
+    # streamed root mode: K calls per message, scatter / gather overlapped with the kernels
+    K = 2
+    sh2 = ShardedPhaseVocoder(C, N, hop)
+    bufs = [torch.from_numpy(np.ascontiguousarray(x[:, i * K * hop:(i + 1) * K * hop])).cuda()
+            for i in range(calls // K)] if rank == 0 else None
+    res = sh2.process_stream_from_root(bufs, pf, K, calls // K)
+    torch.cuda.synchronize()
     ok = True
     if rank == 0:
         with BatchedPhaseVocoder(C, N, hop, device=local) as pv:
             want = pv.run(x, pf)
         got = np.stack(outs).transpose(1, 0, 2).reshape(C, calls * hop)
-        ok = bool(np.array_equal(got, want))
-        print(f"ROOT_SCATTER world={world} bit_identical={ok}")
+        got_stream = np.concatenate([r.cpu().numpy() for r in res], axis=1)
+        ok_stream = bool(np.array_equal(got_stream, want))
+        ok = bool(np.array_equal(got, want)) and ok_stream
+        print(f"ROOT_SCATTER world={world} bit_identical={ok} streamed_bit_identical={ok_stream}")
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()

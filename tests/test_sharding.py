@@ -60,7 +60,17 @@ def _worker(rank, world, port, C, frame, hop, calls, pf, q):
         for t in range(calls):
             blk = torch.from_numpy(np.ascontiguousarray(x[sh2.first:sh2.last, t * hop:(t + 1) * hop]))
             outs_local.append(sh2.process_local(blk, pf).numpy().copy())
-        q.put((rank, (sh.first, sh.last), np.stack(outs_root) if rank == 0 else None, np.stack(outs_local)))
+        # third pass: the streamed root mode (K calls per message, channel-major audio buffers)
+        sh3 = ShardedPhaseVocoder(C, frame, hop, processor_factory=lambda n: _OracleShard(n, frame, hop),
+                                  device=torch.device("cpu"))
+        K = 2
+        bufs = [torch.from_numpy(np.ascontiguousarray(x[:, i * K * hop:(i + 1) * K * hop]))
+                for i in range(calls // K)] if rank == 0 else None
+        res = sh3.process_stream_from_root(bufs, pf, K, calls // K)
+        streamed = np.concatenate([r.numpy() for r in res], axis=1) if rank == 0 else None
+        assert rank == 0 or res == []
+        q.put((rank, (sh.first, sh.last), np.stack(outs_root) if rank == 0 else None, np.stack(outs_local),
+               streamed))
     finally:
         dist.destroy_process_group()
 
@@ -92,5 +102,6 @@ def test_sharded_equals_unsharded_bit_for_bit():
     ref_calls = ref.reshape(C, calls, hop).transpose(1, 0, 2)
     by_rank = {r[0]: r for r in results}
     assert np.array_equal(by_rank[0][2], ref_calls), "root-gathered output differs from unsharded"
-    for rank, (lo, hi), _, local in results:
+    assert np.array_equal(by_rank[0][4], ref), "streamed root mode differs from unsharded"
+    for rank, (lo, hi), _, local, _ in results:
         assert np.array_equal(local, ref_calls[:, lo:hi]), f"rank {rank} shard-resident output differs"
