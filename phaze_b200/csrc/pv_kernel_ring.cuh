@@ -33,6 +33,9 @@ namespace pvb {
 
 // channel pairs (warps) per CTA at frame 1024; two CTAs per SM at 128 registers.  7 fills one wave
 // of 4096 channels on 148 SMs exactly; 8 uses the whole register file (16 warps per SM).
+#ifndef PVB_RING_LANE_FENCE
+#define PVB_RING_LANE_FENCE 1
+#endif
 #ifndef PVB_RING_PAIRS_1024
 #define PVB_RING_PAIRS_1024 7
 #endif
@@ -40,19 +43,29 @@ namespace pvb {
 template <int N_>
 struct RingGeoT {
     static constexpr int N = N_, M = N / 2, NB = M + 1;
-    static constexpr int TP = N / 32;                       // threads per channel pair (16 complex points each)
-    static constexpr int WPP = TP / 32;                     // warps per pair
-    static constexpr int R1 = M / 64;                       // radix of the first pass: 8 or 16
-    static constexpr int LR1 = (R1 == 8) ? 3 : 4;
+    static constexpr int TP = N / 32;                       // threads per channel pair (16 complex points each):
+                                                            // half a warp (512), a warp (1024), two warps (2048)
+    static constexpr int WPP = TP / 32;                     // warps per pair (0: two pairs share a warp)
+    static constexpr int R1 = M / 64;                       // radix of the first pass: 4, 8 or 16
+    static constexpr int LR1 = (R1 == 4) ? 2 : (R1 == 8) ? 3 : 4;
     static constexpr int NB1 = 16 / R1;                     // first-pass butterflies per thread
     static constexpr int KS = M / 8;                        // stride between the outputs of a last-pass butterfly
     static constexpr int SS = KS + KS / 16;                 // the same in spectrum slots
     static constexpr int NJ = N / 128;                      // ring blocks of 128 samples
     static constexpr int SM = M + M / 16;                   // slot of bin M
-    static constexpr int EX_SLOTS = 65 * (R1 - 1) + 64;     // exchange slots of 16 bytes: 65 k1 + 8 r + c
+    // exchange slots of 16 bytes: element 8 r + c of row k1 at RS k1 + G8 r + c.  Rows of 64 at stride
+    // 65; frame 512 (radix-4 first pass: a quarter-warp of pass 3 spans two r) pads every group of 8
+    // and uses stride 74, which keeps all three passes conflict free
+    static constexpr int RS = (R1 >= 8) ? 65 : 74;
+    static constexpr int G8 = (R1 >= 8) ? 8 : 9;
+    static constexpr int EX_SLOTS = RS * (R1 - 1) + 8 * G8;
     static constexpr int XQ_SLOTS = SM + 2;                 // bin k at k + (k >> 4); last slot = dump / halo dummy
     static constexpr int SCR_BYTES = (WPP > 1) ? 4 * TP * 4 + 32 : 0;   // cross-warp key exchange of the region scan
-    static constexpr int PAIR_BYTES = XQ_SLOTS * 16 + SCR_BYTES;
+    static constexpr int BUF_SLOTS = (XQ_SLOTS > EX_SLOTS) ? XQ_SLOTS : EX_SLOTS;
+    // two pairs per warp (frame 512): their buffers sit 16 banks apart, so the 32-bit plane accesses
+    // of the two half-warps (16 consecutive words each) do not collide
+    static constexpr int PAIR_PAD = (TP < 32) ? (64 + 128 - (BUF_SLOTS * 16) % 128) % 128 : 0;
+    static constexpr int PAIR_BYTES = BUF_SLOTS * 16 + SCR_BYTES + PAIR_PAD;
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
     static constexpr int DTAB_BYTES = ((NB + 1 + 4 * ((NB >> 4) + 1)) * 4 + 15) & ~15;   // key table: bin p at p + 4 (p >> 4)
     static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
@@ -67,9 +80,10 @@ struct RingGeoT {
     static constexpr int OFF_WIN = OFF_TWH + TWH_BYTES;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;
-    static constexpr int MAX_PAIRS = (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA; two CTAs per SM
+    static constexpr int MAX_PAIRS = (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA; two CTAs per SM
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
+    static constexpr int MIN_PAIRS = (MIN_THREADS + TP - 1) / TP;
     static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin
 };
 using RingGeo = RingGeoT<1024>;
@@ -107,6 +121,8 @@ template <int TP>
 __device__ __forceinline__ void pair_sync(int pair_in_cta) {
     if constexpr (TP == 32) {
         __syncwarp();
+    } else if constexpr (TP == 16) {
+        __syncwarp(0xFFFFu << (threadIdx.x & 16));          // the other half-warp is another pair
     } else {
         asm volatile("bar.sync %0, %1;" ::"r"(pair_in_cta + 1), "n"(TP) : "memory");
     }
@@ -141,10 +157,11 @@ __device__ __forceinline__ void dft16(cpx2 (&x)[16]) {
     }
 }
 
-// R-point DFT of x[0..R) (R = 8 or 16)
+// R-point DFT of x[0..R) (R = 4, 8 or 16)
 template <int R, bool INV>
 __device__ __forceinline__ void dft_r(cpx2 *x) {
-    if constexpr (R == 8) dft8<INV>(*reinterpret_cast<cpx2(*)[8]>(x));
+    if constexpr (R == 4) dft4<INV>(x[0], x[1], x[2], x[3]);
+    else if constexpr (R == 8) dft8<INV>(*reinterpret_cast<cpx2(*)[8]>(x));
     else dft16<INV>(*reinterpret_cast<cpx2(*)[16]>(x));
 }
 
@@ -240,7 +257,8 @@ pv_process_ring_kernel(const RingParams p) {
     const int pin = threadIdx.x / TP;               // pair within the CTA
     const int pair = blockIdx.x * (blockDim.x / TP) + pin;
     const bool live = 2 * pair < p.num_channels;
-    const unsigned FULL = 0xFFFFFFFFu;
+    // lanes of this thread's pair inside its warp (frame 512: half a warp)
+    const unsigned FULL = (TP == 16) ? (0xFFFFu << (threadIdx.x & 16)) : 0xFFFFFFFFu;
     int *ktab = reinterpret_cast<int *>(smem_raw);
     const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
     const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
@@ -328,6 +346,7 @@ pv_process_ring_kernel(const RingParams p) {
     //   p.early == 2: none of this handle's state was written by the previous kernel -> all of hist
     //   p.early == 1: the previous kernel may be this handle's last call -> all but its newest block
     // The input block always waits (it belongs to the caller's stream order).
+    constexpr int TPH = (TP < 32) ? TP : 32;        // float4 stride between the first-pass butterflies of a thread
     float4 r[16];
     float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + tp;
     const int early = p.flag_mode ? 0 : p.early;
@@ -346,14 +365,14 @@ pv_process_ring_kernel(const RingParams p) {
                 }
                 __nanosleep(200);
             }
-            __syncwarp();
+            if constexpr (TP == 16) pair_sync<TP>(pin); else __syncwarp();
         }
     } else if (live && early) {
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             const int h = e / R1, f = e % R1;
             // f >= NJ - nblk: new input; the nblk blocks below: what the previous call wrote
-            if (f < NJ - nblk && (f < NJ - 2 * nblk || early == 2)) r[e] = hl[32 * h + PVB_RING_OFF(f)];
+            if (f < NJ - nblk && (f < NJ - 2 * nblk || early == 2)) r[e] = hl[TPH * h + PVB_RING_OFF(f)];
         }
         if (early == 2) {
             // warm L2 with the overlap-add ring lines the tail of this kernel adds to
@@ -379,12 +398,12 @@ pv_process_ring_kernel(const RingParams p) {
             if (f >= NJ - nblk) {
                 float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
                 if (i0) {
-                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 64 * h + 128 * (f - (NJ - nblk))));
-                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 64 * h + 128 * (f - (NJ - nblk))));
+                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 2 * TPH * h + 128 * (f - (NJ - nblk))));
+                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 2 * TPH * h + 128 * (f - (NJ - nblk))));
                 }
                 r[e] = make_float4(u0.x, u0.y, u1.x, u1.y);           // interleaved below
             } else if (!(early && (f < NJ - 2 * nblk || early == 2))) {
-                r[e] = hl[32 * h + PVB_RING_OFF(f)];
+                r[e] = hl[TPH * h + PVB_RING_OFF(f)];
             }
         }
     }
@@ -399,7 +418,7 @@ pv_process_ring_kernel(const RingParams p) {
         const int h = e / R1, f = e % R1;
         if (f >= NJ - nblk) {
             r[e] = make_float4(r[e].x, r[e].z, r[e].y, r[e].w);       // (ch0[i], ch1[i], ch0[i+1], ch1[i+1])
-            hl[32 * h + PVB_RING_OFF(f)] = r[e];
+            hl[TPH * h + PVB_RING_OFF(f)] = r[e];
         }
     }
 
@@ -408,11 +427,11 @@ pv_process_ring_kernel(const RingParams p) {
         const float *wl = swin + 2 * tp;
 #pragma unroll
         for (int h = 0; h < G::NB1; h++) {
-            const int nl = tp + 32 * h;
+            const int nl = tp + TPH * h;
             cpx2 x[R1];
 #pragma unroll
             for (int j = 0; j < R1; j++) {
-                const float2 w = *reinterpret_cast<const float2 *>(wl + 64 * h + 128 * j);
+                const float2 w = *reinterpret_cast<const float2 *>(wl + 2 * TPH * h + 128 * j);
                 const float4 v = r[R1 * h + j];
                 x[j].re = mul2(make_float2(v.x, v.y), bc2(w.x));
                 x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
@@ -424,7 +443,7 @@ pv_process_ring_kernel(const RingParams p) {
                 x[k1] = cmul_s(x[k1], w.x, w.y);
             }
 #pragma unroll
-            for (int k1 = 0; k1 < R1; k1++) ex[65 * k1 + nl] = pack4(x[k1]);
+            for (int k1 = 0; k1 < R1; k1++) ex[G::RS * k1 + nl + (G::G8 - 8) * (nl >> 3)] = pack4(x[k1]);
         }
     }
     pair_sync<TP>(pin);
@@ -448,15 +467,15 @@ pv_process_ring_kernel(const RingParams p) {
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            float4 *bp = ex + 65 * ((tp >> 3) + (R1 / 2) * h) + m3l;
+            float4 *bp = ex + G::RS * ((tp >> 3) + (R1 / 2) * h) + m3l;
             cpx2 x[8];
 #pragma unroll
-            for (int m2 = 0; m2 < 8; m2++) x[m2] = unpack4(bp[8 * m2]);
+            for (int m2 = 0; m2 < 8; m2++) x[m2] = unpack4(bp[G::G8 * m2]);
             dft8<false>(x);
 #pragma unroll
             for (int k2 = 1; k2 < 8; k2++) x[k2] = cmul_s(x[k2], w2[k2].x, w2[k2].y);
 #pragma unroll
-            for (int k2 = 0; k2 < 8; k2++) bp[8 * k2] = pack4(x[k2]);
+            for (int k2 = 0; k2 < 8; k2++) bp[G::G8 * k2] = pack4(x[k2]);
         }
     }
     pair_sync<TP>(pin);
@@ -465,8 +484,8 @@ pv_process_ring_kernel(const RingParams p) {
     // thread 0 owns the two self-paired butterflies: A = bins KS j, B = bins KS/2 + KS j
     const bool l0 = tp == 0;
     const int kB = l0 ? KS / 2 : KS - tp;
-    const int exA = 65 * (tp & (R1 - 1)) + 8 * (tp >> G::LR1);
-    const int exB = 65 * (kB & (R1 - 1)) + 8 * (kB >> G::LR1);
+    const int exA = G::RS * (tp & (R1 - 1)) + G::G8 * (tp >> G::LR1);
+    const int exB = G::RS * (kB & (R1 - 1)) + G::G8 * (kB >> G::LR1);
     cpx2 a[8], b[8];
 #pragma unroll
     for (int c = 0; c < 8; c++) {
@@ -541,15 +560,19 @@ pv_process_ring_kernel(const RingParams p) {
             const int ol1 = krun[(31 - __clz(mask1)) & 15], of1 = krun[(__ffs(mask1) - 1) & 15];
             int pk0, nk0, lk0, pk1, nk1, lk1;
             const int none_above = (2 * 8190) << 16;                  // "peak" at +6142; below: key 0 = "peak" at -2048
-            if constexpr (TP == 32) {
-                const uint32_t nz0 = __ballot_sync(FULL, mask0 != 0), nz1 = __ballot_sync(FULL, mask1 != 0);
-                const uint32_t lt = (1u << tp) - 1u, gt = ~((2u << tp) - 1u);
-                pk0 = __shfl_sync(FULL, ol0, (31 - __clz(nz0 & lt)) & 31);
-                nk0 = __shfl_sync(FULL, of0, (__ffs(nz0 & gt) - 1) & 31);
-                lk0 = __shfl_sync(FULL, ol0, (31 - __clz(nz0)) & 31);
-                pk1 = __shfl_sync(FULL, ol1, (31 - __clz(nz1 & lt)) & 31);
-                nk1 = __shfl_sync(FULL, of1, (__ffs(nz1 & gt) - 1) & 31);
-                lk1 = __shfl_sync(FULL, ol1, (31 - __clz(nz1)) & 31);
+            if constexpr (TP <= 32) {
+                // one ballot bit per thread of the pair (frame 512: the pair's half of the warp)
+                constexpr uint32_t PM = (TP == 32) ? 0xFFFFFFFFu : 0xFFFFu;
+                const int hb = (TP == 32) ? 0 : int(threadIdx.x & 16);
+                const uint32_t nz0 = (__ballot_sync(FULL, mask0 != 0) >> hb) & PM;
+                const uint32_t nz1 = (__ballot_sync(FULL, mask1 != 0) >> hb) & PM;
+                const uint32_t lt = (1u << tp) - 1u, gt = ~((2u << tp) - 1u) & PM;
+                pk0 = __shfl_sync(FULL, ol0, hb + ((31 - __clz(nz0 & lt)) & (TP - 1)));
+                nk0 = __shfl_sync(FULL, of0, hb + ((__ffs(nz0 & gt) - 1) & (TP - 1)));
+                lk0 = __shfl_sync(FULL, ol0, hb + ((31 - __clz(nz0)) & (TP - 1)));
+                pk1 = __shfl_sync(FULL, ol1, hb + ((31 - __clz(nz1 & lt)) & (TP - 1)));
+                nk1 = __shfl_sync(FULL, of1, hb + ((__ffs(nz1 & gt) - 1) & (TP - 1)));
+                lk1 = __shfl_sync(FULL, ol1, hb + ((31 - __clz(nz1)) & (TP - 1)));
                 if (!(nz0 & lt)) pk0 = 0;
                 if (!(nz0 & gt)) nk0 = none_above;
                 if (!(nz1 & lt)) pk1 = 0;
@@ -746,7 +769,7 @@ pv_process_ring_kernel(const RingParams p) {
     for (int e = 0; e < 16; e++) {
         const int h = e / R1, f = e % R1;
         q[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < NJ - nblk) q[e] = al[32 * h + PVB_RING_OFF(f)];
+        if (f < NJ - nblk) q[e] = al[TPH * h + PVB_RING_OFF(f)];
     }
 
     // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_M^{k1 (m3 + 8 m2 + 64 toff)}) -------
@@ -754,16 +777,16 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int k1 = (tp >> 3) + (R1 / 2) * h;
-        float4 *bp = ex + 65 * k1 + m3l;
+        float4 *bp = ex + G::RS * k1 + m3l;
         const float2 *twp = tw1 + G::TW1_ROW * k1 + m3l;
         cpx2 x[8];
 #pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) x[k2] = unpack4(bp[8 * k2]);
+        for (int k2 = 0; k2 < 8; k2++) x[k2] = unpack4(bp[G::G8 * k2]);
         dft8<true>(x);
 #pragma unroll
         for (int m2 = 0; m2 < 8; m2++) {
             const float2 w = twp[8 * m2];
-            bp[8 * m2] = pack4(cmul_s(x[m2], w.x, -w.y));
+            bp[G::G8 * m2] = pack4(cmul_s(x[m2], w.x, -w.y));
         }
     }
     pair_sync<TP>(pin);
@@ -774,30 +797,34 @@ pv_process_ring_kernel(const RingParams p) {
         const float *wol = swout + 2 * tp;
 #pragma unroll
         for (int h = 0; h < G::NB1; h++) {
-            const int nl = tp + 32 * h;
+            const int nl = tp + TPH * h;
             cpx2 x[R1];
 #pragma unroll
-            for (int k1 = 0; k1 < R1; k1++) x[k1] = unpack4(ex[65 * k1 + nl]);
+            for (int k1 = 0; k1 < R1; k1++) x[k1] = unpack4(ex[G::RS * k1 + nl + (G::G8 - 8) * (nl >> 3)]);
             dft_r<R1, true>(x);
 #pragma unroll
             for (int j = 0; j < R1; j++) {
                 // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the division
                 // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
-                const float2 wo = *reinterpret_cast<const float2 *>(wol + 64 * h + 128 * j);
+                const float2 wo = *reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * j);
                 const float4 qv = q[R1 * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
                 if (j < nblk) {                                       // head: emit (ola:111-118)
-                    *reinterpret_cast<float2 *>(o0 + 64 * h + 128 * j) = make_float2(y0.x, y1.x);
-                    if (has1) *reinterpret_cast<float2 *>(o0 + hop + 64 * h + 128 * j) = make_float2(y0.y, y1.y);
+                    *reinterpret_cast<float2 *>(o0 + 2 * TPH * h + 128 * j) = make_float2(y0.x, y1.x);
+                    if (has1) *reinterpret_cast<float2 *>(o0 + hop + 2 * TPH * h + 128 * j) = make_float2(y0.y, y1.y);
                 } else {
-                    al[32 * h + PVB_RING_OFF(j)] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    al[TPH * h + PVB_RING_OFF(j)] = make_float4(y0.x, y0.y, y1.x, y1.y);
                 }
             }
         }
     }
-    // release: state and output of this pair are complete for call my_seq
+    // release: state and output of this pair are complete for call my_seq.  The pair barrier orders
+    // every thread's stores before thread 0's release store, which is cumulative at gpu scope;
+    // PVB_RING_LANE_FENCE=1 additionally fences in every thread (the first version of this code).
+#if PVB_RING_LANE_FENCE
     __threadfence();
+#endif
     pair_sync<TP>(pin);
     if (tp == 0)
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done + pair), "r"(p.my_seq) : "memory");

@@ -30,7 +30,7 @@ def xslot(k):
 
 class Geo:
     def __init__(self, n: int):
-        assert n in (1024, 2048)
+        assert n in (512, 1024, 2048)
         self.N = n
         self.M = n // 2                  # complex FFT length
         self.NB = self.M + 1
@@ -39,8 +39,20 @@ class Geo:
         self.KS = self.M // 8            # stride between the outputs of one last-pass butterfly
         self.NJ = n // 128               # ring blocks of 128 samples
         self.XSLOTS = self.M + self.M // 16 + 2
-        self.EX_SLOTS = 65 * (self.R1 - 1) + 64
+        # exchange slot of element i (0..63) of row k1: rows of 64 slots at stride 65; frame 512 (radix-4
+        # first pass: a quarter-warp of pass 3 spans two k2 groups) pads every group of 8 and uses stride 74
+        self.RS = 65 if self.R1 >= 8 else 74
+        self.GP = 0 if self.R1 >= 8 else 1
+        self.EX_SLOTS = self.RS * (self.R1 - 1) + 64 + 8 * self.GP
+        # bytes per pair: frame 512 keeps two pairs per warp 16 banks apart (32-bit plane accesses)
+        self.PAIR_BYTES = max(self.XSLOTS, self.EX_SLOTS) * 16
+        if self.TP < 32:
+            self.PAIR_BYTES += (64 - self.PAIR_BYTES) % 128
         self.T = np.arange(self.TP)
+
+    def exs(self, k1, i):
+        i = np.asarray(i)
+        return self.RS * np.asarray(k1) + i + self.GP * (i >> 3)
 
 
 def tables(g: Geo, overlaps: int):
@@ -70,8 +82,12 @@ class Conflicts:
     def __init__(self):
         self.worst = {}
 
+    pair_bytes = 0          # frame 512: a warp holds two pairs, the second one this many bytes further
+
     def note(self, name, byte_addr, width):
         byte_addr = np.asarray(byte_addr).reshape(-1)
+        if byte_addr.size == 16:
+            byte_addr = np.concatenate([byte_addr, byte_addr + self.pair_bytes])
         for w0 in range(0, byte_addr.size, 32):          # one warp at a time
             self._warp(name, byte_addr[w0:w0 + 32], width)
 
@@ -113,7 +129,7 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     t = int(t) % N
     nblk = hop // 128
     ex = np.zeros((g.EX_SLOTS, 2), C64)            # exchange: slot -> (ch0, ch1) complex
-    nls = [T, T + 32] if TP == 32 else [T]         # pass-1 butterflies of a thread (n mod 64)
+    nls = [T + TP * h for h in range(16 // R1)]   # pass-1 butterflies of a thread (n mod 64)
 
     # ---- load, window, forward pass 1 (DFT over the 128-sample blocks, stride 64) ---------------
     # Registers are indexed by FRAME block f (so the role of every register -- history, new input,
@@ -141,7 +157,7 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
         z = dft(z)
         for k1 in range(R1):
             v = z[k1] * tw[(2 * (nl + 64 * toff) * k1) % N][:, None]      # W_M^{(n + 64 toff) k1}
-            slot = 65 * k1 + nl
+            slot = g.exs(k1, nl)
             ex[slot] = v
             if cf: cf.note("p1_st", slot * 16, 16)
 
@@ -149,20 +165,19 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     m3 = T & 7
     for h in range(2):
         k1 = (T >> 3) + (R1 // 2) * h
-        base = 65 * k1 + m3
-        x = np.stack([ex[base + 8 * m2] for m2 in range(8)])
+        x = np.stack([ex[g.exs(k1, m3 + 8 * m2)] for m2 in range(8)])
         if cf:
-            for m2 in range(8): cf.note("p2_ld", (base + 8 * m2) * 16, 16)
+            for m2 in range(8): cf.note("p2_ld", g.exs(k1, m3 + 8 * m2) * 16, 16)
         x = dft(x)
         for k2 in range(8):
-            ex[base + 8 * k2] = x[k2] * tw[(w64s * m3 * k2) % N][:, None]       # W_64^{m3 k2}
+            ex[g.exs(k1, m3 + 8 * k2)] = x[k2] * tw[(w64s * m3 * k2) % N][:, None]       # W_64^{m3 k2}
 
     # ---- forward pass 3 (DFT over m3): outputs stay in registers -------------------------------
     kA = T.copy()
     kB = KS - T
     kB[0] = KS // 2                                 # thread 0 owns the two self-paired butterflies
-    sA = 65 * (kA % R1) + 8 * (kA // R1)
-    sB = 65 * (kB % R1) + 8 * (kB // R1)
+    sA = g.exs(kA % R1, 8 * (kA // R1))
+    sB = g.exs(kB % R1, 8 * (kB // R1))
     a = dft(np.stack([ex[sA + c] for c in range(8)]))        # a[j] = Z[kA + KS j]
     b = dft(np.stack([ex[sB + c] for c in range(8)]))        # b[j] = Z[kB + KS j]
     if cf:
@@ -291,6 +306,8 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     # ---- Hermitian C2R pre-pass (mirror of the split) -------------------------------------------
     def unsplit(k):
         yk = X[:, xslot(k)].T.copy(); ym = X[:, xslot(M - k)].T.copy()       # [TP][2]
+        if cf and len(set(k.tolist())) > 1:          # planes of 32-bit words: word = slot
+            cf.note("unsplit_ld_k", xslot(k) * 4, 4); cf.note("unsplit_ld_mk", xslot(M - k) * 4, 4)
         z0 = (k == 0)[:, None]
         yk = np.where(z0, yk.real + 0j, yk); ym = np.where(z0, ym.real + 0j, ym)
         e = yk + np.conj(ym)
@@ -322,14 +339,13 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     # ---- inverse pass 2 (DFT over k2 -> m2), twiddle conj(W_M^{k1 (m3 + 8 m2 + 64 toff)}) -------
     for h in range(2):
         k1 = (T >> 3) + (R1 // 2) * h
-        base = 65 * k1 + m3
-        x = dft(np.stack([ex[base + 8 * k2] for k2 in range(8)]), inv=True)
+        x = dft(np.stack([ex[g.exs(k1, m3 + 8 * k2)] for k2 in range(8)]), inv=True)
         for m2 in range(8):
-            ex[base + 8 * m2] = x[m2] * np.conj(tw[(2 * k1 * (m3 + 8 * m2 + 64 * toff)) % N])[:, None]
+            ex[g.exs(k1, m3 + 8 * m2)] = x[m2] * np.conj(tw[(2 * k1 * (m3 + 8 * m2 + 64 * toff)) % N])[:, None]
     # ---- inverse pass 3 (DFT over k1 -> frame block f); window, overlap-add, emit ---------------
     out = np.zeros((2, hop), F32)
     for nl in nls:
-        x = dft(np.stack([ex[65 * k1 + nl] for k1 in range(R1)]), inv=True)
+        x = dft(np.stack([ex[g.exs(k1, nl)] for k1 in range(R1)]), inv=True)
         for f in range(R1):
             j = (f + toff) % NJ
             i = 2 * nl + 128 * j

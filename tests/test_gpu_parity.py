@@ -153,6 +153,28 @@ def test_parity_ring_kernel_2048(oracle, hop, pf):
     assert err <= RMS_EXPECTED
 
 
+@pytest.mark.parametrize("hop", [128, 256])
+@pytest.mark.parametrize("pf", [0.75, 0.8, 1.0, 1.3, 2.0])
+def test_parity_ring_kernel_512(oracle, hop, pf):
+    """frame 512: half a warp per pair (two pairs share a warp), radix-4 first pass"""
+    from phaze_b200 import BatchedPhaseVocoder
+    with BatchedPhaseVocoder(5, 512, hop) as pv:
+        assert "ring" in pv.kernel_name(np.float32(pf))
+    calls = 3 * (512 // hop) + 5
+    x, ref, got = _run_both(oracle, 512, hop, 5, np.float32(pf), calls)
+    err = _rms(got - ref)
+    print(f"N=512 hop={hop} pf={pf}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("C,pf", [(45, 0.8), (70, 1.25), (2, 0.9)])
+def test_parity_ring_kernel_512_many_channels(oracle, C, pf):
+    """several CTAs of 16 pairs, a warp whose second half-warp has no pair, an odd last channel"""
+    x, ref, got = _run_both(oracle, 512, 128, C, np.float32(pf), 13)
+    per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
+    assert per_channel.max() <= RMS_EXPECTED
+
+
 def test_parity_ring_kernel_2048_many_channels(oracle):
     x, ref, got = _run_both(oracle, 2048, 512, 23, np.float32(0.8), 9)
     per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))

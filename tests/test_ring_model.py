@@ -19,6 +19,7 @@ def _rms(a):
     (1024, 512, 1.5, 6, 1), (1024, 256, 1.0, 9, 0), (1024, 256, 3.0, 8, 2),
     (2048, 512, 1.5, 7, 0), (2048, 512, 0.8, 7, 2), (2048, 128, 0.8, 20, 3), (2048, 128, 1.2, 18, 0),
     (2048, 1024, 2.0, 4, 1),
+    (512, 128, 0.8, 12, 0), (512, 128, 1.2, 12, 3), (512, 256, 1.5, 6, 1), (512, 128, 0.75, 12, 2),
 ])
 def test_model_matches_oracle(oracle, frame, hop, pf, calls, start):
     x = signals.channels(11, 2, calls * hop)
@@ -38,5 +39,13 @@ def test_model_shared_memory_patterns_are_conflict_free(oracle):
     model.run(x, 0.8, 256, cf)
     model.run(signals.channels(0, 2, 5 * 512), 0.8, 512, cf, frame=2048)
     for name in ("p1_st", "p2_ld", "p3_ldA", "p3_ldB", "run_ld", "stale_ld"):
+        assert cf.worst[name] == 1.0, (name, cf.worst)
+    assert max(cf.worst.values()) <= 2.0, cf.worst
+    # frame 512: two pairs per warp, PAIR_BYTES apart; padded exchange rows (stride 74, groups of 9)
+    cf = model.Conflicts()
+    cf.pair_bytes = model.Geo(512).PAIR_BYTES
+    assert cf.pair_bytes == 4800
+    model.run(signals.channels(0, 2, 6 * 128), 0.8, 128, cf, frame=512)
+    for name in ("p1_st", "p2_ld", "p3_ldA", "run_ld", "stale_ld"):
         assert cf.worst[name] == 1.0, (name, cf.worst)
     assert max(cf.worst.values()) <= 2.0, cf.worst
