@@ -492,7 +492,7 @@ def run_root_scatter(C, frame, hop, pitch, world, rank, local, steps, host_block
     del sh
     # streamed root mode: audio buffers of Kc calls per message ([C][Kc*hop]), scatter of buffer i+1
     # and gather of buffer i-1 under the kernels of buffer i
-    Kc, nbuf = 16, 12
+    Kc, nbuf = int(os.environ.get("PVB_BENCH_STREAM_CALLS", "16")), 12
     sh = ShardedPhaseVocoder(total, frame, hop, device=torch.device("cuda", local))
     bufs = None
     if rank == 0:

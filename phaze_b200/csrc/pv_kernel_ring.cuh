@@ -34,7 +34,14 @@ namespace pvb {
 // channel pairs (warps) per CTA at frame 1024; two CTAs per SM at 128 registers.  7 fills one wave
 // of 4096 channels on 148 SMs exactly; 8 uses the whole register file (16 warps per SM).
 #ifndef PVB_RING_LANE_FENCE
-#define PVB_RING_LANE_FENCE 1
+#define PVB_RING_LANE_FENCE 0
+#endif
+// The shifted spectrum Y lives in four planes of 32-bit words, bin d at word d + (d >> YSHIFT).  The
+// pad decides which lanes of the scatter collide (lanes own runs 16 bins apart, shifted by their
+// region's delta); 5 is the best single choice over pitch factors 0.75 .. 2 (model: 1.8 - 2.8
+// wavefronts per store; 4: 1.9 - 4.7, worst at pitch factor 1.25).
+#ifndef PVB_RING_YSHIFT
+#define PVB_RING_YSHIFT 5
 #endif
 #ifndef PVB_RING_PAIRS_1024
 #define PVB_RING_PAIRS_1024 7
@@ -233,7 +240,7 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
         const bool take_next = tt < ((4 * e) << 16);
         const int okey = take_next ? nx[e] : pkey;
         const int d = (okey & 0xFFFF) + cb + e;
-        const unsigned slot = min(unsigned(d + (d >> 4)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
+        const unsigned slot = min(unsigned(d + (d >> PVB_RING_YSHIFT)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
         dst[e] = int(4u * slot) | ((tt - ((4 * e) << 16)) & second_flag);
     }
 }
@@ -520,7 +527,7 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- peaks, regions of influence, shift (pv:95-173) -------------------------------------------------
     // X lives in float4 slots (both channels per bin); the shifted spectrum Y is written over it as
-    // four planes of floats (re0 | re1 | im0 | im1, bin d at word d + (d >> 4)): the 32-bit scatter of
+    // four planes of floats (re0 | re1 | im0 | im1, bin d at word d + (d >> YSHIFT)): the 32-bit scatter of
     // threads that own runs 16 bins apart then spreads over all banks.
     if (!(p.skip & 1))
     {
@@ -656,8 +663,8 @@ pv_process_ring_kernel(const RingParams p) {
             for (int i = 0; i < 4; i++) {
                 const int d = M + tp + TP * i + dl0;
                 if (unsigned(d) < unsigned(NB)) {
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4))) = ext[i].x;
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + 2 * PL) = ext[i].z;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT))) = ext[i].x;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT)) + 2 * PL) = ext[i].z;
                 }
             }
         }
@@ -666,8 +673,8 @@ pv_process_ring_kernel(const RingParams p) {
             for (int i = 0; i < 4; i++) {
                 const int d = M + tp + TP * i + dl1;
                 if (unsigned(d) < unsigned(NB)) {
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + PL) = ext[i].y;
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> 4)) + 3 * PL) = ext[i].w;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT)) + PL) = ext[i].y;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT)) + 3 * PL) = ext[i].w;
                 }
             }
         }
@@ -705,10 +712,17 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- Hermitian C2R pre-pass in registers (mirror of the split) -------------------------------------
     {
+        // words of the same bins in the Y planes (pad every 2^YS bins instead of every 16)
+        constexpr int YS = PVB_RING_YSHIFT, YP = 1 << YS;
+        constexpr int YSS = KS + (KS >> YS), YSM = M + (M >> YS);
+        static_assert(KS % YP == 0 && YS >= 4, "Y-plane padding must divide the butterfly stride and fit the buffer");
+        const int yA = tp + (tp >> YS), yB = YSM - tp - ((tp + YP - 1) >> YS);
+        const int yAlo = l0 ? KS / 2 + ((KS / 2) >> YS) : yA, yAhi = l0 ? -4 * YSS : yA;
+        const int yBlo = l0 ? YSM - KS / 2 - ((KS / 2 + YP - 1) >> YS) : yB, yBhi = l0 ? YSM + 4 * YSS : yB;
         cpx2 zk[8], zmk[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int sa = (j < 4 ? sAlo : sAhi) + SS * j, sb = (j < 4 ? sBlo : sBhi) - SS * j;
+            const int sa = (j < 4 ? yAlo : yAhi) + YSS * j, sb = (j < 4 ? yBlo : yBhi) - YSS * j;
             cpx2 yk = ring_load_planes<G::XQ_SLOTS>(mine, sa), ym = ring_load_planes<G::XQ_SLOTS>(mine, sb);
             if (j == 4) {                        // thread 0: k == 0, bins 0 and N/2 enter with their real part only
                 yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
@@ -719,7 +733,7 @@ pv_process_ring_kernel(const RingParams p) {
         }
         cpx2 zh, dummy;
         {
-            const cpx2 y = ring_load_planes<G::XQ_SLOTS>(mine, M / 2 + M / 32);
+            const cpx2 y = ring_load_planes<G::XQ_SLOTS>(mine, M / 2 + ((M / 2) >> YS));
             ring_unsplit(y, y, twh[M / 2], zh, dummy);
         }
         a[0] = sel(l0, zk[4], zk[0]);

@@ -104,6 +104,7 @@ class ShardedPhaseVocoder:
         if processor_factory is None:
             processor_factory = lambda n: _CudaShard(n, frame_size, hop_size, device)   # noqa: E731
         self.engine = processor_factory(self.local_channels)
+        self._gather_group = None       # second communicator: results travel while the next slabs arrive
 
     # -- shard-resident steady state: no collective --------------------------------------------
     def process_local(self, local_block: Optional[torch.Tensor], pitch_factor: float) -> torch.Tensor:
@@ -165,8 +166,9 @@ class ShardedPhaseVocoder:
         A rank's slab of a buffer is contiguous, so it is sent and received in place (one message
         of K hops per peer and direction); the [channel][call] <-> [call][channel] re-ordering the
         kernels need happens on the owning rank.  Messages are posted one buffer ahead: the scatter
-        of buffer i+1 and the gather of buffer i-1 overlap the kernels of buffer i.  The result is
-        bit-identical to `num_buffers * K` process_from_root calls."""
+        of buffer i+1 and the gather of buffer i-1 overlap the kernels of buffer i; the gathers use
+        a communicator of their own (their own NCCL stream), so both NVLink directions are busy at
+        once.  The result is bit-identical to `num_buffers * K` process_from_root calls."""
         hop, K = self.hop_size, calls_per_buffer
         Cl, lo, hi = self.local_channels, self.first, self.last
         is_root = self.rank == root
@@ -177,6 +179,11 @@ class ShardedPhaseVocoder:
                 out = self._engine_many(blocks, pitch_factor)
                 results.append(out.transpose(0, 1).contiguous().view(Cl, K * hop))
             return results
+
+        if self._gather_group is None:
+            self._gather_group = dist.new_group(ranks=list(range(self.world))) if self.group is None \
+                else dist.new_group(ranks=dist.get_process_group_ranks(self.group))
+        ggroup = self._gather_group
 
         def post_scatter(i):
             """-> (works, this rank's [Cl][K*hop] slab of buffer i)"""
@@ -202,9 +209,9 @@ class ShardedPhaseVocoder:
                 res[lo:hi] = out_slab
                 for r, (a, b) in enumerate(self.bounds):
                     if r != root and b > a:
-                        ops.append(dist.P2POp(dist.irecv, res[a:b], r, self.group))
+                        ops.append(dist.P2POp(dist.irecv, res[a:b], r, ggroup))
             elif Cl > 0:
-                ops.append(dist.P2POp(dist.isend, out_slab, root, self.group))
+                ops.append(dist.P2POp(dist.isend, out_slab, root, ggroup))
             return (dist.batch_isend_irecv(ops) if ops else []), res
 
         pending_in = post_scatter(0) if num_buffers > 0 else None

@@ -30,7 +30,7 @@ def xslot(k):
 
 class Geo:
     def __init__(self, n: int):
-        assert n in (512, 1024, 2048)
+        assert n in (512, 1024, 2048, 4096)
         self.N = n
         self.M = n // 2                  # complex FFT length
         self.NB = self.M + 1
@@ -82,6 +82,7 @@ class Conflicts:
     def __init__(self):
         self.worst = {}
 
+    scatter_log = None      # experiments: list of (destination bins, active lanes) per 32-bit scatter access
     pair_bytes = 0          # frame 512: a warp holds two pairs, the second one this many bytes further
 
     def note(self, name, byte_addr, width):
@@ -137,6 +138,39 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     # ring blocks of the rotated register array is the DFT over f times W_R1^{toff k1} (shift theorem),
     # which is folded into the pass-1 twiddle: W_M^{(n + 64 toff) k1}.
     toff = (t // 128) % NJ
+    w32s, w128s = N // 32, N // 128                 # W_32^x = tw[w32s * x], W_128^x = tw[w128s * x]
+    sg = -1.0 if (toff & 1) else 1.0
+    if R1 == 32:
+        # frame 4096: a thread holds 16 of the 32 frame blocks of its column n, those of parity s
+        # (f = 2 f' + s), and does a 16-point DFT over f'; the radix-2 step that completes the
+        # 32-point DFT over f is done by the READER in pass 2, which holds rows k' and k' + 16 anyway:
+        #   row (s, k') = E_s[k'] W_M^{(n + 64 toff) k'} W_32^{s k'}
+        #   X[k'] = row(0) + row(1),  X[k' + 16] = (row(0) - row(1)) W_128^n (-1)^toff
+        assert nblk % 2 == 0
+        n_ = T & 63; s_ = T >> 6
+        z = np.zeros((16, TP, 2), C64)
+        for fp in range(16):
+            f = 2 * fp + s_
+            j = (f + toff) % NJ
+            i = 2 * n_ + 128 * j
+            if fp >= 16 - nblk // 2:                # new block (both parities)
+                si = 2 * n_ + 128 * (f - (NJ - nblk))
+                if inblk is None:
+                    x0 = np.zeros((TP, 2), F32); x1 = np.zeros((TP, 2), F32)
+                else:
+                    x0 = inblk[:, si].T.astype(F32); x1 = inblk[:, si + 1].T.astype(F32)
+                hist2[i] = x0; hist2[i + 1] = x1
+            else:
+                x0 = hist2[i]; x1 = hist2[i + 1]
+            fi = 2 * n_ + 128 * f
+            w0 = win[fi][:, None]; w1 = win[fi + 1][:, None]
+            z[fp] = (x0 * w0).astype(F32) + 1j * (x1 * w1).astype(F32)
+        z = dft(z)
+        for kp in range(16):
+            twd = (tw[(2 * (n_ + 64 * toff) * kp) % N] * tw[(w32s * s_ * kp) % N]).astype(C64)
+            slot = g.exs(16 * s_ + kp, n_)
+            ex[slot] = z[kp] * twd[:, None]
+            if cf: cf.note("p1_st", slot * 16, 16)
     for nl in nls:
         z = np.zeros((R1, TP, 2), C64)
         for f in range(R1):
@@ -163,7 +197,20 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
 
     # ---- forward pass 2 (DFT over m2), in place -------------------------------------------------
     m3 = T & 7
-    for h in range(2):
+    if R1 == 32:
+        kp = T >> 3
+        A0 = np.stack([ex[g.exs(kp, m3 + 8 * m2)] for m2 in range(8)])
+        A1 = np.stack([ex[g.exs(16 + kp, m3 + 8 * m2)] for m2 in range(8)])
+        if cf:
+            for m2 in range(8):
+                cf.note("p2_ld", g.exs(kp, m3 + 8 * m2) * 16, 16); cf.note("p2_ld", g.exs(16 + kp, m3 + 8 * m2) * 16, 16)
+        wn = np.stack([tw[(w128s * (m3 + 8 * m2)) % N] * sg for m2 in range(8)]).astype(C64)
+        x0 = dft((A0 + A1).astype(C64)); x1 = dft(((A0 - A1).astype(C64) * wn[:, :, None]).astype(C64))
+        for k2 in range(8):
+            w = tw[(w64s * m3 * k2) % N][:, None]
+            ex[g.exs(kp, m3 + 8 * k2)] = x0[k2] * w
+            ex[g.exs(16 + kp, m3 + 8 * k2)] = x1[k2] * w
+    for h in range(2 if R1 < 32 else 0):
         k1 = (T >> 3) + (R1 // 2) * h
         x = np.stack([ex[g.exs(k1, m3 + 8 * m2)] for m2 in range(8)])
         if cf:
@@ -284,6 +331,7 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
         written = np.zeros(g.XSLOTS, np.int64)
         for e in range(16):                           # first sub-step: plain stores
             ok = (dest[e] >= 0) & (dest[e] < NB) & first[e]
+            if cf is not None and cf.scatter_log is not None: cf.scatter_log.append((dest[e].copy(), ok.copy()))
             for L in np.nonzero(ok)[0]:
                 written[xslot(dest[e][L])] += 1
                 X[ch, xslot(dest[e][L])] = xv[e][L]
@@ -298,6 +346,7 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
         if contract:
             for e in range(16):                       # second sub-step: left halves add on top
                 ok = (dest[e] >= 0) & (dest[e] < NB) & ~first[e]
+                if cf is not None and cf.scatter_log is not None: cf.scatter_log.append((dest[e].copy(), ok.copy()))
                 for L in np.nonzero(ok)[0]:
                     written[xslot(dest[e][L])] += 1
                     X[ch, xslot(dest[e][L])] += xv[e][L]
@@ -337,13 +386,44 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
         ex[sA + c] = a[c] * np.conj(tw[(w64s * (kA // R1) * c) % N])[:, None]
         ex[sB + c] = b[c] * np.conj(tw[(w64s * (kB // R1) * c) % N])[:, None]
     # ---- inverse pass 2 (DFT over k2 -> m2), twiddle conj(W_M^{k1 (m3 + 8 m2 + 64 toff)}) -------
-    for h in range(2):
+    if R1 == 32:
+        kp = T >> 3
+        d0 = dft(np.stack([ex[g.exs(kp, m3 + 8 * k2)] for k2 in range(8)]), inv=True)
+        d1 = dft(np.stack([ex[g.exs(16 + kp, m3 + 8 * k2)] for k2 in range(8)]), inv=True)
+        for m2 in range(8):
+            nn = m3 + 8 * m2
+            tc = np.conj(tw[(2 * kp * (nn + 64 * toff)) % N])
+            cw = np.conj(tw[(w128s * nn) % N]) * sg
+            v1 = (d1[m2] * cw[:, None]).astype(C64)
+            ex[g.exs(kp, nn)] = ((d0[m2] + v1).astype(C64) * tc[:, None]).astype(C64)
+            ex[g.exs(16 + kp, nn)] = ((d0[m2] - v1).astype(C64)
+                                      * (tc * np.conj(tw[(w32s * kp) % N])).astype(C64)[:, None]).astype(C64)
+    for h in range(2 if R1 < 32 else 0):
         k1 = (T >> 3) + (R1 // 2) * h
         x = dft(np.stack([ex[g.exs(k1, m3 + 8 * k2)] for k2 in range(8)]), inv=True)
         for m2 in range(8):
             ex[g.exs(k1, m3 + 8 * m2)] = x[m2] * np.conj(tw[(2 * k1 * (m3 + 8 * m2 + 64 * toff)) % N])[:, None]
     # ---- inverse pass 3 (DFT over k1 -> frame block f); window, overlap-add, emit ---------------
     out = np.zeros((2, hop), F32)
+    if R1 == 32:
+        n_ = T & 63; s_ = T >> 6
+        x = dft(np.stack([ex[g.exs(16 * s_ + kp, n_)] for kp in range(16)]), inv=True)
+        for fp in range(16):
+            f = 2 * fp + s_
+            j = (f + toff) % NJ
+            i = 2 * n_ + 128 * j
+            fi = 2 * n_ + 128 * f
+            w0 = win_out[fi][:, None]; w1 = win_out[fi + 1][:, None]
+            y0 = (x[fp].real.astype(F32) * w0).astype(F32); y1 = (x[fp].imag.astype(F32) * w1).astype(F32)
+            tail = fp >= 16 - nblk // 2
+            q0 = np.zeros((TP, 2), F32) if tail else acc2[i]
+            q1 = np.zeros((TP, 2), F32) if tail else acc2[i + 1]
+            y0 = y0 + q0; y1 = y1 + q1
+            if fp < nblk // 2:
+                si = 2 * n_ + 128 * f
+                out[:, si] = y0.T; out[:, si + 1] = y1.T
+            else:
+                acc2[i] = y0; acc2[i + 1] = y1
     for nl in nls:
         x = dft(np.stack([ex[g.exs(k1, nl)] for k1 in range(R1)]), inv=True)
         for f in range(R1):
