@@ -66,6 +66,7 @@ std::unordered_map<cudaStream_t, std::vector<RecentIo>> g_recent_io;
 // and a grid-mode launch behind it must not load anything before its griddepcontrol.wait
 std::unordered_map<cudaStream_t, bool> g_last_flag_mode;
 int g_ring_pad_kb = 0;
+int g_ring_4096 = 1;             // PVB_RING_4096=0: frame 4096 falls back to the CTA kernel
 int g_ring_512 = 1;              // PVB_RING_512=0: frame 512 falls back to the CTA kernel
 int g_ring_wpc = 0;              // PVB_RING_WPC: warps (pairs) per CTA of the ring kernel (0: balance one wave)
 bool g_no_flags = false;         // PVB_NO_FLAGS=1: ring kernel always in grid mode (experiments)
@@ -211,43 +212,17 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
 
 // ring-order kernel (pv_kernel_ring.cuh): paired state layout aligned to the time cursor
 bool ring_kernel_applies(const pvb_processor *h, const pvb::FrameParams &fp) {
-    return ((h->n == 512 && g_ring_512) || h->n == 1024 || h->n == 2048) && fast_range(fp) &&
-           h->hop % 128 == 0 && h->hop <= h->n / 2 && g_kernel_1024 == 0 && !g_force_generic;
+    // frame 4096 keeps the frame blocks of one parity per thread: the hop must be a multiple of 256
+    return ((h->n == 512 && g_ring_512) || h->n == 1024 || h->n == 2048 || (h->n == 4096 && g_ring_4096)) &&
+           fast_range(fp) && h->hop % (h->n == 4096 ? 256 : 128) == 0 && h->hop <= h->n / 2 &&
+           g_kernel_1024 == 0 && !g_force_generic;
 }
 
 size_t state_rows(int channels);
 
-cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        const int smem = 227 * 1024;
-        cudaError_t e = cudaSuccess;
-#define PVB_RING_ATTR(N, NBLK)                                                                    \
-        if (e == cudaSuccess)                                                                     \
-            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLK>,                        \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        PVB_RING_ATTR(512, 1) PVB_RING_ATTR(512, 2)
-        PVB_RING_ATTR(1024, 1) PVB_RING_ATTR(1024, 2) PVB_RING_ATTR(1024, 4)
-        PVB_RING_ATTR(2048, 1) PVB_RING_ATTR(2048, 2) PVB_RING_ATTR(2048, 4) PVB_RING_ATTR(2048, 8)
-#undef PVB_RING_ATTR
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
-    const int pairs = (fp.num_channels + 1) / 2;
-    if (pairs == 0) return cudaSuccess;
-    const bool big = h->n == 2048, small = h->n == 512;
-    // pairs per CTA: frame 1024 balances one wave (4..7 warps); frame 2048 uses 4 pairs of two warps;
-    // frame 512 packs 16 half-warp pairs (8 warps)
-    int ppc = big ? 4 : small ? pvb::RingGeoT<512>::MAX_PAIRS : pick_warps_per_cta(pairs, h->num_sms);
-    const int max_ppc = big ? pvb::RingGeoT<2048>::MAX_PAIRS
-                            : small ? pvb::RingGeoT<512>::MAX_PAIRS : pvb::RingGeoT<1024>::MAX_PAIRS;
-    const int min_ppc = big ? pvb::RingGeoT<2048>::MIN_PAIRS
-                            : small ? pvb::RingGeoT<512>::MIN_PAIRS : pvb::RingGeoT<1024>::MIN_PAIRS;
-    if (g_ring_wpc >= min_ppc && g_ring_wpc <= max_ppc) ppc = g_ring_wpc;
-    const int grid = (pairs + ppc - 1) / ppc;
-    const int threads = ppc * (big ? pvb::RingGeoT<2048>::TP : small ? pvb::RingGeoT<512>::TP : pvb::RingGeoT<1024>::TP);
+// everything of a ring-order launch that does not depend on the frame size (one call per launch:
+// it records the caller's buffers and decides between flag mode and grid mode)
+pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
     pvb::RingParams rp;
     rp.in = fp.in;
     rp.out = fp.out;
@@ -297,6 +272,65 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     rp.stuck = h->d_done + (state_rows(h->channels) / 2);
     rp.wait_seq = h->ring_seq;
     rp.my_seq = h->ring_seq + 1;
+    return rp;
+}
+
+cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        const int smem = 227 * 1024;
+        cudaError_t e = cudaSuccess;
+#define PVB_RING_ATTR(N, NBLK)                                                                    \
+        if (e == cudaSuccess)                                                                     \
+            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLK>,                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        PVB_RING_ATTR(512, 1) PVB_RING_ATTR(512, 2)
+        PVB_RING_ATTR(1024, 1) PVB_RING_ATTR(1024, 2) PVB_RING_ATTR(1024, 4)
+        PVB_RING_ATTR(2048, 1) PVB_RING_ATTR(2048, 2) PVB_RING_ATTR(2048, 4) PVB_RING_ATTR(2048, 8)
+        PVB_RING_ATTR(4096, 2) PVB_RING_ATTR(4096, 4) PVB_RING_ATTR(4096, 8) PVB_RING_ATTR(4096, 16)
+#undef PVB_RING_ATTR
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int pairs = (fp.num_channels + 1) / 2;
+    if (pairs == 0) return cudaSuccess;
+    if (h->n == 4096) {
+        using G = pvb::RingGeoT<4096>;
+        int ppc4 = G::MAX_PAIRS;
+        if (g_ring_wpc >= G::MIN_PAIRS && g_ring_wpc <= G::MAX_PAIRS) ppc4 = g_ring_wpc;
+        pvb::RingParams rp = make_ring_params(h, fp, s);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((pairs + ppc4 - 1) / ppc4);
+        cfg.blockDim = dim3(ppc4 * G::TP);
+        cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc4) * G::PAIR_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;
+        switch (rp.hop >> 7) {
+            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 2>, rp);
+            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 4>, rp);
+            case 8: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 8>, rp);
+            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 16>, rp);
+        }
+    }
+    const bool big = h->n == 2048, small = h->n == 512;
+    // pairs per CTA: frame 1024 balances one wave (4..7 warps); frame 2048 uses 4 pairs of two warps;
+    // frame 512 packs 16 half-warp pairs (8 warps)
+    int ppc = big ? 4 : small ? pvb::RingGeoT<512>::MAX_PAIRS : pick_warps_per_cta(pairs, h->num_sms);
+    const int max_ppc = big ? pvb::RingGeoT<2048>::MAX_PAIRS
+                            : small ? pvb::RingGeoT<512>::MAX_PAIRS : pvb::RingGeoT<1024>::MAX_PAIRS;
+    const int min_ppc = big ? pvb::RingGeoT<2048>::MIN_PAIRS
+                            : small ? pvb::RingGeoT<512>::MIN_PAIRS : pvb::RingGeoT<1024>::MIN_PAIRS;
+    if (g_ring_wpc >= min_ppc && g_ring_wpc <= max_ppc) ppc = g_ring_wpc;
+    const int grid = (pairs + ppc - 1) / ppc;
+    const int threads = ppc * (big ? pvb::RingGeoT<2048>::TP : small ? pvb::RingGeoT<512>::TP : pvb::RingGeoT<1024>::TP);
+    pvb::RingParams rp = make_ring_params(h, fp, s);
     // PVB_RING_PAD_KB: occupancy experiment (extra dynamic shared memory per CTA)
     const size_t smem = (big ? pvb::RingGeoT<2048>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<2048>::PAIR_BYTES
                          : small ? pvb::RingGeoT<512>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<512>::PAIR_BYTES
@@ -583,6 +617,8 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         g_no_pdl = env && env[0] == '1';
         env = std::getenv("PVB_RING_PAD_KB");
         g_ring_pad_kb = env ? std::atoi(env) : 0;
+        env = std::getenv("PVB_RING_4096");
+        g_ring_4096 = env ? std::atoi(env) : 1;
         env = std::getenv("PVB_RING_512");
         g_ring_512 = env ? std::atoi(env) : 1;
         env = std::getenv("PVB_RING_WPC");
@@ -658,13 +694,15 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         fail(p, PVB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(PVB_ERR_CUDA);
     }
-    if (n == 512 || n == 1024 || n == 2048) {
+    if (n == 512 || n == 1024 || n == 2048 || n == 4096) {
         const size_t tab_bytes = n == 512 ? pvb::ring_host_table_bytes<512>()
-                                          : n == 1024 ? pvb::ring_host_table_bytes<1024>() : pvb::ring_host_table_bytes<2048>();
+                                 : n == 1024 ? pvb::ring_host_table_bytes<1024>()
+                                 : n == 2048 ? pvb::ring_host_table_bytes<2048>() : pvb::ring_host_table_bytes<4096>();
         std::vector<float2> rt(tab_bytes / sizeof(float2));
         if (n == 512) pvb::ring_host_tables<512>(tw.data(), rt.data());
         else if (n == 1024) pvb::ring_host_tables<1024>(tw.data(), rt.data());
-        else pvb::ring_host_tables<2048>(tw.data(), rt.data());
+        else if (n == 2048) pvb::ring_host_tables<2048>(tw.data(), rt.data());
+        else pvb::ring_host_tables<4096>(tw.data(), rt.data());
         if (cudaMalloc(&p->d_ring_tab, tab_bytes) != cudaSuccess ||
             cudaMemcpy(p->d_ring_tab, rt.data(), tab_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
             fail(p, PVB_ERR_CUDA, "ring table upload failed: %s", cudaGetErrorString(cudaGetLastError()));

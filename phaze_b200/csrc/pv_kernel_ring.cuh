@@ -53,9 +53,14 @@ struct RingGeoT {
     static constexpr int TP = N / 32;                       // threads per channel pair (16 complex points each):
                                                             // half a warp (512), a warp (1024), two warps (2048)
     static constexpr int WPP = TP / 32;                     // warps per pair (0: two pairs share a warp)
-    static constexpr int R1 = M / 64;                       // radix of the first pass: 4, 8 or 16
-    static constexpr int LR1 = (R1 == 4) ? 2 : (R1 == 8) ? 3 : 4;
-    static constexpr int NB1 = 16 / R1;                     // first-pass butterflies per thread
+    static constexpr int R1 = M / 64;                       // radix of the first pass: 4, 8, 16 or 32
+    static constexpr int LR1 = (R1 == 4) ? 2 : (R1 == 8) ? 3 : (R1 == 16) ? 4 : 5;
+    // frame 4096: a thread holds the 16 frame blocks of one parity (f = 2 f' + s) of its column and
+    // does a 16-point DFT over f'; the radix-2 step that completes the 32-point DFT over f is done by
+    // the reader in pass 2 (it holds rows k' and k' + 16 anyway), so there is no fourth exchange
+    static constexpr int RT = (R1 > 16) ? 16 : R1;          // radix a thread does in registers in pass 1
+    static constexpr int NSPL = R1 / RT;                    // 2: rows of the exchange are (s, k')
+    static constexpr int NB1 = 16 / RT;                     // first-pass butterflies per thread
     static constexpr int KS = M / 8;                        // stride between the outputs of a last-pass butterfly
     static constexpr int SS = KS + KS / 16;                 // the same in spectrum slots
     static constexpr int NJ = N / 128;                      // ring blocks of 128 samples
@@ -79,15 +84,18 @@ struct RingGeoT {
     static constexpr int TW1_BYTES = R1 * TW1_ROW * 8;      // tw1[k1][n] = W_M^{n k1}, n < 64
     static constexpr int W64_BYTES = 64 * 8;                // w64[a][b] = W_64^{a b}
     static constexpr int TWH_BYTES = (M + 8) * 8;           // twh[k] = W_N^k, k <= M
-    static constexpr int GTAB_BYTES = TW1_BYTES + W64_BYTES + TWH_BYTES;    // copied verbatim from global
+    static constexpr int W128_BYTES = (NSPL == 2) ? 64 * 8 : 0;             // w128[n] = W_128^n, n < 64 (frame 4096)
+    static constexpr int GTAB_BYTES = TW1_BYTES + W64_BYTES + TWH_BYTES + W128_BYTES;    // copied verbatim from global
     static constexpr int WIN_BYTES = N * 4;                 // window / synthesis window, rotated by t
     static constexpr int OFF_TW1 = DTAB_BYTES;
     static constexpr int OFF_W64 = OFF_TW1 + TW1_BYTES;
     static constexpr int OFF_TWH = OFF_W64 + W64_BYTES;
-    static constexpr int OFF_WIN = OFF_TWH + TWH_BYTES;
+    static constexpr int OFF_W128 = OFF_TWH + TWH_BYTES;
+    static constexpr int OFF_WIN = OFF_W128 + W128_BYTES;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;
-    static constexpr int MAX_PAIRS = (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA; two CTAs per SM
+    static constexpr int MAX_PAIRS = (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA
+    static constexpr int CTAS_PER_SM = (N == 4096) ? 1 : 2; // frame 4096: 77 KB of tables + 4 x 36 KB
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
     static constexpr int MIN_PAIRS = (MIN_THREADS + TP - 1) / TP;
@@ -245,7 +253,45 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
     }
 }
 
-// N = frame size (1024: one warp per pair, 2048: two warps per pair), NBLK = hop / 128.
+// Threads of a pair that hold a peak, as WPP ballot words bal[0..WPP): the nearest such thread
+// below / above thread tp, and the last one (-1: none)
+template <int WPP>
+__device__ __forceinline__ int ring_thread_below(const int *bal, int tp) {
+    int res = -1;
+#pragma unroll
+    for (int w = 0; w < WPP; w++) {
+        const uint32_t m = uint32_t(bal[w]);
+        const int rel = tp - 32 * w;                                  // bits below rel count
+        const uint32_t mm = (rel <= 0) ? 0u : (rel >= 32) ? m : (m & ((1u << rel) - 1u));
+        if (mm) res = 32 * w + 31 - __clz(mm);
+    }
+    return res;
+}
+template <int WPP>
+__device__ __forceinline__ int ring_thread_above(const int *bal, int tp) {
+    int res = -1;
+#pragma unroll
+    for (int w = WPP - 1; w >= 0; w--) {
+        const uint32_t m = uint32_t(bal[w]);
+        const int rel = tp - 32 * w;                                  // bits above rel count
+        const uint32_t mm = (rel >= 31) ? 0u : (rel < 0) ? m : (m & ~((2u << rel) - 1u));
+        if (mm) res = 32 * w + __ffs(mm) - 1;
+    }
+    return res;
+}
+template <int WPP>
+__device__ __forceinline__ int ring_thread_last(const int *bal) {
+    int res = -1;
+#pragma unroll
+    for (int w = 0; w < WPP; w++) {
+        const uint32_t m = uint32_t(bal[w]);
+        if (m) res = 32 * w + 31 - __clz(m);
+    }
+    return res;
+}
+
+// N = frame size (512: half a warp per pair, 1024: one warp, 2048: two warps, 4096: four warps),
+// NBLK = hop / 128.
 // Registers of the first / last FFT pass are indexed by FRAME block f (128 samples), so the role
 // of every register (history / new input / emitted head / zero tail) is a compile-time fact: no
 // predicated duplicates of the global accesses.  Frame block f sits in ring block (f + toff) mod
@@ -254,7 +300,7 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
 // theorem); that factor is folded into the first-pass twiddles, W_M^{(n + 64 toff) k1}: the host
 // keeps one such table per toff and the CTA stages the one it needs.
 template <int N, int NBLK>
-__global__ void __launch_bounds__(RingGeoT<N>::MAX_PAIRS * RingGeoT<N>::TP, 2)
+__global__ void __launch_bounds__(RingGeoT<N>::MAX_PAIRS * RingGeoT<N>::TP, RingGeoT<N>::CTAS_PER_SM)
 pv_process_ring_kernel(const RingParams p) {
     using G = RingGeoT<N>;
     constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
@@ -270,6 +316,7 @@ pv_process_ring_kernel(const RingParams p) {
     const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
     const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
     const float2 *twh = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
+    const float2 *w128 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W128);   // frame 4096 only
     const float *swin = reinterpret_cast<const float *>(smem_raw + G::OFF_WIN);
     const float *swout = reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
     unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(pin) * G::PAIR_BYTES;
@@ -315,9 +362,9 @@ pv_process_ring_kernel(const RingParams p) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_tab + 16 * i), "l"(g_tw1 + i));
         }
 #pragma unroll
-        for (int k = 0; k < ((G::W64_BYTES + G::TWH_BYTES) / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
+        for (int k = 0; k < ((G::W64_BYTES + G::TWH_BYTES + G::W128_BYTES) / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
-            if (i < (G::W64_BYTES + G::TWH_BYTES) / 16)
+            if (i < (G::W64_BYTES + G::TWH_BYTES + G::W128_BYTES) / 16)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_rest + 16 * i), "l"(g_rest + i));
         }
 #pragma unroll
@@ -354,8 +401,21 @@ pv_process_ring_kernel(const RingParams p) {
     //   p.early == 1: the previous kernel may be this handle's last call -> all but its newest block
     // The input block always waits (it belongs to the caller's stream order).
     constexpr int TPH = (TP < 32) ? TP : 32;        // float4 stride between the first-pass butterflies of a thread
+    constexpr int RT = G::RT, NSPL = G::NSPL;
+    static_assert(NBLK % NSPL == 0, "frame 4096: the hop must cover an even number of 128-sample blocks");
+    // register e of a thread: first-pass butterfly h, role index fr (history / new input / emitted head
+    // / zero tail are compile-time facts of fr), frame block f.  Frame 4096: column cn = tp mod 64,
+    // parity sp = tp / 64, f = 2 fr + sp.
+    const int cn = (NSPL == 2) ? (tp & 63) : tp;
+    const int sp = (NSPL == 2) ? (tp >> 6) : 0;
+    constexpr int NEWFROM = RT - NBLK / NSPL;       // fr >= NEWFROM: new input
+    constexpr int OLDTO = RT - 2 * NBLK / NSPL;     // fr < OLDTO: written before the previous call
+    constexpr int HEADTO = NBLK / NSPL;             // fr < HEADTO: emitted
+#define PVB_FR(e) ((NSPL == 2) ? (e) : (e) % RT)
+#define PVB_FH(e) ((NSPL == 2) ? 0 : (e) / RT)
+#define PVB_FB(fr) ((NSPL == 2) ? 2 * (fr) + sp : (fr))
     float4 r[16];
-    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + tp;
+    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + cn;
     const int early = p.flag_mode ? 0 : p.early;
     if (p.flag_mode) {
         if (live) {
@@ -377,9 +437,9 @@ pv_process_ring_kernel(const RingParams p) {
     } else if (live && early) {
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int h = e / R1, f = e % R1;
-            // f >= NJ - nblk: new input; the nblk blocks below: what the previous call wrote
-            if (f < NJ - nblk && (f < NJ - 2 * nblk || early == 2)) r[e] = hl[TPH * h + PVB_RING_OFF(f)];
+            const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
+            // fr >= NEWFROM: new input; the blocks below down to OLDTO: what the previous call wrote
+            if (fr < NEWFROM && (fr < OLDTO || early == 2)) r[e] = hl[TPH * h + PVB_RING_OFF(f)];
         }
         if (early == 2) {
             // warm L2 with the overlap-add ring lines the tail of this kernel adds to
@@ -398,18 +458,18 @@ pv_process_ring_kernel(const RingParams p) {
         asm volatile("griddepcontrol.launch_dependents;");
     }
     if (live) {
-        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * tp : nullptr;
+        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * cn : nullptr;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            const int h = e / R1, f = e % R1;
-            if (f >= NJ - nblk) {
+            const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
+            if (fr >= NEWFROM) {
                 float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
                 if (i0) {
                     u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 2 * TPH * h + 128 * (f - (NJ - nblk))));
                     if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 2 * TPH * h + 128 * (f - (NJ - nblk))));
                 }
                 r[e] = make_float4(u0.x, u0.y, u1.x, u1.y);           // interleaved below
-            } else if (!(early && (f < NJ - 2 * nblk || early == 2))) {
+            } else if (!(early && (fr < OLDTO || early == 2))) {
                 r[e] = hl[TPH * h + PVB_RING_OFF(f)];
             }
         }
@@ -422,8 +482,8 @@ pv_process_ring_kernel(const RingParams p) {
     // the new block joins the history ring (ola:105)
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int h = e / R1, f = e % R1;
-        if (f >= NJ - nblk) {
+        const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
+        if (fr >= NEWFROM) {
             r[e] = make_float4(r[e].x, r[e].z, r[e].y, r[e].w);       // (ch0[i], ch1[i], ch0[i+1], ch1[i+1])
             hl[TPH * h + PVB_RING_OFF(f)] = r[e];
         }
@@ -431,26 +491,27 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- Hann window (pv:55) + forward pass 1: butterflies n = tp (+ 32) over the frame blocks ---
     {
-        const float *wl = swin + 2 * tp;
+        const float *wl = swin + 2 * cn;
+        const int row0 = RT * sp;                                     // frame 4096: rows (s, k') = 16 s + k'
 #pragma unroll
         for (int h = 0; h < G::NB1; h++) {
-            const int nl = tp + TPH * h;
-            cpx2 x[R1];
+            const int nl = cn + TPH * h;
+            cpx2 x[RT];
 #pragma unroll
-            for (int j = 0; j < R1; j++) {
-                const float2 w = *reinterpret_cast<const float2 *>(wl + 2 * TPH * h + 128 * j);
-                const float4 v = r[R1 * h + j];
+            for (int j = 0; j < RT; j++) {
+                const float2 w = *reinterpret_cast<const float2 *>(wl + 2 * TPH * h + 128 * PVB_FB(j));
+                const float4 v = r[RT * h + j];
                 x[j].re = mul2(make_float2(v.x, v.y), bc2(w.x));
                 x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
             }
-            dft_r<R1, false>(x);
+            dft_r<RT, false>(x);
 #pragma unroll
-            for (int k1 = 1; k1 < R1; k1++) {
-                const float2 w = tw1[G::TW1_ROW * k1 + nl];           // W_M^{(n + 64 toff) k1}
+            for (int k1 = 1; k1 < RT; k1++) {
+                const float2 w = tw1[G::TW1_ROW * (row0 + k1) + nl];  // W_M^{(n + 64 toff) k1} (W_32^{s k1})
                 x[k1] = cmul_s(x[k1], w.x, w.y);
             }
 #pragma unroll
-            for (int k1 = 0; k1 < R1; k1++) ex[G::RS * k1 + nl + (G::G8 - 8) * (nl >> 3)] = pack4(x[k1]);
+            for (int k1 = 0; k1 < RT; k1++) ex[G::RS * (row0 + k1) + nl + (G::G8 - 8) * (nl >> 3)] = pack4(x[k1]);
         }
     }
     pair_sync<TP>(pin);
@@ -472,6 +533,32 @@ pv_process_ring_kernel(const RingParams p) {
         float2 w2[8];
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
+        if constexpr (NSPL == 2) {
+            // rows k' and 16 + k' hold E_0 and E_1 (twiddled); X[k'] = E_0 + E_1 and
+            // X[k' + 16] = (E_0 - E_1) W_128^n (-1)^toff, n = m3 + 8 m2; both rows are this thread's
+            float4 *b0 = ex + G::RS * (tp >> 3) + m3l, *b1 = b0 + G::RS * 16;
+            const float sgn = (toff & 1) ? -1.f : 1.f;
+            cpx2 x0[8], x1[8];
+#pragma unroll
+            for (int m2 = 0; m2 < 8; m2++) {
+                const cpx2 e0 = unpack4(b0[G::G8 * m2]), e1 = unpack4(b1[G::G8 * m2]);
+                const float2 w = w128[m3l + 8 * m2];
+                x0[m2] = cadd(e0, e1);
+                x1[m2] = cmul_s(csub(e0, e1), sgn * w.x, sgn * w.y);
+            }
+            dft8<false>(x0);
+            dft8<false>(x1);
+#pragma unroll
+            for (int k2 = 1; k2 < 8; k2++) {
+                x0[k2] = cmul_s(x0[k2], w2[k2].x, w2[k2].y);
+                x1[k2] = cmul_s(x1[k2], w2[k2].x, w2[k2].y);
+            }
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++) {
+                b0[G::G8 * k2] = pack4(x0[k2]);
+                b1[G::G8 * k2] = pack4(x1[k2]);
+            }
+        } else {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             float4 *bp = ex + G::RS * ((tp >> 3) + (R1 / 2) * h) + m3l;
@@ -483,6 +570,7 @@ pv_process_ring_kernel(const RingParams p) {
             for (int k2 = 1; k2 < 8; k2++) x[k2] = cmul_s(x[k2], w2[k2].x, w2[k2].y);
 #pragma unroll
             for (int k2 = 0; k2 < 8; k2++) bp[G::G8 * k2] = pack4(x[k2]);
+        }
         }
     }
     pair_sync<TP>(pin);
@@ -587,23 +675,26 @@ pv_process_ring_kernel(const RingParams p) {
                 any0 = nz0 != 0;
                 any1 = nz1 != 0;
             } else {
-                // two warps per pair: exchange through the pair's scratch area
-                int *scr = reinterpret_cast<int *>(mine + G::XQ_SLOTS * 16);      // [4][TP] keys, [4] ballots
+                // several warps per pair: exchange through the pair's scratch area
+                constexpr int WPP = G::WPP;
+                int *scr = reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16);     // [4][TP] keys, [2][WPP] ballots
                 scr[tp] = ol0; scr[TP + tp] = of0; scr[2 * TP + tp] = ol1; scr[3 * TP + tp] = of1;
                 const uint32_t bl0 = __ballot_sync(FULL, mask0 != 0), bl1 = __ballot_sync(FULL, mask1 != 0);
-                if (lane == 0) { scr[4 * TP + (tp >> 5)] = int(bl0); scr[4 * TP + 2 + (tp >> 5)] = int(bl1); }
+                if (lane == 0) { scr[4 * TP + (tp >> 5)] = int(bl0); scr[4 * TP + WPP + (tp >> 5)] = int(bl1); }
                 pair_sync<TP>(pin);
-                const unsigned long long nz0 = (unsigned long long)uint32_t(scr[4 * TP]) | ((unsigned long long)uint32_t(scr[4 * TP + 1]) << 32);
-                const unsigned long long nz1 = (unsigned long long)uint32_t(scr[4 * TP + 2]) | ((unsigned long long)uint32_t(scr[4 * TP + 3]) << 32);
-                const unsigned long long lt = (1ull << tp) - 1ull, gt = ~((2ull << tp) - 1ull);
-                pk0 = (nz0 & lt) ? scr[63 - __clzll((long long)(nz0 & lt))] : 0;
-                nk0 = (nz0 & gt) ? scr[TP + __ffsll((long long)(nz0 & gt)) - 1] : none_above;
-                lk0 = scr[(63 - __clzll((long long)nz0)) & 63];
-                pk1 = (nz1 & lt) ? scr[2 * TP + 63 - __clzll((long long)(nz1 & lt))] : 0;
-                nk1 = (nz1 & gt) ? scr[3 * TP + __ffsll((long long)(nz1 & gt)) - 1] : none_above;
-                lk1 = scr[2 * TP + ((63 - __clzll((long long)nz1)) & 63)];
-                any0 = nz0 != 0;
-                any1 = nz1 != 0;
+                const int *bal0 = scr + 4 * TP, *bal1 = bal0 + WPP;
+                const int tb0 = ring_thread_below<WPP>(bal0, tp), ta0 = ring_thread_above<WPP>(bal0, tp);
+                const int tl0 = ring_thread_last<WPP>(bal0);
+                const int tb1 = ring_thread_below<WPP>(bal1, tp), ta1 = ring_thread_above<WPP>(bal1, tp);
+                const int tl1 = ring_thread_last<WPP>(bal1);
+                pk0 = (tb0 >= 0) ? scr[tb0] : 0;
+                nk0 = (ta0 >= 0) ? scr[TP + ta0] : none_above;
+                lk0 = scr[tl0 & (TP - 1)];
+                pk1 = (tb1 >= 0) ? scr[2 * TP + tb1] : 0;
+                nk1 = (ta1 >= 0) ? scr[3 * TP + ta1] : none_above;
+                lk1 = scr[2 * TP + (tl1 & (TP - 1))];
+                any0 = tl0 >= 0;
+                any1 = tl1 >= 0;
             }
             dl0 = (lk0 & 0xFFFF) - 32768;
             dl1 = (lk1 & 0xFFFF) - 32768;
@@ -777,17 +868,41 @@ pv_process_ring_kernel(const RingParams p) {
 
     // accumulator values (L2 hits thanks to the prefetch) are requested before the last exchange so
     // that their latency hides behind inverse pass 2; the tail slot starts from zero (ola:134)
-    float4 *al = p.acc2 + size_t(pair) * (N / 2) + tp;
+    float4 *al = p.acc2 + size_t(pair) * (N / 2) + cn;
     float4 q[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        const int h = e / R1, f = e % R1;
+        const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
         q[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < NJ - nblk) q[e] = al[TPH * h + PVB_RING_OFF(f)];
+        if (fr < NEWFROM) q[e] = al[TPH * h + PVB_RING_OFF(f)];
     }
 
     // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_M^{k1 (m3 + 8 m2 + 64 toff)}) -------
-    if (!(p.skip & 2))
+    if constexpr (NSPL == 2) {
+        // mirror of forward pass 2: with Y[k1] the twiddled outputs of rows k' and k' + 16,
+        // row (0, k') = (Y[k'] + Y[k'+16]) and row (1, k') = (Y[k'] - Y[k'+16]) conj(W_32^{k'}); the
+        // conjugates of the two forward tables carry W_M^{k' (n + 64 toff)} (and W_32^{k'})
+        const int kp = tp >> 3;
+        float4 *b0 = ex + G::RS * kp + m3l, *b1 = b0 + G::RS * 16;
+        const float2 *t0 = tw1 + G::TW1_ROW * kp + m3l, *t1 = t0 + G::TW1_ROW * 16;
+        const float sgn = (toff & 1) ? -1.f : 1.f;
+        cpx2 x0[8], x1[8];
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            x0[k2] = unpack4(b0[G::G8 * k2]);
+            x1[k2] = unpack4(b1[G::G8 * k2]);
+        }
+        dft8<true>(x0);
+        dft8<true>(x1);
+#pragma unroll
+        for (int m2 = 0; m2 < 8; m2++) {
+            const float2 w = w128[m3l + 8 * m2];
+            const cpx2 v1 = cmul_s(x1[m2], sgn * w.x, -sgn * w.y);    // conj(W_128^n) (-1)^toff
+            const float2 wa = t0[8 * m2], wb = t1[8 * m2];
+            b0[G::G8 * m2] = pack4(cmul_s(cadd(x0[m2], v1), wa.x, -wa.y));
+            b1[G::G8 * m2] = pack4(cmul_s(csub(x0[m2], v1), wb.x, -wb.y));
+        }
+    } else if (!(p.skip & 2))
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int k1 = (tp >> 3) + (R1 / 2) * h;
@@ -807,28 +922,30 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- inverse pass 3: butterflies n over k1 -> ring samples; window, overlap-add, emit ------------------
     {
-        float *o0 = p.out + size_t(c0) * hop + 2 * tp;
-        const float *wol = swout + 2 * tp;
+        float *o0 = p.out + size_t(c0) * hop + 2 * cn;
+        const float *wol = swout + 2 * cn;
+        const int row0 = RT * sp;
 #pragma unroll
         for (int h = 0; h < G::NB1; h++) {
-            const int nl = tp + TPH * h;
-            cpx2 x[R1];
+            const int nl = cn + TPH * h;
+            cpx2 x[RT];
 #pragma unroll
-            for (int k1 = 0; k1 < R1; k1++) x[k1] = unpack4(ex[G::RS * k1 + nl + (G::G8 - 8) * (nl >> 3)]);
-            dft_r<R1, true>(x);
+            for (int k1 = 0; k1 < RT; k1++) x[k1] = unpack4(ex[G::RS * (row0 + k1) + nl + (G::G8 - 8) * (nl >> 3)]);
+            dft_r<RT, true>(x);
 #pragma unroll
-            for (int j = 0; j < R1; j++) {
+            for (int j = 0; j < RT; j++) {
                 // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the division
                 // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
-                const float2 wo = *reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * j);
-                const float4 qv = q[R1 * h + j];
+                const int fb = PVB_FB(j);
+                const float2 wo = *reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * fb);
+                const float4 qv = q[RT * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
-                if (j < nblk) {                                       // head: emit (ola:111-118)
-                    *reinterpret_cast<float2 *>(o0 + 2 * TPH * h + 128 * j) = make_float2(y0.x, y1.x);
-                    if (has1) *reinterpret_cast<float2 *>(o0 + hop + 2 * TPH * h + 128 * j) = make_float2(y0.y, y1.y);
+                if (j < HEADTO) {                                     // head: emit (ola:111-118)
+                    *reinterpret_cast<float2 *>(o0 + 2 * TPH * h + 128 * fb) = make_float2(y0.x, y1.x);
+                    if (has1) *reinterpret_cast<float2 *>(o0 + hop + 2 * TPH * h + 128 * fb) = make_float2(y0.y, y1.y);
                 } else {
-                    al[TPH * h + PVB_RING_OFF(j)] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    al[TPH * h + PVB_RING_OFF(fb)] = make_float4(y0.x, y0.y, y1.x, y1.y);
                 }
             }
         }
@@ -846,22 +963,31 @@ pv_process_ring_kernel(const RingParams p) {
     // that completion stays transitive along the stream
     if (p.flag_mode) asm volatile("griddepcontrol.wait;" ::: "memory");
 #undef PVB_RING_OFF
+#undef PVB_FR
+#undef PVB_FH
+#undef PVB_FB
 }
 
 // tables the ring-order kernel copies into shared memory: NJ first-pass twiddle tables
 // tw1[toff][k1][n] = W_M^{(n + 64 toff) k1} (rows of TW1_ROW), then w64[a][b] = W_64^{ab}, twh[k] = W_N^k
 template <int N>
-constexpr int ring_host_table_bytes() { return RingGeoT<N>::NJ * RingGeoT<N>::TW1_BYTES + RingGeoT<N>::W64_BYTES + RingGeoT<N>::TWH_BYTES; }
+constexpr int ring_host_table_bytes() { return RingGeoT<N>::NJ * RingGeoT<N>::TW1_BYTES + RingGeoT<N>::W64_BYTES + RingGeoT<N>::TWH_BYTES + RingGeoT<N>::W128_BYTES; }
 
 template <int N>
 inline void ring_host_tables(const float2 *tw /* [N] W_N^j */, float2 *out /* ring_host_table_bytes / 8 */) {
     using G = RingGeoT<N>;
-    float2 *w64 = out + G::NJ * (G::TW1_BYTES / 8), *twh = w64 + G::W64_BYTES / 8;
+    float2 *w64 = out + G::NJ * (G::TW1_BYTES / 8), *twh = w64 + G::W64_BYTES / 8, *w128 = twh + G::TWH_BYTES / 8;
     for (int i = 0; i < ring_host_table_bytes<N>() / 8; i++) out[i] = make_float2(0.f, 0.f);
     for (int toff = 0; toff < G::NJ; toff++)
-        for (int k1 = 0; k1 < G::R1; k1++)
-            for (int n = 0; n < 64; n++)
-                out[toff * (G::TW1_BYTES / 8) + G::TW1_ROW * k1 + n] = tw[(2 * (n + 64 * toff) * k1) & (N - 1)];
+        for (int row = 0; row < G::R1; row++)
+            for (int n = 0; n < 64; n++) {
+                // frame 4096: row = 16 s + k' holds W_M^{(n + 64 toff) k'} W_32^{s k'}
+                const int k1 = row % G::RT, sp = row / G::RT;
+                out[toff * (G::TW1_BYTES / 8) + G::TW1_ROW * row + n] =
+                    tw[(2 * (n + 64 * toff) * k1 + (N / 32) * sp * k1) & (N - 1)];
+            }
+    if (G::NSPL == 2)
+        for (int n = 0; n < 64; n++) w128[n] = tw[((N / 128) * n) & (N - 1)];
     for (int a = 0; a < 8; a++)
         for (int b = 0; b < 8; b++) w64[8 * a + b] = tw[((N / 64) * a * b) & (N - 1)];
     for (int k = 0; k <= G::M; k++) twh[k] = tw[k];

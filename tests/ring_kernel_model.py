@@ -30,7 +30,7 @@ def xslot(k):
 
 class Geo:
     def __init__(self, n: int):
-        assert n in (512, 1024, 2048, 4096)
+        assert n in (256, 512, 1024, 2048, 4096)
         self.N = n
         self.M = n // 2                  # complex FFT length
         self.NB = self.M + 1
@@ -41,13 +41,13 @@ class Geo:
         self.XSLOTS = self.M + self.M // 16 + 2
         # exchange slot of element i (0..63) of row k1: rows of 64 slots at stride 65; frame 512 (radix-4
         # first pass: a quarter-warp of pass 3 spans two k2 groups) pads every group of 8 and uses stride 74
-        self.RS = 65 if self.R1 >= 8 else 74
+        self.RS = 65 if self.R1 >= 8 else 74 if self.R1 == 4 else 76
         self.GP = 0 if self.R1 >= 8 else 1
         self.EX_SLOTS = self.RS * (self.R1 - 1) + 64 + 8 * self.GP
         # bytes per pair: frame 512 keeps two pairs per warp 16 banks apart (32-bit plane accesses)
         self.PAIR_BYTES = max(self.XSLOTS, self.EX_SLOTS) * 16
-        if self.TP < 32:
-            self.PAIR_BYTES += (64 - self.PAIR_BYTES) % 128
+        if self.TP < 32:                 # pairs of one warp: 16 (two pairs) / 8 (four pairs) banks apart
+            self.PAIR_BYTES += ((64 if self.TP == 16 else 32) - self.PAIR_BYTES) % 128
         self.T = np.arange(self.TP)
 
     def exs(self, k1, i):
@@ -89,6 +89,8 @@ class Conflicts:
         byte_addr = np.asarray(byte_addr).reshape(-1)
         if byte_addr.size == 16:
             byte_addr = np.concatenate([byte_addr, byte_addr + self.pair_bytes])
+        elif byte_addr.size == 8:
+            byte_addr = np.concatenate([byte_addr + q * self.pair_bytes for q in range(4)])
         for w0 in range(0, byte_addr.size, 32):          # one warp at a time
             self._warp(name, byte_addr[w0:w0 + 32], width)
 
@@ -121,7 +123,9 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     """One process() call of one channel pair.  hist2/acc2: [N][2] float32 rings (modified in
     place), inblk: [2][hop] or None (paused), t = timeCursor (multiple of hop).  Returns out[2][hop]."""
     N, M, NB, TP, R1, KS, NJ, T = g.N, g.M, g.NB, g.TP, g.R1, g.KS, g.NJ, g.T
-    assert hop % 128 == 0 and hop <= N // 2
+    # frames 256 / 512 also take hops that are odd multiples of 64 (whether a register is in the first
+    # or the second half of its 128-sample block is a compile-time fact there: nl >= 32 <=> h >= 32 / TP)
+    assert (hop % 128 == 0 or (hop % 64 == 0 and TP <= 16)) and hop <= N // 2
     R = N // hop
     win, win_out, tw = tables(g, R)
     w64s = N // 64                                  # W_64^x = tw[w64s * x]
@@ -138,6 +142,7 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
     # ring blocks of the rotated register array is the DFT over f times W_R1^{toff k1} (shift theorem),
     # which is folded into the pass-1 twiddle: W_M^{(n + 64 toff) k1}.
     toff = (t // 128) % NJ
+    half = (t // 64) & 1                            # rings rotated by half a block (hop 64 only)
     w32s, w128s = N // 32, N // 128                 # W_32^x = tw[w32s * x], W_128^x = tw[w128s * x]
     sg = -1.0 if (toff & 1) else 1.0
     if R1 == 32:
@@ -172,12 +177,18 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
             ex[slot] = z[kp] * twd[:, None]
             if cf: cf.note("p1_st", slot * 16, 16)
     for nl in nls:
+        # ring column and block carry of this butterfly (half-block rotation: hop 64)
+        cc = (nl + 32 * half) & 63
+        carry = (nl + 32 * half) >> 6
         z = np.zeros((R1, TP, 2), C64)
         for f in range(R1):
-            j = (f + toff) % NJ
-            i = 2 * nl + 128 * j                    # ring index of sample pair (i, i + 1)
-            if f >= NJ - nblk:                      # new block (ola:91-108)
-                s = 2 * nl + 128 * (f - (NJ - nblk))
+            j = (f + toff + carry) % NJ
+            i = 2 * cc + 128 * j                    # ring index of sample pair (i, i + 1)
+            fi = 2 * nl + 128 * f                   # frame position of the sample pair
+            isnew = fi >= N - hop                   # new block (ola:91-108); static per register
+            assert isnew.all() or not isnew.any()
+            if isnew.all():
+                s = fi - (N - hop)
                 if inblk is None:
                     x0 = np.zeros((TP, 2), F32); x1 = np.zeros((TP, 2), F32)
                 else:
@@ -185,13 +196,13 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 hist2[i] = x0; hist2[i + 1] = x1
             else:
                 x0 = hist2[i]; x1 = hist2[i + 1]
-            fi = 2 * nl + 128 * f                   # frame position of the sample pair
             w0 = win[fi][:, None]; w1 = win[fi + 1][:, None]
             z[f] = (x0 * w0).astype(F32) + 1j * (x1 * w1).astype(F32)
         z = dft(z)
         for k1 in range(R1):
-            v = z[k1] * tw[(2 * (nl + 64 * toff) * k1) % N][:, None]      # W_M^{(n + 64 toff) k1}
-            slot = g.exs(k1, nl)
+            # W_M^{c k1} W_R1^{(toff + carry) k1}: the DFT over ring blocks of registers indexed by frame block
+            v = z[k1] * (tw[(2 * cc * k1) % N] * tw[((N // R1) * (toff + carry) * k1) % N]).astype(C64)[:, None]
+            slot = g.exs(k1, cc)
             ex[slot] = v
             if cf: cf.note("p1_st", slot * 16, 16)
 
@@ -402,7 +413,9 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
         k1 = (T >> 3) + (R1 // 2) * h
         x = dft(np.stack([ex[g.exs(k1, m3 + 8 * k2)] for k2 in range(8)]), inv=True)
         for m2 in range(8):
-            ex[g.exs(k1, m3 + 8 * m2)] = x[m2] * np.conj(tw[(2 * k1 * (m3 + 8 * m2 + 64 * toff)) % N])[:, None]
+            c2 = m3 + 8 * m2
+            cr = toff + (half & (c2 < 32))           # block carry of ring column c2
+            ex[g.exs(k1, c2)] = x[m2] * np.conj(tw[(2 * k1 * c2) % N] * tw[((N // R1) * cr * k1) % N]).astype(C64)[:, None]
     # ---- inverse pass 3 (DFT over k1 -> frame block f); window, overlap-add, emit ---------------
     out = np.zeros((2, hop), F32)
     if R1 == 32:
@@ -425,19 +438,21 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
             else:
                 acc2[i] = y0; acc2[i + 1] = y1
     for nl in nls:
-        x = dft(np.stack([ex[g.exs(k1, nl)] for k1 in range(R1)]), inv=True)
+        cc = (nl + 32 * half) & 63
+        carry = (nl + 32 * half) >> 6
+        x = dft(np.stack([ex[g.exs(k1, cc)] for k1 in range(R1)]), inv=True)
         for f in range(R1):
-            j = (f + toff) % NJ
-            i = 2 * nl + 128 * j
+            j = (f + toff + carry) % NJ
+            i = 2 * cc + 128 * j
             fi = 2 * nl + 128 * f
             w0 = win_out[fi][:, None]; w1 = win_out[fi + 1][:, None]
             y0 = (x[f].real.astype(F32) * w0).astype(F32); y1 = (x[f].imag.astype(F32) * w1).astype(F32)
-            tail = f >= NJ - nblk                       # starts from zero (ola:134)
+            tail = bool((fi >= N - hop).all())          # starts from zero (ola:134)
             q0 = np.zeros((TP, 2), F32) if tail else acc2[i]
             q1 = np.zeros((TP, 2), F32) if tail else acc2[i + 1]
             y0 = y0 + q0; y1 = y1 + q1
-            if f < nblk:                                # head: emit (ola:111-118)
-                s = 2 * nl + 128 * f
+            if bool((fi < hop).all()):                  # head: emit (ola:111-118)
+                s = fi
                 out[:, s] = y0.T; out[:, s + 1] = y1.T
             else:
                 acc2[i] = y0; acc2[i + 1] = y1

@@ -175,6 +175,32 @@ def test_parity_ring_kernel_512_many_channels(oracle, C, pf):
     assert per_channel.max() <= RMS_EXPECTED
 
 
+@pytest.mark.parametrize("hop", [256, 512, 1024, 2048])
+@pytest.mark.parametrize("pf", [0.75, 0.8, 1.0, 1.3, 2.0])
+def test_parity_ring_kernel_4096(oracle, hop, pf):
+    """frame 4096: four warps per pair, each thread holds the frame blocks of one parity (radix-16
+    in registers, the radix-2 step folded into pass 2)"""
+    from phaze_b200 import BatchedPhaseVocoder
+    with BatchedPhaseVocoder(5, 4096, hop) as pv:
+        if "ring" not in pv.kernel_name(np.float32(pf)):
+            pytest.skip("frame-4096 ring-order kernel disabled (PVB_RING_4096=0)")
+    calls = 2 * (4096 // hop) + 3
+    x, ref, got = _run_both(oracle, 4096, hop, 5, np.float32(pf), calls)
+    err = _rms(got - ref)
+    print(f"N=4096 hop={hop} pf={pf}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
+def test_parity_ring_kernel_4096_many_channels(oracle):
+    """more pairs than one CTA holds (4 per CTA), odd last channel; hop 128 stays on the CTA kernel"""
+    from phaze_b200 import BatchedPhaseVocoder
+    x, ref, got = _run_both(oracle, 4096, 1024, 19, np.float32(0.8), 7)
+    per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
+    assert per_channel.max() <= RMS_EXPECTED
+    with BatchedPhaseVocoder(2, 4096, 128) as pv:
+        assert "cta" in pv.kernel_name(np.float32(0.8))
+
+
 def test_parity_ring_kernel_2048_many_channels(oracle):
     x, ref, got = _run_both(oracle, 2048, 512, 23, np.float32(0.8), 9)
     per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
