@@ -66,6 +66,7 @@ std::unordered_map<cudaStream_t, std::vector<RecentIo>> g_recent_io;
 // and a grid-mode launch behind it must not load anything before its griddepcontrol.wait
 std::unordered_map<cudaStream_t, bool> g_last_flag_mode;
 int g_ring_pad_kb = 0;
+int g_ring_256 = 1;              // PVB_RING_256=0: frame 256 falls back to the CTA kernel
 int g_ring_4096 = 1;             // PVB_RING_4096=0: frame 4096 falls back to the CTA kernel
 int g_ring_512 = 1;              // PVB_RING_512=0: frame 512 falls back to the CTA kernel
 int g_ring_wpc = 0;              // PVB_RING_WPC: warps (pairs) per CTA of the ring kernel (0: balance one wave)
@@ -213,8 +214,10 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
 // ring-order kernel (pv_kernel_ring.cuh): paired state layout aligned to the time cursor
 bool ring_kernel_applies(const pvb_processor *h, const pvb::FrameParams &fp) {
     // frame 4096 keeps the frame blocks of one parity per thread: the hop must be a multiple of 256
-    return ((h->n == 512 && g_ring_512) || h->n == 1024 || h->n == 2048 || (h->n == 4096 && g_ring_4096)) &&
-           fast_range(fp) && h->hop % (h->n == 4096 ? 256 : 128) == 0 && h->hop <= h->n / 2 &&
+    // (frame 256 keeps roles in units of 64 samples: hop 64 or 128)
+    return ((h->n == 256 && g_ring_256) || (h->n == 512 && g_ring_512) || h->n == 1024 || h->n == 2048 ||
+            (h->n == 4096 && g_ring_4096)) &&
+           fast_range(fp) && h->hop % (h->n == 4096 ? 256 : h->n == 256 ? 64 : 128) == 0 && h->hop <= h->n / 2 &&
            g_kernel_1024 == 0 && !g_force_generic;
 }
 
@@ -286,6 +289,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
         if (e == cudaSuccess)                                                                     \
             e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLK>,                        \
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        PVB_RING_ATTR(256, 1) PVB_RING_ATTR(256, 2)
         PVB_RING_ATTR(512, 1) PVB_RING_ATTR(512, 2)
         PVB_RING_ATTR(1024, 1) PVB_RING_ATTR(1024, 2) PVB_RING_ATTR(1024, 4)
         PVB_RING_ATTR(2048, 1) PVB_RING_ATTR(2048, 2) PVB_RING_ATTR(2048, 4) PVB_RING_ATTR(2048, 8)
@@ -318,6 +322,26 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
             case 8: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 8>, rp);
             default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 16>, rp);
         }
+    }
+    if (h->n == 256) {
+        using G = pvb::RingGeoT<256>;
+        int ppc2 = G::MAX_PAIRS;
+        if (g_ring_wpc >= G::MIN_PAIRS && g_ring_wpc <= G::MAX_PAIRS) ppc2 = g_ring_wpc;
+        pvb::RingParams rp = make_ring_params(h, fp, s);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((pairs + ppc2 - 1) / ppc2);
+        cfg.blockDim = dim3(ppc2 * G::TP);
+        cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc2) * G::PAIR_BYTES;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;
+        // NBLK counts units of 64 samples at this frame size
+        if (rp.hop == 64) return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<256, 1>, rp);
+        return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<256, 2>, rp);
     }
     const bool big = h->n == 2048, small = h->n == 512;
     // pairs per CTA: frame 1024 balances one wave (4..7 warps); frame 2048 uses 4 pairs of two warps;
@@ -617,6 +641,8 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         g_no_pdl = env && env[0] == '1';
         env = std::getenv("PVB_RING_PAD_KB");
         g_ring_pad_kb = env ? std::atoi(env) : 0;
+        env = std::getenv("PVB_RING_256");
+        g_ring_256 = env ? std::atoi(env) : 1;
         env = std::getenv("PVB_RING_4096");
         g_ring_4096 = env ? std::atoi(env) : 1;
         env = std::getenv("PVB_RING_512");
@@ -694,12 +720,14 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         fail(p, PVB_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(PVB_ERR_CUDA);
     }
-    if (n == 512 || n == 1024 || n == 2048 || n == 4096) {
-        const size_t tab_bytes = n == 512 ? pvb::ring_host_table_bytes<512>()
+    if (n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096) {
+        const size_t tab_bytes = n == 256 ? pvb::ring_host_table_bytes<256>()
+                                 : n == 512 ? pvb::ring_host_table_bytes<512>()
                                  : n == 1024 ? pvb::ring_host_table_bytes<1024>()
                                  : n == 2048 ? pvb::ring_host_table_bytes<2048>() : pvb::ring_host_table_bytes<4096>();
         std::vector<float2> rt(tab_bytes / sizeof(float2));
-        if (n == 512) pvb::ring_host_tables<512>(tw.data(), rt.data());
+        if (n == 256) pvb::ring_host_tables<256>(tw.data(), rt.data());
+        else if (n == 512) pvb::ring_host_tables<512>(tw.data(), rt.data());
         else if (n == 1024) pvb::ring_host_tables<1024>(tw.data(), rt.data());
         else if (n == 2048) pvb::ring_host_tables<2048>(tw.data(), rt.data());
         else pvb::ring_host_tables<4096>(tw.data(), rt.data());

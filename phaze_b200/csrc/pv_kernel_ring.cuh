@@ -54,7 +54,14 @@ struct RingGeoT {
                                                             // half a warp (512), a warp (1024), two warps (2048)
     static constexpr int WPP = TP / 32;                     // warps per pair (0: two pairs share a warp)
     static constexpr int R1 = M / 64;                       // radix of the first pass: 4, 8, 16 or 32
-    static constexpr int LR1 = (R1 == 4) ? 2 : (R1 == 8) ? 3 : (R1 == 16) ? 4 : 5;
+    static constexpr int LR1 = (R1 == 2) ? 1 : (R1 == 4) ? 2 : (R1 == 8) ? 3 : (R1 == 16) ? 4 : 5;
+    // frame 256 also takes hop 64: the rings are then rotated by half a 128-sample block on odd
+    // calls.  Whether a register sits in the first or the second half of its block is a compile-time
+    // fact there (column tp + 8 h >= 32 <=> h >= 4), so roles stay static in units of 64 samples;
+    // NBLK counts those units, and there is one first-pass twiddle table per 64-sample offset.
+    static constexpr bool HB = (N == 256);
+    static constexpr int UNIT = HB ? 64 : 128;              // samples per role unit (NBLK = hop / UNIT)
+    static constexpr int NTAB = HB ? 2 * (N / 128) : N / 128;   // first-pass twiddle tables
     // frame 4096: a thread holds the 16 frame blocks of one parity (f = 2 f' + s) of its column and
     // does a 16-point DFT over f'; the radix-2 step that completes the 32-point DFT over f is done by
     // the reader in pass 2 (it holds rows k' and k' + 16 anyway), so there is no fourth exchange
@@ -68,15 +75,18 @@ struct RingGeoT {
     // exchange slots of 16 bytes: element 8 r + c of row k1 at RS k1 + G8 r + c.  Rows of 64 at stride
     // 65; frame 512 (radix-4 first pass: a quarter-warp of pass 3 spans two r) pads every group of 8
     // and uses stride 74, which keeps all three passes conflict free
-    static constexpr int RS = (R1 >= 8) ? 65 : 74;
+    static constexpr int RS = (R1 >= 8) ? 65 : (R1 == 4) ? 74 : 76;
     static constexpr int G8 = (R1 >= 8) ? 8 : 9;
+    // Y planes: bin d at word d + (d >> YS); the pad must divide the last-pass butterfly stride
+    static constexpr int YS = (KS % (1 << PVB_RING_YSHIFT) == 0) ? PVB_RING_YSHIFT : 4;
     static constexpr int EX_SLOTS = RS * (R1 - 1) + 8 * G8;
     static constexpr int XQ_SLOTS = SM + 2;                 // bin k at k + (k >> 4); last slot = dump / halo dummy
     static constexpr int SCR_BYTES = (WPP > 1) ? 4 * TP * 4 + 32 : 0;   // cross-warp key exchange of the region scan
     static constexpr int BUF_SLOTS = (XQ_SLOTS > EX_SLOTS) ? XQ_SLOTS : EX_SLOTS;
     // two pairs per warp (frame 512): their buffers sit 16 banks apart, so the 32-bit plane accesses
     // of the two half-warps (16 consecutive words each) do not collide
-    static constexpr int PAIR_PAD = (TP < 32) ? (64 + 128 - (BUF_SLOTS * 16) % 128) % 128 : 0;
+    // (frame 256: four pairs per warp, 8 banks apart)
+    static constexpr int PAIR_PAD = (TP < 32) ? ((TP == 16 ? 64 : 32) + 128 - (BUF_SLOTS * 16) % 128) % 128 : 0;
     static constexpr int PAIR_BYTES = BUF_SLOTS * 16 + SCR_BYTES + PAIR_PAD;
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
     static constexpr int DTAB_BYTES = ((NB + 1 + 4 * ((NB >> 4) + 1)) * 4 + 15) & ~15;   // key table: bin p at p + 4 (p >> 4)
@@ -94,7 +104,7 @@ struct RingGeoT {
     static constexpr int OFF_WIN = OFF_W128 + W128_BYTES;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;
-    static constexpr int MAX_PAIRS = (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA
+    static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA
     static constexpr int CTAS_PER_SM = (N == 4096) ? 1 : 2; // frame 4096: 77 KB of tables + 4 x 36 KB
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
@@ -138,6 +148,8 @@ __device__ __forceinline__ void pair_sync(int pair_in_cta) {
         __syncwarp();
     } else if constexpr (TP == 16) {
         __syncwarp(0xFFFFu << (threadIdx.x & 16));          // the other half-warp is another pair
+    } else if constexpr (TP == 8) {
+        __syncwarp(0xFFu << (threadIdx.x & 24));            // four pairs per warp
     } else {
         asm volatile("bar.sync %0, %1;" ::"r"(pair_in_cta + 1), "n"(TP) : "memory");
     }
@@ -172,10 +184,14 @@ __device__ __forceinline__ void dft16(cpx2 (&x)[16]) {
     }
 }
 
-// R-point DFT of x[0..R) (R = 4, 8 or 16)
+// R-point DFT of x[0..R) (R = 2, 4, 8 or 16)
 template <int R, bool INV>
 __device__ __forceinline__ void dft_r(cpx2 *x) {
-    if constexpr (R == 4) dft4<INV>(x[0], x[1], x[2], x[3]);
+    if constexpr (R == 2) {
+        const cpx2 a = cadd(x[0], x[1]), b = csub(x[0], x[1]);
+        x[0] = a;
+        x[1] = b;
+    } else if constexpr (R == 4) dft4<INV>(x[0], x[1], x[2], x[3]);
     else if constexpr (R == 8) dft8<INV>(*reinterpret_cast<cpx2(*)[8]>(x));
     else dft16<INV>(*reinterpret_cast<cpx2(*)[16]>(x));
 }
@@ -229,7 +245,7 @@ __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
 // sub-step, everything else is stored first (right halves are pairwise disjoint after the shift,
 // and so are left halves, for pitch factors >= 0.75).
 // The integer pipe runs at half rate, so this loop is written for the fewest ALU operations.
-template <int DUMP>
+template <int DUMP, int YS>
 __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey, int nkey, const int (&rk)[16],
                                                 int second_flag, int (&dst)[16]) {
     int nx[16];
@@ -248,7 +264,7 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
         const bool take_next = tt < ((4 * e) << 16);
         const int okey = take_next ? nx[e] : pkey;
         const int d = (okey & 0xFFFF) + cb + e;
-        const unsigned slot = min(unsigned(d + (d >> PVB_RING_YSHIFT)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
+        const unsigned slot = min(unsigned(d + (d >> YS)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
         dst[e] = int(4u * slot) | ((tt - ((4 * e) << 16)) & second_flag);
     }
 }
@@ -311,7 +327,8 @@ pv_process_ring_kernel(const RingParams p) {
     const int pair = blockIdx.x * (blockDim.x / TP) + pin;
     const bool live = 2 * pair < p.num_channels;
     // lanes of this thread's pair inside its warp (frame 512: half a warp)
-    const unsigned FULL = (TP == 16) ? (0xFFFFu << (threadIdx.x & 16)) : 0xFFFFFFFFu;
+    const unsigned FULL = (TP == 16) ? (0xFFFFu << (threadIdx.x & 16))
+                          : (TP == 8) ? (0xFFu << (threadIdx.x & 24)) : 0xFFFFFFFFu;
     int *ktab = reinterpret_cast<int *>(smem_raw);
     const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
     const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
@@ -329,6 +346,9 @@ pv_process_ring_kernel(const RingParams p) {
     const int t = p.tmod;
     constexpr int nblk = NBLK;
     const int toff = (t >> 7) & (NJ - 1);           // ring 128-block of frame block 0
+    constexpr bool HB = G::HB;
+    const int half = HB ? ((t >> 6) & 1) : 0;       // rings rotated by half a block (frame 256, hop 64)
+    const int hh = 32 * half;
     // ring float4 offset of frame block f: 64 ((f + toff) mod NJ) == 64 f + (wraps ? ro_wrap : ro_lin)
     const int ro_lin = 64 * toff, ro_wrap = 64 * toff - 64 * NJ;
 #define PVB_RING_OFF(f) (64 * (f) + (((f) + toff >= NJ) ? ro_wrap : ro_lin))
@@ -353,8 +373,8 @@ pv_process_ring_kernel(const RingParams p) {
         const unsigned s_rest = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_W64));
         const unsigned s_win = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WIN));
         const unsigned s_wout = unsigned(__cvta_generic_to_shared(smem_raw + G::OFF_WOUT));
-        const float4 *g_tw1 = p.gtab + toff * (G::TW1_BYTES / 16);            // the table of this toff
-        const float4 *g_rest = p.gtab + NJ * (G::TW1_BYTES / 16);             // w64 | twh
+        const float4 *g_tw1 = p.gtab + (HB ? 2 * toff + half : toff) * (G::TW1_BYTES / 16);   // the table of this offset
+        const float4 *g_rest = p.gtab + G::NTAB * (G::TW1_BYTES / 16);        // w64 | twh
 #pragma unroll
         for (int k = 0; k < (G::TW1_BYTES / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
@@ -408,14 +428,24 @@ pv_process_ring_kernel(const RingParams p) {
     // parity sp = tp / 64, f = 2 fr + sp.
     const int cn = (NSPL == 2) ? (tp & 63) : tp;
     const int sp = (NSPL == 2) ? (tp >> 6) : 0;
-    constexpr int NEWFROM = RT - NBLK / NSPL;       // fr >= NEWFROM: new input
-    constexpr int OLDTO = RT - 2 * NBLK / NSPL;     // fr < OLDTO: written before the previous call
-    constexpr int HEADTO = NBLK / NSPL;             // fr < HEADTO: emitted
+    // roles in units of G::UNIT samples: role(e) = fr, or 2 fr + (second half of the block) for frame 256
+    constexpr int NROLE = HB ? 2 * RT : RT;
+    constexpr int HSPLIT = HB ? 32 / TPH : 1;       // butterflies h >= HSPLIT sit in the second half of their block
+    constexpr int NEWFROM = NROLE - NBLK / NSPL;    // role >= NEWFROM: new input
+    constexpr int OLDTO = NROLE - 2 * NBLK / NSPL;  // role < OLDTO: written before the previous call
+    constexpr int HEADTO = NBLK / NSPL;             // role < HEADTO: emitted
 #define PVB_FR(e) ((NSPL == 2) ? (e) : (e) % RT)
 #define PVB_FH(e) ((NSPL == 2) ? 0 : (e) / RT)
 #define PVB_FB(fr) ((NSPL == 2) ? 2 * (fr) + sp : (fr))
+#define PVB_ROLE(h, fr) (HB ? 2 * (fr) + (((h) >= HSPLIT) ? 1 : 0) : (fr))
+    // ring float4 index (relative to hl / al) of butterfly h, frame block f
+#define PVB_RING_IDX(h, f)                                                                               \
+    (HB ? (((cn + TPH * (h) + hh) & 63) + 64 * (((f) + toff + (((h) >= HSPLIT) ? half : 0)) & (NJ - 1))) \
+        : (TPH * (h) + PVB_RING_OFF(f)))
+    // ring column of butterfly h (exchange slot, first-pass twiddle)
+#define PVB_COL(h) (HB ? ((cn + TPH * (h) + hh) & 63) : (cn + TPH * (h)))
     float4 r[16];
-    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + cn;
+    float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + (HB ? 0 : cn);
     const int early = p.flag_mode ? 0 : p.early;
     if (p.flag_mode) {
         if (live) {
@@ -432,19 +462,20 @@ pv_process_ring_kernel(const RingParams p) {
                 }
                 __nanosleep(200);
             }
-            if constexpr (TP == 16) pair_sync<TP>(pin); else __syncwarp();
+            if constexpr (TP < 32) pair_sync<TP>(pin); else __syncwarp();
         }
     } else if (live && early) {
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
             // fr >= NEWFROM: new input; the blocks below down to OLDTO: what the previous call wrote
-            if (fr < NEWFROM && (fr < OLDTO || early == 2)) r[e] = hl[TPH * h + PVB_RING_OFF(f)];
+            const int role = PVB_ROLE(h, fr);
+            if (role < NEWFROM && (role < OLDTO || early == 2)) r[e] = hl[PVB_RING_IDX(h, f)];
         }
         if (early == 2) {
             // warm L2 with the overlap-add ring lines the tail of this kernel adds to
             const int line = 16 * tp;                                 // float4 index: 256 bytes per thread
-            if ((((line >> 6) - toff) & (NJ - 1)) < NJ - nblk) {
+            if (HB || (((line >> 6) - toff) & (NJ - 1)) < NJ - nblk) {
                 const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
@@ -462,15 +493,18 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
-            if (fr >= NEWFROM) {
+            const int role = PVB_ROLE(h, fr);
+            if (role >= NEWFROM) {
                 float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
                 if (i0) {
-                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + 2 * TPH * h + 128 * (f - (NJ - nblk))));
-                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + 2 * TPH * h + 128 * (f - (NJ - nblk))));
+                    // frame sample 2 (cn + TPH h) + 128 f, minus the N - hop samples of history
+                    const int so = 2 * TPH * h + 128 * f - (N - NBLK * G::UNIT);
+                    u0 = __ldg(reinterpret_cast<const float2 *>(i0 + so));
+                    if (has1) u1 = __ldg(reinterpret_cast<const float2 *>(i0 + hop + so));
                 }
                 r[e] = make_float4(u0.x, u0.y, u1.x, u1.y);           // interleaved below
-            } else if (!(early && (fr < OLDTO || early == 2))) {
-                r[e] = hl[TPH * h + PVB_RING_OFF(f)];
+            } else if (!(early && (role < OLDTO || early == 2))) {
+                r[e] = hl[PVB_RING_IDX(h, f)];
             }
         }
     }
@@ -483,9 +517,9 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
-        if (fr >= NEWFROM) {
+        if (PVB_ROLE(h, fr) >= NEWFROM) {
             r[e] = make_float4(r[e].x, r[e].z, r[e].y, r[e].w);       // (ch0[i], ch1[i], ch0[i+1], ch1[i+1])
-            hl[TPH * h + PVB_RING_OFF(f)] = r[e];
+            hl[PVB_RING_IDX(h, f)] = r[e];
         }
     }
 
@@ -495,7 +529,7 @@ pv_process_ring_kernel(const RingParams p) {
         const int row0 = RT * sp;                                     // frame 4096: rows (s, k') = 16 s + k'
 #pragma unroll
         for (int h = 0; h < G::NB1; h++) {
-            const int nl = cn + TPH * h;
+            const int nl = PVB_COL(h);
             cpx2 x[RT];
 #pragma unroll
             for (int j = 0; j < RT; j++) {
@@ -520,7 +554,7 @@ pv_process_ring_kernel(const RingParams p) {
     // only written, ring [t - hop, t), is skipped)
     {
         const int line = 16 * tp;                                     // float4 index: 256 bytes per thread
-        if (early != 2 && (((line >> 6) - toff) & (NJ - 1)) < NJ - nblk) {
+        if (early != 2 && (HB || (((line >> 6) - toff) & (NJ - 1)) < NJ - nblk)) {
             const float4 *ap = p.acc2 + size_t(pair) * (N / 2) + line;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + 8));
@@ -597,7 +631,7 @@ pv_process_ring_kernel(const RingParams p) {
     const int gA = tp + (tp >> 4);                                    // slot of bin tp
     const int gB = G::SM - tp - ((tp + 15) >> 4);                     // slot of bin M - tp
     const int sAlo = l0 ? KS / 2 + KS / 32 : gA, sAhi = l0 ? -4 * SS : gA;
-    const int sBlo = l0 ? G::SM - KS / 2 - KS / 32 : gB, sBhi = l0 ? G::SM + 4 * SS : gB;
+    const int sBlo = l0 ? G::SM - KS / 2 - ((KS / 2 + 15) >> 4) : gB, sBhi = l0 ? G::SM + 4 * SS : gB;
     const int tlo = l0 ? KS / 2 : tp, thi = l0 ? -4 * KS : tp;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -657,8 +691,8 @@ pv_process_ring_kernel(const RingParams p) {
             const int none_above = (2 * 8190) << 16;                  // "peak" at +6142; below: key 0 = "peak" at -2048
             if constexpr (TP <= 32) {
                 // one ballot bit per thread of the pair (frame 512: the pair's half of the warp)
-                constexpr uint32_t PM = (TP == 32) ? 0xFFFFFFFFu : 0xFFFFu;
-                const int hb = (TP == 32) ? 0 : int(threadIdx.x & 16);
+                constexpr uint32_t PM = (TP == 32) ? 0xFFFFFFFFu : (TP == 16) ? 0xFFFFu : 0xFFu;
+                const int hb = (TP == 32) ? 0 : int(threadIdx.x & (32 - TP));
                 const uint32_t nz0 = (__ballot_sync(FULL, mask0 != 0) >> hb) & PM;
                 const uint32_t nz1 = (__ballot_sync(FULL, mask1 != 0) >> hb) & PM;
                 const uint32_t lt = (1u << tp) - 1u, gt = ~((2u << tp) - 1u) & PM;
@@ -701,8 +735,8 @@ pv_process_ring_kernel(const RingParams p) {
             // both scans run unconditionally (a channel without peaks ends up with every bin on the
             // dump slot): two independent instruction streams the scheduler can interleave
             const int second_flag = contract ? int(0x80000000u) : 0;
-            ring_owner_scan<G::XQ_SLOTS - 1>(mask0, 16 * tp, pk0, nk0, rk, second_flag, dst0);
-            ring_owner_scan<G::XQ_SLOTS - 1>(mask1, 16 * tp, pk1, nk1, rk, second_flag, dst1);
+            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask0, 16 * tp, pk0, nk0, rk, second_flag, dst0);
+            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk, second_flag, dst1);
         }
 
         // sources into registers: own run, bin M and the first stale level (what _realTransform4
@@ -754,8 +788,8 @@ pv_process_ring_kernel(const RingParams p) {
             for (int i = 0; i < 4; i++) {
                 const int d = M + tp + TP * i + dl0;
                 if (unsigned(d) < unsigned(NB)) {
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT))) = ext[i].x;
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT)) + 2 * PL) = ext[i].z;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS))) = ext[i].x;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS)) + 2 * PL) = ext[i].z;
                 }
             }
         }
@@ -764,8 +798,8 @@ pv_process_ring_kernel(const RingParams p) {
             for (int i = 0; i < 4; i++) {
                 const int d = M + tp + TP * i + dl1;
                 if (unsigned(d) < unsigned(NB)) {
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT)) + PL) = ext[i].y;
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> PVB_RING_YSHIFT)) + 3 * PL) = ext[i].w;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS)) + PL) = ext[i].y;
+                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS)) + 3 * PL) = ext[i].w;
                 }
             }
         }
@@ -804,7 +838,7 @@ pv_process_ring_kernel(const RingParams p) {
     // ---- Hermitian C2R pre-pass in registers (mirror of the split) -------------------------------------
     {
         // words of the same bins in the Y planes (pad every 2^YS bins instead of every 16)
-        constexpr int YS = PVB_RING_YSHIFT, YP = 1 << YS;
+        constexpr int YS = G::YS, YP = 1 << YS;
         constexpr int YSS = KS + (KS >> YS), YSM = M + (M >> YS);
         static_assert(KS % YP == 0 && YS >= 4, "Y-plane padding must divide the butterfly stride and fit the buffer");
         const int yA = tp + (tp >> YS), yB = YSM - tp - ((tp + YP - 1) >> YS);
@@ -868,13 +902,13 @@ pv_process_ring_kernel(const RingParams p) {
 
     // accumulator values (L2 hits thanks to the prefetch) are requested before the last exchange so
     // that their latency hides behind inverse pass 2; the tail slot starts from zero (ola:134)
-    float4 *al = p.acc2 + size_t(pair) * (N / 2) + cn;
+    float4 *al = p.acc2 + size_t(pair) * (N / 2) + (HB ? 0 : cn);
     float4 q[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
         q[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fr < NEWFROM) q[e] = al[TPH * h + PVB_RING_OFF(f)];
+        if (PVB_ROLE(h, fr) < NEWFROM) q[e] = al[PVB_RING_IDX(h, f)];
     }
 
     // ---- inverse pass 2: butterflies (k1, m3) over k2, twiddle conj(W_M^{k1 (m3 + 8 m2 + 64 toff)}) -------
@@ -927,7 +961,7 @@ pv_process_ring_kernel(const RingParams p) {
         const int row0 = RT * sp;
 #pragma unroll
         for (int h = 0; h < G::NB1; h++) {
-            const int nl = cn + TPH * h;
+            const int nl = PVB_COL(h);
             cpx2 x[RT];
 #pragma unroll
             for (int k1 = 0; k1 < RT; k1++) x[k1] = unpack4(ex[G::RS * (row0 + k1) + nl + (G::G8 - 8) * (nl >> 3)]);
@@ -941,11 +975,11 @@ pv_process_ring_kernel(const RingParams p) {
                 const float4 qv = q[RT * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
-                if (j < HEADTO) {                                     // head: emit (ola:111-118)
+                if (PVB_ROLE(h, j) < HEADTO) {                        // head: emit (ola:111-118)
                     *reinterpret_cast<float2 *>(o0 + 2 * TPH * h + 128 * fb) = make_float2(y0.x, y1.x);
                     if (has1) *reinterpret_cast<float2 *>(o0 + hop + 2 * TPH * h + 128 * fb) = make_float2(y0.y, y1.y);
                 } else {
-                    al[TPH * h + PVB_RING_OFF(fb)] = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    al[PVB_RING_IDX(h, fb)] = make_float4(y0.x, y0.y, y1.x, y1.y);
                 }
             }
         }
@@ -966,25 +1000,32 @@ pv_process_ring_kernel(const RingParams p) {
 #undef PVB_FR
 #undef PVB_FH
 #undef PVB_FB
+#undef PVB_ROLE
+#undef PVB_RING_IDX
+#undef PVB_COL
 }
 
 // tables the ring-order kernel copies into shared memory: NJ first-pass twiddle tables
 // tw1[toff][k1][n] = W_M^{(n + 64 toff) k1} (rows of TW1_ROW), then w64[a][b] = W_64^{ab}, twh[k] = W_N^k
 template <int N>
-constexpr int ring_host_table_bytes() { return RingGeoT<N>::NJ * RingGeoT<N>::TW1_BYTES + RingGeoT<N>::W64_BYTES + RingGeoT<N>::TWH_BYTES + RingGeoT<N>::W128_BYTES; }
+constexpr int ring_host_table_bytes() { return RingGeoT<N>::NTAB * RingGeoT<N>::TW1_BYTES + RingGeoT<N>::W64_BYTES + RingGeoT<N>::TWH_BYTES + RingGeoT<N>::W128_BYTES; }
 
 template <int N>
 inline void ring_host_tables(const float2 *tw /* [N] W_N^j */, float2 *out /* ring_host_table_bytes / 8 */) {
     using G = RingGeoT<N>;
-    float2 *w64 = out + G::NJ * (G::TW1_BYTES / 8), *twh = w64 + G::W64_BYTES / 8, *w128 = twh + G::TWH_BYTES / 8;
+    float2 *w64 = out + G::NTAB * (G::TW1_BYTES / 8), *twh = w64 + G::W64_BYTES / 8, *w128 = twh + G::TWH_BYTES / 8;
     for (int i = 0; i < ring_host_table_bytes<N>() / 8; i++) out[i] = make_float2(0.f, 0.f);
-    for (int toff = 0; toff < G::NJ; toff++)
+    for (int u = 0; u < G::NTAB; u++)
         for (int row = 0; row < G::R1; row++)
             for (int n = 0; n < 64; n++) {
                 // frame 4096: row = 16 s + k' holds W_M^{(n + 64 toff) k'} W_32^{s k'}
+                // frame 256: table u = 2 toff + half; ring columns n < 32 of a half-rotated ring belong
+                // to the next ring block: W_M^{n k1} W_R1^{(toff + carry) k1}
                 const int k1 = row % G::RT, sp = row / G::RT;
-                out[toff * (G::TW1_BYTES / 8) + G::TW1_ROW * row + n] =
-                    tw[(2 * (n + 64 * toff) * k1 + (N / 32) * sp * k1) & (N - 1)];
+                const int toff = G::HB ? (u >> 1) : u;
+                const int carry = (G::HB && (u & 1) && n < 32) ? 1 : 0;
+                out[u * (G::TW1_BYTES / 8) + G::TW1_ROW * row + n] =
+                    tw[(2 * (n + 64 * (toff + carry)) * k1 + (N / 32) * sp * k1) & (N - 1)];
             }
     if (G::NSPL == 2)
         for (int n = 0; n < 64; n++) w128[n] = tw[((N / 128) * n) & (N - 1)];

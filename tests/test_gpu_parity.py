@@ -175,6 +175,23 @@ def test_parity_ring_kernel_512_many_channels(oracle, C, pf):
     assert per_channel.max() <= RMS_EXPECTED
 
 
+@pytest.mark.parametrize("hop", [64, 128])
+@pytest.mark.parametrize("pf", [0.75, 0.8, 1.0, 1.3, 2.0])
+@pytest.mark.parametrize("C", [5, 70])
+def test_parity_ring_kernel_256(oracle, hop, pf, C):
+    """frame 256: a quarter of a warp per pair (four pairs share a warp, a partly filled last warp
+    and a second CTA at 70 channels); hop 64 rotates the rings by half a 128-sample block on odd calls"""
+    from phaze_b200 import BatchedPhaseVocoder
+    with BatchedPhaseVocoder(C, 256, hop) as pv:
+        if "ring" not in pv.kernel_name(np.float32(pf)):
+            pytest.skip("frame-256 ring-order kernel disabled (PVB_RING_256=0)")
+    calls = 3 * (256 // hop) + 6
+    x, ref, got = _run_both(oracle, 256, hop, C, np.float32(pf), calls)
+    per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
+    print(f"N=256 hop={hop} pf={pf} C={C}: worst channel rms err {per_channel.max():.3e}")
+    assert per_channel.max() <= RMS_EXPECTED
+
+
 @pytest.mark.parametrize("hop", [256, 512, 1024, 2048])
 @pytest.mark.parametrize("pf", [0.75, 0.8, 1.0, 1.3, 2.0])
 def test_parity_ring_kernel_4096(oracle, hop, pf):

@@ -22,6 +22,7 @@ def _rms(a):
     (512, 128, 0.8, 12, 0), (512, 128, 1.2, 12, 3), (512, 256, 1.5, 6, 1), (512, 128, 0.75, 12, 2),
     (4096, 1024, 1.2, 6, 0), (4096, 1024, 0.8, 6, 1), (4096, 512, 0.8, 10, 3), (4096, 256, 1.3, 18, 5),
     (4096, 2048, 1.5, 3, 1),
+    (256, 64, 1.2, 14, 0), (256, 64, 0.8, 14, 1), (256, 64, 0.75, 14, 2), (256, 128, 1.3, 8, 1), (512, 64, 0.8, 20, 3),
 ])
 def test_model_matches_oracle(oracle, frame, hop, pf, calls, start):
     x = signals.channels(11, 2, calls * hop)
