@@ -95,17 +95,23 @@ struct RingGeoT {
     static constexpr int W64_BYTES = 64 * 8;                // w64[a][b] = W_64^{a b}
     static constexpr int TWH_BYTES = (M + 8) * 8;           // twh[k] = W_N^k, k <= M
     static constexpr int W128_BYTES = (NSPL == 2) ? 64 * 8 : 0;             // w128[n] = W_128^n, n < 64 (frame 4096)
-    static constexpr int GTAB_BYTES = TW1_BYTES + W64_BYTES + TWH_BYTES + W128_BYTES;    // copied verbatim from global
-    static constexpr int WIN_BYTES = N * 4;                 // window / synthesis window, rotated by t
+    static constexpr int WIN_BYTES = N * 4;                 // window / synthesis window
+    // frame 4096: the split twiddles and the two windows (49 KB) stay in global memory (read through
+    // L1, every CTA reads the same lines); with them in shared memory only one CTA fits an SM and
+    // nothing overlaps its load phase (measured: 35 % of the roofline against 4x % with two CTAs)
+    static constexpr bool GT = (N == 4096);
+    static constexpr int TWH_SMEM = GT ? 0 : TWH_BYTES, WIN_SMEM = GT ? 0 : WIN_BYTES;
+    // global: NTAB x tw1 | w64 | w128 | twh; shared: ktab | tw1 | w64 | w128 | twh | window | window_out
     static constexpr int OFF_TW1 = DTAB_BYTES;
     static constexpr int OFF_W64 = OFF_TW1 + TW1_BYTES;
-    static constexpr int OFF_TWH = OFF_W64 + W64_BYTES;
-    static constexpr int OFF_W128 = OFF_TWH + TWH_BYTES;
-    static constexpr int OFF_WIN = OFF_W128 + W128_BYTES;
-    static constexpr int OFF_WOUT = OFF_WIN + WIN_BYTES;
-    static constexpr int TAB_BYTES = OFF_WOUT + WIN_BYTES;
-    static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024 : 4;   // pairs per CTA
-    static constexpr int CTAS_PER_SM = (N == 4096) ? 1 : 2; // frame 4096: 77 KB of tables + 4 x 36 KB
+    static constexpr int OFF_W128 = OFF_W64 + W64_BYTES;
+    static constexpr int OFF_TWH = OFF_W128 + W128_BYTES;
+    static constexpr int OFF_WIN = OFF_TWH + TWH_SMEM;
+    static constexpr int OFF_WOUT = OFF_WIN + WIN_SMEM;
+    static constexpr int TAB_BYTES = OFF_WOUT + WIN_SMEM;
+    static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024
+                                     : (N == 2048) ? 4 : 2;                 // pairs per CTA
+    static constexpr int CTAS_PER_SM = 2;                   // frame 4096: 30 KB of tables + 2 x 36 KB per CTA
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
     static constexpr int MIN_PAIRS = (MIN_THREADS + TP - 1) / TP;
@@ -332,10 +338,14 @@ pv_process_ring_kernel(const RingParams p) {
     int *ktab = reinterpret_cast<int *>(smem_raw);
     const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
     const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
-    const float2 *twh = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
+    // (frame 4096: twh and the windows are read from global memory, see RingGeoT::GT)
+    const float2 *twh = G::GT ? reinterpret_cast<const float2 *>(p.gtab + G::NTAB * (G::TW1_BYTES / 16) +
+                                                               (G::W64_BYTES + G::W128_BYTES) / 16)
+                              : reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
     const float2 *w128 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W128);   // frame 4096 only
-    const float *swin = reinterpret_cast<const float *>(smem_raw + G::OFF_WIN);
-    const float *swout = reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
+    const float *swin = G::GT ? p.window2 : reinterpret_cast<const float *>(smem_raw + G::OFF_WIN);
+    const float *swout = G::GT ? p.window_out2 : reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
+#define PVB_TLD2(ptr) (G::GT ? __ldg(ptr) : *(ptr))
     unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(pin) * G::PAIR_BYTES;
     float4 *ex = reinterpret_cast<float4 *>(mine);
     float4 *XQ = reinterpret_cast<float4 *>(mine);
@@ -382,15 +392,15 @@ pv_process_ring_kernel(const RingParams p) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_tab + 16 * i), "l"(g_tw1 + i));
         }
 #pragma unroll
-        for (int k = 0; k < ((G::W64_BYTES + G::TWH_BYTES + G::W128_BYTES) / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
+        for (int k = 0; k < ((G::W64_BYTES + G::W128_BYTES + G::TWH_SMEM) / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
-            if (i < (G::W64_BYTES + G::TWH_BYTES + G::W128_BYTES) / 16)
+            if (i < (G::W64_BYTES + G::W128_BYTES + G::TWH_SMEM) / 16)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_rest + 16 * i), "l"(g_rest + i));
         }
 #pragma unroll
-        for (int k = 0; k < (N / 4 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
+        for (int k = 0; k < (G::WIN_SMEM / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
-            if (i < N / 4) {
+            if (i < G::WIN_SMEM / 16) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_win + 16 * i), "l"(w1 + i));
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_wout + 16 * i), "l"(w2 + i));
             }
@@ -533,7 +543,7 @@ pv_process_ring_kernel(const RingParams p) {
             cpx2 x[RT];
 #pragma unroll
             for (int j = 0; j < RT; j++) {
-                const float2 w = *reinterpret_cast<const float2 *>(wl + 2 * TPH * h + 128 * PVB_FB(j));
+                const float2 w = PVB_TLD2(reinterpret_cast<const float2 *>(wl + 2 * TPH * h + 128 * PVB_FB(j)));
                 const float4 v = r[RT * h + j];
                 x[j].re = mul2(make_float2(v.x, v.y), bc2(w.x));
                 x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
@@ -636,15 +646,15 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const cpx2 za = sel(l0, b[j], a[j]);
-        ring_split(za, b[7 - j], twh[tlo + KS * j], XQ + sAlo + SS * j, XQ + sBlo - SS * j);
+        ring_split(za, b[7 - j], PVB_TLD2(twh + tlo + KS * j), XQ + sAlo + SS * j, XQ + sBlo - SS * j);
     }
 #pragma unroll
     for (int j = 4; j < 8; j++) {
         const cpx2 za = sel(l0, a[j - 4], a[j]);
         const cpx2 zb = sel(l0, a[(12 - j) & 7], b[7 - j]);
-        ring_split(za, zb, twh[thi + KS * j], XQ + sAhi + SS * j, XQ + sBhi - SS * j);
+        ring_split(za, zb, PVB_TLD2(twh + thi + KS * j), XQ + sAhi + SS * j, XQ + sBhi - SS * j);
     }
-    if (l0) ring_split(a[4], a[4], twh[M / 2], XQ + M / 2 + M / 32, XQ + M / 2 + M / 32);
+    if (l0) ring_split(a[4], a[4], PVB_TLD2(twh + M / 2), XQ + M / 2 + M / 32, XQ + M / 2 + M / 32);
     pair_sync<TP>(pin);
 
     // ---- peaks, regions of influence, shift (pv:95-173) -------------------------------------------------
@@ -759,7 +769,7 @@ pv_process_ring_kernel(const RingParams p) {
                 const cpx2 Cv = unpack4(XQ[sm]), D = unpack4(XQ[sm - QO]);         // bins M - q, N/4 - q
                 const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, D.re));
                 const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, D.im));
-                const float2 w = twh[2 * qq];
+                const float2 w = PVB_TLD2(twh + 2 * qq);
                 const cpx2 sv = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
                 if (q) ext[i] = pack4(sv);
             }
@@ -853,13 +863,13 @@ pv_process_ring_kernel(const RingParams p) {
                 yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
                 ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
             }
-            const float2 w = twh[(j < 4 ? tlo : thi) + KS * j];
+            const float2 w = PVB_TLD2(twh + (j < 4 ? tlo : thi) + KS * j);
             ring_unsplit(yk, ym, w, zk[j], zmk[j]);
         }
         cpx2 zh, dummy;
         {
             const cpx2 y = ring_load_planes<G::XQ_SLOTS>(mine, M / 2 + ((M / 2) >> YS));
-            ring_unsplit(y, y, twh[M / 2], zh, dummy);
+            ring_unsplit(y, y, PVB_TLD2(twh + M / 2), zh, dummy);
         }
         a[0] = sel(l0, zk[4], zk[0]);
         a[1] = sel(l0, zk[5], zk[1]);
@@ -971,7 +981,7 @@ pv_process_ring_kernel(const RingParams p) {
                 // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the division
                 // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
                 const int fb = PVB_FB(j);
-                const float2 wo = *reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * fb);
+                const float2 wo = PVB_TLD2(reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * fb));
                 const float4 qv = q[RT * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
@@ -1003,6 +1013,7 @@ pv_process_ring_kernel(const RingParams p) {
 #undef PVB_ROLE
 #undef PVB_RING_IDX
 #undef PVB_COL
+#undef PVB_TLD2
 }
 
 // tables the ring-order kernel copies into shared memory: NJ first-pass twiddle tables
@@ -1013,7 +1024,7 @@ constexpr int ring_host_table_bytes() { return RingGeoT<N>::NTAB * RingGeoT<N>::
 template <int N>
 inline void ring_host_tables(const float2 *tw /* [N] W_N^j */, float2 *out /* ring_host_table_bytes / 8 */) {
     using G = RingGeoT<N>;
-    float2 *w64 = out + G::NTAB * (G::TW1_BYTES / 8), *twh = w64 + G::W64_BYTES / 8, *w128 = twh + G::TWH_BYTES / 8;
+    float2 *w64 = out + G::NTAB * (G::TW1_BYTES / 8), *w128 = w64 + G::W64_BYTES / 8, *twh = w128 + G::W128_BYTES / 8;
     for (int i = 0; i < ring_host_table_bytes<N>() / 8; i++) out[i] = make_float2(0.f, 0.f);
     for (int u = 0; u < G::NTAB; u++)
         for (int row = 0; row < G::R1; row++)
