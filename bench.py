@@ -492,13 +492,13 @@ def run_root_scatter(C, frame, hop, pitch, world, rank, local, steps, host_block
     del sh
     # streamed root mode: audio buffers of Kc calls per message ([C][Kc*hop]), scatter of buffer i+1
     # and gather of buffer i-1 under the kernels of buffer i
-    Kc, nbuf = int(os.environ.get("PVB_BENCH_STREAM_CALLS", "16")), 12
+    Kc, nbuf = int(os.environ.get("PVB_BENCH_STREAM_CALLS", "64")), 6
     sh = ShardedPhaseVocoder(total, frame, hop, device=torch.device("cuda", local))
     bufs = None
     if rank == 0:
         one = torch.from_numpy(np.tile(host_block_src[:, :hop], (world, Kc))).cuda().contiguous()
         bufs = [one.clone() for _ in range(nbuf)]
-    sh.process_stream_from_root(bufs, pitch, Kc, 4)
+    sh.process_stream_from_root(bufs, pitch, Kc, 3)
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
