@@ -1,6 +1,8 @@
-// pv_kernel_ring.cuh — ring-order fused kernel for frame sizes 1024 (one warp per channel pair)
-// and 2048 (two warps per pair; every thread owns 16 complex points of the half-size FFT), sm_100a.  Same reference arithmetic as pv_kernel.cuh (one launch == one process() call,
-// ola-processor.js:159-171 + phase-vocoder.js:45-72), reorganised around one identity:
+// pv_kernel_ring.cuh — ring-order fused kernel, sm_100a, for every frame size: every thread owns 16
+// complex points of the half-size FFT, so a channel pair takes a quarter of a warp (frame 256), half a
+// warp (512), one warp (1024), two (2048) or four warps (4096).  Same reference arithmetic as
+// pv_kernel.cuh (one launch == one process() call, ola-processor.js:159-171 +
+// phase-vocoder.js:45-72), reorganised around one identity:
 //
 //   Both state rings are kept ALIGNED TO THE TIME CURSOR t (frame sample n lives at ring index
 //   (n + t) mod N).  The FFT of the ring-ordered windowed frame is U[k] = X[k] e^{-j 2 pi k t / N},
@@ -21,8 +23,9 @@
 //     registers; delta = round(p * pitchFactor) - p is a 513-entry table built once per CTA;
 //   * no peak list, no descriptors, no prefix sums, no atomics.
 //
-// Valid for hop % 128 == 0, hop <= 512 and pitch factors in [0.75, 64] (first stale level only,
-// right halves and left halves of regions stay pairwise disjoint after the shift).  tests/
+// Valid for hop % 128 == 0 (frame 256: hop 64 or 128; frame 4096: hop % 256 == 0), hop <= N / 2 and
+// pitch factors in [0.75, 64] (first stale level only, right halves and left halves of regions stay
+// pairwise disjoint after the shift).  tests/
 // ring_kernel_model.py restates this file lane by lane in numpy (CPU test of the design).
 #pragma once
 
