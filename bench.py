@@ -357,7 +357,9 @@ def run_ours(args):
     kernel_ms = ms / max(launches, 1)                 # this rank's average launch duration
     achieved = 12.0 * frame * C / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES,
+                "frac": achieved / peak,
+                # the committed ncu capture is of the default workload only
+                "traffic": NCU_TRAFFIC_BYTES if (frame, hop, C, round(pitch, 3)) == (FRAME, HOP, CHANNELS, PITCH) else None,
                 "peak_source": peak_src, "kernel": procs[0].kernel_name(pitch),
                 "algorithmic_bytes_per_launch": 12 * frame * C,
                 "avg_launch_us": kernel_ms * 1e3}
@@ -527,7 +529,7 @@ def phaze_b200_lib():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the
 # committed `ncu --set full` capture (profiles/), for the default workload; None until captured.
-NCU_TRAFFIC_BYTES = 29.51e6   # profiles/r01_ncu_ring_kernel.txt: reads 29.44 MB + writes 0.06 MB (stores retire into L2)
+NCU_TRAFFIC_BYTES = 29.87e6   # profiles/r01_ncu_ring_1024.txt: reads 29.72 MB + writes 0.16 MB (stores retire into L2)
 
 
 def main():
