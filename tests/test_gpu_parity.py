@@ -232,12 +232,13 @@ def test_parity_ring_kernel_many_channels(oracle):
     assert per_channel.max() <= RMS_EXPECTED
 
 
-def test_layout_changes_mid_stream(oracle):
+@pytest.mark.parametrize("N,hop", [(1024, 256), (256, 64), (512, 128), (2048, 512), (4096, 1024)])
+def test_layout_changes_mid_stream(oracle, N, hop):
     """the pitch factor moves between the ring-order kernel (paired state, aligned to the time
     cursor) and the generic kernel (planar state): the state is re-laid on the device each time;
     a paused block, a checkpoint round trip and a time-cursor jump happen in between."""
     from phaze_b200 import BatchedPhaseVocoder
-    N, hop, C = 1024, 256, 5
+    C = 5
     plan = [(0.8, 5), (0.5, 3), (1.2, 4), (0.6, 2), (0.9, 6)]
     total = sum(n for _, n in plan)
     x = signals.channels(3, C, total * hop)
@@ -265,7 +266,8 @@ def test_layout_changes_mid_stream(oracle):
     assert err <= RMS_EXPECTED
 
 
-def test_flag_mode_chained_handles_and_back_to_back(oracle):
+@pytest.mark.parametrize("N,hop", [(1024, 256), (256, 64), (512, 128), (2048, 512), (4096, 1024)])
+def test_flag_mode_chained_handles_and_back_to_back(oracle, N, hop):
     """Consecutive launches of the frame-1024 kernel overlap (per-pair completion flags instead of
     a grid-wide wait).  (a) one handle called back to back on a stream with device buffers: each
     pair waits for its own previous call; (b) two handles chained through ONE device buffer
@@ -273,7 +275,7 @@ def test_flag_mode_chained_handles_and_back_to_back(oracle):
     aliasing and order those launches; (c) no flag was ever lost."""
     import torch
     from phaze_b200 import BatchedPhaseVocoder
-    N, hop, C, calls = 1024, 256, 37, 24
+    C, calls = 37, 24
     pfa, pfb = np.float32(0.8), np.float32(1.25)
     x = signals.channels(7, C, calls * hop)
     oa, ob = oracle.OracleProcessor(N, hop, C), oracle.OracleProcessor(N, hop, C)
