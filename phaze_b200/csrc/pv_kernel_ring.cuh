@@ -46,6 +46,14 @@ namespace pvb {
 #ifndef PVB_RING_YSHIFT
 #define PVB_RING_YSHIFT 5
 #endif
+// Exact first-writer classification while contracting: of a region's left half only the first
+// c = delta_prev - delta_next bins land on the previous region's right half; only those take the
+// read-add-store sub-step, everything else is stored once, and since the shifted regions then cover
+// [0, nb) exactly the zero fill is dropped (5 more integer operations per bin and channel, ~160
+// fewer shared-memory wavefronts per pair).
+#ifndef PVB_RING_EXACT
+#define PVB_RING_EXACT 0
+#endif
 #ifndef PVB_RING_PAIRS_1024
 #define PVB_RING_PAIRS_1024 7
 #endif
@@ -274,7 +282,16 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
         const int okey = take_next ? nx[e] : pkey;
         const int d = (okey & 0xFFFF) + cb + e;
         const unsigned slot = min(unsigned(d + (d >> YS)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
+#if PVB_RING_EXACT
+        // w = -(T - 1) 2^16 + (delta_next + delta_prev), T = 4 b + 2 - 2 next - 2 prev (even; >= 2 on a
+        // left half), deltas <= 0 while contracting  =>  -T = (w >> 16) & ~1; collide <=> T <= 4 c
+        const int w = tt - ((4 * e) << 16);
+        const int c4 = 4 * int(short(pkey - nx[e]));
+        const int q = ((w >> 16) & ~1) + c4;
+        dst[e] = int(4u * slot) | (w & ~q & second_flag);
+#else
         dst[e] = int(4u * slot) | ((tt - ((4 * e) << 16)) & second_flag);
+#endif
     }
 }
 
@@ -778,10 +795,14 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
         pair_sync<TP>(pin);      // every thread holds its sources: the buffer becomes Y
+        // (PVB_RING_EXACT: while contracting every bin of [0, nb) is stored exactly once in the first
+        // sub-step, provided both channels have peaks)
+        if (!(PVB_RING_EXACT && contract && any0 && any1)) {
 #pragma unroll
-        for (int i = 0; i < 17; i++) XQ[tp + TP * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tp < 2) XQ[17 * TP + tp] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pair_sync<TP>(pin);
+            for (int i = 0; i < 17; i++) XQ[tp + TP * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tp < 2) XQ[17 * TP + tp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pair_sync<TP>(pin);
+        }
 
         constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane
         // first sub-step: plain stores (pairwise disjoint destinations)

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
+EXACT = False            # experiment: exact first-writer classification (no zero fill when contracting)
 F32 = np.float32
 C64 = np.complex64
 INVALID_DELTA = 0x3000
@@ -335,10 +336,18 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
             owner = np.where(take_next, nextv[e], P)
             dest[e] = bb + dtab[owner]
             first[e] = ~take_next | (not contract)    # right half of its region, or expanding
+            if EXACT and contract:
+                # only the left-half bins that land on the previous region's right half are added on
+                # top: the first c = delta_prev - delta_next bins of the left half.  With
+                # T = 4 b + 2 - 2 next - 2 prev (even, >= 2 on a left half): collide <=> T <= 4 c
+                Tq = 4 * bb + 2 - 2 * nextv[e] - 2 * P
+                cq = dtab[np.maximum(P, 0)] - dtab[np.minimum(nextv[e], NB)]
+                collide = take_next & (P >= 0) & (nextv[e] < 20000) & (Tq <= 4 * cq)
+                first[e] = ~collide
 
         # every thread holds its sources in registers; zero fill, then two ordered sub-steps
         # (right halves are pairwise disjoint after the shift, and so are left halves: checked here)
-        X[ch, :] = 0
+        X[ch, :] = np.nan if (EXACT and contract) else 0      # EXACT: full coverage, no zero fill
         written = np.zeros(g.XSLOTS, np.int64)
         for e in range(16):                           # first sub-step: plain stores
             ok = (dest[e] >= 0) & (dest[e] < NB) & first[e]
@@ -353,6 +362,9 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 written[xslot(d[L])] += 1
                 X[ch, xslot(d[L])] = ext[i][L]
         assert written.max() <= 1, "two first writers for one bin"
+        if EXACT and contract:
+            assert (written[xslot(np.arange(NB))] == 1).all(), "a bin of the shifted spectrum was never written"
+            X[ch, ~np.isin(np.arange(g.XSLOTS), xslot(np.arange(NB)))] = 0
         written[:] = 0
         if contract:
             for e in range(16):                       # second sub-step: left halves add on top
