@@ -36,8 +36,12 @@ METRIC = "STFT frames/sec (1024-pt, hop 256) at 4096 ch; achieved HBM GB/s vs pe
 
 
 def workload_name(channels, frame, hop, pitch):
-    return (f"{channels} mono channels per GPU, frame {frame} / hop {hop}, pitchFactor {pitch} "
-            f"(BASELINE configs[1])")
+    tag = {(1024, 256, 4096, 0.8): " (BASELINE configs[1])", (2048, 512, 2048, 1.5): " (BASELINE configs[2]: 1024 stereo streams)",
+           (1024, 256, 32768, 1.25): " (BASELINE configs[3], all channels on one GPU)",
+           (2048, 128, 2048, 1.2): " (the reference's own frame / hop)"}.get((frame, hop, channels, round(float(pitch), 3)), "")
+    if not tag and channels == 8192 and hop * 4 == frame:
+        tag = " (BASELINE configs[4] sweep)"
+    return f"{channels} mono channels per GPU, frame {frame} / hop {hop}, pitchFactor {pitch}{tag}"
 UNIT = "frames/s"
 FRAME, HOP, CHANNELS, PITCH = 1024, 256, 4096, 0.8
 L2_BYTES = 126e6
@@ -57,6 +61,8 @@ def parse_args():
                     help="processor instances rotated through (0: enough to exceed 2x L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short device-resident runs of the other BASELINE configs (N=1, default workload only)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--root-scatter", action="store_true",
                     help="N>1: also time the single-root mode (NCCL scatter of input slabs, gather of outputs)")
@@ -364,6 +370,19 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": 12 * frame * C,
                 "avg_launch_us": kernel_ms * 1e3}
 
+    # the other BASELINE configs (parity-test cases, not bench lines): short device-resident runs on
+    # the same terms as `value`, reported as context beside the headline
+    others = None
+    is_default = (frame, hop, C, round(float(args.pitch), 3)) == (FRAME, HOP, CHANNELS, PITCH)
+    if world == 1 and is_default and not args.no_other_configs:
+        for p in procs:
+            p.close()
+        procs = []
+        del outs, blocks
+        torch.cuda.empty_cache()
+        peak_o, _ = measured_peak()
+        others = [quick_config(local, f, h, c, pf, peak_o) for (f, h, c, pf) in OTHER_CONFIGS]
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -390,6 +409,8 @@ def run_ours(args):
         }
         if root_scatter:
             line["root_scatter"] = root_scatter
+        if others:
+            line["other_configs"] = others
         print(json.dumps(line))
     for p in procs:
         p.close()
@@ -457,6 +478,54 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
             "api": f"pvb_process_many(handle, in_host, out_host, {batch}, pitch): pinned host buffers, "
                    "H2D / kernel / D2H of consecutive calls overlapped, synchronous on return",
             "single_call_value": single_value, "out_std": check}
+
+
+# BASELINE configs 3, 4 (one shard's worth per launch) and 5, plus the reference's own 2048 / 128
+OTHER_CONFIGS = [(2048, 512, 2048, 1.5), (1024, 256, 32768, 1.25),
+                 (256, 64, 8192, 1.2), (512, 128, 8192, 1.2), (1024, 256, 8192, 1.2), (2048, 512, 8192, 1.2),
+                 (4096, 1024, 8192, 1.2), (2048, 128, 2048, 1.2)]
+
+
+def quick_config(local, frame, hop, C, pf, peak, steps=300, warm=40):
+    """Device-resident throughput of one configuration, measured like `value`: instances rotated so
+    that state + io exceed L2, one stream, CUDA events around `steps` launches."""
+    import numpy as np
+    import torch
+
+    import phaze_b200
+    from phaze_b200 import signals
+
+    pitch = np.float32(pf)
+    state_bytes = 2 * C * frame * 4 + 2 * C * hop * 4
+    rotate = max(2, int(np.ceil(2.2 * L2_BYTES / state_bytes)))
+    nblk = 4
+    host = signals.channels(0, C, nblk * hop)
+    blocks = torch.from_numpy(np.ascontiguousarray(host.reshape(C, nblk, hop).transpose(1, 0, 2))).cuda()
+    outs = [torch.empty((C, hop), dtype=torch.float32, device="cuda") for _ in range(rotate)]
+    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local) for _ in range(rotate)]
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def step(i):
+        procs[i % rotate].process_device(blocks[i % nblk].data_ptr(), outs[i % rotate].data_ptr(), pitch, sptr)
+
+    for i in range(rotate * (frame // hop) + warm):
+        step(i)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(steps):
+        step(i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    kernel = procs[0].kernel_name(pitch)
+    for p in procs:
+        p.close()
+    achieved = 12.0 * frame * C / (ms * 1e-3) / 1e9
+    return {"workload": workload_name(C, frame, hop, pf), "value": C / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "steps": steps, "roofline_frac": achieved / peak, "achieved_gbs": achieved,
+            "kernel": kernel, "instances_rotated": rotate}
 
 
 def run_root_scatter(C, frame, hop, pitch, world, rank, local, steps, host_block_src):
