@@ -1,8 +1,9 @@
 #!/bin/bash
 # A/B of library builds of the ring-order kernel (see phaze_b200/csrc/pv_kernel_ring.cuh macros):
 #   libphaze_b200_p8.so   -DPVB_RING_PAIRS_1024=8            (16 warps per SM with PVB_RING_WPC=8)
-#   libphaze_b200_nf.so   -DPVB_RING_LANE_FENCE=0            (release by thread 0 only)
+#   libphaze_b200_nf.so   -DPVB_RING_LANE_FENCE=0            (release by thread 0 only; the default since)
 #   libphaze_b200_p8nf.so both
+# (`make -C phaze_b200/csrc variants` builds today's set: p8, lanefence, ys4, exact)
 # usage: profiles/ab_variants.sh   (prints one line per build / setting)
 cd "$(dirname "$0")/.."
 L=$PWD/phaze_b200
