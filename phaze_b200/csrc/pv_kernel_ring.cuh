@@ -364,7 +364,10 @@ pv_process_ring_kernel(const RingParams p) {
                               : reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
     const float2 *w128 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W128);   // frame 4096 only
     const float *swin = G::GT ? p.window2 : reinterpret_cast<const float *>(smem_raw + G::OFF_WIN);
-    const float *swout = G::GT ? p.window_out2 : reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
+    // (frame 4096: the synthesis window is the analysis window times 1 / (2 N R), a power of two, so
+    // only one window table competes for L1 there)
+    const float *swout = G::GT ? p.window2 : reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
+    constexpr float WOUT_SCALE = G::GT ? 1.0f / (2.0f * float(N) * float(N / (NBLK * G::UNIT))) : 1.0f;
 #define PVB_TLD2(ptr) (G::GT ? __ldg(ptr) : *(ptr))
     unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(pin) * G::PAIR_BYTES;
     float4 *ex = reinterpret_cast<float4 *>(mine);
@@ -1005,7 +1008,8 @@ pv_process_ring_kernel(const RingParams p) {
                 // window_out = hannWindow / (2 N R): fromComplexArray, applyHannWindow and the division
                 // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
                 const int fb = PVB_FB(j);
-                const float2 wo = PVB_TLD2(reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * fb));
+                float2 wo = PVB_TLD2(reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * fb));
+                if constexpr (G::GT) wo = make_float2(wo.x * WOUT_SCALE, wo.y * WOUT_SCALE);
                 const float4 qv = q[RT * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
