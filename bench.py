@@ -255,6 +255,20 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; phaze_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    # run this rank's host thread (and so the first touch of its pinned buffers) on the CPUs next to its
+    # GPU: the end-to-end number is PCIe-bound (no effect on the single-node VMs of this pool, where the
+    # e2e value still moved between 2.9e7 and 4.15e7 frames/s from box to box with the same code)
+    orig_affinity = os.sched_getaffinity(0)
+    numa = {"bound": False}
+    try:
+        if os.environ.get("PVB_BENCH_NO_NUMA") == "1":
+            raise RuntimeError("disabled")
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = {"bound": True, "cpus": len(os.sched_getaffinity(0)), "of": len(orig_affinity)}
+    except Exception as e:       # containers without the permission: keep the inherited affinity
+        numa = {"bound": False, "why": type(e).__name__}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -386,6 +400,7 @@ def run_ours(args):
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, orig_affinity)      # the CPU baseline uses every host core
             cpu = cpu_baseline(frame, hop, args.pitch, args.cpu_seconds)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -401,6 +416,7 @@ def run_ours(args):
                                  "each channel pair waits for its own previous call (completion flags)"},
             "roofline": roofline,
             "e2e": e2e,
+            "host_thread_affinity": numa,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "l2_resident_value": l2_value,

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <mutex>
 #include <new>
 #include <unordered_map>
@@ -278,95 +279,21 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
     return rp;
 }
 
-cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        const int smem = 227 * 1024;
-        cudaError_t e = cudaSuccess;
-#define PVB_RING_ATTR(N, NBLK)                                                                    \
-        if (e == cudaSuccess)                                                                     \
-            e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLK>,                        \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        PVB_RING_ATTR(256, 1) PVB_RING_ATTR(256, 2)
-        PVB_RING_ATTR(512, 1) PVB_RING_ATTR(512, 2)
-        PVB_RING_ATTR(1024, 1) PVB_RING_ATTR(1024, 2) PVB_RING_ATTR(1024, 4)
-        PVB_RING_ATTR(2048, 1) PVB_RING_ATTR(2048, 2) PVB_RING_ATTR(2048, 4) PVB_RING_ATTR(2048, 8)
-        PVB_RING_ATTR(4096, 2) PVB_RING_ATTR(4096, 4) PVB_RING_ATTR(4096, 8) PVB_RING_ATTR(4096, 16)
-#undef PVB_RING_ATTR
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
+// one frame size of the ring-order kernel: pairs per CTA, launch configuration (programmatic dependent
+// launch: CTAs of this launch may become resident and stage their tables while the previous kernel on
+// the stream drains; the kernel itself orders its accesses, see pv_kernel_ring.cuh), and the instance
+// for this hop.  NBLK counts role units of RingGeoT<N>::UNIT samples (64 at frame 256, else 128).
+template <int N, int... NBLKS>
+cudaError_t launch_ring_n(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, int ppc) {
+    using G = pvb::RingGeoT<N>;
     const int pairs = (fp.num_channels + 1) / 2;
-    if (pairs == 0) return cudaSuccess;
-    if (h->n == 4096) {
-        using G = pvb::RingGeoT<4096>;
-        int ppc4 = G::MAX_PAIRS;
-        if (g_ring_wpc >= G::MIN_PAIRS && g_ring_wpc <= G::MAX_PAIRS) ppc4 = g_ring_wpc;
-        pvb::RingParams rp = make_ring_params(h, fp, s);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((pairs + ppc4 - 1) / ppc4);
-        cfg.blockDim = dim3(ppc4 * G::TP);
-        cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc4) * G::PAIR_BYTES;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;
-        switch (rp.hop >> 7) {
-            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 2>, rp);
-            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 4>, rp);
-            case 8: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 8>, rp);
-            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<4096, 16>, rp);
-        }
-    }
-    if (h->n == 256) {
-        using G = pvb::RingGeoT<256>;
-        int ppc2 = G::MAX_PAIRS;
-        if (g_ring_wpc >= G::MIN_PAIRS && g_ring_wpc <= G::MAX_PAIRS) ppc2 = g_ring_wpc;
-        pvb::RingParams rp = make_ring_params(h, fp, s);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((pairs + ppc2 - 1) / ppc2);
-        cfg.blockDim = dim3(ppc2 * G::TP);
-        cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc2) * G::PAIR_BYTES;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;
-        // NBLK counts units of 64 samples at this frame size
-        if (rp.hop == 64) return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<256, 1>, rp);
-        return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<256, 2>, rp);
-    }
-    const bool big = h->n == 2048, small = h->n == 512;
-    // pairs per CTA: frame 1024 balances one wave (4..7 warps); frame 2048 uses 4 pairs of two warps;
-    // frame 512 packs 16 half-warp pairs (8 warps)
-    int ppc = big ? 4 : small ? pvb::RingGeoT<512>::MAX_PAIRS : pick_warps_per_cta(pairs, h->num_sms);
-    const int max_ppc = big ? pvb::RingGeoT<2048>::MAX_PAIRS
-                            : small ? pvb::RingGeoT<512>::MAX_PAIRS : pvb::RingGeoT<1024>::MAX_PAIRS;
-    const int min_ppc = big ? pvb::RingGeoT<2048>::MIN_PAIRS
-                            : small ? pvb::RingGeoT<512>::MIN_PAIRS : pvb::RingGeoT<1024>::MIN_PAIRS;
-    if (g_ring_wpc >= min_ppc && g_ring_wpc <= max_ppc) ppc = g_ring_wpc;
-    const int grid = (pairs + ppc - 1) / ppc;
-    const int threads = ppc * (big ? pvb::RingGeoT<2048>::TP : small ? pvb::RingGeoT<512>::TP : pvb::RingGeoT<1024>::TP);
+    if (g_ring_wpc >= G::MIN_PAIRS && g_ring_wpc <= G::MAX_PAIRS) ppc = g_ring_wpc;   // PVB_RING_WPC
     pvb::RingParams rp = make_ring_params(h, fp, s);
-    // PVB_RING_PAD_KB: occupancy experiment (extra dynamic shared memory per CTA)
-    const size_t smem = (big ? pvb::RingGeoT<2048>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<2048>::PAIR_BYTES
-                         : small ? pvb::RingGeoT<512>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<512>::PAIR_BYTES
-                                 : pvb::RingGeoT<1024>::TAB_BYTES + size_t(ppc) * pvb::RingGeoT<1024>::PAIR_BYTES) +
-                        size_t(g_ring_pad_kb) * 1024;
-    // programmatic dependent launch: CTAs of this launch may become resident (and stage their
-    // tables) while the previous kernel on the stream drains; the kernel itself waits
-    // (griddepcontrol.wait) before it touches anything an earlier launch may have written
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(threads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.gridDim = dim3((pairs + ppc - 1) / ppc);
+    cfg.blockDim = dim3(ppc * G::TP);
+    // PVB_RING_PAD_KB: occupancy experiment (extra dynamic shared memory per CTA)
+    cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc) * G::PAIR_BYTES + size_t(g_ring_pad_kb) * 1024;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -374,24 +301,48 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
-    const int nblk = rp.hop >> 7;
-    if (big) {
-        switch (nblk) {
-            case 1: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 1>, rp);
-            case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 2>, rp);
-            case 4: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 4>, rp);
-            default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<2048, 8>, rp);
-        }
+    const int nblk = rp.hop / G::UNIT;
+    cudaError_t e = cudaErrorInvalidValue;                      // no instance for this hop
+    (void)std::initializer_list<int>{
+        (nblk == NBLKS ? (e = cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<N, NBLKS>, rp), 0) : 0)...};
+    return e;
+}
+
+template <int N, int... NBLKS>
+cudaError_t ring_set_smem_attr() {
+    cudaError_t e = cudaSuccess;
+    (void)std::initializer_list<int>{
+        (e == cudaSuccess ? (e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLKS>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), 0)
+                          : 0)...};
+    return e;
+}
+
+cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = ring_set_smem_attr<256, 1, 2>();
+        if (e == cudaSuccess) e = ring_set_smem_attr<512, 1, 2>();
+        if (e == cudaSuccess) e = ring_set_smem_attr<1024, 1, 2, 4>();
+        if (e == cudaSuccess) e = ring_set_smem_attr<2048, 1, 2, 4, 8>();
+        if (e == cudaSuccess) e = ring_set_smem_attr<4096, 2, 4, 8, 16>();
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
     }
-    if (small) {
-        if (nblk == 1) return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<512, 1>, rp);
-        return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<512, 2>, rp);
+    const int pairs = (fp.num_channels + 1) / 2;
+    if (pairs == 0) return cudaSuccess;
+    // pairs per CTA: frame 1024 balances one wave (4..7 warps); the other sizes fill their CTAs (frame 256:
+    // 32 quarter-warp pairs, 512: 16 half-warp pairs, 2048: 4 pairs of two warps, 4096: 2 pairs of four)
+    switch (h->n) {
+        case 256: return launch_ring_n<256, 1, 2>(h, fp, s, pvb::RingGeoT<256>::MAX_PAIRS);
+        case 512: return launch_ring_n<512, 1, 2>(h, fp, s, pvb::RingGeoT<512>::MAX_PAIRS);
+        case 1024: return launch_ring_n<1024, 1, 2, 4>(h, fp, s, pick_warps_per_cta(pairs, h->num_sms));
+        case 2048: return launch_ring_n<2048, 1, 2, 4, 8>(h, fp, s, pvb::RingGeoT<2048>::MAX_PAIRS);
+        case 4096: return launch_ring_n<4096, 2, 4, 8, 16>(h, fp, s, pvb::RingGeoT<4096>::MAX_PAIRS);
     }
-    switch (nblk) {
-        case 1: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 1>, rp);
-        case 2: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 2>, rp);
-        default: return cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<1024, 4>, rp);
-    }
+    return cudaErrorInvalidValue;
 }
 
 // two warps per channel pair (pv_kernel_pair.cuh): same validity range as the warp kernel
