@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
+MIDDLE = "scatter"       # "gather": prototype of the next middle (destination-order gather, see gather_shift)
 EXACT = False            # experiment: exact first-writer classification (no zero fill when contracting)
 F32 = np.float32
 C64 = np.complex64
@@ -83,6 +84,7 @@ class Conflicts:
     def __init__(self):
         self.worst = {}
 
+    gather_log = None       # experiments: byte addresses (-1: lane idle) per 64-bit gather access
     scatter_log = None      # experiments: list of (destination bins, active lanes) per 32-bit scatter access
     pair_bytes = 0          # frame 512: a warp holds two pairs, the second one this many bytes further
 
@@ -118,6 +120,62 @@ def dft(x, inv=False):
     r = x.shape[0]
     w = np.exp((2j if inv else -2j) * np.pi * np.outer(np.arange(r), np.arange(r)) / r)
     return np.tensordot(w, x.astype(np.complex128), axes=(1, 0)).astype(C64)
+
+
+def gather_shift(g: Geo, xfull, peaks, dtab, contract, cf: Conflicts | None = None):
+    """PROTOTYPE of a middle that touches the spectrum once: the shifted spectrum
+    in DESTINATION order.  Every peak writes one descriptor at the first destination bin of its region
+    (delta, overlap with the previous region, source end); a thread owns 16 consecutive destination
+    bins, finds for each the latest descriptor at or below it (forward fill, carry from the threads
+    below) and reads its one or two sources: no zero fill, no second sub-step, and the result stays in
+    registers until the 128-bit store that feeds the unsplit.
+
+    xfull: complex [M + N/8 + 1], bins 0 .. M + N/8 (the stale extension rebuilt once);
+    peaks: ascending peak bins; returns Y[NB].  Equivalent to shiftPeaks (pv:119-173) for pitch
+    factors in [0.75, 64]: at most two regions reach one destination bin."""
+    N, M, NB = g.N, g.M, g.NB
+    src_end_max = xfull.shape[0]                       # sources beyond the first stale level do not exist
+    desc = {}                                          # destination bin -> (delta, overlap, source end, delta_prev)
+    prev_delta = None
+    for i, p in enumerate(peaks):
+        delta = int(dtab[p])
+        if delta == INVALID_DELTA:
+            break                                      # pv:127: this and all later peaks are dropped
+        s = 0 if i == 0 else p - (p - peaks[i - 1]) // 2
+        e = N if i == len(peaks) - 1 else p + -(-(peaks[i + 1] - p) // 2)
+        e = min(e, src_end_max)
+        ds = s + delta
+        overlap = 0 if prev_delta is None else max(0, prev_delta - delta)
+        first = max(ds, 0)
+        if first < NB and e + delta > 0:
+            assert first not in desc, "two regions start at one destination bin"
+            desc[first] = (delta, overlap - (first - ds), e, prev_delta)
+        prev_delta = delta
+    Y = np.zeros(NB, C64)
+    cur = None
+    loads = []                                         # (destination, source) pairs, for the conflict count
+    for d in range(NB):
+        if d in desc:
+            cur = (d,) + desc[d]
+        if cur is None:
+            continue
+        d0, delta, overlap, e, dprev = cur
+        b = d - delta
+        if b < e:
+            Y[d] = xfull[b]; loads.append((d, b))
+        if d - d0 < overlap:
+            Y[d] += xfull[d - dprev]; loads.append((d, d - dprev))
+    if cf is not None:
+        # thread t owns destinations 16 t .. 16 t + 15 (bin M: one more load by the last thread); X as
+        # 8 bytes (re, im) per channel and bin, 16-byte slots padded every 16 bins: first / second sources
+        for which in (0, 1):
+            for e_ in range(16):
+                addr = []
+                for tt in range(g.TP):
+                    srcs = [b for (d, b) in loads if d == 16 * tt + e_]
+                    addr.append(xslot(srcs[which]) * 16 if len(srcs) > which else -1)
+                cf.gather_log.append(np.array(addr))
+    return Y
 
 
 def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
@@ -320,6 +378,19 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 ext[i] = v
                 if cf and contract:
                     cf.note("stale_ld", xslot(qq) * 16, 16); cf.note("stale_ld_m", xslot(M - qq) * 16, 16)
+
+        if MIDDLE == "gather":
+            xfull = np.zeros(M + N // 8 + 1, C64)
+            xfull[:M + 1] = Xc[xslot(np.arange(M + 1))]
+            for i in range(4):
+                q = T + TP * i
+                sel_ = (q > 0) if contract else np.zeros(TP, bool)
+                xfull[M + q[sel_]] = ext[i][sel_]
+            peaks = [int(b0[L]) + e for L in range(TP) for e in range(16) if (int(mask[L]) >> e) & 1]
+            Yc = gather_shift(g, xfull if contract else xfull[:M + 1], peaks, dtab, contract, cf if cf is not None and cf.gather_log is not None else None)
+            X[ch, :] = 0
+            X[ch, xslot(np.arange(NB))] = Yc
+            continue
 
         # owner of every bin of the run: nearest peak, ties to the higher one (pv:132-141)
         nextv = np.zeros((16, TP), np.int64)

@@ -52,3 +52,19 @@ def test_model_shared_memory_patterns_are_conflict_free(oracle):
     for name in ("p1_st", "p2_ld", "p3_ldA", "run_ld", "stale_ld"):
         assert cf.worst[name] == 1.0, (name, cf.worst)
     assert max(cf.worst.values()) <= 2.0, cf.worst
+
+
+@pytest.mark.parametrize("frame,hop,pf,calls", [
+    (1024, 256, 0.8, 9), (1024, 256, 0.75, 9), (1024, 256, 1.25, 8), (1024, 256, 3.0, 7), (256, 64, 0.8, 12),
+    (2048, 512, 1.5, 6), (4096, 1024, 0.85, 4),
+])
+def test_gather_middle_prototype_matches_oracle(oracle, monkeypatch, frame, hop, pf, calls):
+    """the destination-order gather planned as the next middle: one descriptor per
+    peak, every destination bin reads its one or two sources; same output as the scatter in two
+    ordered sub-steps"""
+    monkeypatch.setattr(model, "MIDDLE", "gather")
+    x = signals.channels(5, 2, calls * hop)
+    ref = oracle.OracleProcessor(frame, hop, 2).run(x, np.float32(pf))
+    got = model.run(x, pf, hop, frame=frame)
+    assert _rms(ref) > 1e-2
+    assert _rms(got - ref) <= 2e-8
