@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import numpy as np
 
+ROWS = False             # gather_lanes: destinations in row order (lane l handles bins TP r + l) instead of runs
 MIDDLE = "scatter"       # "gather": prototype of the next middle (destination-order gather, see gather_shift)
 EXACT = False            # experiment: exact first-writer classification (no zero fill when contracting)
 F32 = np.float32
@@ -175,6 +176,124 @@ def gather_shift(g: Geo, xfull, peaks, dtab, contract, cf: Conflicts | None = No
                     srcs = [b for (d, b) in loads if d == 16 * tt + e_]
                     addr.append(xslot(srcs[which]) * 16 if len(srcs) > which else -1)
                 cf.gather_log.append(np.array(addr))
+    return Y
+
+
+def gather_shift_lanes(g: Geo, xfull, mask, prev_before, next_after, dtab, contract, cf: Conflicts | None = None):
+    """gather_shift restated thread by thread, the way a kernel would do it (blueprint for the CUDA):
+
+    A. every thread walks the peaks of its own SOURCE run (bits of `mask`; the nearest peaks below /
+       above its run come from the ballot exchange the kernel already has) and stores one 32-bit
+       descriptor per peak at the first destination bin of the peak's region, in a zeroed array
+       D[nb]: contracting (delta <= 0, regions overlap, never leave gaps): delta | overlap << 16;
+       expanding (no overlaps, gaps): delta | source_end << 16.  Bit 31 marks "present".
+    B. every thread owns the DESTINATION run 16 tp .. 16 tp + 15 (the last thread also bin M): it
+       reads its 16 descriptors, gets the latest descriptor below its run (word and start bin) from
+       the nearest lower thread that has one (ballot + two shuffles), forward-fills, and gathers
+       Y[d] = X[d - delta] (+ X[d - delta - overlap] on the first `overlap` bins of a region).
+    """
+    N, M, NB, TP = g.N, g.M, g.NB, g.TP
+    PRESENT = 1 << 31
+    D = np.zeros(NB + 15, np.int64)                    # zeroed every call (8 x 128-bit stores per lane and pair)
+    n_src = xfull.shape[0]
+    desc_st = []
+    for L in range(TP):                                # ---- A: descriptors --------------------------------
+        pp = int(prev_before[L]); has_prev = pp >= 0
+        bits = [e for e in range(16) if (int(mask[L]) >> e) & 1]
+        for j, e in enumerate(bits):
+            p = 16 * L + e
+            nxt = 16 * L + bits[j + 1] if j + 1 < len(bits) else int(next_after[L])
+            has_next = nxt < 20000
+            delta = int(dtab[p])
+            if delta != INVALID_DELTA:
+                s = p - ((p - pp) >> 1) if has_prev else 0
+                e_end = min(p + ((nxt - p + 1) >> 1) if has_next else N, n_src)
+                dprev = int(dtab[pp]) if has_prev else delta
+                ds = s + delta
+                first = max(ds, 0)
+                if first < NB and e_end + delta > 0:
+                    if contract:
+                        ovl = max(0, dprev - delta)
+                        assert ds >= 0 or ovl == 0
+                        word = PRESENT | ((delta + 4096) & 0x1FFF) | (ovl << 16)
+                    else:
+                        word = PRESENT | ((delta + 4096) & 0x1FFF) | (e_end << 16)
+                    assert D[first] == 0, "two regions start at one destination bin"
+                    D[first] = word
+                    desc_st.append((L, first * 4))
+            pp, has_prev = p, True
+    if ROWS:
+        # ---- B': destinations in ROW order: lane l of the pair handles d = TP r + l, r = 0 .. 15 (and bin
+        # M in one more row).  Consecutive lanes read consecutive sources (delta is piecewise constant), so
+        # the 64-bit gathers are conflict free; the latest descriptor at or below d comes from a ballot of
+        # the row (nearest set lane at or below) or, if the row has none below, from the carry of the
+        # rows before.  Y[TP r + l] is exactly what the unsplit of thread l needs for bins l + 64 j
+        # (r = 2 j at frame 1024), and bins M - l - 64 j sit in lane TP - l of row 15 - 2 j: one shuffle
+        # per value, the shifted spectrum never goes through shared memory.
+        Y = np.zeros(NB, C64)
+        carry, cstart = 0, 0
+        for r in range((NB + TP - 1) // TP):
+            drow = TP * r + np.arange(TP)
+            words = np.array([int(D[d]) if d < NB else 0 for d in drow])
+            present = words != 0
+            addr = [np.full(TP, -1), np.full(TP, -1)]
+            for l in range(TP):
+                d = int(drow[l])
+                if d >= NB:
+                    continue
+                below = [k for k in range(l + 1) if present[k]]          # ballot & ((2 << l) - 1), then clz
+                cur, dstart = (int(words[below[-1]]), TP * r + below[-1]) if below else (carry, cstart)
+                if not cur:
+                    continue
+                delta = (cur & 0x1FFF) - 4096
+                hi = (cur >> 16) & 0x7FFF
+                b = d - delta
+                if contract:
+                    Y[d] = xfull[b]; addr[0][l] = 8 * (b + 2 * (b >> 4))
+                    if d - dstart < hi:
+                        Y[d] += xfull[b - hi]; addr[1][l] = 8 * (b - hi + 2 * ((b - hi) >> 4))
+                elif b < hi:
+                    Y[d] = xfull[b]; addr[0][l] = 8 * (b + 2 * (b >> 4))
+            if present.any():
+                k = int(np.nonzero(present)[0][-1])
+                carry, cstart = int(words[k]), TP * r + k
+            if cf is not None and cf.gather_log is not None:
+                cf.gather_log.extend(addr)
+        return Y
+    # ---- B: forward fill + gather ---------------------------------------------------------------
+    own = D[:16 * TP].reshape(TP, 16)
+    last_pos = np.array([max([e for e in range(16) if own[L, e]], default=-1) for L in range(TP)])
+    Y = np.zeros(NB, C64)
+    loads = []
+    for L in range(TP):
+        lower = [l for l in range(L) if last_pos[l] >= 0]          # ballot + shuffle in the kernel
+        cur, dstart = (int(own[lower[-1], last_pos[lower[-1]]]), 16 * lower[-1] + int(last_pos[lower[-1]])) if lower else (0, 0)
+        dests = list(range(16 * L, 16 * L + 16)) + ([M] if L == TP - 1 else [])
+        for d in dests:
+            w = int(D[d])
+            if w:
+                cur, dstart = w, d
+            if not cur:
+                continue
+            delta = (cur & 0x1FFF) - 4096
+            hi = (cur >> 16) & 0x7FFF
+            b = d - delta
+            if contract:
+                Y[d] = xfull[b]; loads.append((L, d, b))
+                if d - dstart < hi:
+                    Y[d] += xfull[b - hi]; loads.append((L, d, b - hi))
+            elif b < hi:
+                Y[d] = xfull[b]; loads.append((L, d, b))
+    if cf is not None and cf.gather_log is not None:
+        # X per channel as 8-byte (re, im) slots, one pad slot per 16 bins: byte address 8 (b + (b >> 4))
+        for which in (0, 1):
+            for e_ in range(16):
+                addr = np.full(TP, -1)
+                for L in range(TP):
+                    srcs = [b for (l, d, b) in loads if l == L and d == 16 * L + e_]
+                    if len(srcs) > which:
+                        addr[L] = 8 * (srcs[which] + (srcs[which] >> 4))
+                cf.gather_log.append(addr)
     return Y
 
 
@@ -379,7 +498,7 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 if cf and contract:
                     cf.note("stale_ld", xslot(qq) * 16, 16); cf.note("stale_ld_m", xslot(M - qq) * 16, 16)
 
-        if MIDDLE == "gather":
+        if MIDDLE in ("gather", "gather_lanes"):
             xfull = np.zeros(M + N // 8 + 1, C64)
             xfull[:M + 1] = Xc[xslot(np.arange(M + 1))]
             for i in range(4):
@@ -387,7 +506,12 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
                 sel_ = (q > 0) if contract else np.zeros(TP, bool)
                 xfull[M + q[sel_]] = ext[i][sel_]
             peaks = [int(b0[L]) + e for L in range(TP) for e in range(16) if (int(mask[L]) >> e) & 1]
-            Yc = gather_shift(g, xfull if contract else xfull[:M + 1], peaks, dtab, contract, cf if cf is not None and cf.gather_log is not None else None)
+            if MIDDLE == "gather_lanes":
+                Yc = gather_shift_lanes(g, xfull if contract else xfull[:M + 1], mask, prev_before, next_after,
+                                        dtab, contract, cf)
+            else:
+                Yc = gather_shift(g, xfull if contract else xfull[:M + 1], peaks, dtab, contract,
+                                  cf if cf is not None and cf.gather_log is not None else None)
             X[ch, :] = 0
             X[ch, xslot(np.arange(NB))] = Yc
             continue

@@ -58,11 +58,14 @@ def test_model_shared_memory_patterns_are_conflict_free(oracle):
     (1024, 256, 0.8, 9), (1024, 256, 0.75, 9), (1024, 256, 1.25, 8), (1024, 256, 3.0, 7), (256, 64, 0.8, 12),
     (2048, 512, 1.5, 6), (4096, 1024, 0.85, 4),
 ])
-def test_gather_middle_prototype_matches_oracle(oracle, monkeypatch, frame, hop, pf, calls):
+@pytest.mark.parametrize("variant", ["reference", "runs", "rows"])
+def test_gather_middle_prototype_matches_oracle(oracle, monkeypatch, frame, hop, pf, calls, variant):
     """the destination-order gather planned as the next middle: one descriptor per
     peak, every destination bin reads its one or two sources; same output as the scatter in two
-    ordered sub-steps"""
-    monkeypatch.setattr(model, "MIDDLE", "gather")
+    ordered sub-steps.  "reference": whole-array restatement; "runs" / "rows": thread by thread with
+    32-bit descriptors, destinations owned as runs of 16 or in row order (lane l: bins TP r + l)"""
+    monkeypatch.setattr(model, "MIDDLE", "gather" if variant == "reference" else "gather_lanes")
+    monkeypatch.setattr(model, "ROWS", variant == "rows")
     x = signals.channels(5, 2, calls * hop)
     ref = oracle.OracleProcessor(frame, hop, 2).run(x, np.float32(pf))
     got = model.run(x, pf, hop, frame=frame)
