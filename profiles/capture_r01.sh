@@ -12,7 +12,7 @@ timeout 300 python bench.py 2>$O/bench_1gpu.err | tail -1 > $O/bench_1gpu.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>$O/bench_ref.err | tail -1 > $O/bench_ref.json
 [ -n "$SKIP_TESTS" ] || timeout 300 bash profiles/sweep_configs.sh > $O/sweep_configs.log 2>&1
 NCU="ncu --clock-control none"
-B="--steps 40 --warmup 10 --no-cpu-baseline --no-e2e"
+B="--steps 40 --warmup 10 --no-cpu-baseline --no-e2e --no-other-configs"
 timeout 200 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $O/launches.csv python bench.py $B > $O/launches.out 2>&1
 cap() { # name, bench args: capture, summarise on the box (the reports are 13 MB each), keep the text
   timeout 200 $NCU --set full --import-source on -k regex:pv_process_ring -s 30 -c 1 -f -o $O/$1 python bench.py $B $2 > $O/$1.out 2>&1
