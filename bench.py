@@ -64,8 +64,8 @@ def parse_args():
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short device-resident runs of the other BASELINE configs (N=1, default workload only)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
-    ap.add_argument("--root-scatter", action="store_true",
-                    help="N>1: also time the single-root mode (NCCL scatter of input slabs, gather of outputs)")
+    ap.add_argument("--no-root-scatter", action="store_true",
+                    help="N>1: skip the single-root mode (NCCL scatter of input slabs, gather of outputs)")
     return ap.parse_args()
 
 
@@ -289,7 +289,10 @@ def run_ours(args):
     blocks_np = np.ascontiguousarray(host.reshape(C, nblk, hop).transpose(1, 0, 2))
     blocks = torch.from_numpy(blocks_np).cuda()
     outs = [torch.empty((C, hop), dtype=torch.float32, device="cuda") for _ in range(rotate)]
-    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local) for _ in range(rotate)]
+    # inputs_ready: the input blocks are resident in HBM before anything is timed (the library's default
+    # is strict stream order: the first launch of every submission waits for the whole stream, because
+    # its input could come from a kernel the library knows nothing about)
+    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local, inputs_ready=1) for _ in range(rotate)]
     # a real (non-NULL) stream: NULL would select the handle's own stream and the events
     # below would not bracket the kernels
     stream = torch.cuda.Stream()
@@ -306,35 +309,64 @@ def run_ours(args):
         step(i)
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    for i in range(W):
-        step(i)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
+    # The clock sampler runs on rank 0 only (one NVML thread per node instead of one per GPU)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+
+    def timed_run(steps, warm):
+        """barrier -> gate -> `warm` untimed launches -> ev0 -> `steps` launches -> ev1, all queued
+        back to back on one stream.  The gate (a ~1.5 ms device-side sleep in front of the warm-up)
+        lets the host enqueue the whole sequence before the GPU starts on it, so even a 20-step run
+        measures the launches at their steady-state spacing instead of the host's enqueue rate or a
+        cold start after a synchronize(); nothing but our own launches sits between the two events."""
         torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda._sleep(int(3e6))
+        for i in range(warm):
+            step(i)
+        e0.record(stream)
+        for i in range(steps):
+            step(warm + i)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    timed_run(max(W, 20), 0)           # untimed: first-use costs (module load, allocator, clocks ramp)
     launches0 = sum(p.kernel_launches for p in procs)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.mark_begin()
-    ev0.record(stream)
-    for i in range(K):
-        step(i)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    sampler.mark_end()
+    if sampler:
+        sampler.mark_begin()
+    ms = timed_run(K, W)
+    if sampler:
+        sampler.mark_end()
     if dist:
         dist.barrier()
         torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    launches = sum(p.kernel_launches for p in procs) - launches0
-    sampler.stop()
+    launches = sum(p.kernel_launches for p in procs) - launches0 - W
+    if sampler:
+        sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     frames_total = world * K * C
     value = frames_total / (ms_max * 1e-3)
+
+    # the same K steps with the launch chaining switched off (PVB_OPT_LAUNCH_MODE): 1 = programmatic
+    # dependent launch with a whole-grid wait, 2 = plain stream-ordered launches.  The difference to
+    # `value` is what the overlap of consecutive launches buys (evidence for the roofline figure: an
+    # ncu launch list times every launch alone and cold, like mode 2).
+    chain = {}
+    for mode, name in ((1, "pdl_grid_wait"), (2, "plain_launches")):
+        for p in procs:
+            p.set_option("launch_mode", mode)
+        ms_m = timed_run(K, W)
+        chain[name] = {"value": K * C / (ms_m * 1e-3), "avg_launch_us": 1e3 * ms_m / K}
+    for p in procs:
+        p.set_option("launch_mode", 0)
 
     # context only: (a) one instance, state stays in L2; (b) every instance on its own stream
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -370,16 +402,20 @@ def run_ours(args):
         e2e = run_e2e(procs, blocks_np, C, hop, pitch, K, dist)
 
     root_scatter = None
-    if dist and args.root_scatter:
+    if dist and not args.no_root_scatter:
         root_scatter = run_root_scatter(C, frame, hop, pitch, world, rank, local, min(K, 300), host)
 
     peak, peak_src = measured_peak()
+    traffic, traffic_src = (ncu_traffic_bytes() if (frame, hop, C, round(float(pitch), 3)) == (FRAME, HOP, CHANNELS, PITCH)
+                            else (None, None))
+    assert launches == K, (launches, K)
     kernel_ms = ms / max(launches, 1)                 # this rank's average launch duration
     achieved = 12.0 * frame * C / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                # the committed ncu capture is of the default workload only
-                "traffic": NCU_TRAFFIC_BYTES if (frame, hop, C, round(pitch, 3)) == (FRAME, HOP, CHANNELS, PITCH) else None,
+                # dram__bytes_read + dram__bytes_write per launch, parsed from the newest committed
+                # `ncu --set full` summary of this kernel (default workload only)
+                "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "kernel": procs[0].kernel_name(pitch),
                 "algorithmic_bytes_per_launch": 12 * frame * C,
                 "avg_launch_us": kernel_ms * 1e3}
@@ -413,12 +449,15 @@ def run_ours(args):
                                     f"({rotate * state_bytes / 2**20:.0f} MiB of state+io) rotated per step",
                        "parallelism": f"channel-sharded x{world}, no data-path collective",
                        "launch": "one stream; consecutive launches chained by programmatic dependent launch, "
-                                 "each channel pair waits for its own previous call (completion flags)"},
+                                 "each channel pair waits for its own previous call (completion flags)",
+                       "timed_region": "barrier, device-side gate, W warm-up launches, event, K launches, event: "
+                                       "queued back to back, no synchronize between warm-up and timed launches"},
             "roofline": roofline,
             "e2e": e2e,
             "host_thread_affinity": numa,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
+            "launch_chaining": chain,
             "l2_resident_value": l2_value,
             "concurrent_streams_value": streams_value,
             "cpu_baseline": cpu,
@@ -487,13 +526,40 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
     value = timed(many, steps, batch)
     single_value = timed(single, int(min(K, 400)), 1)
     check = float(np.ctypeslib.as_array(Ct.cast(hout, Ct.POINTER(Ct.c_float)), (C * hop,)).std())
+    # what bounds it: the host link.  Probe: the same two pinned buffers copied both ways at once on
+    # two streams, nothing else running (GB/s in each direction)
+    dev_a = torch.empty(nbytes * batch // 4, dtype=torch.float32, device="cuda")
+    dev_b = torch.empty(nbytes * batch // 4, dtype=torch.float32, device="cuda")
+    rt = Ct.CDLL("libcudart.so.12")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    def both_ways():
+        rt.cudaMemcpyAsync(Ct.c_void_p(dev_a.data_ptr()), Ct.c_void_p(hin), Ct.c_size_t(nbytes * batch), 1, Ct.c_void_p(s1.cuda_stream))
+        rt.cudaMemcpyAsync(Ct.c_void_p(hout), Ct.c_void_p(dev_b.data_ptr()), Ct.c_size_t(nbytes * batch), 2, Ct.c_void_p(s2.cuda_stream))
+    probe = None
+    try:
+        both_ways()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            both_ways()
+        torch.cuda.synchronize()
+        probe = 4 * nbytes * batch / (time.perf_counter() - t0) / 1e9
+    except Exception:       # pragma: no cover
+        pass
+    world = dist.get_world_size() if dist else 1
     lib.pvb_free_host(hin)
     lib.pvb_free_host(hout)
     return {"value": value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
             "steps": steps, "calls_per_submission": batch,
             "api": f"pvb_process_many(handle, in_host, out_host, {batch}, pitch): pinned host buffers, "
                    "H2D / kernel / D2H of consecutive calls overlapped, synchronous on return",
-            "single_call_value": single_value, "out_std": check}
+            "single_call_value": single_value, "out_std": check,
+            "bound": "pcie (host link): every frame moves hop*4 bytes each way",
+            "gbs_each_way_per_gpu": value / world * hop * 4 / 1e9,
+            "pcie_probe_gbs_each_way_per_gpu": probe,
+            "pcie_probe": "the same pinned buffers copied H2D and D2H concurrently, all ranks at once, no kernels"}
 
 
 # BASELINE configs 3, 4 (one shard's worth per launch) and 5, plus the reference's own 2048 / 128
@@ -518,20 +584,23 @@ def quick_config(local, frame, hop, C, pf, peak, steps=300, warm=40):
     host = signals.channels(0, C, nblk * hop)
     blocks = torch.from_numpy(np.ascontiguousarray(host.reshape(C, nblk, hop).transpose(1, 0, 2))).cuda()
     outs = [torch.empty((C, hop), dtype=torch.float32, device="cuda") for _ in range(rotate)]
-    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local) for _ in range(rotate)]
+    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local, inputs_ready=1) for _ in range(rotate)]
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
     def step(i):
         procs[i % rotate].process_device(blocks[i % nblk].data_ptr(), outs[i % rotate].data_ptr(), pitch, sptr)
 
-    for i in range(rotate * (frame // hop) + warm):
+    for i in range(rotate * (frame // hop)):
         step(i)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda._sleep(int(3e6))        # gate: the whole sequence is queued before the GPU starts on it
+    for i in range(warm):
+        step(i)
     ev0.record(stream)
     for i in range(steps):
-        step(i)
+        step(warm + i)
     ev1.record(stream)
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / steps
@@ -612,9 +681,24 @@ def phaze_b200_lib():
     return phaze_b200.load_library()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the
-# committed `ncu --set full` capture (profiles/), for the default workload; None until captured.
-NCU_TRAFFIC_BYTES = 29.87e6   # profiles/r01_ncu_ring_1024.txt: reads 29.72 MB + writes 0.16 MB (stores retire into L2)
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel, parsed from the
+    newest committed `ncu --set full` summary under profiles/ (r<NN>_ncu_ring_1024.txt, written by
+    profiles/ncu_summary.py from a capture of this bench command).  (None, None) when there is none."""
+    import glob
+    import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_ring_1024.txt")), reverse=True):
+        total, seen = 0.0, 0
+        with open(path) as f:
+            for ln in f:
+                m = re.match(r"dram__bytes_(read|write)\.sum\s+(\w+)\s+([0-9.eE+-]+)", ln)
+                if m and m.group(2) in unit:
+                    total += float(m.group(3)) * unit[m.group(2)]
+                    seen += 1
+                if seen == 2:
+                    return total, os.path.relpath(path, ROOT)
+    return None, None
 
 
 def main():

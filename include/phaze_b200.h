@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PVB_VERSION 100 /* 0.1.0 */
+#define PVB_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define PVB_API __attribute__((visibility("default")))
@@ -106,6 +106,34 @@ PVB_API int32_t pvb_resize(pvb_processor *p, int32_t num_channels);
 /* back to the freshly constructed state (all zero, timeCursor 0) */
 PVB_API int32_t pvb_reset(pvb_processor *p);
 
+/* Per-handle options (none of them changes results beyond what is stated; 0 == default).
+ * Returns PVB_ERR_BAD_ARG for an unknown option or value. */
+enum {
+    /* Which kernel family serves process() calls: 0 auto (the ring-order kernel wherever it applies),
+       1 ring-order, 2 one warp per pair in frame order (frame 1024), 3 CTA-cooperative, 4 generic.
+       A family that does not cover the handle's frame / hop / pitch factor falls through to the next
+       one, exactly like auto.  Exists for tests and A/B measurements. */
+    PVB_OPT_KERNEL = 1,
+    /* How consecutive launches are chained: 0 auto (programmatic dependent launch + per-pair completion
+       flags), 1 programmatic dependent launch, whole-grid wait, 2 plain stream-ordered launches. */
+    PVB_OPT_LAUNCH_MODE = 2,
+    /* Device entry points only.  0 (default): strict stream order -- the first launch of every
+       submission waits for everything enqueued on the stream before it (the caller's input may be
+       produced by a kernel the library knows nothing about).  1: the caller guarantees that the input
+       buffers it passes are complete and visible when the call is SUBMITTED (resident data, or
+       produced by work the host has synchronised with); launches then overlap with whatever precedes
+       them on the stream as far as the handle's own state allows. */
+    PVB_OPT_INPUTS_READY = 3,
+    /* Peak picking (phase-vocoder.js:82-116) compares float32 roundings of float64 |X|^2.  0 (default):
+       the kernel computes |X|^2 from its float32 FFT and re-decides, per channel and call, every frame
+       in which a comparison falls inside the float32 error bound with a float64 transform that follows
+       fft.js operation by operation (bit-identical peak sets on any input, e.g. noise-free tones).
+       1: never re-decide (float32 decisions only).  2: always re-decide (tests). */
+    PVB_OPT_PEAK_GUARD = 4
+};
+PVB_API int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value);
+PVB_API int64_t pvb_get_option(const pvb_processor *p, int32_t option);
+
 /* introspection */
 PVB_API int32_t pvb_frame_size(const pvb_processor *p);
 PVB_API int32_t pvb_hop_size(const pvb_processor *p);
@@ -113,14 +141,16 @@ PVB_API int32_t pvb_num_channels(const pvb_processor *p);
 /* this.timeCursor (phase-vocoder.js:31,71): hop_size * (process calls so far) */
 PVB_API double pvb_time_cursor(const pvb_processor *p);
 PVB_API int32_t pvb_set_time_cursor(pvb_processor *p, double samples);
-/* name of the CUDA kernel a process() call with this pitch factor launches on this handle
- * (two kernels exist: the warp-synchronous one for frame 1024 and the generic one) */
+/* name of the CUDA kernel a process() call with this pitch factor launches on this handle */
 PVB_API const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor);
 /* number of CUDA kernels this handle has launched since creation */
 PVB_API int64_t pvb_kernel_launches(const pvb_processor *p);
-/* Diagnostics: consecutive launches of the frame-1024 kernel synchronise per channel pair through
-   completion flags in device memory (bounded spin); this counts flags that never arrived.  Must
-   stay 0.  Synchronises the handle's stream; -1 on CUDA error. */
+/* Diagnostics: consecutive launches of the ring-order kernel synchronise per channel pair through
+   completion flags in device memory.  A flag that does not arrive within the spin bound makes the
+   pair fall back to waiting for the whole previous grid; if it is still missing after that, the
+   pair is NOT processed, the handle's sticky device-error word is set and every later pvb_process* /
+   pvb_sync / pvb_get_state on the handle returns PVB_ERR_CUDA (pvb_reset / pvb_resize clear it).
+   This returns the number of such pairs so far (0 on a healthy handle); -1 on CUDA error. */
 PVB_API int64_t pvb_ring_stuck_count(pvb_processor *p);
 
 /* checkpoint / resume of the per-channel state.  Blob layout (float32):

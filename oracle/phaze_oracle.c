@@ -352,8 +352,14 @@ static void pv_shift_peaks(pv_core *c, double pitch_factor, double time_cursor)
     for (int i = 0; i < c->nb_peaks; i++) {
         const int p = c->peaks[i];
         /* Math.round: nearest, ties toward +inf; p*pf is exact in f64 here */
-        const int ps = (int)floor((double)p * pitch_factor + 0.5);
-        if (ps > nb) break;                                       /* pv:127 */
+        const double psd = floor((double)p * pitch_factor + 0.5);
+        /* NaN (pitchFactor NaN): pv:127 and pv:150 compare false and pv:169-170 write the property
+         * "NaN" of the Array, i.e. no element: the region contributes nothing */
+        if (psd != psd) continue;
+        if (psd > (double)nb) break;                              /* pv:127 */
+        /* far below zero every shifted bin is negative: named properties again (see bs < 0 below) */
+        if (psd < -(double)(2 * n)) continue;
+        const int ps = (int)psd;
 
         int start = 0, end = n;                                   /* pv:132-133 */
         if (i > 0) {

@@ -13,6 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PVB_LIBRARY") or os.path.join(_HERE, "libphaze_b200.so")
 
 PVB_OK, PVB_ERR_BAD_SIZE, PVB_ERR_BAD_ARG, PVB_ERR_CUDA, PVB_ERR_NOMEM = 0, -1, -2, -3, -4
+# pvb_set_option (include/phaze_b200.h)
+PVB_OPT_KERNEL, PVB_OPT_LAUNCH_MODE, PVB_OPT_INPUTS_READY, PVB_OPT_PEAK_GUARD = 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_RING, KERNEL_WARP, KERNEL_CTA, KERNEL_GENERIC = 0, 1, 2, 3, 4
 
 
 class PvbConfig(C.Structure):
@@ -39,6 +42,8 @@ _SIGNATURES = {
     "pvb_process_many_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p]),
     "pvb_process_many": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float]),
     "pvb_sync": (C.c_int32, [C.c_void_p]),
+    "pvb_set_option": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64]),
+    "pvb_get_option": (C.c_int64, [C.c_void_p, C.c_int32]),
     "pvb_resize": (C.c_int32, [C.c_void_p, C.c_int32]),
     "pvb_reset": (C.c_int32, [C.c_void_p]),
     "pvb_frame_size": (C.c_int32, [C.c_void_p]),

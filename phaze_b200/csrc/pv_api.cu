@@ -6,7 +6,6 @@
 #include "../../include/phaze_b200.h"
 #include "pv_kernel.cuh"
 #include "pv_kernel_warp.cuh"
-#include "pv_kernel_pair.cuh"
 #include "pv_kernel_cta.cuh"
 #include "pv_kernel_ring.cuh"
 
@@ -33,8 +32,14 @@ struct pvb_processor {
     int num_sms = 148;
     float2 *d_tw = nullptr;
     float4 *d_ring_tab = nullptr;    // tables of the ring-order kernel (frames 1024 and 2048)
-    unsigned *d_done = nullptr;      // [pairs] + 1: per-pair completion flags of the ring-order kernel, stuck counter
+    unsigned *d_done = nullptr;      // [pairs]: per-pair completion flags of the ring-order kernel
     unsigned ring_seq = 0;           // sequence number of this handle's last ring-order launch
+    // sticky device-error word: pinned, mapped host memory the kernels write only when a completion flag
+    // is still missing after the whole previous grid has drained (h_err[0]: pairs lost so far)
+    unsigned *h_err = nullptr, *d_err = nullptr;
+    // pvb_set_option
+    int opt_kernel = 0, opt_launch_mode = 0, opt_inputs_ready = 0, opt_peak_guard = 0;
+    cudaStream_t last_stream = nullptr;   // stream of the most recent submission (state entry points wait for it)
     float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
     size_t staging_floats = 0;
     cudaStream_t stream = nullptr;
@@ -47,33 +52,55 @@ struct pvb_processor {
 namespace {
 
 thread_local char g_create_err[256] = "";
-bool g_force_generic = false;    // PVB_FORCE_GENERIC=1: always use the generic kernel (tests)
-int g_kernel_1024 = 0;           // PVB_KERNEL_1024: 0 (default) ring-order kernel, 1 warp kernel, 2 two warps per pair, 3 CTA kernel
-bool g_no_aligned = false;       // PVB_NO_ALIGNED=1: never use the hop %% 128 == 0 specialisation (tests)
-int g_skip = 0;                  // PVB_SKIP: phase-skipping timing experiments of the ring kernel (wrong results)
-int g_early = -1;                // PVB_EARLY=0/1/2: cap on the ring kernel's pre-wait state loads (experiments)
 // Which handle launched the library's most recent kernel on each stream.  The ring-order kernel uses
 // it to decide how much of its state is provably older than the kernel in front of it (see
 // RingParams::early); every launch path records itself here.
 std::mutex g_stream_mu;
 std::unordered_map<cudaStream_t, const void *> g_last_on_stream;
-// caller buffers of the library's most recent launches per stream: flag mode lets launches overlap
-// beyond their immediate predecessor, so a new call whose input aliases a recent output (handles
-// chained through a buffer) or whose output aliases a recent input falls back to grid mode
-struct RecentIo { const char *in_lo, *in_hi, *out_lo, *out_hi; };
+// Caller buffers of the library's flag-mode launches per stream since the last launch that waited for
+// the whole stream (grid mode / plain): flag mode lets launches overlap beyond their immediate
+// predecessor, so a new call whose input aliases a recent output (handles chained through a buffer)
+// or whose output aliases a recent input falls back to grid mode.  How far back can a launch
+// overlap?  Every flag-mode kernel ends with griddepcontrol.wait, so its CTAs stay resident until the
+// launch before it has completed: launches k .. k + d can only be in flight together while all their
+// CTAs fit the device, i.e. d <= (2 CTAs x SMs) / (CTAs per launch) <= 2 x SMs.  The window keeps
+// that many entries; when it is full the next launch runs in grid mode (waits for everything) and the
+// window restarts.
+struct RecentIo { const char *in_lo, *in_hi, *out_lo, *out_hi; const void *handle; };
 std::unordered_map<cudaStream_t, std::vector<RecentIo>> g_recent_io;
 // whether the library's previous launch on the stream ran in flag mode: such a kernel releases its
 // dependents without waiting, so "older than the kernel in front of us" no longer means "complete"
 // and a grid-mode launch behind it must not load anything before its griddepcontrol.wait
 std::unordered_map<cudaStream_t, bool> g_last_flag_mode;
-int g_ring_pad_kb = 0;
-int g_ring_256 = 1;              // PVB_RING_256=0: frame 256 falls back to the CTA kernel
-int g_ring_4096 = 1;             // PVB_RING_4096=0: frame 4096 falls back to the CTA kernel
-int g_ring_512 = 1;              // PVB_RING_512=0: frame 512 falls back to the CTA kernel
-int g_ring_wpc = 0;              // PVB_RING_WPC: warps (pairs) per CTA of the ring kernel (0: balance one wave)
-bool g_no_flags = false;         // PVB_NO_FLAGS=1: ring kernel always in grid mode (experiments)
-bool g_no_pdl = false;           // PVB_NO_PDL=1: ring kernel without programmatic dependent launch (experiments)
-int g_stagger_ns = 0;            // PVB_STAGGER_NS: start offset between warps sharing an SM (single-wave launches)
+
+// Timing experiments of profiles/*.sh: compiled in only with -DPVB_EXPERIMENTS (make variants), read
+// from the environment once per process.  The default build has none of them.
+#ifdef PVB_EXPERIMENTS
+struct Experiments {
+    int skip = 0;          // PVB_SKIP: phase-skipping timing experiments of the ring kernel (WRONG results)
+    int early = -1;        // PVB_EARLY=0/1/2: cap on the ring kernel's pre-wait state loads
+    int ring_pad_kb = 0;   // PVB_RING_PAD_KB: extra dynamic shared memory per CTA (occupancy experiment)
+    int ring_wpc = 0;      // PVB_RING_WPC: pairs per CTA of the ring kernel (0: default)
+    int stagger_ns = 0;    // PVB_STAGGER_NS: start offset between warps sharing an SM
+    bool no_aligned = false;   // PVB_NO_ALIGNED=1: warp kernel without the hop % 128 == 0 specialisation
+    Experiments() {
+        auto geti = [](const char *name, int dflt) { const char *e = std::getenv(name); return e ? std::atoi(e) : dflt; };
+        skip = geti("PVB_SKIP", 0);
+        early = geti("PVB_EARLY", -1);
+        ring_pad_kb = geti("PVB_RING_PAD_KB", 0);
+        ring_wpc = geti("PVB_RING_WPC", 0);
+        stagger_ns = geti("PVB_STAGGER_NS", 0);
+        no_aligned = geti("PVB_NO_ALIGNED", 0) == 1;
+    }
+};
+const Experiments &experiments() { static const Experiments e; return e; }
+#else
+struct Experiments {
+    static constexpr int skip = 0, early = -1, ring_pad_kb = 0, ring_wpc = 0, stagger_ns = 0;
+    static constexpr bool no_aligned = false;
+};
+constexpr Experiments experiments() { return Experiments(); }
+#endif
 
 // pitch_factor == mant * 2^-shift exactly; shift outside [1, 62] -> 0 (kernel uses float64)
 void split_pitch_factor(float pf, int *mant, int *shift) {
@@ -204,8 +231,8 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
     wp.f = fp;
     wp.window_out = window_out;
     wp.num_sms = num_sms;
-    wp.stagger_ns = (grid <= 2 * num_sms) ? g_stagger_ns : 0;
-    if (fp.hop % 128 == 0 && !g_no_aligned)
+    wp.stagger_ns = (grid <= 2 * num_sms) ? experiments().stagger_ns : 0;
+    if (fp.hop % 128 == 0 && !experiments().no_aligned)
         pvb::pv_process_warp_kernel<true><<<grid, wpc * 32, size_t(wpc) * W::WARP_BYTES, s>>>(wp);
     else
         pvb::pv_process_warp_kernel<false><<<grid, wpc * 32, size_t(wpc) * W::WARP_BYTES, s>>>(wp);
@@ -213,20 +240,34 @@ cudaError_t launch_warp(const pvb::FrameParams &fp, const float *window_out, int
 }
 
 // ring-order kernel (pv_kernel_ring.cuh): paired state layout aligned to the time cursor
-bool ring_kernel_applies(const pvb_processor *h, const pvb::FrameParams &fp) {
+bool ring_geometry_ok(const pvb_processor *h) {
     // frame 4096 keeps the frame blocks of one parity per thread: the hop must be a multiple of 256
     // (frame 256 keeps roles in units of 64 samples: hop 64 or 128)
-    return ((h->n == 256 && g_ring_256) || (h->n == 512 && g_ring_512) || h->n == 1024 || h->n == 2048 ||
-            (h->n == 4096 && g_ring_4096)) &&
-           fast_range(fp) && h->hop % (h->n == 4096 ? 256 : h->n == 256 ? 64 : 128) == 0 && h->hop <= h->n / 2 &&
-           g_kernel_1024 == 0 && !g_force_generic;
+    return h->hop % (h->n == 4096 ? 256 : h->n == 256 ? 64 : 128) == 0 && h->hop <= h->n / 2;
 }
+
+enum KernelFamily { K_RING = 1, K_WARP = 2, K_CTA = 3, K_GENERIC = 4 };
+
+// the kernel family a call with these parameters runs on (PVB_OPT_KERNEL: first family to try)
+KernelFamily pick_kernel(const pvb_processor *h, const pvb::FrameParams &fp) {
+    const int first = h->opt_kernel ? h->opt_kernel : K_RING;
+    if (first <= K_RING && fast_range(fp) && ring_geometry_ok(h)) return K_RING;
+    if (first <= K_WARP && warp_kernel_applies(h->n, fp)) return K_WARP;
+    if (first <= K_CTA && fast_range(fp)) return K_CTA;
+    return K_GENERIC;
+}
+bool ring_kernel_applies(const pvb_processor *h, const pvb::FrameParams &fp) { return pick_kernel(h, fp) == K_RING; }
 
 size_t state_rows(int channels);
 
 // everything of a ring-order launch that does not depend on the frame size (one call per launch:
-// it records the caller's buffers and decides between flag mode and grid mode)
-pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+// it records the caller's buffers and decides between flag mode and grid mode).
+// `input_ready`: the caller's input is known to be complete and visible before this launch can start
+// (see PVB_OPT_INPUTS_READY; always true for the library's own staging buffers and for the second and
+// later launches of one submission, which start behind a launch that waited for the whole stream or
+// behind one that already had the guarantee).
+pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s,
+                                 bool input_ready) {
     pvb::RingParams rp;
     rp.in = fp.in;
     rp.out = fp.out;
@@ -241,39 +282,45 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
     rp.pitch_factor = fp.pitch_factor;
     rp.pf_mant = fp.pf_mant;
     rp.pf_shift = fp.pf_shift;
-    rp.stagger_ns = g_stagger_ns;
-    rp.skip = g_skip;
+    rp.stagger_ns = experiments().stagger_ns;
+    rp.skip = experiments().skip;
+    const bool pdl = h->opt_launch_mode != 2;
     {
         // early state loads: 2 when another handle's kernel (which passed its own wait before it let
         // us launch) sits between this handle's previous call and this one, else 1
         std::lock_guard<std::mutex> lk(g_stream_mu);
         auto it = g_last_on_stream.find(s);
         rp.early = (it != g_last_on_stream.end() && it->second != h) ? 2 : 1;
-        if (g_no_pdl) rp.early = 0;
-        if (g_early >= 0 && rp.early > g_early) rp.early = g_early;
-        // flag mode needs the caller's buffers to be disjoint from those of the recent launches
+        if (!pdl) rp.early = 0;
+        if (experiments().early >= 0 && rp.early > experiments().early) rp.early = experiments().early;
+        // flag mode needs the caller's buffers to be disjoint from those of every launch it may overlap
         const size_t io_bytes = size_t(fp.num_channels) * size_t(fp.hop) * sizeof(float);
         RecentIo io;
         io.in_lo = reinterpret_cast<const char *>(fp.in);
         io.in_hi = fp.in ? io.in_lo + io_bytes : io.in_lo;
         io.out_lo = reinterpret_cast<const char *>(fp.out);
         io.out_hi = io.out_lo + io_bytes;
+        io.handle = h;
         auto &recent = g_recent_io[s];
-        bool safe = !g_no_pdl && !g_no_flags;
+        bool safe = pdl && h->opt_launch_mode == 0 && input_ready;
         for (const RecentIo &r : recent) {
             if (io.in_lo < r.out_hi && r.out_lo < io.in_hi) safe = false;      // reads what a recent call writes
             if (io.out_lo < r.in_hi && r.in_lo < io.out_hi) safe = false;      // writes what a recent call reads
+            // writes what a recent call writes: ordered only when it is the same handle writing the same
+            // rows (every pair waits for its own previous call)
+            if (io.out_lo < r.out_hi && r.out_lo < io.out_hi && !(r.handle == h && r.out_lo == io.out_lo))
+                safe = false;
         }
+        if (recent.size() >= size_t(2 * h->num_sms + 8)) safe = false;         // window full (see g_recent_io)
         if (!safe) recent.clear();          // a grid-mode launch waits for everything before it
         recent.push_back(io);
-        if (recent.size() > 8) recent.erase(recent.begin());
         rp.flag_mode = safe ? 1 : 0;
         bool &last_flag = g_last_flag_mode[s];
         if (last_flag) rp.early = 0;
         last_flag = safe;
     }
     rp.done = h->d_done;
-    rp.stuck = h->d_done + (state_rows(h->channels) / 2);
+    rp.err = h->d_err;
     rp.wait_seq = h->ring_seq;
     rp.my_seq = h->ring_seq + 1;
     return rp;
@@ -284,20 +331,22 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
 // the stream drains; the kernel itself orders its accesses, see pv_kernel_ring.cuh), and the instance
 // for this hop.  NBLK counts role units of RingGeoT<N>::UNIT samples (64 at frame 256, else 128).
 template <int N, int... NBLKS>
-cudaError_t launch_ring_n(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, int ppc) {
+cudaError_t launch_ring_n(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, int ppc,
+                          bool input_ready) {
     using G = pvb::RingGeoT<N>;
     const int pairs = (fp.num_channels + 1) / 2;
-    if (g_ring_wpc >= G::MIN_PAIRS && g_ring_wpc <= G::MAX_PAIRS) ppc = g_ring_wpc;   // PVB_RING_WPC
-    pvb::RingParams rp = make_ring_params(h, fp, s);
+    if (experiments().ring_wpc >= G::MIN_PAIRS && experiments().ring_wpc <= G::MAX_PAIRS)
+        ppc = experiments().ring_wpc;                           // PVB_RING_WPC
+    pvb::RingParams rp = make_ring_params(h, fp, s, input_ready);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((pairs + ppc - 1) / ppc);
     cfg.blockDim = dim3(ppc * G::TP);
     // PVB_RING_PAD_KB: occupancy experiment (extra dynamic shared memory per CTA)
-    cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc) * G::PAIR_BYTES + size_t(g_ring_pad_kb) * 1024;
+    cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc) * G::PAIR_BYTES + size_t(experiments().ring_pad_kb) * 1024;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
+    attr[0].val.programmaticStreamSerializationAllowed = h->opt_launch_mode == 2 ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
@@ -318,7 +367,7 @@ cudaError_t ring_set_smem_attr() {
     return e;
 }
 
-cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -336,61 +385,23 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     // pairs per CTA: frame 1024 balances one wave (4..7 warps); the other sizes fill their CTAs (frame 256:
     // 32 quarter-warp pairs, 512: 16 half-warp pairs, 2048: 4 pairs of two warps, 4096: 2 pairs of four)
     switch (h->n) {
-        case 256: return launch_ring_n<256, 1, 2>(h, fp, s, pvb::RingGeoT<256>::MAX_PAIRS);
-        case 512: return launch_ring_n<512, 1, 2>(h, fp, s, pvb::RingGeoT<512>::MAX_PAIRS);
-        case 1024: return launch_ring_n<1024, 1, 2, 4>(h, fp, s, pick_warps_per_cta(pairs, h->num_sms));
-        case 2048: return launch_ring_n<2048, 1, 2, 4, 8>(h, fp, s, pvb::RingGeoT<2048>::MAX_PAIRS);
-        case 4096: return launch_ring_n<4096, 2, 4, 8, 16>(h, fp, s, pvb::RingGeoT<4096>::MAX_PAIRS);
+        case 256: return launch_ring_n<256, 1, 2>(h, fp, s, pvb::RingGeoT<256>::MAX_PAIRS, input_ready);
+        case 512: return launch_ring_n<512, 1, 2>(h, fp, s, pvb::RingGeoT<512>::MAX_PAIRS, input_ready);
+        case 1024: return launch_ring_n<1024, 1, 2, 4>(h, fp, s, pick_warps_per_cta(pairs, h->num_sms), input_ready);
+        case 2048: return launch_ring_n<2048, 1, 2, 4, 8>(h, fp, s, pvb::RingGeoT<2048>::MAX_PAIRS, input_ready);
+        case 4096: return launch_ring_n<4096, 2, 4, 8, 16>(h, fp, s, pvb::RingGeoT<4096>::MAX_PAIRS, input_ready);
     }
     return cudaErrorInvalidValue;
 }
 
-// two warps per channel pair (pv_kernel_pair.cuh): same validity range as the warp kernel
-cudaError_t launch_pair(const pvb::FrameParams &fp, const float *window_out, int num_sms,
-                        cudaStream_t s) {
-    using G = pvb::PairGeo;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(pvb::pv_process_pair_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(G::MAX_PAIRS * G::PAIR_BYTES));
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
-    const int pairs = (fp.num_channels + 1) / 2;
-    if (pairs == 0) return cudaSuccess;
-    const int ppc = pick_warps_per_cta(pairs, num_sms);          // pairs per CTA, 4..7
-    const int grid = (pairs + ppc - 1) / ppc;
-    pvb::WarpParams wp;
-    wp.f = fp;
-    wp.window_out = window_out;
-    wp.num_sms = num_sms;
-    wp.stagger_ns = (grid <= 2 * num_sms) ? g_stagger_ns : 0;
-    pvb::pv_process_pair_kernel<<<grid, ppc * 64, size_t(ppc) * G::PAIR_BYTES, s>>>(wp);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s);
-
-cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
-    const cudaError_t e = launch_any(h, fp, s);
-    std::lock_guard<std::mutex> lk(g_stream_mu);
-    if (!ring_kernel_applies(h, fp)) g_last_flag_mode[s] = false;     // the other kernels are plain launches
-    if (g_last_on_stream.size() > 4096) g_last_on_stream.clear();     // streams come and go; unknown == conservative
-    g_last_on_stream[s] = h;
-    return e;
-}
-
-cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s) {
+cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready) {
     const int n = h->n;
-    if (ring_kernel_applies(h, fp)) return launch_ring(h, fp, s);
-    if (warp_kernel_applies(n, fp) && !g_force_generic && g_kernel_1024 != 3) {
-        if (g_kernel_1024 == 2) return launch_pair(fp, h->d_window_out, h->num_sms, s);
-        return launch_warp(fp, h->d_window_out, h->num_sms, s);
+    switch (pick_kernel(h, fp)) {
+        case K_RING: return launch_ring(h, fp, s, input_ready);
+        case K_WARP: return launch_warp(fp, h->d_window_out, h->num_sms, s);
+        case K_CTA: return launch_cta(n, fp, h->d_window_out, s);
+        case K_GENERIC: break;
     }
-    if (fast_range(fp) && !g_force_generic) return launch_cta(n, fp, h->d_window_out, s);
     switch (n) {
         case 256: return launch_n<256>(fp, s);
         case 512: return launch_n<512>(fp, s);
@@ -399,6 +410,22 @@ cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaS
         case 4096: return launch_n<4096>(fp, s);
     }
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready) {
+    const cudaError_t e = launch_any(h, fp, s, input_ready);
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    if (!ring_kernel_applies(h, fp)) {       // the other kernels are plain launches: they wait for everything
+        g_last_flag_mode[s] = false;
+        g_recent_io[s].clear();
+    }
+    if (g_last_on_stream.size() > 4096) {    // streams come and go; unknown == conservative
+        g_last_on_stream.clear();
+        g_recent_io.clear();
+        g_last_flag_mode.clear();
+    }
+    g_last_on_stream[s] = h;
+    return e;
 }
 
 // number of source bins that can land inside [0, nb): for pitchFactor >= 1 only bins
@@ -428,7 +455,8 @@ int alloc_state(pvb_processor *p, int channels) {
         cudaGetLastError();
         return fail(p, PVB_ERR_NOMEM, "cudaMalloc of %zu state bytes failed", 2 * bytes);
     }
-    const size_t flag_bytes = (state_rows(channels) / 2 + 1) * sizeof(unsigned);
+    const size_t flag_bytes = (state_rows(channels) / 2) * sizeof(unsigned);
+    if (p->h_err) *p->h_err = 0;
     if (cudaMalloc(&p->d_done, flag_bytes) != cudaSuccess) {
         cudaGetLastError();
         return fail(p, PVB_ERR_NOMEM, "cudaMalloc of the completion flags failed");
@@ -492,6 +520,14 @@ int ensure_staging(pvb_processor *p, size_t floats) {
     return PVB_OK;
 }
 
+// wait for everything this handle has submitted: its own stream and the caller stream of the most
+// recent device submission
+cudaError_t sync_all(pvb_processor *p) {
+    cudaError_t e = cudaStreamSynchronize(p->stream);
+    if (e == cudaSuccess && p->last_stream && p->last_stream != p->stream) e = cudaStreamSynchronize(p->last_stream);
+    return e;
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {
@@ -508,9 +544,26 @@ struct CallHooks {
     virtual void after(int k, cudaStream_t s) = 0;
 };
 
+// sticky device error (a completion flag that never arrived): the handle refuses further work
+int check_device_error(pvb_processor *p) {
+    if (p->h_err && *reinterpret_cast<volatile unsigned *>(p->h_err) != 0)
+        return fail(p, PVB_ERR_CUDA, "ring-order kernel: %u channel pair(s) never saw the completion flag of their "
+                    "previous call and were not processed; state is stale (pvb_reset / pvb_resize to recover)",
+                    *reinterpret_cast<volatile unsigned *>(p->h_err));
+    return PVB_OK;
+}
+
+// `inputs_ready`: the input of the FIRST launch is known to be complete before it can start (the
+// library's own staging buffers, or PVB_OPT_INPUTS_READY); later launches of the submission start
+// behind the first one and inherit the guarantee
 int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls, float pf,
-           cudaStream_t s, CallHooks *hooks = nullptr) {
+           cudaStream_t s, bool inputs_ready, CallHooks *hooks = nullptr) {
     const size_t block = size_t(p->channels) * size_t(p->hop);
+    {
+        const int rc = check_device_error(p);
+        if (rc != PVB_OK) return rc;
+    }
+    p->last_stream = s;
     for (int k = 0; k < num_calls; k++) {
         if (hooks) hooks->before(k, s);
         pvb::FrameParams fp;
@@ -534,7 +587,7 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
             if (rc != PVB_OK) return rc;
             fp.hist = p->d_hist;
             fp.acc = p->d_acc;
-            PVB_CUDA(p, launch(p, fp, s));
+            PVB_CUDA(p, launch(p, fp, s, inputs_ready || k > 0));
             p->launches++;
         }
         p->ring_calls++;
@@ -574,39 +627,6 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         return fail(nullptr, PVB_ERR_BAD_SIZE, "hop %d must divide frame %d and be a multiple of 4", hop, n);
     if (cfg->num_channels < 0) return fail(nullptr, PVB_ERR_BAD_ARG, "negative channel count");
 
-    // test / experiment switches, re-read at every create (unset == default)
-    {
-        const char *env = std::getenv("PVB_FORCE_GENERIC");
-        g_force_generic = env && env[0] == '1';
-    }
-    if (const char *env = std::getenv("PVB_KERNEL_1024"))
-        g_kernel_1024 = (env[0] >= '0' && env[0] <= '3') ? env[0] - '0' : 0;
-    else
-        g_kernel_1024 = 0;
-    {
-        const char *env = std::getenv("PVB_STAGGER_NS");
-        g_stagger_ns = env ? std::atoi(env) : 0;
-        env = std::getenv("PVB_NO_ALIGNED");
-        g_no_aligned = env && env[0] == '1';
-        env = std::getenv("PVB_NO_PDL");
-        g_no_pdl = env && env[0] == '1';
-        env = std::getenv("PVB_RING_PAD_KB");
-        g_ring_pad_kb = env ? std::atoi(env) : 0;
-        env = std::getenv("PVB_RING_256");
-        g_ring_256 = env ? std::atoi(env) : 1;
-        env = std::getenv("PVB_RING_4096");
-        g_ring_4096 = env ? std::atoi(env) : 1;
-        env = std::getenv("PVB_RING_512");
-        g_ring_512 = env ? std::atoi(env) : 1;
-        env = std::getenv("PVB_RING_WPC");
-        g_ring_wpc = env ? std::atoi(env) : 0;
-        env = std::getenv("PVB_NO_FLAGS");
-        g_no_flags = env && env[0] == '1';
-        env = std::getenv("PVB_SKIP");
-        g_skip = env ? std::atoi(env) : 0;
-        env = std::getenv("PVB_EARLY");
-        g_early = env ? std::atoi(env) : -1;
-    }
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -634,6 +654,13 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
         fail(p, PVB_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail(PVB_ERR_CUDA);
     }
+
+    if (cudaHostAlloc(reinterpret_cast<void **>(&p->h_err), sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void **>(&p->d_err), p->h_err, 0) != cudaSuccess) {
+        fail(p, PVB_ERR_NOMEM, "allocation of the device-error word failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail(PVB_ERR_NOMEM);
+    }
+    *p->h_err = 0;
 
     // tables, computed in double like the JS and rounded once to float32
     std::vector<float> win(2 * n), win_out(2 * n);    // stored twice: the ring-order kernel reads them rotated
@@ -702,6 +729,13 @@ void pvb_destroy(pvb_processor *p) {
     if (!p) return;
     DeviceGuard guard(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->last_stream && p->last_stream != p->stream) cudaStreamSynchronize(p->last_stream);
+    {
+        // forget this handle's address: a new handle may be allocated at the same one
+        std::lock_guard<std::mutex> lk(g_stream_mu);
+        for (auto &kv : g_last_on_stream) if (kv.second == p) kv.second = nullptr;
+        for (auto &kv : g_recent_io) for (RecentIo &r : kv.second) if (r.handle == p) r.handle = nullptr;
+    }
     cudaFree(p->d_hist);
     cudaFree(p->d_acc);
     cudaFree(p->d_window);
@@ -711,6 +745,7 @@ void pvb_destroy(pvb_processor *p) {
     cudaFree(p->d_done);
     cudaFree(p->d_in);
     cudaFree(p->d_out);
+    if (p->h_err) cudaFreeHost(p->h_err);
     for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_done) cudaEventDestroy(e);
     if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -725,7 +760,7 @@ int32_t pvb_process_many_device(pvb_processor *p, const float *in_dev, float *ou
     if (!out_dev || num_calls < 0) return fail(p, PVB_ERR_BAD_ARG, "pvb_process: bad argument");
     DeviceGuard guard(p->device);
     return submit(p, in_dev, out_dev, num_calls, pitch_factor,
-                  stream ? static_cast<cudaStream_t>(stream) : p->stream);
+                  stream ? static_cast<cudaStream_t>(stream) : p->stream, p->opt_inputs_ready != 0);
 }
 
 int32_t pvb_process_device(pvb_processor *p, const float *in_dev, float *out_dev,
@@ -749,11 +784,13 @@ int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t 
     if (rc != PVB_OK) return rc;
     if (num_calls == 1) {
         if (in) PVB_CUDA(p, cudaMemcpyAsync(p->d_in, in, floats * sizeof(float), cudaMemcpyHostToDevice, p->stream));
-        rc = submit(p, in ? p->d_in : nullptr, p->d_out, 1, pitch_factor, p->stream);
+        // (the input copy precedes the launch on the same stream: a copy engine operation, complete
+        // before the kernel is eligible)
+        rc = submit(p, in ? p->d_in : nullptr, p->d_out, 1, pitch_factor, p->stream, true);
         if (rc != PVB_OK) return rc;
         PVB_CUDA(p, cudaMemcpyAsync(out, p->d_out, floats * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
         PVB_CUDA(p, cudaStreamSynchronize(p->stream));
-        return PVB_OK;
+        return check_device_error(p);
     }
     // several calls: the input copy of call k+1, the kernel of call k and the output copy of
     // call k-1 overlap (three streams chained by events); results are those of K single calls
@@ -797,12 +834,13 @@ int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t 
     pipe.group = (block * sizeof(float) >= (size_t(16) << 20)) ? 1
                  : int((size_t(16) << 20) / (block * sizeof(float)));
     if (pipe.group > 8) pipe.group = 8;
-    rc = submit(p, in ? p->d_in : nullptr, p->d_out, num_calls, pitch_factor, p->stream, &pipe);
+    // (every launch waits for the event of its input copy before it becomes eligible)
+    rc = submit(p, in ? p->d_in : nullptr, p->d_out, num_calls, pitch_factor, p->stream, true, &pipe);
     if (rc != PVB_OK) return rc;
     PVB_CUDA(p, pipe.err);
     PVB_CUDA(p, cudaStreamSynchronize(p->s_out));
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
-    return PVB_OK;
+    return check_device_error(p);
 }
 
 int32_t pvb_process(pvb_processor *p, const float *in, float *out, float pitch_factor) {
@@ -812,20 +850,20 @@ int32_t pvb_process(pvb_processor *p, const float *in, float *out, float pitch_f
 int32_t pvb_sync(pvb_processor *p) {
     if (!p) return PVB_ERR_BAD_ARG;
     DeviceGuard guard(p->device);
-    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
-    return PVB_OK;
+    PVB_CUDA(p, sync_all(p));
+    return check_device_error(p);
 }
 
 int32_t pvb_resize(pvb_processor *p, int32_t num_channels) {
     if (!p) return PVB_ERR_BAD_ARG;
     if (num_channels < 0) return fail(p, PVB_ERR_BAD_ARG, "negative channel count");
     DeviceGuard guard(p->device);
-    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    PVB_CUDA(p, sync_all(p));
     cudaFree(p->d_in);
     cudaFree(p->d_out);
     p->d_in = p->d_out = nullptr;
     p->staging_floats = 0;
-    int rc = alloc_state(p, num_channels);     // ola:54-88: fresh zeroed buffers
+    int rc = alloc_state(p, num_channels);     // ola:54-88: fresh zeroed buffers (also clears the error word)
     if (rc != PVB_OK) return rc;
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
     return PVB_OK;
@@ -835,9 +873,13 @@ int32_t pvb_reset(pvb_processor *p) {
     if (!p) return PVB_ERR_BAD_ARG;
     DeviceGuard guard(p->device);
     const size_t bytes = state_rows(p->channels) * size_t(p->n) * sizeof(float);
+    PVB_CUDA(p, sync_all(p));
     PVB_CUDA(p, cudaMemsetAsync(p->d_hist, 0, bytes, p->stream));
     PVB_CUDA(p, cudaMemsetAsync(p->d_acc, 0, bytes, p->stream));
+    PVB_CUDA(p, cudaMemsetAsync(p->d_done, 0, (state_rows(p->channels) / 2) * sizeof(unsigned), p->stream));
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    p->ring_seq = 0;
+    if (p->h_err) *p->h_err = 0;
     p->ring_calls = 0;
     p->cursor_calls = 0;
     p->layout = pvb_processor::ZERO;
@@ -851,13 +893,44 @@ double pvb_time_cursor(const pvb_processor *p) { return p ? double(p->cursor_cal
 int64_t pvb_kernel_launches(const pvb_processor *p) { return p ? p->launches : 0; }
 
 int64_t pvb_ring_stuck_count(pvb_processor *p) {
-    if (!p || !p->d_done) return 0;
+    if (!p || !p->h_err) return 0;
     DeviceGuard guard(p->device);
-    unsigned v = 0;
-    if (cudaStreamSynchronize(p->stream) != cudaSuccess) return -1;
-    if (cudaMemcpy(&v, p->d_done + state_rows(p->channels) / 2, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
-        return -1;
-    return int64_t(v);
+    if (sync_all(p) != cudaSuccess) return -1;
+    return int64_t(*reinterpret_cast<volatile unsigned *>(p->h_err));
+}
+
+int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    switch (option) {
+        case PVB_OPT_KERNEL:
+            if (value < 0 || value > 4) break;
+            p->opt_kernel = int(value);
+            return PVB_OK;
+        case PVB_OPT_LAUNCH_MODE:
+            if (value < 0 || value > 2) break;
+            p->opt_launch_mode = int(value);
+            return PVB_OK;
+        case PVB_OPT_INPUTS_READY:
+            if (value < 0 || value > 1) break;
+            p->opt_inputs_ready = int(value);
+            return PVB_OK;
+        case PVB_OPT_PEAK_GUARD:
+            if (value < 0 || value > 2) break;
+            p->opt_peak_guard = int(value);
+            return PVB_OK;
+    }
+    return fail(p, PVB_ERR_BAD_ARG, "pvb_set_option: unknown option %d or bad value %lld", int(option), (long long)value);
+}
+
+int64_t pvb_get_option(const pvb_processor *p, int32_t option) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    switch (option) {
+        case PVB_OPT_KERNEL: return p->opt_kernel;
+        case PVB_OPT_LAUNCH_MODE: return p->opt_launch_mode;
+        case PVB_OPT_INPUTS_READY: return p->opt_inputs_ready;
+        case PVB_OPT_PEAK_GUARD: return p->opt_peak_guard;
+    }
+    return PVB_ERR_BAD_ARG;
 }
 
 const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
@@ -866,25 +939,20 @@ const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
     fp.pitch_factor = pitch_factor;
     fp.overlaps = p->overlaps;
     split_pitch_factor(pitch_factor, &fp.pf_mant, &fp.pf_shift);
-    if (ring_kernel_applies(p, fp)) return "pvb::pv_process_ring_kernel";
-    if (warp_kernel_applies(p->n, fp) && !g_force_generic && g_kernel_1024 != 3)
-        return g_kernel_1024 == 2 ? "pvb::pv_process_pair_kernel" : "pvb::pv_process_warp_kernel";
-    if (fast_range(fp) && !g_force_generic) {
-        switch (p->n) {
-            case 256: return "pvb::pv_process_cta_kernel<256>";
-            case 512: return "pvb::pv_process_cta_kernel<512>";
-            case 1024: return "pvb::pv_process_cta_kernel<1024>";
-            case 2048: return "pvb::pv_process_cta_kernel<2048>";
-            default: return "pvb::pv_process_cta_kernel<4096>";
-        }
+    static const char *cta[] = {"pvb::pv_process_cta_kernel<256>", "pvb::pv_process_cta_kernel<512>",
+                                "pvb::pv_process_cta_kernel<1024>", "pvb::pv_process_cta_kernel<2048>",
+                                "pvb::pv_process_cta_kernel<4096>"};
+    static const char *gen[] = {"pvb::pv_process_kernel<256>", "pvb::pv_process_kernel<512>",
+                                "pvb::pv_process_kernel<1024>", "pvb::pv_process_kernel<2048>",
+                                "pvb::pv_process_kernel<4096>"};
+    const int idx = p->n == 256 ? 0 : p->n == 512 ? 1 : p->n == 1024 ? 2 : p->n == 2048 ? 3 : 4;
+    switch (pick_kernel(p, fp)) {
+        case K_RING: return "pvb::pv_process_ring_kernel";
+        case K_WARP: return "pvb::pv_process_warp_kernel";
+        case K_CTA: return cta[idx];
+        case K_GENERIC: break;
     }
-    switch (p->n) {
-        case 256: return "pvb::pv_process_kernel<256>";
-        case 512: return "pvb::pv_process_kernel<512>";
-        case 1024: return "pvb::pv_process_kernel<1024>";
-        case 2048: return "pvb::pv_process_kernel<2048>";
-        default: return "pvb::pv_process_kernel<4096>";
-    }
+    return gen[idx];
 }
 
 int32_t pvb_set_time_cursor(pvb_processor *p, double samples) {
@@ -895,6 +963,7 @@ int32_t pvb_set_time_cursor(pvb_processor *p, double samples) {
         return fail(p, PVB_ERR_BAD_ARG, "timeCursor must be a non-negative multiple of the hop size");
     if (p->layout == pvb_processor::PAIRED) {       // the paired rings are aligned to the cursor
         DeviceGuard guard(p->device);
+        PVB_CUDA(p, sync_all(p));
         const int rc = ensure_layout(p, pvb_processor::PLANAR, p->stream);
         if (rc != PVB_OK) return rc;
     }
@@ -913,9 +982,11 @@ int32_t pvb_get_state(pvb_processor *p, float *blob) {
     const size_t cn = size_t(p->channels) * size_t(p->n);
     if (cn == 0) return PVB_OK;
     std::vector<float> ring(2 * cn);
-    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    PVB_CUDA(p, sync_all(p));
     {
-        const int rc = ensure_layout(p, pvb_processor::PLANAR, p->stream);
+        int rc = check_device_error(p);
+        if (rc != PVB_OK) return rc;
+        rc = ensure_layout(p, pvb_processor::PLANAR, p->stream);
         if (rc != PVB_OK) return rc;
     }
     PVB_CUDA(p, cudaMemcpy(ring.data(), p->d_hist, cn * sizeof(float), cudaMemcpyDeviceToHost));
@@ -950,7 +1021,7 @@ int32_t pvb_set_state(pvb_processor *p, const float *blob) {
             a[(j + rb) & (n - 1)] = (j < n - hop) ? ai[j] : 0.0f;
         }
     }
-    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    PVB_CUDA(p, sync_all(p));
     p->layout = pvb_processor::PLANAR;      // whatever was there is replaced
     PVB_CUDA(p, cudaMemcpy(p->d_hist, ring.data(), cn * sizeof(float), cudaMemcpyHostToDevice));
     PVB_CUDA(p, cudaMemcpy(p->d_acc, ring.data() + cn, cn * sizeof(float), cudaMemcpyHostToDevice));

@@ -52,7 +52,14 @@ __device__ __forceinline__ int round_shifted_peak(int p, const FrameParams &fp) 
         const long long r = v >> fp.pf_shift;
         return r > 0x3fffffff ? 0x3fffffff : (r < -0x3fffffff ? -0x3fffffff : int(r));
     }
-    return __double2int_rd(fma(double(p), double(fp.pitch_factor), 0.5));
+    // float64 fallback (pitch factors whose exponent does not fit the integer form, infinities, NaN).
+    // Math.round(NaN) is NaN: every comparison of pv:127 / pv:150 is false and the writes go to the
+    // property "NaN" of the Array, i.e. nowhere -- the shifted spectrum stays zero.  A value beyond nb
+    // has the same effect here (pv:127 `break`).
+    const double v = fma(double(p), double(fp.pitch_factor), 0.5);
+    if (v != v) return 0x3fffffff;
+    const double r = floor(v);
+    return r > 1073741823.0 ? 0x3fffffff : (r < -1073741823.0 ? -0x3fffffff : int(r));
 }
 
 // ---------------------------------------------------------------------------

@@ -141,18 +141,26 @@ struct RingParams {
     int num_channels;
     int hop;
     int tmod;                   // timeCursor mod N (multiple of hop)
-    int stagger_ns;             // experiment: delay odd warps by this much before the first pass
-    int skip;                   // experiment (PVB_SKIP, results become wrong): bit 0 the whole middle, bit 1 forward
-                                // and inverse pass 2
+    int stagger_ns;             // -DPVB_EXPERIMENTS only: delay odd warps by this much before the first pass
+    int skip;                   // -DPVB_EXPERIMENTS only (PVB_SKIP, results become wrong): bit 0 the whole middle,
+                                // bit 1 forward and inverse pass 2
     int early;                  // which state loads may precede griddepcontrol.wait (0, 1, 2; see the kernel)
     // per-pair completion flags: done[pair] holds the sequence number of the last call of this handle
     // whose state / output for that pair is complete (release store at the end of every launch)
     unsigned *done;
     unsigned wait_seq, my_seq;  // this call may touch a pair once done[pair] >= wait_seq; it stores my_seq
     int flag_mode;              // 1: synchronise on done[] per pair instead of waiting for the whole previous grid
-    unsigned *stuck;            // incremented if a flag never arrives (bounded spin; see pvb_ring_stuck_count)
+    unsigned *err;              // sticky device-error word (mapped host memory): pairs whose flag never arrived
     float pitch_factor;
     int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
+    // peak guard (see ring_exact_peak_mask): 0 auto, 1 off, 2 always
+    int guard;
+    const double *xtw;          // [2N] fft.js table: cos(pi i / N), -sin(pi i / N) pairs (bundle:13-17), float64
+    const int *xrev;            // [1 << width] fft.js _bitrev (bundle:31-38)
+    double *xpool;              // scratch slots of 2N doubles, shared by every handle of this frame size on the device
+    unsigned *xlocks;           // one lock word per slot
+    int xslots;
+    unsigned long long *xcount; // number of channel frames re-decided so far (diagnostics)
 };
 
 __device__ __forceinline__ float4 pack4(cpx2 v) { return make_float4(v.re.x, v.re.y, v.im.x, v.im.y); }
@@ -332,6 +340,132 @@ __device__ __forceinline__ int ring_thread_last(const int *bal) {
     return res;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Peak guard.  findPeaks (pv:95-116) compares float32 ROUNDINGS OF FLOAT64 squared magnitudes
+// (pv:82-92); this kernel computes them from a float32 FFT.  Where a frame has bins near or below the
+// float32 round-off floor of its own energy (noise-free tones, digital silence followed by a tone,
+// band-limited material) the two disagree about peaks, and one displaced peak changes which stale
+// upper bins a contracting shift pulls in: 5.7e-3 RMS on clean tones at pitch factor 0.8.
+//
+// Detection (every call, every channel): with |dX_k| <= a |X_k| + b rms(X) for the float32 transform
+// (a = 3e-7, b = 1.2e-6: measured bounds of this kernel's FFT, tests/test_peak_guard_model.py), the
+// squared magnitudes m carry dm <= 2 a m + 2 b rms sqrt(m), so the comparison of a bin against the
+// largest of its four neighbours is UNCERTAIN when  D^2 <= q (8 a^2 q + 16 b^2 E),  D = m - nbmax,
+// q = m + nbmax, E = mean of m over the frame.  A channel with no uncertain comparison provably has
+// the reference's peak set.
+//
+// Re-decision (rare; all of a tonal stream): the pair recomputes that channel's squared magnitudes with
+// ring_exact_peak_mask below -- fft.js's realTransform restated operation by operation in float64 on
+// the windowed frame (same tables, same association order, no fused multiply-add), rounded to float32
+// like pv:88 -- so the peak set is the reference's bit for bit.  Everything downstream of the peak set
+// is continuous in the spectrum, and stays in float32.
+// ---------------------------------------------------------------------------------------------------
+#define PVB_GUARD_A 3.0e-7f
+#define PVB_GUARD_B 1.2e-6f
+
+// radix-4 stage of fft.js _realTransform4 (bundle:334-441) on `out` (2N doubles, in place): butterfly
+// `ii` of block `blk`.  Literal order of operations; __d*_rn keeps the compiler from fusing.
+__device__ __forceinline__ void exact_real_butterfly(double *out, const double *tw, int base, int ii, int step,
+                                                     int q, int h, int hq) {
+    const int i = 2 * ii, k = ii * step;
+    const int pa = base + i, pb = pa + q, pc = pb + q, pd = pc + q;
+    const double ar = __ldcg(out + pa), ai = __ldcg(out + pa + 1);
+    const double br = __ldcg(out + pb), bi = __ldcg(out + pb + 1);
+    const double cr = __ldcg(out + pc), ci = __ldcg(out + pc + 1);
+    const double dr = __ldcg(out + pd), di = __ldcg(out + pd + 1);
+    const double wbr = __ldg(tw + k), wbi = __ldg(tw + k + 1);
+    const double wcr = __ldg(tw + 2 * k), wci = __ldg(tw + 2 * k + 1);
+    const double wdr = __ldg(tw + 3 * k), wdi = __ldg(tw + 3 * k + 1);
+    const double mbr = __dsub_rn(__dmul_rn(br, wbr), __dmul_rn(bi, wbi)), mbi = __dadd_rn(__dmul_rn(br, wbi), __dmul_rn(bi, wbr));
+    const double mcr = __dsub_rn(__dmul_rn(cr, wcr), __dmul_rn(ci, wci)), mci = __dadd_rn(__dmul_rn(cr, wci), __dmul_rn(ci, wcr));
+    const double mdr = __dsub_rn(__dmul_rn(dr, wdr), __dmul_rn(di, wdi)), mdi = __dadd_rn(__dmul_rn(dr, wdi), __dmul_rn(di, wdr));
+    const double s0r = __dadd_rn(ar, mcr), s0i = __dadd_rn(ai, mci);
+    const double s1r = __dsub_rn(ar, mcr), s1i = __dsub_rn(ai, mci);
+    const double s2r = __dadd_rn(mbr, mdr), s2i = __dadd_rn(mbi, mdi);
+    const double s3r = __dsub_rn(mbr, mdr), s3i = __dsub_rn(mbi, mdi);        // inv == 1
+    __stcg(out + pa, __dadd_rn(s0r, s2r));
+    __stcg(out + pa + 1, __dadd_rn(s0i, s2i));
+    __stcg(out + pb, __dadd_rn(s1r, s3i));
+    __stcg(out + pb + 1, __dsub_rn(s1i, s3r));
+    if (i == 0) {                                                              // bundle:400-406
+        __stcg(out + pc, __dsub_rn(s0r, s2r));
+        __stcg(out + pc + 1, __dsub_rn(s0i, s2i));
+        return;
+    }
+    if (i == hq) return;                                                       // bundle:409-410
+    // mirrored outputs, bundle:417-438: ST0 = (s1r, -s1i), ST1 = (s0r, -s0i), ST2 = (-s3i, -s3r), ST3 = (-s2i, -s2r)
+    const int sa = base + q - i, sb = base + h - i;
+    __stcg(out + sa, __dadd_rn(s1r, -s3i));
+    __stcg(out + sa + 1, __dadd_rn(-s1i, -s3r));
+    __stcg(out + sb, __dadd_rn(s0r, -s2r));
+    __stcg(out + sb + 1, __dsub_rn(-s0i, -s2i));
+}
+
+// 16-bit peak mask of this thread's run (bins 16 tp .. 16 tp + 15) of channel `ch`, decided exactly as
+// the reference does: float64 realTransform in fft.js's own order, |X|^2 in float64, rounded to float32
+// (pv:82-92), 5-point strict maxima (pv:95-116).  Cooperative among the TP threads of the pair; `out`
+// is the pair's scratch slot (2N doubles in global memory, L2 resident).
+template <int N, int TP>
+__device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__ ring /* the pair's history ring [N] */,
+                                                      const float *__restrict__ win /* [N] Hann, float32 */,
+                                                      const double *__restrict__ tw, const int *__restrict__ rev,
+                                                      double *out, int t, int ch, int tp, int pin) {
+    constexpr int SIZE = 2 * N;
+    constexpr int POWER = (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : 12;
+    constexpr int WIDTH = (POWER % 2 == 0) ? POWER - 1 : POWER;               // bundle:28
+    // windowed sample n of the frame (applyHannWindow, pv:75-79: one correctly rounded float32 product)
+    auto xw = [&](int n) -> double {
+        const float2 sv = __ldcg(ring + ((n + t) & (N - 1)));
+        return double(__fmul_rn(ch ? sv.y : sv.x, __ldg(win + n)));
+    };
+    if constexpr (POWER % 2 == 0) {
+        // _singleRealTransform4 (bundle:468-508): N/4 four-point transforms of the digit-reversed input
+        for (int u = tp; u < N / 4; u += TP) {
+            const int off = int(unsigned(__ldg(rev + u)) >> 1);
+            const double a = xw(off), b = xw(off + N / 4), c = xw(off + N / 2), d = xw(off + 3 * (N / 4));
+            const double s0 = __dadd_rn(a, c), s1 = __dsub_rn(a, c), s2 = __dadd_rn(b, d), s3 = __dsub_rn(b, d);
+            double *o = out + 8 * u;
+            __stcg(o, __dadd_rn(s0, s2)); __stcg(o + 1, 0.0);
+            __stcg(o + 2, s1); __stcg(o + 3, -s3);
+            __stcg(o + 4, __dsub_rn(s0, s2)); __stcg(o + 5, 0.0);
+            __stcg(o + 6, s1); __stcg(o + 7, s3);
+        }
+    } else {
+        // _singleRealTransform2 (bundle:447-463): N/2 two-point transforms
+        for (int u = tp; u < N / 2; u += TP) {
+            const int off = int(unsigned(__ldg(rev + u)) >> 1);
+            const double e = xw(off), qv = xw(off + N / 2);
+            double *o = out + 4 * u;
+            __stcg(o, __dadd_rn(e, qv)); __stcg(o + 1, 0.0);
+            __stcg(o + 2, __dsub_rn(e, qv)); __stcg(o + 3, 0.0);
+        }
+    }
+    pair_sync<TP>(pin);
+    for (int step = (1 << WIDTH) >> 2; step >= 2; step >>= 2) {
+        const int len = (SIZE / step) << 1, h = len >> 1, q = h >> 1, hq = q >> 1;
+        const int cpb = (hq >> 1) + 1;                                        // butterflies per block: i = 0, 2, .. hq
+        const int total = (SIZE / len) * cpb;
+        for (int j = tp; j < total; j += TP) {
+            const int blk = j / cpb, ii = j - blk * cpb;
+            exact_real_butterfly(out, tw, blk * len, ii, step, q, h, hq);
+        }
+        pair_sync<TP>(pin);
+    }
+    int m[20];
+#pragma unroll
+    for (int i = 0; i < 20; i++) {
+        int bin = 16 * tp - 2 + i;
+        bin = bin < 0 ? 0 : (bin > N / 2 ? N / 2 : bin);
+        const double re = __ldcg(out + 2 * bin), im = __ldcg(out + 2 * bin + 1);
+        m[i] = __float_as_int(__double2float_rn(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im))));   // pv:85-88
+    }
+    uint32_t mask = ring_peak_mask(m);
+    if (tp == 0) mask &= ~3u;                                                 // i >= 2
+    if (tp == TP - 1) mask &= ~(1u << 15);                                    // i <= nb - 3
+    pair_sync<TP>(pin);                                                       // the slot may be reused (other channel)
+    return mask;
+}
+
 // N = frame size (512: half a warp per pair, 1024: one warp, 2048: two warps, 4096: four warps),
 // NBLK = hop / 128.
 // Registers of the first / last FFT pass are indexed by FRAME block f (128 samples), so the role
@@ -351,7 +485,12 @@ pv_process_ring_kernel(const RingParams p) {
     const int tp = threadIdx.x % TP;                // thread within the pair
     const int pin = threadIdx.x / TP;               // pair within the CTA
     const int pair = blockIdx.x * (blockDim.x / TP) + pin;
-    const bool live = 2 * pair < p.num_channels;
+    bool live = 2 * pair < p.num_channels;
+#ifdef PVB_EXPERIMENTS
+    const int xskip = p.skip, xstagger = p.stagger_ns;
+#else
+    constexpr int xskip = 0, xstagger = 0;
+#endif
     // lanes of this thread's pair inside its warp (frame 512: half a warp)
     const unsigned FULL = (TP == 16) ? (0xFFFFu << (threadIdx.x & 16))
                           : (TP == 8) ? (0xFFu << (threadIdx.x & 24)) : 0xFFFFFFFFu;
@@ -482,20 +621,31 @@ pv_process_ring_kernel(const RingParams p) {
     const int early = p.flag_mode ? 0 : p.early;
     if (p.flag_mode) {
         if (live) {
-            // acquire: the previous call of this handle has finished with this pair (bounded spin: a
-            // lost flag must not hang the device; the host can read the stuck counter)
+            // acquire: the previous call of this handle has finished with this pair.  The spin is bounded:
+            // when the flag does not arrive (time slicing, a debugger, a launch that never ran) the pair
+            // falls back to a real ordering -- it waits for the whole previous grid -- and looks again.
+            // A flag that is still missing then means the previous call never completed this pair: the
+            // pair is not processed (stale state must not be built upon) and the sticky error word makes
+            // every later entry point on the handle fail.
             unsigned v;
             int it = 0;
+            bool ok = true;
             for (;;) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done + pair) : "memory");
                 if (int(v - p.wait_seq) >= 0) break;
                 if (++it > 200000) {
-                    if (tp == 0) atomicAdd(p.stuck, 1u);
+                    asm volatile("griddepcontrol.wait;" ::: "memory");
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done + pair) : "memory");
+                    if (int(v - p.wait_seq) < 0) {
+                        ok = false;
+                        if (tp == 0) atomicAdd(p.err, 1u);
+                    }
                     break;
                 }
                 __nanosleep(200);
             }
             if constexpr (TP < 32) pair_sync<TP>(pin); else __syncwarp();
+            live = ok;
         }
     } else if (live && early) {
 #pragma unroll
@@ -545,7 +695,7 @@ pv_process_ring_kernel(const RingParams p) {
     __syncthreads();
     if (!live) return;          // no CTA-wide barriers below
 
-    if (p.stagger_ns > 0 && (pin & 1)) __nanosleep(unsigned(p.stagger_ns));
+    if (xstagger > 0 && (pin & 1)) __nanosleep(unsigned(xstagger));
     // the new block joins the history ring (ola:105)
 #pragma unroll
     for (int e = 0; e < 16; e++) {
@@ -596,7 +746,7 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- forward pass 2: butterflies (k1, m3) over m2, in place -----------------------------------
     const int m3l = tp & 7;
-    if (!(p.skip & 2)) {
+    if (!(xskip & 2)) {
         float2 w2[8];
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
@@ -684,7 +834,7 @@ pv_process_ring_kernel(const RingParams p) {
     // X lives in float4 slots (both channels per bin); the shifted spectrum Y is written over it as
     // four planes of floats (re0 | re1 | im0 | im1, bin d at word d + (d >> YSHIFT)): the 32-bit scatter of
     // threads that own runs 16 bins apart then spreads over all banks.
-    if (!(p.skip & 1))
+    if (!(xskip & 1))
     {
         const bool contract = p.pitch_factor < 1.0f;
         const float4 *runp = XQ + 17 * tp;                            // slot of bin 16 tp
@@ -973,7 +1123,7 @@ pv_process_ring_kernel(const RingParams p) {
             b0[G::G8 * m2] = pack4(cmul_s(cadd(x0[m2], v1), wa.x, -wa.y));
             b1[G::G8 * m2] = pack4(cmul_s(csub(x0[m2], v1), wb.x, -wb.y));
         }
-    } else if (!(p.skip & 2))
+    } else if (!(xskip & 2))
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int k1 = (tp >> 3) + (R1 / 2) * h;

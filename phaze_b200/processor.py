@@ -33,7 +33,7 @@ class BatchedPhaseVocoder:
     """
 
     def __init__(self, num_channels: int, frame_size: int = BUFFERED_BLOCK_SIZE,
-                 hop_size: int = WEBAUDIO_BLOCK_SIZE, device: int = -1):
+                 hop_size: int = WEBAUDIO_BLOCK_SIZE, device: int = -1, **options):
         self._lib = _lib.load()
         cfg = _lib.PvbConfig(frame_size, hop_size, num_channels, device)
         h = C.c_void_p()
@@ -43,6 +43,8 @@ class BatchedPhaseVocoder:
         self._h = h
         self.frame_size = self._lib.pvb_frame_size(h)
         self.hop_size = self._lib.pvb_hop_size(h)
+        for name, value in options.items():
+            self.set_option(name, value)
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):
@@ -81,8 +83,22 @@ class BatchedPhaseVocoder:
 
     @property
     def ring_stuck_count(self) -> int:
-        """completion flags of the frame-1024 kernel that never arrived (must stay 0)"""
+        """channel pairs whose completion flag never arrived (0 on a healthy handle)"""
         return self._lib.pvb_ring_stuck_count(self._h)
+
+    _OPTIONS = {"kernel": _lib.PVB_OPT_KERNEL, "launch_mode": _lib.PVB_OPT_LAUNCH_MODE,
+                "inputs_ready": _lib.PVB_OPT_INPUTS_READY, "peak_guard": _lib.PVB_OPT_PEAK_GUARD}
+    _KERNELS = {"auto": 0, "ring": 1, "warp": 2, "cta": 3, "generic": 4}
+
+    def set_option(self, name: str, value) -> None:
+        """pvb_set_option: kernel ("auto" | "ring" | "warp" | "cta" | "generic"), launch_mode (0 flags,
+        1 grid-wide wait, 2 plain launches), inputs_ready (0 | 1), peak_guard (0 auto, 1 off, 2 always)."""
+        if name == "kernel" and isinstance(value, str):
+            value = self._KERNELS[value]
+        _lib.check(self._h, self._lib.pvb_set_option(self._h, self._OPTIONS[name], int(value)))
+
+    def get_option(self, name: str) -> int:
+        return int(self._lib.pvb_get_option(self._h, self._OPTIONS[name]))
 
     def kernel_name(self, pitch_factor: float) -> str:
         return self._lib.pvb_kernel_name(self._h, np.float32(pitch_factor)).decode()

@@ -114,8 +114,13 @@ class ShardedPhaseVocoder:
     # -- single-root mode: scatter, process, gather ----------------------------------------------
     def process_from_root(self, full_block: Optional[torch.Tensor], pitch_factor: float,
                           root: int = 0) -> Optional[torch.Tensor]:
-        """full_block [C][hop] on `root` (ignored elsewhere).  Returns the [C][hop] output on root."""
+        """full_block [C][hop] on `root` (ignored elsewhere); None on root == paused input
+        (ola-processor.js:93-100): the root then scatters blocks of zeros, which is exactly what the
+        reference feeds its frames, so no extra message is needed to tell the other ranks.
+        Returns the [C][hop] output on root."""
         hop = self.hop_size
+        if full_block is None and self.rank == root and self.world > 1:
+            full_block = torch.zeros((self.num_channels, hop), dtype=torch.float32, device=self.device)
         local = torch.empty((self.local_channels, hop), dtype=torch.float32, device=self.device)
         if self.world == 1:
             local = full_block

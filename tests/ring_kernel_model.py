@@ -297,7 +297,7 @@ def gather_shift_lanes(g: Geo, xfull, mask, prev_before, next_after, dtab, contr
     return Y
 
 
-def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
+def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None, capture: dict | None = None):
     """One process() call of one channel pair.  hist2/acc2: [N][2] float32 rings (modified in
     place), inblk: [2][hop] or None (paused), t = timeCursor (multiple of hop).  Returns out[2][hop]."""
     N, M, NB, TP, R1, KS, NJ, T = g.N, g.M, g.NB, g.TP, g.R1, g.KS, g.NJ, g.T
@@ -452,6 +452,8 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None):
         split(za, zb, split_k(j))
     split(a[4], a[4], np.full(TP, M // 2), active=(T == 0))
 
+    if capture is not None:                          # the float32 spectrum (2x scaled, ring order) per channel
+        capture["X"] = X[:, xslot(np.arange(NB))].copy()
     # ---- per channel: peaks, owners, shift ------------------------------------------------------
     for ch in range(2):
         Xc = X[ch]

@@ -11,11 +11,11 @@ RMS_BAR = 1e-4          # north_star: "within 1e-4 RMS (float32)"
 RMS_EXPECTED = 2e-6     # what a correct float32 pipeline actually achieves on these inputs
 
 
-def _run_both(oracle, N, hop, C, pf, calls, first_channel=0, sig=None):
+def _run_both(oracle, N, hop, C, pf, calls, first_channel=0, sig=None, **options):
     from phaze_b200 import BatchedPhaseVocoder
     x = signals.channels(first_channel, C, calls * hop) if sig is None else sig
     ref = oracle.OracleProcessor(N, hop, C).run(x, pf)
-    with BatchedPhaseVocoder(C, N, hop) as pv:
+    with BatchedPhaseVocoder(C, N, hop, **options) as pv:
         got = pv.run(x, pf)
         launches = pv.kernel_launches
     assert launches == calls
@@ -57,15 +57,12 @@ def test_parity_frame_size_sweep(oracle, N, pf):
 
 
 @pytest.mark.parametrize("pf", [0.8, 0.67, 0.7, 0.75, 0.9, 1.0, 1.2, 1.5, 2.0, 3.0])
-@pytest.mark.parametrize("kernel", ["ring", "pair", "warp", "cta", "generic"])
-def test_parity_1024_all_kernels(oracle, monkeypatch, pf, kernel):
-    """frame 1024 has five CUDA paths: the ring-order kernel (default for pitch factors in
-    [0.75, 64] and hop % 128 == 0), one warp per channel pair (PVB_KERNEL_1024=1), two warps per
-    pair (=2), the CTA kernel (=3) and the generic kernel; all must match."""
-    monkeypatch.setenv("PVB_FORCE_GENERIC", "1" if kernel == "generic" else "0")
-    monkeypatch.setenv("PVB_KERNEL_1024",
-                       {"ring": "0", "warp": "1", "pair": "2", "cta": "3", "generic": "1"}[kernel])
-    x, ref, got = _run_both(oracle, 1024, 256, 5, np.float32(pf), 17)
+@pytest.mark.parametrize("kernel", ["ring", "warp", "cta", "generic"])
+def test_parity_1024_all_kernels(oracle, pf, kernel):
+    """frame 1024 has four CUDA paths: the ring-order kernel (default for pitch factors in
+    [0.75, 64] and hop % 128 == 0), one warp per channel pair in frame order, the CTA kernel and the
+    generic kernel (pvb_set_option PVB_OPT_KERNEL); all must match."""
+    x, ref, got = _run_both(oracle, 1024, 256, 5, np.float32(pf), 17, kernel=kernel)
     err = _rms(got - ref)
     print(f"pf={pf} kernel={kernel}: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
@@ -87,18 +84,14 @@ def test_parity_hop128_warp_kernel(oracle):
 
 @pytest.mark.parametrize("N", [256, 512, 2048, 4096])
 @pytest.mark.parametrize("pf", [0.75, 0.9, 1.0, 1.3, 2.5])
-@pytest.mark.parametrize("force_generic", ["0", "1", "cta"])
-def test_parity_other_frame_sizes_both_kernels(oracle, monkeypatch, N, pf, force_generic):
-    """frame sizes other than 1024: the default kernel (ring-order at 2048, CTA kernel with the
-    in-place shift elsewhere; pitch factors in [0.75, 64]), the CTA kernel everywhere
-    (PVB_KERNEL_1024=3) and the fully generic kernel must all match the oracle."""
-    monkeypatch.setenv("PVB_FORCE_GENERIC", "1" if force_generic == "1" else "0")
-    if force_generic == "cta":
-        monkeypatch.setenv("PVB_KERNEL_1024", "3")
+@pytest.mark.parametrize("kernel", ["auto", "cta", "generic"])
+def test_parity_other_frame_sizes_both_kernels(oracle, N, pf, kernel):
+    """frame sizes other than 1024: the default kernel (ring-order), the CTA kernel with the in-place
+    shift (pitch factors in [0.75, 64]) and the fully generic kernel must all match the oracle."""
     hop = N // 4
-    x, ref, got = _run_both(oracle, N, hop, 5, np.float32(pf), 13)
+    x, ref, got = _run_both(oracle, N, hop, 5, np.float32(pf), 13, kernel=kernel)
     err = _rms(got - ref)
-    print(f"N={N} pf={pf} generic={force_generic}: rms err {err:.3e}")
+    print(f"N={N} pf={pf} kernel={kernel}: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
 
 
@@ -111,17 +104,13 @@ def test_parity_native_2048_128_r16(oracle):
 
 @pytest.mark.parametrize("hop", [32, 64, 128, 256, 512, 1024])
 @pytest.mark.parametrize("pf", [0.8, 1.3])
-@pytest.mark.parametrize("no_aligned", ["0", "1"])
-def test_parity_1024_hop_sweep(oracle, monkeypatch, hop, pf, no_aligned):
-    """warp kernel at every hop (R = 32 ... 1): hop % 128 == 0 takes the ring-order specialisation
-    (rotation folded into the twiddles), the others the general addressing; PVB_NO_ALIGNED=1
-    forces the general one everywhere."""
-    monkeypatch.setenv("PVB_KERNEL_1024", "1")
-    monkeypatch.setenv("PVB_NO_ALIGNED", no_aligned)
+def test_parity_1024_hop_sweep(oracle, hop, pf):
+    """warp kernel at every hop (R = 32 ... 1): hop % 128 == 0 takes the specialisation with the
+    rotation folded into the twiddles, the others the general addressing."""
     calls = 2 * (1024 // hop) + 7
-    x, ref, got = _run_both(oracle, 1024, hop, 3, np.float32(pf), calls)
+    x, ref, got = _run_both(oracle, 1024, hop, 3, np.float32(pf), calls, kernel="warp")
     err = _rms(got - ref)
-    print(f"hop={hop} pf={pf} no_aligned={no_aligned}: rms err {err:.3e}")
+    print(f"hop={hop} pf={pf}: rms err {err:.3e}")
     assert err <= RMS_EXPECTED
 
 
@@ -183,8 +172,7 @@ def test_parity_ring_kernel_256(oracle, hop, pf, C):
     and a second CTA at 70 channels); hop 64 rotates the rings by half a 128-sample block on odd calls"""
     from phaze_b200 import BatchedPhaseVocoder
     with BatchedPhaseVocoder(C, 256, hop) as pv:
-        if "ring" not in pv.kernel_name(np.float32(pf)):
-            pytest.skip("frame-256 ring-order kernel disabled (PVB_RING_256=0)")
+        assert "ring" in pv.kernel_name(np.float32(pf))
     calls = 3 * (256 // hop) + 6
     x, ref, got = _run_both(oracle, 256, hop, C, np.float32(pf), calls)
     per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
@@ -199,8 +187,7 @@ def test_parity_ring_kernel_4096(oracle, hop, pf):
     in registers, the radix-2 step folded into pass 2)"""
     from phaze_b200 import BatchedPhaseVocoder
     with BatchedPhaseVocoder(5, 4096, hop) as pv:
-        if "ring" not in pv.kernel_name(np.float32(pf)):
-            pytest.skip("frame-4096 ring-order kernel disabled (PVB_RING_4096=0)")
+        assert "ring" in pv.kernel_name(np.float32(pf))
     calls = 2 * (4096 // hop) + 3
     x, ref, got = _run_both(oracle, 4096, hop, 5, np.float32(pf), calls)
     err = _rms(got - ref)
@@ -290,8 +277,9 @@ def test_flag_mode_chained_handles_and_back_to_back(oracle, N, hop):
     mid = torch.empty((C, hop), dtype=torch.float32, device="cuda")        # shared by both handles
     out_a = torch.empty((calls, C, hop), dtype=torch.float32, device="cuda")
     out_b = torch.empty((calls, C, hop), dtype=torch.float32, device="cuda")
-    with BatchedPhaseVocoder(C, N, hop) as a, BatchedPhaseVocoder(C, N, hop) as b, \
-            BatchedPhaseVocoder(C, N, hop) as solo:
+    # inputs_ready: xin is resident before the first submission, so launches may run in flag mode
+    with BatchedPhaseVocoder(C, N, hop, inputs_ready=1) as a, BatchedPhaseVocoder(C, N, hop, inputs_ready=1) as b, \
+            BatchedPhaseVocoder(C, N, hop, inputs_ready=1) as solo:
         torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             for k in range(calls):
@@ -304,3 +292,58 @@ def test_flag_mode_chained_handles_and_back_to_back(oracle, N, hop):
     got_b = out_b.cpu().numpy().transpose(1, 0, 2).reshape(C, calls * hop)
     assert _rms(got_a - ref_a) <= RMS_EXPECTED
     assert _rms(got_b - ref_b) <= RMS_EXPECTED
+
+
+def test_flag_mode_chained_through_deep_buffer(oracle):
+    """Two handles chained through a [K][C][hop] buffer, K = 24 calls per submission, few channels
+    (tiny grids: many launches are co-resident) and a faster second handle: B's call j reads what
+    A's call j wrote 24 launches earlier.  The library must order them (its alias window covers the
+    real overlap depth, not just the last few launches)."""
+    import torch
+    from phaze_b200 import BatchedPhaseVocoder
+    C, K, rounds = 6, 24, 3
+    Na, Nb, hop = 2048, 256, 128
+    pfa, pfb = np.float32(0.8), np.float32(1.25)
+    x = signals.channels(11, C, rounds * K * hop)
+    ref_a = oracle.OracleProcessor(Na, hop, C).run(x, pfa)
+    ref_b = oracle.OracleProcessor(Nb, hop, C).run(ref_a, pfb)
+    stream = torch.cuda.Stream()
+    xin = torch.from_numpy(np.ascontiguousarray(x.reshape(C, rounds * K, hop).transpose(1, 0, 2))).cuda()
+    mid = torch.empty((K, C, hop), dtype=torch.float32, device="cuda")
+    out_b = torch.empty((rounds * K, C, hop), dtype=torch.float32, device="cuda")
+    with BatchedPhaseVocoder(C, Na, hop, inputs_ready=1) as a, BatchedPhaseVocoder(C, Nb, hop, inputs_ready=1) as b:
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            for r in range(rounds):
+                a.process_device(xin[r * K].data_ptr(), mid.data_ptr(), pfa, stream.cuda_stream, num_calls=K)
+                b.process_device(mid.data_ptr(), out_b[r * K].data_ptr(), pfb, stream.cuda_stream, num_calls=K)
+        stream.synchronize()
+        assert a.ring_stuck_count == 0 and b.ring_stuck_count == 0
+    got_b = out_b.cpu().numpy().transpose(1, 0, 2).reshape(C, rounds * K * hop)
+    assert _rms(got_b - ref_b) <= RMS_EXPECTED
+
+
+def test_strict_stream_order_after_foreign_producer(oracle):
+    """Default (PVB_OPT_INPUTS_READY = 0): the input of a device submission may be produced by a
+    kernel the library knows nothing about, enqueued on the same stream just before the call."""
+    import torch
+    from phaze_b200 import BatchedPhaseVocoder
+    C, N, hop, calls = 64, 1024, 256, 12
+    pf = np.float32(0.8)
+    x = signals.channels(5, C, calls * hop)
+    ref = oracle.OracleProcessor(N, hop, C).run(x, pf)
+    stream = torch.cuda.Stream()
+    src = torch.from_numpy(np.ascontiguousarray(x.reshape(C, calls, hop).transpose(1, 0, 2))).cuda()
+    buf = torch.zeros((C, hop), dtype=torch.float32, device="cuda")
+    big = torch.zeros(32 << 20, dtype=torch.float32, device="cuda")
+    out = torch.empty((calls, C, hop), dtype=torch.float32, device="cuda")
+    with BatchedPhaseVocoder(C, N, hop) as pv:
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            for k in range(calls):
+                big.add_(1.0)                    # keeps the stream busy in front of the producer
+                buf.copy_(src[k] * 2.0).mul_(0.5)   # foreign kernels write the input just before the call
+                pv.process_device(buf.data_ptr(), out[k].data_ptr(), pf, stream.cuda_stream)
+        stream.synchronize()
+    got = out.cpu().numpy().transpose(1, 0, 2).reshape(C, calls * hop)
+    assert _rms(got - ref) <= RMS_EXPECTED

@@ -51,6 +51,8 @@ def _worker(rank, world, port, C, frame, hop, calls, pf, q):
         outs_root, outs_local = [], []
         for t in range(calls):
             blk = torch.from_numpy(np.ascontiguousarray(x[:, t * hop:(t + 1) * hop]))
+            if t == 3:
+                blk = None                        # paused on the root (ola:93-100): every rank must follow
             res = sh.process_from_root(blk if rank == 0 else None, pf)
             if rank == 0:
                 outs_root.append(res.numpy().copy())
@@ -59,7 +61,7 @@ def _worker(rank, world, port, C, frame, hop, calls, pf, q):
                                   device=torch.device("cpu"))
         for t in range(calls):
             blk = torch.from_numpy(np.ascontiguousarray(x[sh2.first:sh2.last, t * hop:(t + 1) * hop]))
-            outs_local.append(sh2.process_local(blk, pf).numpy().copy())
+            outs_local.append(sh2.process_local(None if t == 3 else blk, pf).numpy().copy())
         # third pass: the streamed root mode (K calls per message, channel-major audio buffers)
         sh3 = ShardedPhaseVocoder(C, frame, hop, processor_factory=lambda n: _OracleShard(n, frame, hop),
                                   device=torch.device("cpu"))
@@ -99,7 +101,10 @@ def test_sharded_equals_unsharded_bit_for_bit():
         assert p.exitcode == 0
     x = signals.channels(0, C, calls * hop)
     ref = oracle_lib.OracleProcessor(frame, hop, C).run(x, pf)               # unsharded
-    ref_calls = ref.reshape(C, calls, hop).transpose(1, 0, 2)
+    xp = x.copy()
+    xp[:, 3 * hop:4 * hop] = 0                                               # call 3 is paused in passes 1 and 2
+    ref_p = oracle_lib.OracleProcessor(frame, hop, C).run(xp, pf)
+    ref_calls = ref_p.reshape(C, calls, hop).transpose(1, 0, 2)
     by_rank = {r[0]: r for r in results}
     assert np.array_equal(by_rank[0][2], ref_calls), "root-gathered output differs from unsharded"
     assert np.array_equal(by_rank[0][4], ref), "streamed root mode differs from unsharded"
