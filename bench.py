@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--pitch", type=float, default=PITCH)
     ap.add_argument("--rotate", type=int, default=0,
                     help="processor instances rotated through (0: enough to exceed 2x L2)")
+    ap.add_argument("--peak-guard", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="PVB_OPT_PEAK_GUARD of the timed handles: 0 default policy, 1 off, 2 always, 3 strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true",
@@ -292,7 +294,8 @@ def run_ours(args):
     # inputs_ready: the input blocks are resident in HBM before anything is timed (the library's default
     # is strict stream order: the first launch of every submission waits for the whole stream, because
     # its input could come from a kernel the library knows nothing about)
-    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local, inputs_ready=1) for _ in range(rotate)]
+    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local, inputs_ready=1, peak_guard=args.peak_guard)
+             for _ in range(rotate)]
     # a real (non-NULL) stream: NULL would select the handle's own stream and the events
     # below would not bracket the kernels
     stream = torch.cuda.Stream()
@@ -337,6 +340,7 @@ def run_ours(args):
 
     timed_run(max(W, 20), 0)           # untimed: first-use costs (module load, allocator, clocks ramp)
     launches0 = sum(p.kernel_launches for p in procs)
+    guard0 = sum(p.peak_guard_count for p in procs)
     if sampler:
         sampler.mark_begin()
     ms = timed_run(K, W)
@@ -346,6 +350,7 @@ def run_ours(args):
         dist.barrier()
         torch.cuda.synchronize()
     launches = sum(p.kernel_launches for p in procs) - launches0 - W
+    guard_frames = sum(p.peak_guard_count for p in procs) - guard0
     if sampler:
         sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -458,6 +463,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "launch_chaining": chain,
+            "peak_guard": {"option": args.peak_guard, "frames_redecided_in_float64": int(guard_frames),
+                           "of_frames": int((K + W) * C),
+                           "note": "channel frames whose peak set was re-decided with the fft.js-order float64 "
+                                   "transform during warm-up + timed launches (this rank)"},
             "l2_resident_value": l2_value,
             "concurrent_streams_value": streams_value,
             "cpu_baseline": cpu,

@@ -124,11 +124,15 @@ enum {
        produced by work the host has synchronised with); launches then overlap with whatever precedes
        them on the stream as far as the handle's own state allows. */
     PVB_OPT_INPUTS_READY = 3,
-    /* Peak picking (phase-vocoder.js:82-116) compares float32 roundings of float64 |X|^2.  0 (default):
-       the kernel computes |X|^2 from its float32 FFT and re-decides, per channel and call, every frame
-       in which a comparison falls inside the float32 error bound with a float64 transform that follows
-       fft.js operation by operation (bit-identical peak sets on any input, e.g. noise-free tones).
-       1: never re-decide (float32 decisions only).  2: always re-decide (tests). */
+    /* Peak picking (phase-vocoder.js:82-116) compares float32 roundings of float64 |X|^2; the kernels
+       compute |X|^2 from a float32 FFT and mark every comparison that falls inside the float32 error
+       bound of the frame as uncertain.  A channel frame can be RE-DECIDED with a float64 transform that
+       follows fft.js operation by operation (bit-identical peak set on any input).
+       0 (default): re-decide frames with two or more uncertain comparisons (noise-free tones, band-limited
+       material, silence followed by a tone: bins at the round-off floor come in clusters); a single
+       natural near-tie in a broadband frame keeps its float32 decision.
+       1: never (float32 decisions only, the test itself is skipped).  2: always (tests).
+       3 strict: re-decide frames with one or more uncertain comparisons. */
     PVB_OPT_PEAK_GUARD = 4
 };
 PVB_API int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value);
@@ -152,6 +156,9 @@ PVB_API int64_t pvb_kernel_launches(const pvb_processor *p);
    pvb_sync / pvb_get_state on the handle returns PVB_ERR_CUDA (pvb_reset / pvb_resize clear it).
    This returns the number of such pairs so far (0 on a healthy handle); -1 on CUDA error. */
 PVB_API int64_t pvb_ring_stuck_count(pvb_processor *p);
+/* Diagnostics: number of channel frames whose peak set was re-decided with the float64 transform so
+   far (see PVB_OPT_PEAK_GUARD).  Synchronises the handle's streams; -1 on CUDA error. */
+PVB_API int64_t pvb_peak_guard_count(pvb_processor *p);
 
 /* checkpoint / resume of the per-channel state.  Blob layout (float32):
  * [num_channels][frame_size] input history in time order (oldest first),

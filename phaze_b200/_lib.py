@@ -53,6 +53,7 @@ _SIGNATURES = {
     "pvb_set_time_cursor": (C.c_int32, [C.c_void_p, C.c_double]),
     "pvb_kernel_launches": (C.c_int64, [C.c_void_p]),
     "pvb_ring_stuck_count": (C.c_int64, [C.c_void_p]),
+    "pvb_peak_guard_count": (C.c_int64, [C.c_void_p]),
     "pvb_kernel_name": (C.c_char_p, [C.c_void_p, C.c_float]),
     "pvb_state_bytes": (C.c_size_t, [C.c_void_p]),
     "pvb_get_state": (C.c_int32, [C.c_void_p, C.c_void_p]),

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
+#include <map>
 #include <mutex>
 #include <new>
 #include <unordered_map>
@@ -37,6 +38,9 @@ struct pvb_processor {
     // sticky device-error word: pinned, mapped host memory the kernels write only when a completion flag
     // is still missing after the whole previous grid has drained (h_err[0]: pairs lost so far)
     unsigned *h_err = nullptr, *d_err = nullptr;
+    // peak guard (pv_kernel_ring.cuh): shared per (device, frame size), see acquire_exact_pool
+    struct ExactPool *xpool = nullptr;
+    unsigned long long *d_xcount = nullptr;   // channel frames re-decided in float64 so far
     // pvb_set_option
     int opt_kernel = 0, opt_launch_mode = 0, opt_inputs_ready = 0, opt_peak_guard = 0;
     cudaStream_t last_stream = nullptr;   // stream of the most recent submission (state entry points wait for it)
@@ -131,6 +135,83 @@ int fail(pvb_processor *p, int code, const char *fmt, ...) {
         if (e_ != cudaSuccess)                                                         \
             return fail((p), PVB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
+
+}  // namespace
+
+// Device resources of the peak guard's exact path, shared by all handles of one frame size on one
+// device: fft.js's own float64 tables (bundle:13-17, 31-38) and a pool of scratch slots of 2N doubles
+// (one per channel pair that can be resident on the device at a time; L2-resident in practice).
+struct ExactPool {
+    double *pool = nullptr, *tw = nullptr;
+    unsigned *locks = nullptr;
+    int *rev = nullptr;
+    int slots = 0, refs = 0;
+};
+
+namespace {
+
+std::mutex g_pool_mu;
+std::map<std::pair<int, int>, ExactPool> g_pools;       // (device, frame size)
+
+int ring_max_pairs(int n) {
+    switch (n) {
+        case 256: return pvb::RingGeoT<256>::MAX_PAIRS;
+        case 512: return pvb::RingGeoT<512>::MAX_PAIRS;
+        case 1024: return pvb::RingGeoT<1024>::MAX_PAIRS;
+        case 2048: return pvb::RingGeoT<2048>::MAX_PAIRS;
+    }
+    return pvb::RingGeoT<4096>::MAX_PAIRS;
+}
+
+ExactPool *acquire_exact_pool(int dev, int n, int num_sms) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    ExactPool &e = g_pools[{dev, n}];
+    if (e.refs++ > 0) return &e;
+    // function FFT(size), bundle:4-43, in the same float64 arithmetic (libm cos / sin like the JS Math object)
+    std::vector<double> tw(2 * size_t(n));
+    const double pi = 3.14159265358979323846;
+    for (int i = 0; i < 2 * n; i += 2) {
+        const double angle = pi * i / n;
+        tw[i] = std::cos(angle);
+        tw[i + 1] = -std::sin(angle);
+    }
+    int power = 0;
+    for (int t = 1; n > t; t <<= 1) power++;
+    const int width = (power % 2 == 0) ? power - 1 : power;
+    std::vector<int> rev(size_t(1) << width);
+    for (int j = 0; j < (1 << width); j++) {
+        int32_t r = 0;
+        for (int shift = 0; shift < width; shift += 2) {
+            const int back = width - shift - 2;                     // may be -1: JS masks shift counts to 5 bits
+            r |= int32_t(uint32_t((j >> shift) & 3) << (back & 31));
+        }
+        rev[j] = r;
+    }
+    e.slots = 2 * num_sms * ring_max_pairs(n) + 8;
+    const size_t pool_bytes = size_t(e.slots) * 2 * size_t(n) * sizeof(double);
+    bool ok = cudaMalloc(&e.pool, pool_bytes) == cudaSuccess &&
+              cudaMalloc(&e.locks, size_t(e.slots) * sizeof(unsigned)) == cudaSuccess &&
+              cudaMalloc(&e.tw, tw.size() * sizeof(double)) == cudaSuccess &&
+              cudaMalloc(&e.rev, rev.size() * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMemset(e.locks, 0, size_t(e.slots) * sizeof(unsigned)) == cudaSuccess &&
+         cudaMemcpy(e.tw, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(e.rev, rev.data(), rev.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        cudaFree(e.pool); cudaFree(e.locks); cudaFree(e.tw); cudaFree(e.rev);
+        g_pools.erase({dev, n});
+        return nullptr;
+    }
+    return &e;
+}
+
+void release_exact_pool(int dev, int n) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pools.find({dev, n});
+    if (it == g_pools.end() || --it->second.refs > 0) return;
+    cudaFree(it->second.pool); cudaFree(it->second.locks); cudaFree(it->second.tw); cudaFree(it->second.rev);
+    g_pools.erase(it);
+}
 
 bool valid_frame(int n) { return n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096; }
 
@@ -319,6 +400,14 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
         if (last_flag) rp.early = 0;
         last_flag = safe;
     }
+    // PVB_OPT_PEAK_GUARD: 0 auto (two or more uncertain comparisons), 1 off, 2 always, 3 strict (one or more)
+    rp.guard_min = h->opt_peak_guard == 1 ? 0x7fffffff : h->opt_peak_guard == 2 ? 0 : h->opt_peak_guard == 3 ? 1 : 2;
+    rp.xtw = h->xpool->tw;
+    rp.xrev = h->xpool->rev;
+    rp.xpool = h->xpool->pool;
+    rp.xlocks = h->xpool->locks;
+    rp.xslots = h->xpool->slots;
+    rp.xcount = h->d_xcount;
     rp.done = h->d_done;
     rp.err = h->d_err;
     rp.wait_seq = h->ring_seq;
@@ -715,6 +804,13 @@ int32_t pvb_create(const pvb_config *cfg, pvb_processor **out) {
             return bail(PVB_ERR_CUDA);
         }
     }
+    p->xpool = acquire_exact_pool(dev, n, p->num_sms);
+    if (!p->xpool || cudaMalloc(&p->d_xcount, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(p->d_xcount, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError();
+        fail(p, PVB_ERR_NOMEM, "allocation of the peak-guard scratch pool failed");
+        return bail(PVB_ERR_NOMEM);
+    }
     int rc = alloc_state(p, cfg->num_channels);
     if (rc != PVB_OK) return bail(rc);
     if (cudaStreamSynchronize(p->stream) != cudaSuccess) {
@@ -746,6 +842,8 @@ void pvb_destroy(pvb_processor *p) {
     cudaFree(p->d_in);
     cudaFree(p->d_out);
     if (p->h_err) cudaFreeHost(p->h_err);
+    cudaFree(p->d_xcount);
+    if (p->xpool) release_exact_pool(p->device, p->n);
     for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_done) cudaEventDestroy(e);
     if (p->s_in) cudaStreamDestroy(p->s_in);
@@ -899,6 +997,15 @@ int64_t pvb_ring_stuck_count(pvb_processor *p) {
     return int64_t(*reinterpret_cast<volatile unsigned *>(p->h_err));
 }
 
+int64_t pvb_peak_guard_count(pvb_processor *p) {
+    if (!p || !p->d_xcount) return 0;
+    DeviceGuard guard(p->device);
+    unsigned long long v = 0;
+    if (sync_all(p) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, p->d_xcount, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return int64_t(v);
+}
+
 int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value) {
     if (!p) return PVB_ERR_BAD_ARG;
     switch (option) {
@@ -915,7 +1022,7 @@ int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value) {
             p->opt_inputs_ready = int(value);
             return PVB_OK;
         case PVB_OPT_PEAK_GUARD:
-            if (value < 0 || value > 2) break;
+            if (value < 0 || value > 3) break;
             p->opt_peak_guard = int(value);
             return PVB_OK;
     }

@@ -92,7 +92,9 @@ struct RingGeoT {
     static constexpr int YS = (KS % (1 << PVB_RING_YSHIFT) == 0) ? PVB_RING_YSHIFT : 4;
     static constexpr int EX_SLOTS = RS * (R1 - 1) + 8 * G8;
     static constexpr int XQ_SLOTS = SM + 2;                 // bin k at k + (k >> 4); last slot = dump / halo dummy
-    static constexpr int SCR_BYTES = (WPP > 1) ? 4 * TP * 4 + 32 : 0;   // cross-warp key exchange of the region scan
+    // cross-warp exchange of the region scan: [4][TP] keys, [2][WPP] ballots; then the peak guard's
+    // [2][WPP] energy sums, [2][WPP] uncertainty ballots and its scratch slot number
+    static constexpr int SCR_BYTES = (WPP > 1) ? 4 * TP * 4 + 32 + 96 : 0;
     static constexpr int BUF_SLOTS = (XQ_SLOTS > EX_SLOTS) ? XQ_SLOTS : EX_SLOTS;
     // two pairs per warp (frame 512): their buffers sit 16 banks apart, so the 32-bit plane accesses
     // of the two half-warps (16 consecutive words each) do not collide
@@ -153,8 +155,9 @@ struct RingParams {
     unsigned *err;              // sticky device-error word (mapped host memory): pairs whose flag never arrived
     float pitch_factor;
     int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
-    // peak guard (see ring_exact_peak_mask): 0 auto, 1 off, 2 always
-    int guard;
+    // peak guard (see ring_exact_peak_mask): a channel frame is re-decided in float64 when it has at least
+    // this many uncertain comparisons (0: always; 0x7fffffff: never, and the test itself is skipped)
+    int guard_min;
     const double *xtw;          // [2N] fft.js table: cos(pi i / N), -sin(pi i / N) pairs (bundle:13-17), float64
     const int *xrev;            // [1 << width] fft.js _bitrev (bundle:31-38)
     double *xpool;              // scratch slots of 2N doubles, shared by every handle of this frame size on the device
@@ -246,6 +249,10 @@ __device__ __forceinline__ cpx2 ring_load_planes(const unsigned char *mine, int 
     return cpx2{make_float2(y[0], y[PLW]), make_float2(y[2 * PLW], y[3 * PLW])};
 }
 
+// error model of the float32 forward transform (see "Peak guard" below): |dX_k| <= a |X_k| + c ||X||_2
+#define PVB_GUARD_A 3.0e-7f
+#define PVB_GUARD_C 5.5e-8f
+
 // 5-point strict maxima (pv:95-116) of bins b0 .. b0+15 from squared magnitudes m[0..19] of bins
 // b0-2 .. b0+17 (non-negative floats order like their bit patterns)
 __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
@@ -259,6 +266,38 @@ __device__ __forceinline__ uint32_t ring_peak_mask(const int (&m)[20]) {
         mask = __funnelshift_l(uint32_t(nb_max - m[e + 2]), mask, 1);
     }
     return mask;
+}
+
+// Both channels at once: the peak masks of ring_peak_mask plus, per channel, the 16-bit mask of
+// UNCERTAIN comparisons (see "Peak guard" below): bit e is set when the squared magnitude of bin e and
+// the largest of its four neighbours are closer than the float32 transform can tell apart,
+//   D^2 <= q (rho q + kappa),  D = m - nbmax,  q = m + nbmax,
+// nkappa = -(kappa0, kappa1) per channel (16 c^2 times the summed squared magnitudes of the frame),
+// rho = 8 a^2.  Five packed float operations and two funnel shifts per bin.
+__device__ __forceinline__ void ring_peak_masks_guarded(const int (&m0)[20], const int (&m1)[20], float2 nkappa,
+                                                        uint32_t &mask0, uint32_t &mask1, uint32_t &unc0,
+                                                        uint32_t &unc1) {
+    constexpr float NRHO = -8.0f * PVB_GUARD_A * PVB_GUARD_A;
+    int q0[19], q1[19];
+#pragma unroll
+    for (int t = 0; t < 19; t++) {
+        q0[t] = max(m0[t], m0[t + 1]);
+        q1[t] = max(m1[t], m1[t + 1]);
+    }
+    mask0 = mask1 = unc0 = unc1 = 0;
+#pragma unroll
+    for (int e = 15; e >= 0; e--) {
+        const int nb0 = max(q0[e], q0[e + 3]), nb1 = max(q1[e], q1[e + 3]);   // bins e-2, e-1, e+1, e+2
+        mask0 = __funnelshift_l(uint32_t(nb0 - m0[e + 2]), mask0, 1);
+        mask1 = __funnelshift_l(uint32_t(nb1 - m1[e + 2]), mask1, 1);
+        const float2 c = make_float2(__int_as_float(m0[e + 2]), __int_as_float(m1[e + 2]));
+        const float2 nbm = make_float2(__int_as_float(nb0), __int_as_float(nb1));
+        const float2 D = sub2(c, nbm), qq = add2(c, nbm);
+        const float2 v = mul2(qq, fma2(qq, bc2(NRHO), nkappa));               // -q (rho q + kappa)
+        const float2 u = fma2(D, D, v);                                       // < 0 <=> uncertain
+        unc0 = __funnelshift_l(uint32_t(__float_as_int(u.x)), unc0, 1);
+        unc1 = __funnelshift_l(uint32_t(__float_as_int(u.y)), unc1, 1);
+    }
 }
 
 // Region of influence of every bin of the run, for one channel (pv:124-141): the owner of a bin
@@ -347,12 +386,20 @@ __device__ __forceinline__ int ring_thread_last(const int *bal) {
 // band-limited material) the two disagree about peaks, and one displaced peak changes which stale
 // upper bins a contracting shift pulls in: 5.7e-3 RMS on clean tones at pitch factor 0.8.
 //
-// Detection (every call, every channel): with |dX_k| <= a |X_k| + b rms(X) for the float32 transform
-// (a = 3e-7, b = 1.2e-6: measured bounds of this kernel's FFT, tests/test_peak_guard_model.py), the
-// squared magnitudes m carry dm <= 2 a m + 2 b rms sqrt(m), so the comparison of a bin against the
-// largest of its four neighbours is UNCERTAIN when  D^2 <= q (8 a^2 q + 16 b^2 E),  D = m - nbmax,
-// q = m + nbmax, E = mean of m over the frame.  A channel with no uncertain comparison provably has
-// the reference's peak set.
+// Detection (every call, every channel, ~3 % of the kernel's instructions): the float32 transform obeys |dX_k| <= a |X_k| + c ||X||_2
+// (the classical FFT error bound; a = 3e-7, c = 5.5e-8 hold with a 1.3x margin at every frame size
+// for this kernel's decomposition, tests/test_peak_guard_model.py), so the squared magnitudes m carry
+// dm <= 2 a m + 2 c sqrt(S m), S = sum of m over the frame, and the comparison of a bin against the
+// largest of its four neighbours is UNCERTAIN when  D^2 <= q (8 a^2 q + 16 c^2 S),  D = m - nbmax,
+// q = m + nbmax.  A channel with no uncertain comparison has the reference's peak set.
+//
+// Policy (RingParams::guard_min; PVB_OPT_PEAK_GUARD).  Frames in trouble have CLUSTERS of bins at the
+// round-off floor, i.e. many uncertain comparisons; a well-conditioned broadband frame has none, or
+// (0.6 % of frames at a -20 dB floor) a single natural near-tie, which the float32 decision gets right
+// 24 times out of 25.  The default re-decides every frame with two or more uncertain comparisons
+// (clean tones: ~95 % of frames; the benchmark's input: 2e-5 of frames), "strict" every frame with one
+// or more (outputs identical to re-deciding everything, at the price of ~25 slow channel pairs in
+// every 4096-channel launch, which the launch chain has to wait for).
 //
 // Re-decision (rare; all of a tonal stream): the pair recomputes that channel's squared magnitudes with
 // ring_exact_peak_mask below -- fft.js's realTransform restated operation by operation in float64 on
@@ -360,27 +407,34 @@ __device__ __forceinline__ int ring_thread_last(const int *bal) {
 // like pv:88 -- so the peak set is the reference's bit for bit.  Everything downstream of the peak set
 // is continuous in the spectrum, and stays in float32.
 // ---------------------------------------------------------------------------------------------------
-#define PVB_GUARD_A 3.0e-7f
-#define PVB_GUARD_B 1.2e-6f
-
 // radix-4 stage of fft.js _realTransform4 (bundle:334-441) on `out` (2N doubles, in place): butterfly
-// `ii` of block `blk`.  Literal order of operations; __d*_rn keeps the compiler from fusing.
-__device__ __forceinline__ void exact_real_butterfly(double *out, const double *tw, int base, int ii, int step,
-                                                     int q, int h, int hq) {
+// `ii` of the block at `base`.  Literal order of operations; __d*_rn keeps the compiler from fusing.
+// Split into the loads and the rest so that a thread can have the operands of several butterflies in
+// flight (the scratch slot lives in L2: a dependent round trip per butterfly would dominate).
+struct ExactOperands {
+    double ar, ai, br, bi, cr, ci, dr, di;
+};
+__device__ __forceinline__ ExactOperands exact_real_load(const double *out, int base, int ii, int q) {
+    const int pa = base + 2 * ii, pb = pa + q, pc = pb + q, pd = pc + q;
+    ExactOperands o;
+    o.ar = __ldcg(out + pa); o.ai = __ldcg(out + pa + 1);
+    o.br = __ldcg(out + pb); o.bi = __ldcg(out + pb + 1);
+    o.cr = __ldcg(out + pc); o.ci = __ldcg(out + pc + 1);
+    o.dr = __ldcg(out + pd); o.di = __ldcg(out + pd + 1);
+    return o;
+}
+__device__ __forceinline__ void exact_real_finish(double *out, const double *tw, const ExactOperands &o, int base,
+                                                  int ii, int step, int q, int h, int hq) {
     const int i = 2 * ii, k = ii * step;
-    const int pa = base + i, pb = pa + q, pc = pb + q, pd = pc + q;
-    const double ar = __ldcg(out + pa), ai = __ldcg(out + pa + 1);
-    const double br = __ldcg(out + pb), bi = __ldcg(out + pb + 1);
-    const double cr = __ldcg(out + pc), ci = __ldcg(out + pc + 1);
-    const double dr = __ldcg(out + pd), di = __ldcg(out + pd + 1);
+    const int pa = base + i, pb = pa + q, pc = pb + q;
     const double wbr = __ldg(tw + k), wbi = __ldg(tw + k + 1);
     const double wcr = __ldg(tw + 2 * k), wci = __ldg(tw + 2 * k + 1);
     const double wdr = __ldg(tw + 3 * k), wdi = __ldg(tw + 3 * k + 1);
-    const double mbr = __dsub_rn(__dmul_rn(br, wbr), __dmul_rn(bi, wbi)), mbi = __dadd_rn(__dmul_rn(br, wbi), __dmul_rn(bi, wbr));
-    const double mcr = __dsub_rn(__dmul_rn(cr, wcr), __dmul_rn(ci, wci)), mci = __dadd_rn(__dmul_rn(cr, wci), __dmul_rn(ci, wcr));
-    const double mdr = __dsub_rn(__dmul_rn(dr, wdr), __dmul_rn(di, wdi)), mdi = __dadd_rn(__dmul_rn(dr, wdi), __dmul_rn(di, wdr));
-    const double s0r = __dadd_rn(ar, mcr), s0i = __dadd_rn(ai, mci);
-    const double s1r = __dsub_rn(ar, mcr), s1i = __dsub_rn(ai, mci);
+    const double mbr = __dsub_rn(__dmul_rn(o.br, wbr), __dmul_rn(o.bi, wbi)), mbi = __dadd_rn(__dmul_rn(o.br, wbi), __dmul_rn(o.bi, wbr));
+    const double mcr = __dsub_rn(__dmul_rn(o.cr, wcr), __dmul_rn(o.ci, wci)), mci = __dadd_rn(__dmul_rn(o.cr, wci), __dmul_rn(o.ci, wcr));
+    const double mdr = __dsub_rn(__dmul_rn(o.dr, wdr), __dmul_rn(o.di, wdi)), mdi = __dadd_rn(__dmul_rn(o.dr, wdi), __dmul_rn(o.di, wdr));
+    const double s0r = __dadd_rn(o.ar, mcr), s0i = __dadd_rn(o.ai, mci);
+    const double s1r = __dsub_rn(o.ar, mcr), s1i = __dsub_rn(o.ai, mci);
     const double s2r = __dadd_rn(mbr, mdr), s2i = __dadd_rn(mbi, mdi);
     const double s3r = __dsub_rn(mbr, mdr), s3i = __dsub_rn(mbi, mdi);        // inv == 1
     __stcg(out + pa, __dadd_rn(s0r, s2r));
@@ -420,6 +474,7 @@ __device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__
     };
     if constexpr (POWER % 2 == 0) {
         // _singleRealTransform4 (bundle:468-508): N/4 four-point transforms of the digit-reversed input
+#pragma unroll 4
         for (int u = tp; u < N / 4; u += TP) {
             const int off = int(unsigned(__ldg(rev + u)) >> 1);
             const double a = xw(off), b = xw(off + N / 4), c = xw(off + N / 2), d = xw(off + 3 * (N / 4));
@@ -432,6 +487,7 @@ __device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__
         }
     } else {
         // _singleRealTransform2 (bundle:447-463): N/2 two-point transforms
+#pragma unroll 8
         for (int u = tp; u < N / 2; u += TP) {
             const int off = int(unsigned(__ldg(rev + u)) >> 1);
             const double e = xw(off), qv = xw(off + N / 2);
@@ -441,13 +497,27 @@ __device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__
         }
     }
     pair_sync<TP>(pin);
+    // (butterflies of one stage touch disjoint slots -- the mirrored outputs land in the half of their
+    // sub-block no butterfly of the stage reads -- so they run in any order and in parallel)
+#pragma unroll
     for (int step = (1 << WIDTH) >> 2; step >= 2; step >>= 2) {
         const int len = (SIZE / step) << 1, h = len >> 1, q = h >> 1, hq = q >> 1;
         const int cpb = (hq >> 1) + 1;                                        // butterflies per block: i = 0, 2, .. hq
         const int total = (SIZE / len) * cpb;
-        for (int j = tp; j < total; j += TP) {
-            const int blk = j / cpb, ii = j - blk * cpb;
-            exact_real_butterfly(out, tw, blk * len, ii, step, q, h, hq);
+        constexpr int BATCH = 3;                                              // operand sets in flight per thread
+        for (int j0 = tp; j0 < total; j0 += BATCH * TP) {
+            ExactOperands ops[BATCH];
+            int blk[BATCH], ii[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const int j = j0 + u * TP;
+                blk[u] = j / cpb;
+                ii[u] = j - blk[u] * cpb;
+                if (j < total) ops[u] = exact_real_load(out, blk[u] * len, ii[u], q);
+            }
+#pragma unroll
+            for (int u = 0; u < BATCH; u++)
+                if (j0 + u * TP < total) exact_real_finish(out, tw, ops[u], blk[u] * len, ii[u], step, q, h, hq);
         }
         pair_sync<TP>(pin);
     }
@@ -842,6 +912,7 @@ pv_process_ring_kernel(const RingParams p) {
         {
             const float4 *hlo = tp ? runp - 3 : XQ;                   // bins 16 tp - 2, - 1 (thread 0: unused)
             int m0[20], m1[20];
+            float2 esum = make_float2(0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < 20; i++) {
                 const float4 v = (i < 2) ? hlo[i] : (i < 18) ? runp[i - 2] : runp[i - 1];   // i >= 18: bins 16 tp + 16, + 17 (slot 16 is padding)
@@ -849,11 +920,84 @@ pv_process_ring_kernel(const RingParams p) {
                 const float2 mg = fma2(re, re, mul2(im, im));         // pv:82-92, float32
                 m0[i] = __float_as_int(mg.x);
                 m1[i] = __float_as_int(mg.y);
+                if (i >= 2 && i < 18) esum = add2(esum, mg);          // own run: energy of the frame
             }
-            mask0 = ring_peak_mask(m0);
-            mask1 = ring_peak_mask(m1);
-            if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; }              // i >= 2
-            if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); }       // i <= nb - 3
+            if (p.guard_min == 0x7fffffff) {
+                mask0 = ring_peak_mask(m0);
+                mask1 = ring_peak_mask(m1);
+                if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; }          // i >= 2
+                if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); }       // i <= nb - 3
+            } else {
+                // ---- peak guard: frame energy per channel, uncertain comparisons, exact re-decision ----
+                constexpr int TPW = (TP < 32) ? TP : 32;
+#pragma unroll
+                for (int off = TPW / 2; off > 0; off >>= 1) {
+                    esum = add2(esum, make_float2(__shfl_xor_sync(FULL, esum.x, off), __shfl_xor_sync(FULL, esum.y, off)));
+                }
+                int *gscr = reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16) + 4 * TP + 8;   // multi-warp pairs only
+                if constexpr (G::WPP > 1) {
+                    if (lane == 0) {
+                        gscr[tp >> 5] = __float_as_int(esum.x);
+                        gscr[G::WPP + (tp >> 5)] = __float_as_int(esum.y);
+                    }
+                    pair_sync<TP>(pin);
+                    esum = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int w = 0; w < G::WPP; w++)
+                        esum = add2(esum, make_float2(__int_as_float(gscr[w]), __int_as_float(gscr[G::WPP + w])));
+                }
+                constexpr float KSCALE = -16.0f * PVB_GUARD_C * PVB_GUARD_C;
+                uint32_t unc0, unc1;
+                ring_peak_masks_guarded(m0, m1, mul2(esum, bc2(KSCALE)), mask0, mask1, unc0, unc1);
+                if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; unc0 &= ~3u; unc1 &= ~3u; }
+                if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); unc0 &= ~(1u << 15); unc1 &= ~(1u << 15); }
+                // uncertain comparisons of the whole frame, per channel
+                int n0 = __reduce_add_sync(FULL, __popc(unc0)), n1 = __reduce_add_sync(FULL, __popc(unc1));
+                if constexpr (G::WPP > 1) {
+                    if (lane == 0) {
+                        gscr[8 + (tp >> 5)] = n0;
+                        gscr[8 + G::WPP + (tp >> 5)] = n1;
+                    }
+                    pair_sync<TP>(pin);
+                    n0 = n1 = 0;
+#pragma unroll
+                    for (int w = 0; w < G::WPP; w++) {
+                        n0 += gscr[8 + w];
+                        n1 += gscr[8 + G::WPP + w];
+                    }
+                }
+                bool redo0 = n0 >= p.guard_min, redo1 = n1 >= p.guard_min;
+                redo1 = redo1 && has1;
+                if (redo0 | redo1) {
+                    // a scratch slot of 2N doubles from the pool (at least as many slots as pairs can be
+                    // resident on the device, so the probe always ends)
+                    int slot = 0;
+                    if (tp == 0) {
+                        slot = int((unsigned(pair) * 2654435761u) % unsigned(p.xslots));
+                        while (atomicCAS(p.xlocks + slot, 0u, 1u) != 0u) {
+                            slot = (slot + 1 == p.xslots) ? 0 : slot + 1;
+                            __nanosleep(100);
+                        }
+                        __threadfence();
+                        atomicAdd(p.xcount, (unsigned long long)(int(redo0) + int(redo1)));
+                    }
+                    if constexpr (G::WPP > 1) {
+                        if (tp == 0) gscr[16] = slot;
+                        pair_sync<TP>(pin);
+                        slot = gscr[16];
+                    } else {
+                        slot = __shfl_sync(FULL, slot, (TP == 32) ? 0 : int(threadIdx.x & (32 - TP)));
+                    }
+                    double *xo = p.xpool + size_t(slot) * size_t(2 * N);
+                    const float2 *ring = reinterpret_cast<const float2 *>(p.hist2 + size_t(pair) * (N / 2));
+                    if (redo0) mask0 = ring_exact_peak_mask<N, TP>(ring, p.window2, p.xtw, p.xrev, xo, t, 0, tp, pin);
+                    if (redo1) mask1 = ring_exact_peak_mask<N, TP>(ring, p.window2, p.xtw, p.xrev, xo, t, 1, tp, pin);
+                    if (tp == 0) {
+                        __threadfence();
+                        atomicExch(p.xlocks + slot, 0u);
+                    }
+                }
+            }
         }
 
         int dst0[16], dst1[16];

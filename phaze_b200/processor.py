@@ -86,6 +86,11 @@ class BatchedPhaseVocoder:
         """channel pairs whose completion flag never arrived (0 on a healthy handle)"""
         return self._lib.pvb_ring_stuck_count(self._h)
 
+    @property
+    def peak_guard_count(self) -> int:
+        """channel frames whose peak set was re-decided with the float64 transform so far"""
+        return self._lib.pvb_peak_guard_count(self._h)
+
     _OPTIONS = {"kernel": _lib.PVB_OPT_KERNEL, "launch_mode": _lib.PVB_OPT_LAUNCH_MODE,
                 "inputs_ready": _lib.PVB_OPT_INPUTS_READY, "peak_guard": _lib.PVB_OPT_PEAK_GUARD}
     _KERNELS = {"auto": 0, "ring": 1, "warp": 2, "cta": 3, "generic": 4}

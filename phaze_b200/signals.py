@@ -41,3 +41,17 @@ def uniform_noise(first: int, count: int, num_samples: int, amp: float = 1.0) ->
         rng = np.random.Generator(np.random.Philox(key=SEED_BASE + 0x10000000 + first + i))
         out[i] = (amp * rng.uniform(-1.0, 1.0, num_samples)).astype(np.float32)
     return out
+
+
+def bin_centred_sine(num_samples: int, frame: int, bin_index: int, amp: float = 0.5, phase: float = 0.3) -> np.ndarray:
+    """A sine whose period divides the frame: every bin but one is exactly zero in exact arithmetic,
+    so the reference's peak picking runs on its own float64 round-off pattern."""
+    n = np.arange(num_samples, dtype=np.float64)
+    return (amp * np.sin(2 * np.pi * bin_index * n / frame + phase)).astype(np.float32)
+
+
+def silence_then_tone(c: int, num_samples: int, start: int) -> np.ndarray:
+    """Digital silence, then noise-free tones (frames that are partly exact zeros)."""
+    x = channel(c, num_samples, noise=0.0)
+    x[:start] = 0.0
+    return x

@@ -43,10 +43,26 @@ CASES = [
 ]
 
 
-def run_case(name, frame, hop, channels, pf, calls, first):
+# ill-conditioned input (round 2): name, frame, hop, pitch factor, calls, signal maker(num_samples, frame)
+TONAL_CASES = [
+    ("tonal_1024_256_pf0.8_clean", 1024, 256, 0.8, 12,
+     lambda n, N: np.stack([signals.channel(30 + c, n, noise=0.0) for c in range(2)])),
+    ("tonal_2048_128_pf0.8_clean", None, None, 0.8, 20,
+     lambda n, N: np.stack([signals.channel(32, n, noise=0.0)])),
+    ("tonal_1024_256_pf1.2_noise1e-5", 1024, 256, 1.2, 10,
+     lambda n, N: np.stack([signals.channel(33, n, noise=1e-5)])),
+    ("sine_1024_256_pf0.8_bin40", 1024, 256, 0.8, 10,
+     lambda n, N: np.stack([signals.bin_centred_sine(n, N, 40)])),
+    ("silence_then_tone_1024_256_pf0.8", 1024, 256, 0.8, 12,
+     lambda n, N: np.stack([signals.silence_then_tone(70, n, 4 * 256 + 17)])),
+]
+
+
+def run_case(name, frame, hop, channels, pf, calls, first, make=None):
     ref = jsmini.ReferenceProcessor(frame, hop)
     N, H = ref.frame, ref.hop
-    x = signals.channels(first, channels, calls * H)
+    x = signals.channels(first, channels, calls * H) if make is None else make(calls * H, N)
+    channels = x.shape[0]
     y = ref.run(x, np.float32(pf))
     obj = ref.obj
     spec = np.array(obj.get("freqComplexBuffer").items, dtype=np.float64)      # last channel, last call
@@ -92,6 +108,10 @@ def run_scenario():
 
 
 if __name__ == "__main__":
-    for case in CASES:
-        run_case(*case)
-    run_scenario()
+    only_tonal = len(sys.argv) > 1 and sys.argv[1] == "tonal"
+    if not only_tonal:
+        for case in CASES:
+            run_case(*case)
+        run_scenario()
+    for name, frame, hop, pf, calls, make in TONAL_CASES:
+        run_case(name, frame, hop, 0, pf, calls, 0, make)
