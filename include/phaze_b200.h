@@ -97,6 +97,16 @@ PVB_API int32_t pvb_process_many_device(pvb_processor *p, const float *in_dev, f
 PVB_API int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t num_calls,
                          float pitch_factor);
 
+/* process() with ONE PITCH FACTOR PER CHANNEL: pitch_factors is a HOST array of num_channels float32
+ * (both variants; it is small, and the library needs its range to pick a kernel).  The reference takes
+ * one scalar per processor and call (phase-vocoder.js:47); a host that runs thousands of independent
+ * streams through one handle gives each its own.  Channel c gets exactly what a processor with the
+ * scalar pitch_factors[c] would compute.  The array is cached on the device and re-uploaded only when
+ * it changes. */
+PVB_API int32_t pvb_process_pf(pvb_processor *p, const float *in, float *out, const float *pitch_factors);
+PVB_API int32_t pvb_process_pf_device(pvb_processor *p, const float *in_dev, float *out_dev,
+                                      const float *pitch_factors, void *stream);
+
 /* wait for everything submitted on the handle's own stream */
 PVB_API int32_t pvb_sync(pvb_processor *p);
 
@@ -128,9 +138,9 @@ enum {
        compute |X|^2 from a float32 FFT and mark every comparison that falls inside the float32 error
        bound of the frame as uncertain.  A channel frame can be RE-DECIDED with a float64 transform that
        follows fft.js operation by operation (bit-identical peak set on any input).
-       0 (default): re-decide frames with two or more uncertain comparisons (noise-free tones, band-limited
-       material, silence followed by a tone: bins at the round-off floor come in clusters); a single
-       natural near-tie in a broadband frame keeps its float32 decision.
+       0 (default): re-decide frames with five or more uncertain comparisons (noise-free tones, band-limited
+       material, silence followed by a tone: bins at the round-off floor come in clusters); one or two
+       natural near-ties in a broadband frame keep their float32 decision.
        1: never (float32 decisions only, the test itself is skipped).  2: always (tests).
        3 strict: re-decide frames with one or more uncertain comparisons. */
     PVB_OPT_PEAK_GUARD = 4

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "pvb_process_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "pvb_process_many_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p]),
     "pvb_process_many": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float]),
+    "pvb_process_pf": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pvb_process_pf_device": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pvb_sync": (C.c_int32, [C.c_void_p]),
     "pvb_set_option": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64]),
     "pvb_get_option": (C.c_int64, [C.c_void_p, C.c_int32]),

@@ -8,6 +8,7 @@
 #include "pv_kernel_warp.cuh"
 #include "pv_kernel_cta.cuh"
 #include "pv_kernel_ring.cuh"
+#include "pv_ring_launch.h"
 
 #include <cmath>
 #include <cstdarg>
@@ -41,6 +42,10 @@ struct pvb_processor {
     // peak guard (pv_kernel_ring.cuh): shared per (device, frame size), see acquire_exact_pool
     struct ExactPool *xpool = nullptr;
     unsigned long long *d_xcount = nullptr;   // channel frames re-decided in float64 so far
+    // per-channel pitch factors (pvb_process_pf): last array uploaded, its device copy, its range
+    std::vector<float> h_pf;
+    float *d_pf = nullptr;
+    bool pf_fast = false;            // every channel inside the ring-order kernel's range
     // pvb_set_option
     int opt_kernel = 0, opt_launch_mode = 0, opt_inputs_ready = 0, opt_peak_guard = 0;
     cudaStream_t last_stream = nullptr;   // stream of the most recent submission (state entry points wait for it)
@@ -332,6 +337,12 @@ enum KernelFamily { K_RING = 1, K_WARP = 2, K_CTA = 3, K_GENERIC = 4 };
 // the kernel family a call with these parameters runs on (PVB_OPT_KERNEL: first family to try)
 KernelFamily pick_kernel(const pvb_processor *h, const pvb::FrameParams &fp) {
     const int first = h->opt_kernel ? h->opt_kernel : K_RING;
+    if (fp.pf_ch) {
+        // per-channel pitch factors: the ring-order kernel when every channel is in its range, else the
+        // generic kernel (the only other family that reads pf_ch)
+        if (first <= K_RING && h->pf_fast && fp.overlaps <= 32 && ring_geometry_ok(h)) return K_RING;
+        return K_GENERIC;
+    }
     if (first <= K_RING && fast_range(fp) && ring_geometry_ok(h)) return K_RING;
     if (first <= K_WARP && warp_kernel_applies(h->n, fp)) return K_WARP;
     if (first <= K_CTA && fast_range(fp)) return K_CTA;
@@ -363,6 +374,7 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
     rp.pitch_factor = fp.pitch_factor;
     rp.pf_mant = fp.pf_mant;
     rp.pf_shift = fp.pf_shift;
+    rp.pf_ch = fp.pf_ch;
     rp.stagger_ns = experiments().stagger_ns;
     rp.skip = experiments().skip;
     const bool pdl = h->opt_launch_mode != 2;
@@ -400,8 +412,9 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
         if (last_flag) rp.early = 0;
         last_flag = safe;
     }
-    // PVB_OPT_PEAK_GUARD: 0 auto (two or more uncertain comparisons), 1 off, 2 always, 3 strict (one or more)
-    rp.guard_min = h->opt_peak_guard == 1 ? 0x7fffffff : h->opt_peak_guard == 2 ? 0 : h->opt_peak_guard == 3 ? 1 : 2;
+    // PVB_OPT_PEAK_GUARD: 0 auto (five or more uncertain comparisons: one natural near-tie between two
+    // neighbouring bins makes two), 1 off, 2 always, 3 strict (one or more)
+    rp.guard_min = h->opt_peak_guard == 1 ? 0x7fffffff : h->opt_peak_guard == 2 ? 0 : h->opt_peak_guard == 3 ? 1 : 5;
     rp.xtw = h->xpool->tw;
     rp.xrev = h->xpool->rev;
     rp.xpool = h->xpool->pool;
@@ -415,70 +428,39 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
     return rp;
 }
 
-// one frame size of the ring-order kernel: pairs per CTA, launch configuration (programmatic dependent
-// launch: CTAs of this launch may become resident and stage their tables while the previous kernel on
-// the stream drains; the kernel itself orders its accesses, see pv_kernel_ring.cuh), and the instance
-// for this hop.  NBLK counts role units of RingGeoT<N>::UNIT samples (64 at frame 256, else 128).
-template <int N, int... NBLKS>
-cudaError_t launch_ring_n(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, int ppc,
-                          bool input_ready) {
-    using G = pvb::RingGeoT<N>;
-    const int pairs = (fp.num_channels + 1) / 2;
-    if (experiments().ring_wpc >= G::MIN_PAIRS && experiments().ring_wpc <= G::MAX_PAIRS)
-        ppc = experiments().ring_wpc;                           // PVB_RING_WPC
-    pvb::RingParams rp = make_ring_params(h, fp, s, input_ready);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((pairs + ppc - 1) / ppc);
-    cfg.blockDim = dim3(ppc * G::TP);
-    // PVB_RING_PAD_KB: occupancy experiment (extra dynamic shared memory per CTA)
-    cfg.dynamicSmemBytes = G::TAB_BYTES + size_t(ppc) * G::PAIR_BYTES + size_t(experiments().ring_pad_kb) * 1024;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = h->opt_launch_mode == 2 ? 0 : 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
-    const int nblk = rp.hop / G::UNIT;
-    cudaError_t e = cudaErrorInvalidValue;                      // no instance for this hop
-    (void)std::initializer_list<int>{
-        (nblk == NBLKS ? (e = cudaLaunchKernelEx(&cfg, pvb::pv_process_ring_kernel<N, NBLKS>, rp), 0) : 0)...};
-    return e;
-}
-
-template <int N, int... NBLKS>
-cudaError_t ring_set_smem_attr() {
-    cudaError_t e = cudaSuccess;
-    (void)std::initializer_list<int>{
-        (e == cudaSuccess ? (e = cudaFuncSetAttribute(pvb::pv_process_ring_kernel<N, NBLKS>,
-                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), 0)
-                          : 0)...};
-    return e;
-}
-
+// The ring-order kernel instances live in pv_ring_inst.cu (one translation unit per frame size).
+// Pairs per CTA: frame 1024 balances one wave (4..7 warps); the other sizes fill their CTAs (frame 256:
+// 32 quarter-warp pairs, 512: 16 half-warp pairs, 2048: 4 pairs of two warps, 4096: 2 pairs of four).
 cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = ring_set_smem_attr<256, 1, 2>();
-        if (e == cudaSuccess) e = ring_set_smem_attr<512, 1, 2>();
-        if (e == cudaSuccess) e = ring_set_smem_attr<1024, 1, 2, 4>();
-        if (e == cudaSuccess) e = ring_set_smem_attr<2048, 1, 2, 4, 8>();
-        if (e == cudaSuccess) e = ring_set_smem_attr<4096, 2, 4, 8, 16>();
+        cudaError_t e = pvb::ring_configure_256();
+        if (e == cudaSuccess) e = pvb::ring_configure_512();
+        if (e == cudaSuccess) e = pvb::ring_configure_1024();
+        if (e == cudaSuccess) e = pvb::ring_configure_2048();
+        if (e == cudaSuccess) e = pvb::ring_configure_4096();
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    const int pairs = (fp.num_channels + 1) / 2;
-    if (pairs == 0) return cudaSuccess;
-    // pairs per CTA: frame 1024 balances one wave (4..7 warps); the other sizes fill their CTAs (frame 256:
-    // 32 quarter-warp pairs, 512: 16 half-warp pairs, 2048: 4 pairs of two warps, 4096: 2 pairs of four)
+    pvb::RingLaunch l;
+    l.pairs = (fp.num_channels + 1) / 2;
+    if (l.pairs == 0) return cudaSuccess;
+    l.ppc = (h->n == 1024) ? pick_warps_per_cta(l.pairs, h->num_sms) : 0;
+    if (experiments().ring_wpc > 0) l.ppc = experiments().ring_wpc;           // PVB_RING_WPC
+    l.pad_kb = experiments().ring_pad_kb;                                     // PVB_RING_PAD_KB
+    l.pdl = h->opt_launch_mode != 2;
+    l.pch = fp.pf_ch != nullptr;
+    l.stream = s;
+    pvb::RingParams rp = make_ring_params(h, fp, s, input_ready);
+    const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
     switch (h->n) {
-        case 256: return launch_ring_n<256, 1, 2>(h, fp, s, pvb::RingGeoT<256>::MAX_PAIRS, input_ready);
-        case 512: return launch_ring_n<512, 1, 2>(h, fp, s, pvb::RingGeoT<512>::MAX_PAIRS, input_ready);
-        case 1024: return launch_ring_n<1024, 1, 2, 4>(h, fp, s, pick_warps_per_cta(pairs, h->num_sms), input_ready);
-        case 2048: return launch_ring_n<2048, 1, 2, 4, 8>(h, fp, s, pvb::RingGeoT<2048>::MAX_PAIRS, input_ready);
-        case 4096: return launch_ring_n<4096, 2, 4, 8, 16>(h, fp, s, pvb::RingGeoT<4096>::MAX_PAIRS, input_ready);
+        case 256: return pvb::ring_launch_256(rp, l);
+        case 512: return pvb::ring_launch_512(rp, l);
+        case 1024: return pvb::ring_launch_1024(rp, l);
+        case 2048: return pvb::ring_launch_2048(rp, l);
+        case 4096: return pvb::ring_launch_4096(rp, l);
     }
     return cudaErrorInvalidValue;
 }
@@ -642,17 +624,52 @@ int check_device_error(pvb_processor *p) {
     return PVB_OK;
 }
 
+// Per-channel pitch factors: keep the last array on the device; a changed array is copied on the
+// launch stream (stream-ordered behind every launch that still reads the old one).
+int upload_pitch_factors(pvb_processor *p, const float *pf_host, cudaStream_t s) {
+    const size_t c = size_t(p->channels);
+    if (c == 0) return PVB_OK;
+    if (p->d_pf && p->h_pf.size() == c && std::memcmp(p->h_pf.data(), pf_host, c * sizeof(float)) == 0) return PVB_OK;
+    if (!p->d_pf || p->h_pf.size() != c) {
+        PVB_CUDA(p, sync_all(p));
+        cudaFree(p->d_pf);
+        p->d_pf = nullptr;
+        if (cudaMalloc(&p->d_pf, state_rows(p->channels) * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(p, PVB_ERR_NOMEM, "cudaMalloc of the pitch-factor array failed");
+        }
+    }
+    p->h_pf.assign(pf_host, pf_host + c);
+    p->pf_fast = true;
+    for (size_t i = 0; i < c; i++) {
+        int m = 0, sh = 0;
+        split_pitch_factor(pf_host[i], &m, &sh);
+        if (!(sh >= 1 && pf_host[i] >= 0.75f && pf_host[i] <= 64.0f)) p->pf_fast = false;
+    }
+    // (pageable source: the runtime stages it before returning, so h_pf may change right after)
+    PVB_CUDA(p, cudaMemcpyAsync(p->d_pf, p->h_pf.data(), c * sizeof(float), cudaMemcpyHostToDevice, s));
+    std::lock_guard<std::mutex> lk(g_stream_mu);
+    g_last_flag_mode[s] = false;        // the copy waited for everything before it; so does what follows
+    g_recent_io[s].clear();
+    return PVB_OK;
+}
+
 // `inputs_ready`: the input of the FIRST launch is known to be complete before it can start (the
 // library's own staging buffers, or PVB_OPT_INPUTS_READY); later launches of the submission start
-// behind the first one and inherit the guarantee
+// behind the first one and inherit the guarantee.  `pf_host`: per-channel pitch factors or nullptr.
 int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls, float pf,
-           cudaStream_t s, bool inputs_ready, CallHooks *hooks = nullptr) {
+           cudaStream_t s, bool inputs_ready, CallHooks *hooks = nullptr, const float *pf_host = nullptr) {
     const size_t block = size_t(p->channels) * size_t(p->hop);
     {
         const int rc = check_device_error(p);
         if (rc != PVB_OK) return rc;
     }
     p->last_stream = s;
+    if (pf_host) {
+        const int rc = upload_pitch_factors(p, pf_host, s);
+        if (rc != PVB_OK) return rc;
+        pf = 1.0f;
+    }
     for (int k = 0; k < num_calls; k++) {
         if (hooks) hooks->before(k, s);
         pvb::FrameParams fp;
@@ -669,6 +686,7 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         fp.step_mod_r = int(p->cursor_calls % uint64_t(p->overlaps));
         fp.src_limit = source_limit(p->n, pf);
         fp.pitch_factor = pf;
+        fp.pf_ch = (pf_host && p->channels > 0) ? p->d_pf : nullptr;
         split_pitch_factor(pf, &fp.pf_mant, &fp.pf_shift);
         if (p->channels > 0) {
             const int rc = ensure_layout(p, ring_kernel_applies(p, fp) ? pvb_processor::PAIRED
@@ -843,6 +861,7 @@ void pvb_destroy(pvb_processor *p) {
     cudaFree(p->d_out);
     if (p->h_err) cudaFreeHost(p->h_err);
     cudaFree(p->d_xcount);
+    cudaFree(p->d_pf);
     if (p->xpool) release_exact_pool(p->device, p->n);
     for (cudaEvent_t e : p->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : p->ev_done) cudaEventDestroy(e);
@@ -945,6 +964,35 @@ int32_t pvb_process(pvb_processor *p, const float *in, float *out, float pitch_f
     return pvb_process_many(p, in, out, 1, pitch_factor);
 }
 
+int32_t pvb_process_pf_device(pvb_processor *p, const float *in_dev, float *out_dev,
+                              const float *pitch_factors, void *stream) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    if (!out_dev || !pitch_factors) return fail(p, PVB_ERR_BAD_ARG, "pvb_process_pf: bad argument");
+    DeviceGuard guard(p->device);
+    return submit(p, in_dev, out_dev, 1, 1.0f, stream ? static_cast<cudaStream_t>(stream) : p->stream,
+                  p->opt_inputs_ready != 0, nullptr, pitch_factors);
+}
+
+int32_t pvb_process_pf(pvb_processor *p, const float *in, float *out, const float *pitch_factors) {
+    if (!p) return PVB_ERR_BAD_ARG;
+    if (!out || !pitch_factors) return fail(p, PVB_ERR_BAD_ARG, "pvb_process_pf: bad argument");
+    DeviceGuard guard(p->device);
+    const size_t floats = size_t(p->channels) * size_t(p->hop);
+    if (floats == 0) {
+        p->ring_calls++;
+        p->cursor_calls++;
+        return PVB_OK;
+    }
+    int rc = ensure_staging(p, floats);
+    if (rc != PVB_OK) return rc;
+    if (in) PVB_CUDA(p, cudaMemcpyAsync(p->d_in, in, floats * sizeof(float), cudaMemcpyHostToDevice, p->stream));
+    rc = submit(p, in ? p->d_in : nullptr, p->d_out, 1, 1.0f, p->stream, true, nullptr, pitch_factors);
+    if (rc != PVB_OK) return rc;
+    PVB_CUDA(p, cudaMemcpyAsync(out, p->d_out, floats * sizeof(float), cudaMemcpyDeviceToHost, p->stream));
+    PVB_CUDA(p, cudaStreamSynchronize(p->stream));
+    return check_device_error(p);
+}
+
 int32_t pvb_sync(pvb_processor *p) {
     if (!p) return PVB_ERR_BAD_ARG;
     DeviceGuard guard(p->device);
@@ -961,6 +1009,9 @@ int32_t pvb_resize(pvb_processor *p, int32_t num_channels) {
     cudaFree(p->d_out);
     p->d_in = p->d_out = nullptr;
     p->staging_floats = 0;
+    cudaFree(p->d_pf);
+    p->d_pf = nullptr;
+    p->h_pf.clear();
     int rc = alloc_state(p, num_channels);     // ola:54-88: fresh zeroed buffers (also clears the error word)
     if (rc != PVB_OK) return rc;
     PVB_CUDA(p, cudaStreamSynchronize(p->stream));
@@ -1043,6 +1094,7 @@ int64_t pvb_get_option(const pvb_processor *p, int32_t option) {
 const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
     if (!p) return "";
     pvb::FrameParams fp{};
+    fp.pf_ch = nullptr;
     fp.pitch_factor = pitch_factor;
     fp.overlaps = p->overlaps;
     split_pitch_factor(pitch_factor, &fp.pf_mant, &fp.pf_shift);

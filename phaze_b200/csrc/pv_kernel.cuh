@@ -43,20 +43,41 @@ struct FrameParams {
     float pitch_factor;
     int pf_mant;           // pitch_factor == pf_mant * 2^-pf_shift exactly (float32 mantissa)
     int pf_shift;          // in [1, 62] when the integer form is usable, else 0 (use float64)
+    const float *pf_ch;    // per-channel pitch factors [C] (pvb_process_pf) or nullptr: pitch_factor for all
 };
 
+// pitch factor of channel c as the exact fraction mant * 2^-shift (shift 0: use float64)
+struct PitchFactor {
+    float value;
+    int mant, shift;
+};
+__device__ __forceinline__ PitchFactor channel_pitch_factor(const FrameParams &fp, int c) {
+    PitchFactor r{fp.pitch_factor, fp.pf_mant, fp.pf_shift};
+    if (fp.pf_ch) {
+        r.value = __ldg(fp.pf_ch + c);
+        const unsigned b = __float_as_uint(r.value);
+        const int e = int((b >> 23) & 0xFFu);
+        // normal, finite, non-zero: value == (-1)^sign (2^23 + fraction) 2^(e - 150)
+        const int m = int((b & 0x7FFFFFu) | 0x800000u);
+        r.mant = (b >> 31) ? -m : m;
+        r.shift = 150 - e;
+        if (e == 0 || e == 255 || r.shift < 1 || r.shift > 62) r.shift = 0;
+    }
+    return r;
+}
+
 // Math.round(p * pitchFactor) (pv:125): round half up of an exact product
-__device__ __forceinline__ int round_shifted_peak(int p, const FrameParams &fp) {
-    if (fp.pf_shift > 0) {
-        const long long v = (long long)fp.pf_mant * p + (1ll << (fp.pf_shift - 1));
-        const long long r = v >> fp.pf_shift;
+__device__ __forceinline__ int round_shifted_peak(int p, int pf_mant, int pf_shift, float pitch_factor) {
+    if (pf_shift > 0) {
+        const long long v = (long long)pf_mant * p + (1ll << (pf_shift - 1));
+        const long long r = v >> pf_shift;
         return r > 0x3fffffff ? 0x3fffffff : (r < -0x3fffffff ? -0x3fffffff : int(r));
     }
     // float64 fallback (pitch factors whose exponent does not fit the integer form, infinities, NaN).
     // Math.round(NaN) is NaN: every comparison of pv:127 / pv:150 is false and the writes go to the
     // property "NaN" of the Array, i.e. nowhere -- the shifted spectrum stays zero.  A value beyond nb
     // has the same effect here (pv:127 `break`).
-    const double v = fma(double(p), double(fp.pitch_factor), 0.5);
+    const double v = fma(double(p), double(pitch_factor), 0.5);
     if (v != v) return 0x3fffffff;
     const double r = floor(v);
     return r > 1073741823.0 ? 0x3fffffff : (r < -1073741823.0 ? -0x3fffffff : int(r));
@@ -407,8 +428,12 @@ pv_process_kernel(const FrameParams p) {
 
     // ---- P4: shift every region of influence to its new place -----------------------------
     {
-        const int limit = p.src_limit;
-        const bool contract = p.pitch_factor < 1.0f;     // only then two sources can hit one bin
+        // per-channel pitch factors (pvb_process_pf): every source bin may land, and colliding regions
+        // are possible whenever some channel contracts (adding to a zeroed bin is exact, so the atomic
+        // path is taken for all channels then)
+        const int limit = p.pf_ch ? N : p.src_limit;
+        const bool contract = p.pf_ch ? true : p.pitch_factor < 1.0f;     // only then two sources can hit one bin
+        const PitchFactor pfa = channel_pitch_factor(p, has0 ? c0 : 0), pfb = channel_pitch_factor(p, has1 ? c1 : (has0 ? c0 : 0));
         const int rmask = p.overlaps - 1;
         const int rstride = N / p.overlaps;
         for (int idx = t; idx < 2 * limit; idx += T) {
@@ -417,7 +442,8 @@ pv_process_kernel(const FrameParams p) {
             const uint32_t *pkc = pk + ch * NWORDS;
             const int pi = owner_peak(pkc, b, NWORDS);
             if (pi < 0) continue;                                        // no peaks at all
-            const int ps = round_shifted_peak(pi, p);                    // Math.round, pv:125
+            const PitchFactor &pfc = ch ? pfb : pfa;
+            const int ps = round_shifted_peak(pi, pfc.mant, pfc.shift, pfc.value);     // Math.round, pv:125
             if (ps > NB) continue;                                       // pv:127
             const int delta = ps - pi;
             const int d = b + delta;

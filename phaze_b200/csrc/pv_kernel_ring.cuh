@@ -58,8 +58,10 @@ namespace pvb {
 #define PVB_RING_PAIRS_1024 7
 #endif
 
-template <int N_>
+// PCH: per-channel pitch factors (pvb_process_pf): the key table becomes per pair (two deltas per bin)
+template <int N_, bool PCH_ = false>
 struct RingGeoT {
+    static constexpr bool PCH = PCH_;
     static constexpr int N = N_, M = N / 2, NB = M + 1;
     static constexpr int TP = N / 32;                       // threads per channel pair (16 complex points each):
                                                             // half a warp (512), a warp (1024), two warps (2048)
@@ -99,10 +101,13 @@ struct RingGeoT {
     // two pairs per warp (frame 512): their buffers sit 16 banks apart, so the 32-bit plane accesses
     // of the two half-warps (16 consecutive words each) do not collide
     // (frame 256: four pairs per warp, 8 banks apart)
-    static constexpr int PAIR_PAD = (TP < 32) ? ((TP == 16 ? 64 : 32) + 128 - (BUF_SLOTS * 16) % 128) % 128 : 0;
-    static constexpr int PAIR_BYTES = BUF_SLOTS * 16 + SCR_BYTES + PAIR_PAD;
+    // key table: bin p at p + 4 (p >> 4).  One per CTA (scalar pitch factor) or one per pair (PCH)
+    static constexpr int DTAB_BYTES = ((NB + 1 + 4 * ((NB >> 4) + 1)) * 4 + 15) & ~15;
+    static constexpr int KT_BYTES = PCH ? DTAB_BYTES : 0;
+    static constexpr int PAIR_RAW = BUF_SLOTS * 16 + SCR_BYTES + KT_BYTES;
+    static constexpr int PAIR_PAD = (TP < 32) ? ((TP == 16 ? 64 : 32) + 128 - PAIR_RAW % 128) % 128 : 0;
+    static constexpr int PAIR_BYTES = PAIR_RAW + PAIR_PAD;
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
-    static constexpr int DTAB_BYTES = ((NB + 1 + 4 * ((NB >> 4) + 1)) * 4 + 15) & ~15;   // key table: bin p at p + 4 (p >> 4)
     static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
     static constexpr int TW1_BYTES = R1 * TW1_ROW * 8;      // tw1[k1][n] = W_M^{n k1}, n < 64
     static constexpr int W64_BYTES = 64 * 8;                // w64[a][b] = W_64^{a b}
@@ -115,7 +120,7 @@ struct RingGeoT {
     static constexpr bool GT = (N == 4096);
     static constexpr int TWH_SMEM = GT ? 0 : TWH_BYTES, WIN_SMEM = GT ? 0 : WIN_BYTES;
     // global: NTAB x tw1 | w64 | w128 | twh; shared: ktab | tw1 | w64 | w128 | twh | window | window_out
-    static constexpr int OFF_TW1 = DTAB_BYTES;
+    static constexpr int OFF_TW1 = PCH ? 0 : DTAB_BYTES;
     static constexpr int OFF_W64 = OFF_TW1 + TW1_BYTES;
     static constexpr int OFF_W128 = OFF_W64 + W64_BYTES;
     static constexpr int OFF_TWH = OFF_W128 + W128_BYTES;
@@ -123,12 +128,13 @@ struct RingGeoT {
     static constexpr int OFF_WOUT = OFF_WIN + WIN_SMEM;
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_SMEM;
     static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024
-                                     : (N == 2048) ? 4 : 2;                 // pairs per CTA
+                                     : (N == 2048) ? (PCH ? 3 : 4) : 2;     // pairs per CTA (two CTAs per SM must fit 227 KB)
     static constexpr int CTAS_PER_SM = 2;                   // frame 4096: 30 KB of tables + 2 x 36 KB per CTA
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
     static constexpr int MIN_PAIRS = (MIN_THREADS + TP - 1) / TP;
     static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin
+    static_assert(2 * (TAB_BYTES + MAX_PAIRS * PAIR_BYTES) <= 227 * 1024, "two CTAs per SM must fit the shared memory");
 };
 using RingGeo = RingGeoT<1024>;
 
@@ -155,6 +161,7 @@ struct RingParams {
     unsigned *err;              // sticky device-error word (mapped host memory): pairs whose flag never arrived
     float pitch_factor;
     int pf_mant, pf_shift;      // pitch_factor == pf_mant * 2^-pf_shift (exact)
+    const float *pf_ch;         // PCH kernels: [C] pitch factor per channel, every one in the kernel's range
     // peak guard (see ring_exact_peak_mask): a channel frame is re-decided in float64 when it has at least
     // this many uncertain comparisons (0: always; 0x7fffffff: never, and the test itself is skipped)
     int guard_min;
@@ -394,12 +401,14 @@ __device__ __forceinline__ int ring_thread_last(const int *bal) {
 // q = m + nbmax.  A channel with no uncertain comparison has the reference's peak set.
 //
 // Policy (RingParams::guard_min; PVB_OPT_PEAK_GUARD).  Frames in trouble have CLUSTERS of bins at the
-// round-off floor, i.e. many uncertain comparisons; a well-conditioned broadband frame has none, or
-// (0.6 % of frames at a -20 dB floor) a single natural near-tie, which the float32 decision gets right
-// 24 times out of 25.  The default re-decides every frame with two or more uncertain comparisons
-// (clean tones: ~95 % of frames; the benchmark's input: 2e-5 of frames), "strict" every frame with one
-// or more (outputs identical to re-deciding everything, at the price of ~25 slow channel pairs in
-// every 4096-channel launch, which the launch chain has to wait for).
+// round-off floor, i.e. tens of uncertain comparisons; a well-conditioned broadband frame has none, or
+// (0.6 % of frames at a -20 dB floor) one natural near-tie between two neighbouring bins, which shows
+// up as two uncertain comparisons (each bin against the other) and which the float32 decision gets
+// right in most cases (measured: tests/test_gpu_peak_guard.py).  The default re-decides every frame
+// with FIVE or more uncertain comparisons (clean tones: ~95 % of frames; the benchmark's input: none
+// in 4 million frames); "strict" re-decides on one or more -- its outputs are identical to re-deciding
+// everything, at the price of ~25 slow channel pairs in every 4096-channel launch, and since every
+// launch of the chain has to wait for its slowest pair that costs 30 % of the throughput.
 //
 // Re-decision (rare; all of a tonal stream): the pair recomputes that channel's squared magnitudes with
 // ring_exact_peak_mask below -- fft.js's realTransform restated operation by operation in float64 on
@@ -545,10 +554,10 @@ __device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__
 // ring blocks of the rotated register array is the DFT over f times W_R1^{toff k1} (shift
 // theorem); that factor is folded into the first-pass twiddles, W_M^{(n + 64 toff) k1}: the host
 // keeps one such table per toff and the CTA stages the one it needs.
-template <int N, int NBLK>
-__global__ void __launch_bounds__(RingGeoT<N>::MAX_PAIRS * RingGeoT<N>::TP, RingGeoT<N>::CTAS_PER_SM)
+template <int N, int NBLK, bool PCH = false>
+__global__ void __launch_bounds__(RingGeoT<N, PCH>::MAX_PAIRS * RingGeoT<N, PCH>::TP, RingGeoT<N, PCH>::CTAS_PER_SM)
 pv_process_ring_kernel(const RingParams p) {
-    using G = RingGeoT<N>;
+    using G = RingGeoT<N, PCH>;
     constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -564,7 +573,6 @@ pv_process_ring_kernel(const RingParams p) {
     // lanes of this thread's pair inside its warp (frame 512: half a warp)
     const unsigned FULL = (TP == 16) ? (0xFFFFu << (threadIdx.x & 16))
                           : (TP == 8) ? (0xFFu << (threadIdx.x & 24)) : 0xFFFFFFFFu;
-    int *ktab = reinterpret_cast<int *>(smem_raw);
     const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
     const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
     // (frame 4096: twh and the windows are read from global memory, see RingGeoT::GT)
@@ -579,6 +587,10 @@ pv_process_ring_kernel(const RingParams p) {
     constexpr float WOUT_SCALE = G::GT ? 1.0f / (2.0f * float(N) * float(N / (NBLK * G::UNIT))) : 1.0f;
 #define PVB_TLD2(ptr) (G::GT ? __ldg(ptr) : *(ptr))
     unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(pin) * G::PAIR_BYTES;
+    // key table: what a peak at bin pk contributes to the region scan.  Scalar pitch factor: one table per
+    // CTA, entry = position | delta.  PCH: one per pair, entry = delta of channel 0 | delta of channel 1
+    // (the position is the index)
+    int *ktab = PCH ? reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16 + G::SCR_BYTES) : reinterpret_cast<int *>(smem_raw);
     float4 *ex = reinterpret_cast<float4 *>(mine);
     float4 *XQ = reinterpret_cast<float4 *>(mine);
 
@@ -637,18 +649,19 @@ pv_process_ring_kernel(const RingParams p) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_wout + 16 * i), "l"(w2 + i));
             }
         }
-        // key table: what a peak at bin pk contributes to the region scan: its position and
         // delta = round(pk * pitchFactor) - pk in exact integer arithmetic (pv:125-127)
-        const long long pf_m = p.pf_mant;
-        const int pf_s = p.pf_shift;
-        const long long half = 1ll << (pf_s - 1);
+        if constexpr (!PCH) {
+            const long long pf_m = p.pf_mant;
+            const int pf_s = p.pf_shift;
+            const long long half = 1ll << (pf_s - 1);
 #pragma unroll
-        for (int k = 0; k < (NB + 1 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
-            const int pk = threadIdx.x + k * blockDim.x;
-            if (pk <= NB) {
-                const long long ps = (pf_m * pk + half) >> pf_s;
-                const int delta = (ps <= NB) ? int(ps) - pk : G::INVALID_DELTA;
-                ktab[pk + 4 * (pk >> 4)] = ((2 * (pk + 2048)) << 16) | (delta + 32768);
+            for (int k = 0; k < (NB + 1 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
+                const int pk = threadIdx.x + k * blockDim.x;
+                if (pk <= NB) {
+                    const long long ps = (pf_m * pk + half) >> pf_s;
+                    const int delta = (ps <= NB) ? int(ps) - pk : G::INVALID_DELTA;
+                    ktab[pk + 4 * (pk >> 4)] = ((2 * (pk + 2048)) << 16) | (delta + 32768);
+                }
             }
         }
     }
@@ -758,6 +771,25 @@ pv_process_ring_kernel(const RingParams p) {
                 r[e] = make_float4(u0.x, u0.y, u1.x, u1.y);           // interleaved below
             } else if (!(early && (role < OLDTO || early == 2))) {
                 r[e] = hl[PVB_RING_IDX(h, f)];
+            }
+        }
+    }
+    float pfc0 = p.pitch_factor, pfc1 = p.pitch_factor;               // pitch factor of each channel of the pair
+    if constexpr (PCH) {
+        // (placed here so that the integer work runs under the frame loads issued above)
+        if (live) {
+            pfc0 = __ldg(p.pf_ch + 2 * pair);
+            pfc1 = (2 * pair + 1 < p.num_channels) ? __ldg(p.pf_ch + 2 * pair + 1) : 1.0f;
+            // float32 == mant * 2^-shift exactly (the host admits only normal values in the kernel's range)
+            const unsigned b0 = __float_as_uint(pfc0), b1 = __float_as_uint(pfc1);
+            const long long m0 = (long long)((b0 & 0x7FFFFFu) | 0x800000u), m1 = (long long)((b1 & 0x7FFFFFu) | 0x800000u);
+            const int s0 = 150 - int((b0 >> 23) & 0xFFu), s1 = 150 - int((b1 >> 23) & 0xFFu);
+            const long long h0 = 1ll << (s0 - 1), h1 = 1ll << (s1 - 1);
+            for (int pk = tp; pk <= NB; pk += TP) {
+                const long long ps0 = (m0 * pk + h0) >> s0, ps1 = (m1 * pk + h1) >> s1;
+                const int d0 = (ps0 <= NB) ? int(ps0) - pk : G::INVALID_DELTA;
+                const int d1 = (ps1 <= NB) ? int(ps1) - pk : G::INVALID_DELTA;
+                ktab[pk + 4 * (pk >> 4)] = (d0 + 32768) | ((d1 + 32768) << 16);
             }
         }
     }
@@ -906,7 +938,10 @@ pv_process_ring_kernel(const RingParams p) {
     // threads that own runs 16 bins apart then spreads over all banks.
     if (!(xskip & 1))
     {
-        const bool contract = p.pitch_factor < 1.0f;
+        // contracting shifts (pitch factor < 1) read stale upper bins and let regions collide; per channel
+        // with per-channel pitch factors, and the pair takes the extra steps if either channel needs them
+        const bool contract0 = pfc0 < 1.0f, contract1 = pfc1 < 1.0f;
+        const bool contract = contract0 | contract1;
         const float4 *runp = XQ + 17 * tp;                            // slot of bin 16 tp
         uint32_t mask0, mask1;
         {
@@ -1005,15 +1040,32 @@ pv_process_ring_kernel(const RingParams p) {
         bool any0, any1;
         {
             const int *krun = ktab + 20 * tp;                         // keys of bins 16 tp .. + 15
-            int rk[16];
+            int rk[16], rk1[16];                                      // (rk1: PCH only)
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int4 kv = *reinterpret_cast<const int4 *>(krun + 4 * i);
                 rk[4 * i] = kv.x; rk[4 * i + 1] = kv.y; rk[4 * i + 2] = kv.z; rk[4 * i + 3] = kv.w;
             }
+            // PCH: table word = delta field of channel 0 | channel 1; key = position of the bin | delta field
+            const int posk = (2 * (16 * tp + 2048)) << 16;            // position part of the key of bin 16 tp
+            if constexpr (PCH) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int w = rk[e];
+                    rk[e] = (w & 0xFFFF) + posk + (e << 17);
+                    rk1[e] = int(unsigned(w) >> 16) + posk + (e << 17);
+                }
+            }
             // keys of the nearest peaks below / above this thread's run, and of the last peak
-            const int ol0 = krun[(31 - __clz(mask0)) & 15], of0 = krun[(__ffs(mask0) - 1) & 15];
-            const int ol1 = krun[(31 - __clz(mask1)) & 15], of1 = krun[(__ffs(mask1) - 1) & 15];
+            const int il0 = (31 - __clz(mask0)) & 15, if0 = (__ffs(mask0) - 1) & 15;
+            const int il1 = (31 - __clz(mask1)) & 15, if1 = (__ffs(mask1) - 1) & 15;
+            int ol0 = krun[il0], of0 = krun[if0], ol1 = krun[il1], of1 = krun[if1];
+            if constexpr (PCH) {
+                ol0 = (ol0 & 0xFFFF) + posk + (il0 << 17);
+                of0 = (of0 & 0xFFFF) + posk + (if0 << 17);
+                ol1 = int(unsigned(ol1) >> 16) + posk + (il1 << 17);
+                of1 = int(unsigned(of1) >> 16) + posk + (if1 << 17);
+            }
             int pk0, nk0, lk0, pk1, nk1, lk1;
             const int none_above = (2 * 8190) << 16;                  // "peak" at +6142; below: key 0 = "peak" at -2048
             if constexpr (TP <= 32) {
@@ -1061,9 +1113,11 @@ pv_process_ring_kernel(const RingParams p) {
             dl1 = (lk1 & 0xFFFF) - 32768;
             // both scans run unconditionally (a channel without peaks ends up with every bin on the
             // dump slot): two independent instruction streams the scheduler can interleave
-            const int second_flag = contract ? int(0x80000000u) : 0;
-            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask0, 16 * tp, pk0, nk0, rk, second_flag, dst0);
-            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk, second_flag, dst1);
+            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask0, 16 * tp, pk0, nk0, rk, contract0 ? int(0x80000000u) : 0, dst0);
+            if constexpr (PCH)
+                ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk1, contract1 ? int(0x80000000u) : 0, dst1);
+            else
+                ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk, contract1 ? int(0x80000000u) : 0, dst1);
         }
 
         // sources into registers: own run, bin M and the first stale level (what _realTransform4
@@ -1369,7 +1423,7 @@ inline void ring_host_tables(const float2 *tw /* [N] W_N^j */, float2 *out /* ri
 
 // planar [C'][N] rings (pv_kernel.cuh conventions: frame sample n at hist[(n + rb + hop) mod N],
 // accumulator sample k at acc[(k + rb) mod N]) <-> paired rings aligned to t
-__global__ void pv_ring_convert_kernel(float *hist_planar, float *acc_planar, float2 *hist2, float2 *acc2,
+static __global__ void pv_ring_convert_kernel(float *hist_planar, float *acc_planar, float2 *hist2, float2 *acc2,
                                        int pairs, int n, int hop, int rb, int tmod, int to_paired) {
     const long long total = (long long)pairs * n;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;

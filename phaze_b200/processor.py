@@ -126,6 +126,46 @@ class BatchedPhaseVocoder:
         _lib.check(self._h, rc)
         return out
 
+    def process_pf(self, block: np.ndarray | None, pitch_factors: np.ndarray,
+                   out: np.ndarray | None = None) -> np.ndarray:
+        """One process() call with one pitch factor per channel (pvb_process_pf): channel c is
+        processed exactly as a processor with the scalar pitch_factors[c] would."""
+        Cn, hop = self.num_channels, self.hop_size
+        pf = np.ascontiguousarray(pitch_factors, np.float32)
+        if pf.shape != (Cn,):
+            raise ValueError(f"expected {Cn} pitch factors, got shape {pf.shape}")
+        if out is None:
+            out = np.empty((Cn, hop), np.float32)
+        inp = None
+        if block is not None:
+            block = np.ascontiguousarray(block, np.float32)
+            if block.shape != (Cn, hop):
+                raise ValueError(f"expected block of shape {(Cn, hop)}, got {block.shape}")
+            inp = block.ctypes.data
+        rc = self._lib.pvb_process_pf(self._h, inp, out.ctypes.data, pf.ctypes.data)
+        _lib.check(self._h, rc)
+        return out
+
+    def process_pf_device(self, in_ptr: int | None, out_ptr: int, pitch_factors: np.ndarray,
+                          stream: int | None = None):
+        """Asynchronous per-channel-pitch call on device pointers; pitch_factors is a host array."""
+        pf = np.ascontiguousarray(pitch_factors, np.float32)
+        assert pf.shape == (self.num_channels,)
+        _lib.check(self._h, self._lib.pvb_process_pf_device(self._h, in_ptr, out_ptr, pf.ctypes.data, stream))
+
+    def run_pf(self, signal: np.ndarray, pitch_factors: np.ndarray) -> np.ndarray:
+        """signal [C][T*hop] -> [C][T*hop] with per-channel pitch factors ([C], or [T][C] per call)."""
+        signal = np.ascontiguousarray(signal, np.float32)
+        Cn, total = signal.shape
+        hop = self.hop_size
+        T = total // hop
+        pf = np.asarray(pitch_factors, np.float32)
+        out = np.empty_like(signal)
+        for k in range(T):
+            out[:, k * hop:(k + 1) * hop] = self.process_pf(signal[:, k * hop:(k + 1) * hop],
+                                                            pf[k] if pf.ndim == 2 else pf)
+        return out
+
     def process_many(self, blocks: np.ndarray, pitch_factor: float,
                      out: np.ndarray | None = None) -> np.ndarray:
         """K consecutive process() calls: blocks [K][C][hop] float32."""

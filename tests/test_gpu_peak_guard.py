@@ -104,7 +104,7 @@ def test_guard_is_rare_and_complete_on_broadband_input(oracle):
     """On the benchmark's input (0.1 broadband floor), over 160k channel frames:
     (a) the STRICT guard (re-decide on one or more uncertain comparisons) catches every frame whose
         float32 decision differs from the exact one: its output is IDENTICAL to re-deciding every frame;
-    (b) it fires on under 2 % of the frames, the default policy (two or more) on under 0.05 %;
+    (b) it fires on under 2 % of the frames, the default policy (five or more) on under 0.01 %;
     (c) the default policy stays within the expected float32 error of the oracle."""
     from phaze_b200 import BatchedPhaseVocoder
     N, hop, C, calls = 1024, 256, 4096, 40
@@ -125,7 +125,7 @@ def test_guard_is_rare_and_complete_on_broadband_input(oracle):
           f"policy differs from the exact decision: {differ} of {C}, rms of the difference {_rms(a - b):.3e}")
     assert n_always == frames
     assert np.array_equal(s, b)
-    assert n_strict <= 0.02 * frames and n_auto <= 0.0005 * frames
+    assert n_strict <= 0.02 * frames and n_auto <= 0.0001 * frames
     assert _rms(a - b) <= RMS_BAR / 4
     sel = np.arange(0, C, 97)
     ref = oracle.OracleProcessor(N, hop, len(sel)).run(x[sel], pf)
