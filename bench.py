@@ -63,6 +63,7 @@ def parse_args():
                     help="PVB_OPT_PEAK_GUARD of the timed handles: 0 default policy, 1 off, 2 always, 3 strict")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the batched (64 calls per launch) run")
     ap.add_argument("--no-other-configs", action="store_true",
                     help="skip the short device-resident runs of the other BASELINE configs (N=1, default workload only)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
@@ -373,6 +374,48 @@ def run_ours(args):
     for p in procs:
         p.set_option("launch_mode", 0)
 
+    # batched mode (pvb_process_many_device): Kb consecutive calls per launch, every
+    # channel pair loops over them, its state goes through L1 / L2 instead of HBM.  Compulsory DRAM traffic
+    # drops to 8*hop bytes per frame (+ 12*N / Kb), so this is NOT scored against the 12*N roofline: it is
+    # reported as frames/s and against the non-tensor FP32 ceiling (BASELINE.md contract).
+    batched = None
+    if not args.no_batched:
+        Kb = 64
+        bin_ = blocks.repeat((Kb + nblk - 1) // nblk, 1, 1)[:Kb].contiguous()        # [Kb][C][hop]
+        bouts = [torch.empty((Kb, C, hop), dtype=torch.float32, device="cuda") for _ in range(2)]
+        nb = max(2, min(rotate, K // Kb))
+
+        for p in procs:
+            p.set_option("many_mode", 1)
+
+        def bstep(i):
+            procs[i % rotate].process_device(bin_.data_ptr(), bouts[i % 2].data_ptr(), pitch, sptr, num_calls=Kb)
+
+        for i in range(rotate):
+            bstep(i)
+        torch.cuda.synchronize()
+        eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eb0.record(stream)
+        for i in range(nb):
+            bstep(i)
+        eb1.record(stream)
+        torch.cuda.synchronize()
+        bms = eb0.elapsed_time(eb1)
+        bval = nb * Kb * C / (bms * 1e-3)
+        flop_per_frame = 6.0e4 * frame / 1024          # ~60 k float32 flop per 1024-point frame
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # non-tensor FP32, TFLOP/s at the maximum SM clock
+        batched = {"value": bval, "unit": UNIT, "calls_per_launch": Kb, "launches": nb,
+                   "us_per_call": 1e3 * bms / (nb * Kb),
+                   "vs_one_launch_per_call": bval / (K * C / (ms * 1e-3)),
+                   "compulsory_dram_bytes_per_frame": 8 * hop + 12.0 * frame / Kb,
+                   "fp32": {"flop_per_frame_estimate": flop_per_frame, "achieved_tflops": bval * flop_per_frame / 1e12,
+                            "peak_tflops": fp32_peak, "frac": bval * flop_per_frame / 1e12 / fp32_peak},
+                   "api": f"pvb_process_many_device(handle, in_dev, out_dev, {Kb}, pitch, stream) with "
+                          "PVB_OPT_MANY_MODE = 1: one launch, bit-identical to the same calls one by one"}
+        del bin_, bouts
+        for p in procs:
+            p.set_option("many_mode", 0)
+
     # context only: (a) one instance, state stays in L2; (b) every instance on its own stream
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(min(W, 50)):
@@ -463,6 +506,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "launch_chaining": chain,
+            "batched": batched,
             "peak_guard": {"option": args.peak_guard, "frames_redecided_in_float64": int(guard_frames),
                            "of_frames": int((K + W) * C),
                            "note": "channel frames whose peak set was re-decided with the fft.js-order float64 "

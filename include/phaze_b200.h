@@ -91,7 +91,10 @@ PVB_API int32_t pvb_process_device(pvb_processor *p, const float *in_dev, float 
 
 /* K consecutive process() calls of one pitch factor in a single submission
  * (in/out: [K][num_channels][hop_size]); bit-identical to K pvb_process_device
- * calls.  Host variant copies once each way. */
+ * calls.  With PVB_OPT_MANY_MODE = 1 the calls share kernel launches where the
+ * ring-order kernel applies (one DRAM round trip of the state per launch instead
+ * of per call).  The host variant overlaps the copies of consecutive groups of
+ * calls with the kernels. */
 PVB_API int32_t pvb_process_many_device(pvb_processor *p, const float *in_dev, float *out_dev,
                                 int32_t num_calls, float pitch_factor, void *stream);
 PVB_API int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t num_calls,
@@ -143,7 +146,14 @@ enum {
        natural near-ties in a broadband frame keep their float32 decision.
        1: never (float32 decisions only, the test itself is skipped).  2: always (tests).
        3 strict: re-decide frames with one or more uncertain comparisons. */
-    PVB_OPT_PEAK_GUARD = 4
+    PVB_OPT_PEAK_GUARD = 4,
+    /* pvb_process_many[_device]: 0 (default) one kernel launch per call, chained (see PVB_OPT_LAUNCH_MODE);
+       1: consecutive calls share a kernel launch where the ring-order kernel applies (up to 64 calls per
+       launch: each channel pair loops over the calls, its state goes through L1 / L2 instead of HBM and
+       the rings make one DRAM round trip per launch).  Results are bit-identical.  The chained single
+       launches are the faster of the two on B200 (the path is bound by the SMs, not by DRAM, and the loop
+       costs the kernel registers), so this is an option, not the default. */
+    PVB_OPT_MANY_MODE = 5
 };
 PVB_API int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value);
 PVB_API int64_t pvb_get_option(const pvb_processor *p, int32_t option);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PVB_LIBRARY") or os.path.join(_HERE, "libphaze_b200.s
 
 PVB_OK, PVB_ERR_BAD_SIZE, PVB_ERR_BAD_ARG, PVB_ERR_CUDA, PVB_ERR_NOMEM = 0, -1, -2, -3, -4
 # pvb_set_option (include/phaze_b200.h)
-PVB_OPT_KERNEL, PVB_OPT_LAUNCH_MODE, PVB_OPT_INPUTS_READY, PVB_OPT_PEAK_GUARD = 1, 2, 3, 4
+PVB_OPT_KERNEL, PVB_OPT_LAUNCH_MODE, PVB_OPT_INPUTS_READY, PVB_OPT_PEAK_GUARD, PVB_OPT_MANY_MODE = 1, 2, 3, 4, 5
 KERNEL_AUTO, KERNEL_RING, KERNEL_WARP, KERNEL_CTA, KERNEL_GENERIC = 0, 1, 2, 3, 4
 
 

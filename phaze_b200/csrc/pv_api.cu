@@ -47,7 +47,7 @@ struct pvb_processor {
     float *d_pf = nullptr;
     bool pf_fast = false;            // every channel inside the ring-order kernel's range
     // pvb_set_option
-    int opt_kernel = 0, opt_launch_mode = 0, opt_inputs_ready = 0, opt_peak_guard = 0;
+    int opt_kernel = 0, opt_launch_mode = 0, opt_inputs_ready = 0, opt_peak_guard = 0, opt_many_mode = 0;
     cudaStream_t last_stream = nullptr;   // stream of the most recent submission (state entry points wait for it)
     float *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry points
     size_t staging_floats = 0;
@@ -359,8 +359,9 @@ size_t state_rows(int channels);
 // later launches of one submission, which start behind a launch that waited for the whole stream or
 // behind one that already had the guarantee).
 pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s,
-                                 bool input_ready) {
+                                 bool input_ready, int num_hops) {
     pvb::RingParams rp;
+    rp.num_hops = num_hops;
     rp.in = fp.in;
     rp.out = fp.out;
     rp.hist2 = reinterpret_cast<float4 *>(fp.hist);
@@ -387,7 +388,7 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
         if (!pdl) rp.early = 0;
         if (experiments().early >= 0 && rp.early > experiments().early) rp.early = experiments().early;
         // flag mode needs the caller's buffers to be disjoint from those of every launch it may overlap
-        const size_t io_bytes = size_t(fp.num_channels) * size_t(fp.hop) * sizeof(float);
+        const size_t io_bytes = size_t(num_hops) * size_t(fp.num_channels) * size_t(fp.hop) * sizeof(float);
         RecentIo io;
         io.in_lo = reinterpret_cast<const char *>(fp.in);
         io.in_hi = fp.in ? io.in_lo + io_bytes : io.in_lo;
@@ -431,7 +432,8 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
 // The ring-order kernel instances live in pv_ring_inst.cu (one translation unit per frame size).
 // Pairs per CTA: frame 1024 balances one wave (4..7 warps); the other sizes fill their CTAs (frame 256:
 // 32 quarter-warp pairs, 512: 16 half-warp pairs, 2048: 4 pairs of two warps, 4096: 2 pairs of four).
-cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready) {
+cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready,
+                        int num_hops) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -452,8 +454,9 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     l.pad_kb = experiments().ring_pad_kb;                                     // PVB_RING_PAD_KB
     l.pdl = h->opt_launch_mode != 2;
     l.pch = fp.pf_ch != nullptr;
+    l.multi = num_hops > 1;
     l.stream = s;
-    pvb::RingParams rp = make_ring_params(h, fp, s, input_ready);
+    pvb::RingParams rp = make_ring_params(h, fp, s, input_ready, num_hops);
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
     switch (h->n) {
         case 256: return pvb::ring_launch_256(rp, l);
@@ -465,10 +468,12 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready) {
+// num_hops > 1 (several consecutive calls in one launch) only with the ring-order kernel
+cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready,
+                       int num_hops) {
     const int n = h->n;
     switch (pick_kernel(h, fp)) {
-        case K_RING: return launch_ring(h, fp, s, input_ready);
+        case K_RING: return launch_ring(h, fp, s, input_ready, num_hops);
         case K_WARP: return launch_warp(fp, h->d_window_out, h->num_sms, s);
         case K_CTA: return launch_cta(n, fp, h->d_window_out, s);
         case K_GENERIC: break;
@@ -483,8 +488,9 @@ cudaError_t launch_any(const pvb_processor *h, const pvb::FrameParams &fp, cudaS
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready) {
-    const cudaError_t e = launch_any(h, fp, s, input_ready);
+cudaError_t launch(const pvb_processor *h, const pvb::FrameParams &fp, cudaStream_t s, bool input_ready,
+                   int num_hops = 1) {
+    const cudaError_t e = launch_any(h, fp, s, input_ready, num_hops);
     std::lock_guard<std::mutex> lk(g_stream_mu);
     if (!ring_kernel_applies(h, fp)) {       // the other kernels are plain launches: they wait for everything
         g_last_flag_mode[s] = false;
@@ -613,6 +619,7 @@ struct DeviceGuard {
 struct CallHooks {
     virtual void before(int k, cudaStream_t s) = 0;
     virtual void after(int k, cudaStream_t s) = 0;
+    int group = 1;      // calls [g * group, (g + 1) * group) share their copies: they may share a launch too
 };
 
 // sticky device error (a completion flag that never arrived): the handle refuses further work
@@ -670,8 +677,9 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         if (rc != PVB_OK) return rc;
         pf = 1.0f;
     }
-    for (int k = 0; k < num_calls; k++) {
-        if (hooks) hooks->before(k, s);
+    // most calls per launch of the MULTI ring-order kernels (a launch of 64 hops at 4096 channels runs ~1 ms)
+    constexpr int MAX_HOPS_PER_LAUNCH = 64;
+    for (int k = 0; k < num_calls;) {
         pvb::FrameParams fp;
         fp.in = in_dev ? in_dev + size_t(k) * block : nullptr;
         fp.out = out_dev + size_t(k) * block;
@@ -688,18 +696,28 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         fp.pitch_factor = pf;
         fp.pf_ch = (pf_host && p->channels > 0) ? p->d_pf : nullptr;
         split_pitch_factor(pf, &fp.pf_mant, &fp.pf_shift);
+        // how many consecutive calls this launch does: all that remain (up to the end of their copy
+        // group on the pipelined host path) when the ring-order kernel takes them, else one
+        int hops = 1;
+        if (p->channels > 0 && !pf_host && p->opt_many_mode == 1 && ring_kernel_applies(p, fp)) {
+            hops = num_calls - k;
+            if (hooks && hops > hooks->group - k % hooks->group) hops = hooks->group - k % hooks->group;
+            if (hops > MAX_HOPS_PER_LAUNCH) hops = MAX_HOPS_PER_LAUNCH;
+        }
+        if (hooks) for (int j = k; j < k + hops; j++) hooks->before(j, s);
         if (p->channels > 0) {
             const int rc = ensure_layout(p, ring_kernel_applies(p, fp) ? pvb_processor::PAIRED
                                                                        : pvb_processor::PLANAR, s);
             if (rc != PVB_OK) return rc;
             fp.hist = p->d_hist;
             fp.acc = p->d_acc;
-            PVB_CUDA(p, launch(p, fp, s, inputs_ready || k > 0));
+            PVB_CUDA(p, launch(p, fp, s, inputs_ready || k > 0, hops));
             p->launches++;
         }
-        p->ring_calls++;
-        p->cursor_calls++;   // pv:71, once per call for all channels
-        if (hooks) hooks->after(k, s);
+        p->ring_calls += hops;
+        p->cursor_calls += hops;   // pv:71, once per call for all channels
+        if (hooks) for (int j = k; j < k + hops; j++) hooks->after(j, s);
+        k += hops;
     }
     return PVB_OK;
 }
@@ -925,7 +943,7 @@ int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t 
     // copies move `group` calls at a time (16 MiB chunks at the default workload run the PCIe
     // link ~5 % faster than 4 MiB ones)
     struct Pipe : CallHooks {
-        pvb_processor *p; const float *in; float *out; size_t block; int calls, group;
+        pvb_processor *p; const float *in; float *out; size_t block; int calls;
         cudaError_t err = cudaSuccess;
         void note(cudaError_t e) { if (err == cudaSuccess) err = e; }
         void before(int k, cudaStream_t s) override {
@@ -1076,6 +1094,10 @@ int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value) {
             if (value < 0 || value > 3) break;
             p->opt_peak_guard = int(value);
             return PVB_OK;
+        case PVB_OPT_MANY_MODE:
+            if (value < 0 || value > 1) break;
+            p->opt_many_mode = int(value);
+            return PVB_OK;
     }
     return fail(p, PVB_ERR_BAD_ARG, "pvb_set_option: unknown option %d or bad value %lld", int(option), (long long)value);
 }
@@ -1087,6 +1109,7 @@ int64_t pvb_get_option(const pvb_processor *p, int32_t option) {
         case PVB_OPT_LAUNCH_MODE: return p->opt_launch_mode;
         case PVB_OPT_INPUTS_READY: return p->opt_inputs_ready;
         case PVB_OPT_PEAK_GUARD: return p->opt_peak_guard;
+        case PVB_OPT_MANY_MODE: return p->opt_many_mode;
     }
     return PVB_ERR_BAD_ARG;
 }

@@ -57,6 +57,14 @@ namespace pvb {
 #ifndef PVB_RING_PAIRS_1024
 #define PVB_RING_PAIRS_1024 7
 #endif
+// Destinations outside [0, nb) are clamped to one write-only "dump" word per plane instead of being
+// predicated off (one integer operation less per bin): several lanes may store to it at once, which
+// compute-sanitizer's racecheck reports as write-after-write hazards.  -DPVB_RING_NO_DUMP=1 predicates
+// those stores off instead; that build must be racecheck-clean (profiles/sanitize.sh), which shows that
+// the dump word is the only shared-memory word ever written by two lanes between two barriers.
+#ifndef PVB_RING_NO_DUMP
+#define PVB_RING_NO_DUMP 0
+#endif
 
 // PCH: per-channel pitch factors (pvb_process_pf): the key table becomes per pair (two deltas per bin)
 template <int N_, bool PCH_ = false>
@@ -129,6 +137,9 @@ struct RingGeoT {
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_SMEM;
     static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024
                                      : (N == 2048) ? (PCH ? 3 : 4) : 2;     // pairs per CTA (two CTAs per SM must fit 227 KB)
+    // MULTI kernels (a loop over process() calls around the body) need more than 128 registers per thread
+    // to stay out of local memory: three quarters of the pairs per CTA, 168 registers
+    static constexpr int MULTI_PAIRS = (N == 4096) ? 2 : (3 * MAX_PAIRS) / 4 + ((N == 1024) ? 1 : 0);
     static constexpr int CTAS_PER_SM = 2;                   // frame 4096: 30 KB of tables + 2 x 36 KB per CTA
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
@@ -148,7 +159,8 @@ struct RingParams {
     const float4 *gtab;         // NJ x tw1 | w64 | twh, built by the host (ring_host_tables)
     int num_channels;
     int hop;
-    int tmod;                   // timeCursor mod N (multiple of hop)
+    int num_hops;               // MULTI kernels: consecutive process() calls done by this launch (in / out: [K][C][hop])
+    int tmod;                   // timeCursor mod N (multiple of hop) at the first of them
     int stagger_ns;             // -DPVB_EXPERIMENTS only: delay odd warps by this much before the first pass
     int skip;                   // -DPVB_EXPERIMENTS only (PVB_SKIP, results become wrong): bit 0 the whole middle,
                                 // bit 1 forward and inverse pass 2
@@ -554,17 +566,26 @@ __device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__
 // ring blocks of the rotated register array is the DFT over f times W_R1^{toff k1} (shift
 // theorem); that factor is folded into the first-pass twiddles, W_M^{(n + 64 toff) k1}: the host
 // keeps one such table per toff and the CTA stages the one it needs.
-template <int N, int NBLK, bool PCH = false>
-__global__ void __launch_bounds__(RingGeoT<N, PCH>::MAX_PAIRS * RingGeoT<N, PCH>::TP, RingGeoT<N, PCH>::CTAS_PER_SM)
-pv_process_ring_kernel(const RingParams p) {
+//
+// One process() call of one channel pair (the whole body of the kernel).  `hopi`: index of the call
+// inside a MULTI launch (0 otherwise); `live`: the pair exists and its state is usable.  Returns `live`
+// (false once a completion flag is lost).
+// PHASE: 0 the only call of the launch; 1 the first call of a MULTI launch; 2 a later call of a MULTI
+// launch (no flags, no waits: the pair itself wrote the state it reads).  In phase 2 the thread indices
+// pass through an identity the compiler cannot see through: the body then re-derives its index arithmetic
+// at every call instead of hoisting dozens of indices out of the loop and spilling.
+template <int N, int NBLK, bool PCH, int PHASE>
+__device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hopi, bool live) {
     using G = RingGeoT<N, PCH>;
+    constexpr bool MULTI = PHASE != 0;
     constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int tp = threadIdx.x % TP;                // thread within the pair
-    const int pin = threadIdx.x / TP;               // pair within the CTA
+    int tid = threadIdx.x;
+    if constexpr (PHASE == 2) asm volatile("" : "+r"(tid));
+    const int lane = tid & 31;
+    const int tp = tid % TP;                        // thread within the pair
+    const int pin = tid / TP;                       // pair within the CTA
     const int pair = blockIdx.x * (blockDim.x / TP) + pin;
-    bool live = 2 * pair < p.num_channels;
 #ifdef PVB_EXPERIMENTS
     const int xskip = p.skip, xstagger = p.stagger_ns;
 #else
@@ -597,8 +618,9 @@ pv_process_ring_kernel(const RingParams p) {
     const int c0 = 2 * pair;
     const bool has1 = c0 + 1 < p.num_channels;
     const int hop = p.hop;
-    const int t = p.tmod;
     constexpr int nblk = NBLK;
+    constexpr bool first = PHASE != 2;
+    const int t = MULTI ? ((p.tmod + hopi * hop) & (N - 1)) : p.tmod;
     const int toff = (t >> 7) & (NJ - 1);           // ring 128-block of frame block 0
     constexpr bool HB = G::HB;
     const int half = HB ? ((t >> 6) & 1) : 0;       // rings rotated by half a block (frame 256, hop 64)
@@ -617,7 +639,8 @@ pv_process_ring_kernel(const RingParams p) {
     //    the compute phase of its SM neighbour.
     //  * grid mode: griddepcontrol.wait before the first dependent access; everything up to it
     //    touches only constant tables (and state that is provably older than the previous kernel).
-    if (p.flag_mode) asm volatile("griddepcontrol.launch_dependents;");
+    if (first && p.flag_mode) asm volatile("griddepcontrol.launch_dependents;");
+    if (MULTI && !first) __syncthreads();           // every pair is done with the previous hop's first-pass twiddles
     // ---- CTA-shared tables: asynchronous 16-byte copies, fixed trip counts (CTAs have at least
     // MIN_THREADS threads; no division by blockDim) --------------------------------------------------
     {
@@ -635,22 +658,23 @@ pv_process_ring_kernel(const RingParams p) {
             if (i < G::TW1_BYTES / 16)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_tab + 16 * i), "l"(g_tw1 + i));
         }
+        // (everything below is the same for every hop of the launch)
 #pragma unroll
         for (int k = 0; k < ((G::W64_BYTES + G::W128_BYTES + G::TWH_SMEM) / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
-            if (i < (G::W64_BYTES + G::W128_BYTES + G::TWH_SMEM) / 16)
+            if (first && i < (G::W64_BYTES + G::W128_BYTES + G::TWH_SMEM) / 16)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_rest + 16 * i), "l"(g_rest + i));
         }
 #pragma unroll
         for (int k = 0; k < (G::WIN_SMEM / 16 + G::MIN_THREADS - 1) / G::MIN_THREADS; k++) {
             const int i = threadIdx.x + k * blockDim.x;
-            if (i < G::WIN_SMEM / 16) {
+            if (first && i < G::WIN_SMEM / 16) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_win + 16 * i), "l"(w1 + i));
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_wout + 16 * i), "l"(w2 + i));
             }
         }
         // delta = round(pk * pitchFactor) - pk in exact integer arithmetic (pv:125-127)
-        if constexpr (!PCH) {
+        if (!PCH && first) {
             const long long pf_m = p.pf_mant;
             const int pf_s = p.pf_shift;
             const long long half = 1ll << (pf_s - 1);
@@ -701,8 +725,10 @@ pv_process_ring_kernel(const RingParams p) {
 #define PVB_COL(h) (HB ? ((cn + TPH * (h) + hh) & 63) : (cn + TPH * (h)))
     float4 r[16];
     float4 *hl = p.hist2 + size_t(live ? pair : 0) * (N / 2) + (HB ? 0 : cn);
-    const int early = p.flag_mode ? 0 : p.early;
-    if (p.flag_mode) {
+    const int early = (p.flag_mode || !first) ? 0 : p.early;
+    if (!first) {
+        // later hops of a MULTI launch: the pair itself wrote the state it reads
+    } else if (p.flag_mode) {
         if (live) {
             // acquire: the previous call of this handle has finished with this pair.  The spin is bounded:
             // when the flag does not arrive (time slicing, a debugger, a launch that never ran) the pair
@@ -748,14 +774,14 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
-    if (!p.flag_mode) {
+    if (first && !p.flag_mode) {
         // our dependents may launch only now: whoever starts behind us can rely on everything older
         // than us being complete
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;");
     }
     if (live) {
-        const float *i0 = p.in ? p.in + size_t(c0) * hop + 2 * cn : nullptr;
+        const float *i0 = p.in ? p.in + (size_t(hopi) * p.num_channels + c0) * hop + 2 * cn : nullptr;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             const int h = PVB_FH(e), fr = PVB_FR(e), f = PVB_FB(fr);
@@ -777,7 +803,7 @@ pv_process_ring_kernel(const RingParams p) {
     float pfc0 = p.pitch_factor, pfc1 = p.pitch_factor;               // pitch factor of each channel of the pair
     if constexpr (PCH) {
         // (placed here so that the integer work runs under the frame loads issued above)
-        if (live) {
+        if (live && first) {
             pfc0 = __ldg(p.pf_ch + 2 * pair);
             pfc1 = (2 * pair + 1 < p.num_channels) ? __ldg(p.pf_ch + 2 * pair + 1) : 1.0f;
             // float32 == mant * 2^-shift exactly (the host admits only normal values in the kernel's range)
@@ -795,7 +821,7 @@ pv_process_ring_kernel(const RingParams p) {
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    if (!live) return;          // no CTA-wide barriers below
+    if (!live) return false;    // no CTA-wide barriers below (MULTI: none before the next call's)
 
     if (xstagger > 0 && (pin & 1)) __nanosleep(unsigned(xstagger));
     // the new block joins the history ring (ola:105)
@@ -1156,14 +1182,19 @@ pv_process_ring_kernel(const RingParams p) {
         }
 
         constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane
+#if PVB_RING_NO_DUMP
+#define PVB_NOT_DUMP(d) (((d) & 0x7fffffff) != 4 * (G::XQ_SLOTS - 1))
+#else
+#define PVB_NOT_DUMP(d) true
+#endif
         // first sub-step: plain stores (pairwise disjoint destinations)
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            if (dst0[e] >= 0) {
+            if (dst0[e] >= 0 && PVB_NOT_DUMP(dst0[e])) {
                 *reinterpret_cast<float *>(mine + dst0[e]) = xv[e].x;
                 *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL) = xv[e].z;
             }
-            if (dst1[e] >= 0) {
+            if (dst1[e] >= 0 && PVB_NOT_DUMP(dst1[e])) {
                 *reinterpret_cast<float *>(mine + dst1[e] + PL) = xv[e].y;
                 *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = xv[e].w;
             }
@@ -1200,17 +1231,17 @@ pv_process_ring_kernel(const RingParams p) {
                 for (int i = 0; i < 8; i++) {
                     const int e = 8 * g + i;
                     o0r[i] = o0i[i] = o1r[i] = o1i[i] = 0.f;
-                    if (dst0[e] < 0) { o0r[i] = *reinterpret_cast<float *>(mine2 + dst0[e]); o0i[i] = *reinterpret_cast<float *>(mine2 + dst0[e] + 2 * PL); }
-                    if (dst1[e] < 0) { o1r[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + 3 * PL); }
+                    if (dst0[e] < 0 && PVB_NOT_DUMP(dst0[e])) { o0r[i] = *reinterpret_cast<float *>(mine2 + dst0[e]); o0i[i] = *reinterpret_cast<float *>(mine2 + dst0[e] + 2 * PL); }
+                    if (dst1[e] < 0 && PVB_NOT_DUMP(dst1[e])) { o1r[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + 3 * PL); }
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int e = 8 * g + i;
-                    if (dst0[e] < 0) {
+                    if (dst0[e] < 0 && PVB_NOT_DUMP(dst0[e])) {
                         *reinterpret_cast<float *>(mine2 + dst0[e]) = o0r[i] + xv[e].x;
                         *reinterpret_cast<float *>(mine2 + dst0[e] + 2 * PL) = o0i[i] + xv[e].z;
                     }
-                    if (dst1[e] < 0) {
+                    if (dst1[e] < 0 && PVB_NOT_DUMP(dst1[e])) {
                         *reinterpret_cast<float *>(mine2 + dst1[e] + PL) = o1r[i] + xv[e].y;
                         *reinterpret_cast<float *>(mine2 + dst1[e] + 3 * PL) = o1i[i] + xv[e].w;
                     }
@@ -1341,7 +1372,7 @@ pv_process_ring_kernel(const RingParams p) {
 
     // ---- inverse pass 3: butterflies n over k1 -> ring samples; window, overlap-add, emit ------------------
     {
-        float *o0 = p.out + size_t(c0) * hop + 2 * cn;
+        float *o0 = p.out + (size_t(hopi) * p.num_channels + c0) * hop + 2 * cn;
         const float *wol = swout + 2 * cn;
         const int row0 = RT * sp;
 #pragma unroll
@@ -1370,6 +1401,41 @@ pv_process_ring_kernel(const RingParams p) {
             }
         }
     }
+    return true;
+#undef PVB_NOT_DUMP
+#undef PVB_RING_OFF
+#undef PVB_FR
+#undef PVB_FH
+#undef PVB_FB
+#undef PVB_ROLE
+#undef PVB_RING_IDX
+#undef PVB_COL
+#undef PVB_TLD2
+}
+
+// N = frame size (512: half a warp per pair, 1024: one warp, 2048: two warps, 4096: four warps),
+// NBLK = hop / 128 (see ring_one_call).
+//
+// MULTI: the launch does p.num_hops consecutive process() calls (pvb_process_many): every pair loops over
+// the calls, its state goes back and forth through L1 / L2 instead of HBM (one DRAM round trip of the
+// rings per launch instead of per call), completion flags are taken and released once, and only the
+// first-pass twiddle table is re-staged per call.  Bit-identical to num_hops single launches.
+template <int N, int NBLK, bool PCH = false, bool MULTI = false>
+__global__ void __launch_bounds__((MULTI ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP,
+                                  RingGeoT<N, PCH>::CTAS_PER_SM)
+pv_process_ring_kernel(const RingParams p) {
+    constexpr int TP = RingGeoT<N, PCH>::TP;
+    const int tp = threadIdx.x % TP, pin = threadIdx.x / TP;
+    const int pair = blockIdx.x * (blockDim.x / TP) + pin;
+    bool live = 2 * pair < p.num_channels;
+    if constexpr (MULTI) {
+        live = ring_one_call<N, NBLK, PCH, 1>(p, 0, live);
+#pragma unroll 1
+        for (int hopi = 1; hopi < p.num_hops; hopi++) live = ring_one_call<N, NBLK, PCH, 2>(p, hopi, live);
+    } else {
+        live = ring_one_call<N, NBLK, PCH, 0>(p, 0, live);
+    }
+    if (!live) return;
     // release: state and output of this pair are complete for call my_seq.  The pair barrier orders
     // every thread's stores before thread 0's release store, which is cumulative at gpu scope;
     // PVB_RING_LANE_FENCE=1 additionally fences in every thread (the first version of this code).
@@ -1382,14 +1448,6 @@ pv_process_ring_kernel(const RingParams p) {
     // flag mode skipped the wait at the top: take it here, where the previous grid is long gone, so
     // that completion stays transitive along the stream
     if (p.flag_mode) asm volatile("griddepcontrol.wait;" ::: "memory");
-#undef PVB_RING_OFF
-#undef PVB_FR
-#undef PVB_FH
-#undef PVB_FB
-#undef PVB_ROLE
-#undef PVB_RING_IDX
-#undef PVB_COL
-#undef PVB_TLD2
 }
 
 // tables the ring-order kernel copies into shared memory: NJ first-pass twiddle tables

@@ -13,11 +13,12 @@ namespace pvb {
 namespace {
 
 // NBLK counts role units of RingGeoT<N>::UNIT samples (64 at frame 256, else 128)
-template <int N, bool PCH, int... NBLKS>
+template <int N, bool PCH, bool MULTI, int... NBLKS>
 cudaError_t launch_t(const RingParams &rp, const RingLaunch &l) {
     using G = RingGeoT<N, PCH>;
+    constexpr int CAP = MULTI ? G::MULTI_PAIRS : G::MAX_PAIRS;   // what the kernel's launch bounds allow
     int ppc = l.ppc;
-    if (ppc < G::MIN_PAIRS || ppc > G::MAX_PAIRS) ppc = G::MAX_PAIRS;
+    if (ppc < G::MIN_PAIRS || ppc > CAP) ppc = CAP;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((l.pairs + ppc - 1) / ppc);
     cfg.blockDim = dim3(ppc * G::TP);
@@ -33,15 +34,15 @@ cudaError_t launch_t(const RingParams &rp, const RingLaunch &l) {
     const int nblk = rp.hop / G::UNIT;
     cudaError_t e = cudaErrorInvalidValue;                      // no instance for this hop
     (void)std::initializer_list<int>{
-        (nblk == NBLKS ? (e = cudaLaunchKernelEx(&cfg, pv_process_ring_kernel<N, NBLKS, PCH>, rp), 0) : 0)...};
+        (nblk == NBLKS ? (e = cudaLaunchKernelEx(&cfg, pv_process_ring_kernel<N, NBLKS, PCH, MULTI>, rp), 0) : 0)...};
     return e;
 }
 
-template <int N, bool PCH, int... NBLKS>
+template <int N, bool PCH, bool MULTI, int... NBLKS>
 cudaError_t configure_t() {
     cudaError_t e = cudaSuccess;
     (void)std::initializer_list<int>{
-        (e == cudaSuccess ? (e = cudaFuncSetAttribute(pv_process_ring_kernel<N, NBLKS, PCH>,
+        (e == cudaSuccess ? (e = cudaFuncSetAttribute(pv_process_ring_kernel<N, NBLKS, PCH, MULTI>,
                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), 0)
                           : 0)...};
     return e;
@@ -49,13 +50,18 @@ cudaError_t configure_t() {
 
 }  // namespace
 
+// three instances per (frame, hop): scalar pitch factor, per-channel pitch factors, several calls per launch
 #define PVB_RING_DEFINE(N, ...)                                                                     \
     cudaError_t ring_launch_##N(const RingParams &rp, const RingLaunch &l) {                        \
-        return l.pch ? launch_t<N, true, __VA_ARGS__>(rp, l) : launch_t<N, false, __VA_ARGS__>(rp, l); \
+        if (l.pch) return l.multi ? cudaErrorInvalidValue : launch_t<N, true, false, __VA_ARGS__>(rp, l); \
+        return l.multi ? launch_t<N, false, true, __VA_ARGS__>(rp, l)                               \
+                       : launch_t<N, false, false, __VA_ARGS__>(rp, l);                             \
     }                                                                                               \
     cudaError_t ring_configure_##N() {                                                              \
-        const cudaError_t e = configure_t<N, false, __VA_ARGS__>();                                 \
-        return e != cudaSuccess ? e : configure_t<N, true, __VA_ARGS__>();                          \
+        cudaError_t e = configure_t<N, false, false, __VA_ARGS__>();                                \
+        if (e == cudaSuccess) e = configure_t<N, true, false, __VA_ARGS__>();                       \
+        if (e == cudaSuccess) e = configure_t<N, false, true, __VA_ARGS__>();                       \
+        return e;                                                                                   \
     }
 
 #if PVB_RING_INST_N == 256

@@ -15,6 +15,7 @@ struct RingLaunch {
     int pad_kb;           // extra dynamic shared memory per CTA (occupancy experiments)
     bool pdl;             // programmatic dependent launch allowed
     bool pch;             // per-channel pitch factors (RingParams::pf_ch)
+    bool multi;           // several process() calls per launch (RingParams::num_hops; scalar pitch factor only)
     cudaStream_t stream;
 };
 

@@ -92,12 +92,14 @@ class BatchedPhaseVocoder:
         return self._lib.pvb_peak_guard_count(self._h)
 
     _OPTIONS = {"kernel": _lib.PVB_OPT_KERNEL, "launch_mode": _lib.PVB_OPT_LAUNCH_MODE,
-                "inputs_ready": _lib.PVB_OPT_INPUTS_READY, "peak_guard": _lib.PVB_OPT_PEAK_GUARD}
+                "inputs_ready": _lib.PVB_OPT_INPUTS_READY, "peak_guard": _lib.PVB_OPT_PEAK_GUARD,
+                "many_mode": _lib.PVB_OPT_MANY_MODE}
     _KERNELS = {"auto": 0, "ring": 1, "warp": 2, "cta": 3, "generic": 4}
 
     def set_option(self, name: str, value) -> None:
         """pvb_set_option: kernel ("auto" | "ring" | "warp" | "cta" | "generic"), launch_mode (0 flags,
-        1 grid-wide wait, 2 plain launches), inputs_ready (0 | 1), peak_guard (0 auto, 1 off, 2 always)."""
+        1 grid-wide wait, 2 plain launches), inputs_ready (0 | 1), peak_guard (0 auto, 1 off, 2 always,
+        3 strict), many_mode (0: consecutive calls share launches, 1: one launch per call)."""
         if name == "kernel" and isinstance(value, str):
             value = self._KERNELS[value]
         _lib.check(self._h, self._lib.pvb_set_option(self._h, self._OPTIONS[name], int(value)))

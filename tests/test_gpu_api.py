@@ -79,17 +79,42 @@ def test_pitch_factor_takes_last_element():
     assert np.array_equal(outs[0], outs[1])
 
 
-@pytest.mark.parametrize("N,hop,pf", [(1024, 256, 0.8), (2048, 512, 1.5)])
-def test_process_many_is_bit_identical_to_single_calls(N, hop, pf):
+@pytest.mark.parametrize("N,hop,pf", [(1024, 256, 0.8), (2048, 512, 1.5), (2048, 128, 0.8), (256, 64, 1.2),
+                                      (512, 128, 0.9), (4096, 1024, 1.25), (1024, 64, 0.8), (1024, 256, 0.5)])
+@pytest.mark.parametrize("K", [4, 16, 64, 70])
+def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
+    """K consecutive calls in one submission: with PVB_OPT_MANY_MODE = 1 they share
+    kernel launches where the ring-order kernel applies (each pair loops over the hops, state stays in
+    L1 / L2); elsewhere
+    (hop 64 at frame 1024, pitch factor 0.5) it is K launches.  Both must equal K single calls bit for
+    bit, through the host entry point (copies pipelined in groups) and the device entry point."""
+    import torch
     from phaze_b200 import BatchedPhaseVocoder
-    C, calls = 6, 12
+    C = 7
+    calls = K + 3
     x = signals.channels(0, C, calls * hop)
     blocks = np.ascontiguousarray(x.reshape(C, calls, hop).transpose(1, 0, 2))
-    with BatchedPhaseVocoder(C, N, hop) as a, BatchedPhaseVocoder(C, N, hop) as b:
+    with BatchedPhaseVocoder(C, N, hop) as a, BatchedPhaseVocoder(C, N, hop, many_mode=1) as b, \
+            BatchedPhaseVocoder(C, N, hop, many_mode=1) as c:
         one = np.stack([a.process(blocks[t], pf) for t in range(calls)])
-        many = b.process_many(blocks, pf)
+        many = np.concatenate([b.process_many(blocks[:3], pf), b.process_many(blocks[3:], pf)])
         assert a.time_cursor == b.time_cursor == calls * hop
-    assert np.array_equal(one, many)
+        kernel = b.kernel_name(np.float32(pf))
+        ring = "ring" in kernel
+        assert b.kernel_launches < calls if ring else b.kernel_launches == calls
+        din = torch.from_numpy(blocks).cuda()
+        dout = torch.empty_like(din)
+        torch.cuda.synchronize()
+        c.process_device(din.data_ptr(), dout.data_ptr(), pf, None, num_calls=calls)
+        c.sync()
+        dev = dout.cpu().numpy()
+    if "pv_process_kernel" in kernel:
+        # the generic kernel adds colliding regions with shared-memory atomics: the order, and so the last
+        # bit, is not reproducible from run to run
+        assert np.abs(one - many).max() <= 1e-6 and np.abs(one - dev).max() <= 1e-6
+    else:
+        assert np.array_equal(one, many)
+        assert np.array_equal(one, dev)
 
 
 @pytest.mark.parametrize("N,hop,pf", [(1024, 256, 0.8), (2048, 128, 1.2)])
@@ -183,7 +208,7 @@ def test_full_size_config2_properties(oracle):
     assert _rms(y1[:, d:] - 0.375 * x[:, :-d]) <= 2e-7
     with BatchedPhaseVocoder(C, N, hop) as pv:
         y = pv.run(x, np.float32(0.8))
-        assert pv.kernel_launches == calls
+        assert 0 < pv.kernel_launches <= calls
     picks = sorted({c for lo, hi in shard_bounds(C, 8) for c in (lo, lo + 1, hi - 2, hi - 1)} | {777, 2049})
     want = oracle.OracleProcessor(N, hop, len(picks)).run(x[picks], np.float32(0.8))
     err = _rms(y[picks] - want)

@@ -15,10 +15,20 @@ def _run_both(oracle, N, hop, C, pf, calls, first_channel=0, sig=None, **options
     from phaze_b200 import BatchedPhaseVocoder
     x = signals.channels(first_channel, C, calls * hop) if sig is None else sig
     ref = oracle.OracleProcessor(N, hop, C).run(x, pf)
+    # one launch per call (default), then consecutive calls sharing launches (PVB_OPT_MANY_MODE = 1: up to
+    # 16 per launch here, where the ring-order kernel applies): both paths must give the same bits
     with BatchedPhaseVocoder(C, N, hop, **options) as pv:
         got = pv.run(x, pf)
-        launches = pv.kernel_launches
-    assert launches == calls
+        assert pv.kernel_launches == calls
+    with BatchedPhaseVocoder(C, N, hop, many_mode=1, **options) as pv:
+        got_many = pv.run(x, pf)
+        assert 0 < pv.kernel_launches <= calls
+        kernel = pv.kernel_name(pf)
+    if "pv_process_kernel" in kernel:
+        # the generic kernel adds colliding regions with shared-memory atomics: the last bit depends on their order
+        assert np.abs(got - got_many).max() <= 1e-6
+    else:
+        assert np.array_equal(got, got_many), "calls sharing a launch differ from one launch per call"
     return x, ref, got
 
 
