@@ -189,6 +189,33 @@ PVB_API size_t pvb_state_bytes(const pvb_processor *p);
 PVB_API int32_t pvb_get_state(pvb_processor *p, float *blob_host);
 PVB_API int32_t pvb_set_state(pvb_processor *p, const float *blob_host);
 
+/* ---- one logical processor over several GPUs of a node, in one process --------------------------------
+ * (device_ids[], num_devices.)  Channels are independent on this path (phase-vocoder.js:49-53)
+ * and timeCursor advances identically everywhere, so shard i owns a contiguous, pair-aligned block of
+ * channels on device_ids[i] and no call exchanges anything but the caller's own blocks.  Results are
+ * bit-identical to one handle with all the channels.  cfg->device is ignored; a device may be listed
+ * more than once (logical shards). */
+typedef struct pvb_multi pvb_multi;
+PVB_API int32_t pvb_multi_create(const pvb_config *cfg, const int32_t *device_ids, int32_t num_devices,
+                                 pvb_multi **out);
+PVB_API void pvb_multi_destroy(pvb_multi *m);
+PVB_API const char *pvb_multi_last_error(const pvb_multi *m);
+PVB_API int32_t pvb_multi_num_devices(const pvb_multi *m);
+PVB_API int32_t pvb_multi_num_channels(const pvb_multi *m);
+/* the single-device handle of shard `index` and the channels it owns (introspection, options, state) */
+PVB_API pvb_processor *pvb_multi_shard(pvb_multi *m, int32_t index, int32_t *first_channel, int32_t *num_channels);
+PVB_API int32_t pvb_multi_set_option(pvb_multi *m, int32_t option, int64_t value);
+/* process() on HOST buffers [num_channels][hop] (K calls: [K][num_channels][hop]): every device copies its
+ * own slab in and out (pinned host memory recommended), all devices run concurrently; synchronous. */
+PVB_API int32_t pvb_multi_process(pvb_multi *m, const float *in, float *out, float pitch_factor);
+PVB_API int32_t pvb_multi_process_many(pvb_multi *m, const float *in, float *out, int32_t num_calls,
+                                       float pitch_factor);
+/* The single-root mode of a sharded deployment: in / out are DEVICE buffers on device_ids[0]
+ * ([num_calls][num_channels][hop], complete before the call).  Slabs are scattered to the other devices
+ * and results gathered back with peer copies on the copy engines over NVLink; synchronous. */
+PVB_API int32_t pvb_multi_process_root(pvb_multi *m, const float *in_dev, float *out_dev, int32_t num_calls,
+                                       float pitch_factor);
+
 /* pinned host memory for callers that want the host<->device copies of
  * pvb_process() to run at full PCIe speed */
 PVB_API void *pvb_alloc_host(size_t bytes);

@@ -60,6 +60,16 @@ _SIGNATURES = {
     "pvb_state_bytes": (C.c_size_t, [C.c_void_p]),
     "pvb_get_state": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "pvb_set_state": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "pvb_multi_create": (C.c_int32, [C.POINTER(PvbConfig), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
+    "pvb_multi_destroy": (None, [C.c_void_p]),
+    "pvb_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "pvb_multi_num_devices": (C.c_int32, [C.c_void_p]),
+    "pvb_multi_num_channels": (C.c_int32, [C.c_void_p]),
+    "pvb_multi_shard": (C.c_void_p, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pvb_multi_set_option": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64]),
+    "pvb_multi_process": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]),
+    "pvb_multi_process_many": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float]),
+    "pvb_multi_process_root": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float]),
     "pvb_alloc_host": (C.c_void_p, [C.c_size_t]),
     "pvb_free_host": (None, [C.c_void_p]),
 }

@@ -228,6 +228,74 @@ class BatchedPhaseVocoder:
         self.time_cursor = state["time_cursor"]
 
 
+class MultiDevicePhaseVocoder:
+    """One logical processor sharded over several GPUs of a node inside one process (pvb_multi_*):
+    `devices` lists the CUDA ordinals, shard i owns a contiguous pair-aligned block of channels on
+    devices[i].  Bit-identical to a single BatchedPhaseVocoder with all the channels."""
+
+    def __init__(self, num_channels: int, frame_size: int = BUFFERED_BLOCK_SIZE,
+                 hop_size: int = WEBAUDIO_BLOCK_SIZE, devices: Sequence[int] = (0,), **options):
+        self._lib = _lib.load()
+        cfg = _lib.PvbConfig(frame_size, hop_size, num_channels, -1)
+        ids = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self._lib.pvb_multi_create(C.byref(cfg), ids, len(devices), C.byref(h))
+        if rc != _lib.PVB_OK:
+            raise _lib.PhazeError(rc, (self._lib.pvb_multi_last_error(None) or b"").decode())
+        self._h = h
+        self.num_channels, self.frame_size, self.hop_size = num_channels, frame_size, hop_size
+        for name, value in options.items():
+            if name == "kernel" and isinstance(value, str):
+                value = BatchedPhaseVocoder._KERNELS[value]
+            self._check(self._lib.pvb_multi_set_option(h, BatchedPhaseVocoder._OPTIONS[name], int(value)))
+
+    def _check(self, rc):
+        if rc != _lib.PVB_OK:
+            raise _lib.PhazeError(rc, (self._lib.pvb_multi_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pvb_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def shards(self):
+        """[(first_channel, num_channels)] per device"""
+        out = []
+        for i in range(self._lib.pvb_multi_num_devices(self._h)):
+            lo, n = C.c_int32(), C.c_int32()
+            self._lib.pvb_multi_shard(self._h, i, C.byref(lo), C.byref(n))
+            out.append((lo.value, n.value))
+        return out
+
+    def process_many(self, blocks: np.ndarray | None, pitch_factor: float, num_calls: int | None = None) -> np.ndarray:
+        """blocks [K][C][hop] on the host (None == paused, give num_calls) -> [K][C][hop]"""
+        K = num_calls if blocks is None else blocks.shape[0]
+        inp = None
+        if blocks is not None:
+            blocks = np.ascontiguousarray(blocks, np.float32)
+            assert blocks.shape == (K, self.num_channels, self.hop_size)
+            inp = blocks.ctypes.data
+        out = np.empty((K, self.num_channels, self.hop_size), np.float32)
+        self._check(self._lib.pvb_multi_process_many(self._h, inp, out.ctypes.data, K, np.float32(pitch_factor)))
+        return out
+
+    def process(self, block: np.ndarray | None, pitch_factor: float) -> np.ndarray:
+        return self.process_many(None if block is None else block[None], pitch_factor, 1)[0]
+
+    def process_root(self, in_ptr: int | None, out_ptr: int, pitch_factor: float, num_calls: int = 1):
+        """in / out: device pointers on devices[0], [num_calls][C][hop]; synchronous"""
+        self._check(self._lib.pvb_multi_process_root(self._h, in_ptr, out_ptr, num_calls, np.float32(pitch_factor)))
+
+
 class PhaseVocoderProcessor:
     """Drop-in mirror of the reference class (phase-vocoder.js:16-174).
 

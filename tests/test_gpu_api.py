@@ -227,3 +227,42 @@ def test_full_size_config3_properties(oracle):
     want = oracle.OracleProcessor(N, hop, 8).run(x, np.float32(1.5))
     assert _rms(y[:8] - want) <= RMS_EXPECTED
     assert np.array_equal(y[:8], y[C - 8:])            # identical channels -> identical bits everywhere
+
+
+@pytest.mark.parametrize("N,hop,C,pf", [
+    (1024, 256, 32768, 1.25),      # BASELINE config 4: all 32768 channels (4681 CTAs of 7 pairs at frame 1024)
+    (256, 64, 8192, 1.2),          # BASELINE config 5: 8192 channels at every frame size of the sweep
+    (512, 128, 8192, 0.8),
+    (1024, 256, 8192, 1.2),
+    (2048, 512, 8192, 0.8),
+    (4096, 1024, 8192, 1.2),       # 2048 CTAs of 2 pairs
+])
+def test_full_size_configs_4_and_5(oracle, N, hop, C, pf):
+    """BASELINE configs 4 and 5 at their full channel counts (the grid-size edges the small parity cases do
+    not reach).  (a) A spread of channels -- both ends of the range, both sides of every 8-way shard
+    boundary, every 1021st channel -- matches the CPU oracle; (b) size-independent: the same channels
+    processed alone in a small handle give the same bits (channels are independent, pv:49-53), and a
+    silent channel pair in the middle of the batch stays exactly zero."""
+    from phaze_b200 import BatchedPhaseVocoder
+    from phaze_b200.sharded import shard_bounds
+    calls = N // hop + 6
+    rng = np.random.default_rng(N + C)
+    base = signals.channels(200, 128, calls * hop)
+    gain = rng.uniform(0.5, 1.0, C).astype(np.float32)
+    x = np.ascontiguousarray(base[np.arange(C) % 128] * gain[:, None])       # every channel its own roundings
+    quiet = 2 * (C // 4)
+    x[quiet:quiet + 2] = 0.0
+    picks = sorted({c for lo, hi in shard_bounds(C, 8) for c in (lo, lo + 1, hi - 2, hi - 1)} | set(range(5, C, 1021)))
+    with BatchedPhaseVocoder(C, N, hop) as pv:
+        y = pv.run(x, np.float32(pf))
+        assert pv.kernel_launches == calls and pv.ring_stuck_count == 0
+    assert not y[quiet:quiet + 2].any()
+    want = oracle.OracleProcessor(N, hop, len(picks)).run(x[picks], np.float32(pf))
+    err = _rms(y[picks] - want)
+    print(f"N={N} C={C} pf={pf}: {len(picks)} channels vs oracle rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+    pairs = sorted({c & ~1 for c in picks})[:24]
+    idx = [c for p in pairs for c in (p, p + 1)]
+    with BatchedPhaseVocoder(len(idx), N, hop) as pv:
+        small = pv.run(x[idx], np.float32(pf))
+    assert np.array_equal(small, y[idx])
