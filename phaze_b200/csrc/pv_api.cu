@@ -92,6 +92,7 @@ struct Experiments {
     int ring_wpc = 0;      // PVB_RING_WPC: pairs per CTA of the ring kernel (0: default)
     int stagger_ns = 0;    // PVB_STAGGER_NS: start offset between warps sharing an SM
     bool no_aligned = false;   // PVB_NO_ALIGNED=1: warp kernel without the hop % 128 == 0 specialisation
+    int trace = 0;         // PVB_TRACE=n: %globaltimer start / end stamps of the first n ring launches of the process
     Experiments() {
         auto geti = [](const char *name, int dflt) { const char *e = std::getenv(name); return e ? std::atoi(e) : dflt; };
         skip = geti("PVB_SKIP", 0);
@@ -100,13 +101,17 @@ struct Experiments {
         ring_wpc = geti("PVB_RING_WPC", 0);
         stagger_ns = geti("PVB_STAGGER_NS", 0);
         no_aligned = geti("PVB_NO_ALIGNED", 0) == 1;
+        trace = geti("PVB_TRACE", 0);
     }
 };
 const Experiments &experiments() { static const Experiments e; return e; }
+unsigned long long *g_trace_buf = nullptr;
+int g_trace_next = 0;
 #else
 struct Experiments {
     static constexpr int skip = 0, early = -1, ring_pad_kb = 0, ring_wpc = 0, stagger_ns = 0;
     static constexpr bool no_aligned = false;
+    static constexpr int trace = 0;
 };
 constexpr Experiments experiments() { return Experiments(); }
 #endif
@@ -422,6 +427,20 @@ pvb::RingParams make_ring_params(const pvb_processor *h, const pvb::FrameParams 
     rp.xlocks = h->xpool->locks;
     rp.xslots = h->xpool->slots;
     rp.xcount = h->d_xcount;
+    rp.stamps = nullptr;
+#ifdef PVB_EXPERIMENTS
+    if (experiments().trace > 0) {
+        // one (start, end) pair per launch, in launch order; pvb_trace_dump() prints them
+        std::lock_guard<std::mutex> lk(g_stream_mu);
+        if (!g_trace_buf) {
+            cudaMalloc(&g_trace_buf, size_t(experiments().trace) * 2 * sizeof(unsigned long long));
+            std::vector<unsigned long long> init(size_t(experiments().trace) * 2);
+            for (size_t i = 0; i < init.size(); i += 2) { init[i] = ~0ull; init[i + 1] = 0; }
+            cudaMemcpy(g_trace_buf, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+        }
+        if (g_trace_next < experiments().trace) rp.stamps = g_trace_buf + 2 * size_t(g_trace_next++);
+    }
+#endif
     rp.done = h->d_done;
     rp.err = h->d_err;
     rp.wait_seq = h->ring_seq;
@@ -449,7 +468,8 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     pvb::RingLaunch l;
     l.pairs = (fp.num_channels + 1) / 2;
     if (l.pairs == 0) return cudaSuccess;
-    l.ppc = (h->n == 1024) ? pick_warps_per_cta(l.pairs, h->num_sms) : 0;
+    // (builds with more than 7 pairs per CTA at frame 1024, -DPVB_RING_PAIRS_1024: always full CTAs)
+    l.ppc = (h->n == 1024 && pvb::RingGeoT<1024>::MAX_PAIRS <= 7) ? pick_warps_per_cta(l.pairs, h->num_sms) : 0;
     if (experiments().ring_wpc > 0) l.ppc = experiments().ring_wpc;           // PVB_RING_WPC
     l.pad_kb = experiments().ring_pad_kb;                                     // PVB_RING_PAD_KB
     l.pdl = h->opt_launch_mode != 2;
@@ -1074,6 +1094,16 @@ int64_t pvb_peak_guard_count(pvb_processor *p) {
     if (cudaMemcpy(&v, p->d_xcount, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return int64_t(v);
 }
+
+#ifdef PVB_EXPERIMENTS
+// experiment builds only: copy the launch stamps out (ns; start = earliest CTA start, end = latest CTA end)
+PVB_API int32_t pvb_trace_dump(unsigned long long *out, int32_t capacity) {
+    cudaDeviceSynchronize();
+    const int n = g_trace_next < capacity ? g_trace_next : capacity;
+    if (n > 0) cudaMemcpy(out, g_trace_buf, size_t(n) * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    return n;
+}
+#endif
 
 int32_t pvb_set_option(pvb_processor *p, int32_t option, int64_t value) {
     if (!p) return PVB_ERR_BAD_ARG;

@@ -135,7 +135,8 @@ struct RingGeoT {
     static constexpr int OFF_WIN = OFF_TWH + TWH_SMEM;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_SMEM;
     static constexpr int TAB_BYTES = OFF_WOUT + WIN_SMEM;
-    static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16 : (N == 1024) ? PVB_RING_PAIRS_1024
+    static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16
+                                     : (N == 1024) ? ((PCH && PVB_RING_PAIRS_1024 > 7) ? 7 : PVB_RING_PAIRS_1024)
                                      : (N == 2048) ? (PCH ? 3 : 4) : 2;     // pairs per CTA (two CTAs per SM must fit 227 KB)
     // MULTI kernels (a loop over process() calls around the body) need more than 128 registers per thread
     // to stay out of local memory: three quarters of the pairs per CTA, 168 registers
@@ -183,6 +184,9 @@ struct RingParams {
     unsigned *xlocks;           // one lock word per slot
     int xslots;
     unsigned long long *xcount; // number of channel frames re-decided so far (diagnostics)
+    // -DPVB_EXPERIMENTS only: [2] earliest CTA start / latest CTA end of this launch in %globaltimer
+    // nanoseconds (profiles/overlap_trace.py: how far consecutive launches overlap), or nullptr
+    unsigned long long *stamps;
 };
 
 __device__ __forceinline__ float4 pack4(cpx2 v) { return make_float4(v.re.x, v.re.y, v.im.x, v.im.y); }
@@ -1154,7 +1158,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
         float4 ext[4];
         ext[0] = ext[1] = ext[2] = ext[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (l0) ext[0] = XQ[G::SM];
-        if (contract) {
+        if (contract && !(xskip & 32)) {
             constexpr int QO = N / 4 + N / 64;                        // slots between bins k and k + N/4
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -1174,7 +1178,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
         pair_sync<TP>(pin);      // every thread holds its sources: the buffer becomes Y
         // (PVB_RING_EXACT: while contracting every bin of [0, nb) is stored exactly once in the first
         // sub-step, provided both channels have peaks)
-        if (!(PVB_RING_EXACT && contract && any0 && any1)) {
+        if (!(PVB_RING_EXACT && contract && any0 && any1) && !(xskip & 8)) {
 #pragma unroll
             for (int i = 0; i < 17; i++) XQ[tp + TP * i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tp < 2) XQ[17 * TP + tp] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1188,6 +1192,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #define PVB_NOT_DUMP(d) true
 #endif
         // first sub-step: plain stores (pairwise disjoint destinations)
+        if (!(xskip & 16))
 #pragma unroll
         for (int e = 0; e < 16; e++) {
             if (dst0[e] >= 0 && PVB_NOT_DUMP(dst0[e])) {
@@ -1219,7 +1224,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 }
             }
         }
-        if (contract) {
+        if (contract && !(xskip & 4)) {
             // second sub-step: left halves add on top (pairwise disjoint among themselves, so the
             // loads of a batch can all be issued before the first store)
             pair_sync<TP>(pin);
@@ -1428,6 +1433,13 @@ pv_process_ring_kernel(const RingParams p) {
     const int tp = threadIdx.x % TP, pin = threadIdx.x / TP;
     const int pair = blockIdx.x * (blockDim.x / TP) + pin;
     bool live = 2 * pair < p.num_channels;
+#ifdef PVB_EXPERIMENTS
+    if (p.stamps && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMin(p.stamps, now);
+    }
+#endif
     if constexpr (MULTI) {
         live = ring_one_call<N, NBLK, PCH, 1>(p, 0, live);
 #pragma unroll 1
@@ -1435,6 +1447,13 @@ pv_process_ring_kernel(const RingParams p) {
     } else {
         live = ring_one_call<N, NBLK, PCH, 0>(p, 0, live);
     }
+#ifdef PVB_EXPERIMENTS
+    if (p.stamps && threadIdx.x == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(p.stamps + 1, now);
+    }
+#endif
     if (!live) return;
     // release: state and output of this pair are complete for call my_seq.  The pair barrier orders
     // every thread's stores before thread 0's release store, which is cumulative at gpu scope;
