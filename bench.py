@@ -5,9 +5,11 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1]): 4096 mono channels PER GPU, frame 1024 / hop 256,
-pitchFactor 0.8.  One "step" == one process() call over one 4096-channel batch == 4096
-STFT frames (window -> FFT -> peak shift -> IFFT -> overlap-add, 12*N algorithmic bytes
-each).  State of one batch (32 MiB) would fit in the 126 MB L2, so the
+pitchFactor 0.8.  One "step" == one batch of synthetic input == --calls-per-step (64) consecutive
+hops of all 4096 channels == 64 process() calls == 64 launches of the fused kernel == 262144 STFT
+frames (window -> FFT -> peak shift -> IFFT -> overlap-add, 12*N algorithmic bytes each, SURVEY.md
+section 8d).  (Round 1 timed one call per step: at the driver's --steps 20 the timed region was then
+0.35 ms and a fifth of it was the drain of the last launch, which nothing overlaps.)  State of one batch (32 MiB) would fit in the 126 MB L2, so the
 timed loop rotates over `rotate` independent 4096-channel processor instances whose
 combined state exceeds L2 (timing rule: inputs larger than L2).
 
@@ -50,8 +52,11 @@ L2_BYTES = 126e6
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--calls-per-step", type=int, default=64,
+                    help="process() calls per step: one step = one batch of this many consecutive hops "
+                         "of every channel (64 x 4096 frames at the default workload)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frame", type=int, default=FRAME)
     ap.add_argument("--hop", type=int, default=0, help="default: frame/4")
@@ -215,16 +220,17 @@ def run_reference(args):
     frame, hop = args.frame, (args.hop or args.frame // 4)
     threads = os.cpu_count() or 1
     pitch = np.float32(args.pitch)
-    # one step == one process() call over a bounded sample of the per-GPU batch
+    # one step == calls_per_step process() calls over a bounded sample of the per-GPU batch
+    cps = max(1, args.calls_per_step)
     probe, _ = cpu_port_rate(frame, hop, pitch, 8 * threads, 8, threads)
     budget_s = 120.0
-    total = args.steps + args.warmup
+    total = (args.steps + args.warmup) * cps
     chans = int(min(args.channels, max(threads, probe * budget_s / max(total, 1))))
     chans = max(threads, chans - chans % threads)
     if args.warmup:
-        cpu_port_rate(frame, hop, pitch, chans, args.warmup, threads)
-    rate, dt = cpu_port_rate(frame, hop, pitch, chans, args.steps, threads)
-    sample = (f"each step = one process() call over {chans} of the {args.channels} channels "
+        cpu_port_rate(frame, hop, pitch, chans, args.warmup * cps, threads)
+    rate, dt = cpu_port_rate(frame, hop, pitch, chans, args.steps * cps, threads)
+    sample = (f"each step = {cps} process() calls over {chans} of the {args.channels} channels "
               f"({frame}/{hop}, pf={args.pitch}); {threads} host threads, one processor instance each")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
@@ -233,7 +239,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": workload_name(args.channels, frame, hop, args.pitch),
                    "frame": frame, "hop": hop, "pitch_factor": args.pitch,
-                   "channels_per_gpu": args.channels, "channels_per_step": chans},
+                   "channels_per_gpu": args.channels, "calls_per_step": cps, "channels_per_step": chans},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -280,6 +286,7 @@ def run_ours(args):
 
     frame, hop = args.frame, (args.hop or args.frame // 4)
     C, K, W = args.channels, args.steps, args.warmup
+    CPS = max(1, args.calls_per_step)
     R = frame // hop
     pitch = np.float32(args.pitch)
     state_bytes = 2 * C * frame * 4 + 2 * C * hop * 4
@@ -307,13 +314,18 @@ def run_ours(args):
     sptr = stream.cuda_stream
     assert sptr != 0
 
-    def step(i):
+    def call(i):
         procs[i % rotate].process_device(blocks[i % nblk].data_ptr(), outs[i % rotate].data_ptr(),
                                          pitch, sptr)
 
+    def step(i):
+        # one step: CPS consecutive process() calls, round-robin over the resident processor instances
+        for j in range(i * CPS, (i + 1) * CPS):
+            call(j)
+
     # prime: fill every instance's history so all frames carry signal
     for i in range(rotate * R):
-        step(i)
+        call(i)
     torch.cuda.synchronize()
 
     # The clock sampler runs on rank 0 only (one NVML thread per node instead of one per GPU)
@@ -342,7 +354,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
-    timed_run(max(W, 20), 0)           # untimed: first-use costs (module load, allocator, clocks ramp)
+    timed_run(max(W, 3), 0)            # untimed: first-use costs (module load, allocator, clocks ramp)
     launches0 = sum(p.kernel_launches for p in procs)
     guard0 = sum(p.peak_guard_count for p in procs)
     if sampler:
@@ -353,7 +365,7 @@ def run_ours(args):
     if dist:
         dist.barrier()
         torch.cuda.synchronize()
-    launches = sum(p.kernel_launches for p in procs) - launches0 - W
+    launches = sum(p.kernel_launches for p in procs) - launches0 - W * CPS
     guard_frames = sum(p.peak_guard_count for p in procs) - guard0
     if sampler:
         sampler.stop()
@@ -361,7 +373,7 @@ def run_ours(args):
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    frames_total = world * K * C
+    frames_total = world * K * CPS * C
     value = frames_total / (ms_max * 1e-3)
 
     # the same K steps with the launch chaining switched off (PVB_OPT_LAUNCH_MODE): 1 = programmatic
@@ -373,7 +385,7 @@ def run_ours(args):
         for p in procs:
             p.set_option("launch_mode", mode)
         ms_m = timed_run(K, W)
-        chain[name] = {"value": K * C / (ms_m * 1e-3), "avg_launch_us": 1e3 * ms_m / K}
+        chain[name] = {"value": K * CPS * C / (ms_m * 1e-3), "avg_launch_us": 1e3 * ms_m / (K * CPS)}
     for p in procs:
         p.set_option("launch_mode", 0)
 
@@ -386,7 +398,7 @@ def run_ours(args):
         Kb = 64
         bin_ = blocks.repeat((Kb + nblk - 1) // nblk, 1, 1)[:Kb].contiguous()        # [Kb][C][hop]
         bouts = [torch.empty((Kb, C, hop), dtype=torch.float32, device="cuda") for _ in range(2)]
-        nb = max(2, min(rotate, K // Kb))
+        nb = max(2, min(rotate, K * CPS // Kb))
 
         for p in procs:
             p.set_option("many_mode", 1)
@@ -409,7 +421,7 @@ def run_ours(args):
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12     # non-tensor FP32, TFLOP/s at the maximum SM clock
         batched = {"value": bval, "unit": UNIT, "calls_per_launch": Kb, "launches": nb,
                    "us_per_call": 1e3 * bms / (nb * Kb),
-                   "vs_one_launch_per_call": bval / (K * C / (ms * 1e-3)),
+                   "vs_one_launch_per_call": bval / (K * CPS * C / (ms * 1e-3)),
                    "compulsory_dram_bytes_per_frame": 8 * hop + 12.0 * frame / Kb,
                    "fp32": {"flop_per_frame_estimate": flop_per_frame, "achieved_tflops": bval * flop_per_frame / 1e12,
                             "peak_tflops": fp32_peak, "frac": bval * flop_per_frame / 1e12 / fp32_peak},
@@ -421,14 +433,15 @@ def run_ours(args):
 
     # context only: (a) one instance, state stays in L2; (b) every instance on its own stream
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for i in range(min(W, 50)):
+    KC = K * CPS                       # calls of the context runs
+    for i in range(50):
         procs[0].process_device(blocks[i % nblk].data_ptr(), outs[0].data_ptr(), pitch, sptr)
     ev2.record(stream)
-    for i in range(K):
+    for i in range(KC):
         procs[0].process_device(blocks[i % nblk].data_ptr(), outs[0].data_ptr(), pitch, sptr)
     ev3.record(stream)
     torch.cuda.synchronize()
-    l2_value = K * C / (ev2.elapsed_time(ev3) * 1e-3)
+    l2_value = KC * C / (ev2.elapsed_time(ev3) * 1e-3)
 
     side = [torch.cuda.Stream() for _ in range(rotate)]
     ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -436,7 +449,7 @@ def run_ours(args):
     ev4.record(stream)
     for st in side:
         st.wait_event(ev4)
-    for i in range(K):
+    for i in range(KC):
         procs[i % rotate].process_device(blocks[i % nblk].data_ptr(), outs[i % rotate].data_ptr(),
                                          pitch, side[i % rotate].cuda_stream)
     for st in side:
@@ -445,22 +458,22 @@ def run_ours(args):
         stream.wait_event(e)
     ev5.record(stream)
     torch.cuda.synchronize()
-    streams_value = K * C / (ev4.elapsed_time(ev5) * 1e-3)
+    streams_value = KC * C / (ev4.elapsed_time(ev5) * 1e-3)
 
     # e2e: host buffers through the C ABI (pinned), H2D + D2H in the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(procs, blocks_np, C, hop, pitch, K, dist)
+        e2e = run_e2e(procs, blocks_np, C, hop, pitch, K, CPS, dist)
 
     root_scatter = None
     if dist and not args.no_root_scatter:
-        root_scatter = run_root_scatter(C, frame, hop, pitch, world, rank, local, min(K, 300), host)
+        root_scatter = run_root_scatter(C, frame, hop, pitch, world, rank, local, min(KC, 300), host)
 
     peak, peak_src = measured_peak()
     traffic, traffic_src = (ncu_traffic_bytes() if (frame, hop, C, round(float(pitch), 3)) == (FRAME, HOP, CHANNELS, PITCH)
                             else (None, None))
-    assert launches == K, (launches, K)
-    kernel_ms = ms / max(launches, 1)                 # this rank's average launch duration
+    assert launches == K * CPS, (launches, K, CPS)
+    kernel_ms = ms / max(launches, 1)                 # this rank's average launch duration (start to start)
     achieved = 12.0 * frame * C / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
@@ -495,14 +508,16 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(C, frame, hop, args.pitch),
                        "frame": frame, "hop": hop, "pitch_factor": args.pitch,
-                       "channels_per_gpu": C, "frames_per_step": C * world,
+                       "channels_per_gpu": C, "calls_per_step": CPS, "frames_per_step": C * CPS * world,
+                       "step": f"one batch of {CPS} consecutive hops of every channel = {CPS} process() calls = "
+                               f"{CPS} kernel launches (round-robin over the resident processor instances)",
                        "l2_policy": f"inputs larger than L2: {rotate} processor instances "
-                                    f"({rotate * state_bytes / 2**20:.0f} MiB of state+io) rotated per step",
+                                    f"({rotate * state_bytes / 2**20:.0f} MiB of state+io) rotated per call",
                        "parallelism": f"channel-sharded x{world}, no data-path collective",
                        "launch": "one stream; consecutive launches chained by programmatic dependent launch, "
                                  "each channel pair waits for its own previous call (completion flags)",
-                       "timed_region": "barrier, device-side gate, W warm-up launches, event, K launches, event: "
-                                       "queued back to back, no synchronize between warm-up and timed launches"},
+                       "timed_region": "barrier, device-side gate, W warm-up steps, event, K steps, event: "
+                                       "queued back to back, no synchronize between warm-up and timed steps"},
             "roofline": roofline,
             "e2e": e2e,
             "host_thread_affinity": numa,
@@ -511,7 +526,7 @@ def run_ours(args):
             "launch_chaining": chain,
             "batched": batched,
             "peak_guard": {"option": args.peak_guard, "frames_redecided_in_float64": int(guard_frames),
-                           "of_frames": int((K + W) * C),
+                           "of_frames": int((K + W) * CPS * C),
                            "note": "channel frames whose peak set was re-decided with the fft.js-order float64 "
                                    "transform during warm-up + timed launches (this rank)"},
             "l2_resident_value": l2_value,
@@ -530,7 +545,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
+def run_e2e(procs, blocks_np, C, hop, pitch, K, CPS, dist):
     """Same metric through the host-buffer entry points: every step copies its input block from
     pinned host memory to the device and its output block back (4 MiB each way at the default
     workload).  `value` uses pvb_process_many (128 consecutive process() calls per submission,
@@ -544,7 +559,7 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
     lib = phaze_b200_lib()
     nblk = blocks_np.shape[0]
     nbytes = C * hop * 4
-    batch = 128
+    batch = CPS                       # one submission == one step: CPS process() calls
     hin = lib.pvb_alloc_host(nbytes * batch)
     hout = lib.pvb_alloc_host(nbytes * batch)
     for k in range(batch):
@@ -578,9 +593,9 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
         rc = lib.pvb_process(procs[i % len(procs)]._h, hin + (i % batch) * nbytes, hout, pitch)
         assert rc == 0, rc
 
-    steps = int(max(batch, min(K, 4096) // batch * batch))
+    steps = int(min(K, 64)) * batch                   # process() calls: K steps (at most 64) of `batch` calls
     value = timed(many, steps, batch)
-    single_value = timed(single, int(min(K, 400)), 1)
+    single_value = timed(single, int(min(K * CPS, 400)), 1)
     check = float(np.ctypeslib.as_array(Ct.cast(hout, Ct.POINTER(Ct.c_float)), (C * hop,)).std())
     # what bounds it: the host link.  Probe: the same two pinned buffers copied both ways at once on
     # two streams, nothing else running (GB/s in each direction)
@@ -607,8 +622,8 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, dist):
     world = dist.get_world_size() if dist else 1
     lib.pvb_free_host(hin)
     lib.pvb_free_host(hout)
-    return {"value": value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-            "steps": steps, "calls_per_submission": batch,
+    return {"value": value, "unit": UNIT, "h2d_bytes_per_step": nbytes * batch, "d2h_bytes_per_step": nbytes * batch,
+            "steps": steps // batch, "calls_per_submission": batch,
             "api": f"pvb_process_many(handle, in_host, out_host, {batch}, pitch): pinned host buffers, "
                    "H2D / kernel / D2H of consecutive calls overlapped, synchronous on return",
             "single_call_value": single_value, "out_std": check,
