@@ -65,6 +65,17 @@ namespace pvb {
 #ifndef PVB_RING_NO_DUMP
 #define PVB_RING_NO_DUMP 0
 #endif
+// Gather middle (see "gather middle" in ring_one_call): the shifted spectrum is GATHERED in the order the
+// Hermitian pre-pass wants it, from region descriptors in destination space; it never exists in shared
+// memory (no zero fill, no scatter, no read-add-store sub-step, no owner scan per bin).  Measured on B200 at
+// frame 1024 (profiles/r02_gather_ab.txt): parity-green on every GPU test, shared-memory wavefronts per
+// pair 1706 -> 1410, but 4652 instead of 4296 instructions per pair (the per-peak descriptor loop runs as
+// long as the busiest lane's run has peaks, and a quarter of its instructions copy descriptors to group
+// starts), and the kernel retires instructions at the same rate either way: 17.9 us against 16.5 us per
+// launch.  The default build therefore keeps the scatter middle; `make gather` builds this variant.
+#ifndef PVB_RING_GATHER
+#define PVB_RING_GATHER 0
+#endif
 
 // PCH: per-channel pitch factors (pvb_process_pf): the key table becomes per pair (two deltas per bin)
 template <int N_, bool PCH_ = false>
@@ -105,7 +116,23 @@ struct RingGeoT {
     // cross-warp exchange of the region scan: [4][TP] keys, [2][WPP] ballots; then the peak guard's
     // [2][WPP] energy sums, [2][WPP] uncertainty ballots and its scratch slot number
     static constexpr int SCR_BYTES = (WPP > 1) ? 4 * TP * 4 + 32 + 96 : 0;
-    static constexpr int BUF_SLOTS = (XQ_SLOTS > EX_SLOTS) ? XQ_SLOTS : EX_SLOTS;
+    // ---- gather middle: X as four planes of 32-bit words (re0 | re1 | im0 | im1, bin k at word k, the first
+    // stale level behind bin M), the squared magnitudes as (ch0, ch1) pairs padded every 16 bins for the run
+    // reads, and later in their place one array of region descriptors per channel
+    static constexpr bool GATHER = PVB_RING_GATHER && !PCH_ && (N_ == 1024);
+    static constexpr int XPW = M + N / 8;                   // words per plane: bins 0 .. M + N/8 - 1
+    static constexpr int X_BYTES = 4 * XPW * 4;
+    static constexpr int MAG_UNITS = 17 * TP + 6;           // bin k at unit k + (k >> 4) + 3
+    static constexpr int DW = M + 4;                        // descriptor words per channel (destinations 0 .. M)
+    static constexpr int B_BYTES = GATHER ? ((MAG_UNITS * 8 > 2 * DW * 4) ? MAG_UNITS * 8 : 2 * DW * 4) : 0;
+    static constexpr int A_SLOTS = GATHER ? ((X_BYTES / 16 > EX_SLOTS) ? X_BYTES / 16 : EX_SLOTS)
+                                          : ((XQ_SLOTS > EX_SLOTS) ? XQ_SLOTS : EX_SLOTS);
+    static constexpr int BUF_SLOTS = A_SLOTS + B_BYTES / 16;
+    static constexpr int A_BYTES = A_SLOTS * 16;
+    // descriptor fields: T' (low TB bits) | overlap c (CB bits) | -delta (signed, the rest)
+    static constexpr int TB = (N_ == 256) ? 8 : (N_ == 512) ? 9 : (N_ == 1024) ? 10 : (N_ == 2048) ? 11 : 12;
+    static constexpr int CB = 9;
+    static constexpr int LRW = (TP >= 32) ? 5 : (TP == 16) ? 4 : 3;     // log2 of the lanes of a pair in one warp
     // two pairs per warp (frame 512): their buffers sit 16 banks apart, so the 32-bit plane accesses
     // of the two half-warps (16 consecutive words each) do not collide
     // (frame 256: four pairs per warp, 8 banks apart)
@@ -126,7 +153,12 @@ struct RingGeoT {
     // L1, every CTA reads the same lines); with them in shared memory only one CTA fits an SM and
     // nothing overlaps its load phase (measured: 35 % of the roofline against 4x % with two CTAs)
     static constexpr bool GT = (N == 4096);
-    static constexpr int TWH_SMEM = GT ? 0 : TWH_BYTES, WIN_SMEM = GT ? 0 : WIN_BYTES;
+    // gather middle: 14.3 KB per pair instead of 8.5; two CTAs of seven pairs still fit an SM once the split
+    // twiddles are read through L1 (22 loads per thread and call) and the synthesis window is derived from the
+    // analysis window (times 1 / (2 N R), a power of two: exact)
+    static constexpr bool TWH_GLOBAL = GT || GATHER, WOUT_DERIVED = GT || GATHER;
+    static constexpr int TWH_SMEM = TWH_GLOBAL ? 0 : TWH_BYTES, WIN_SMEM = GT ? 0 : WIN_BYTES;
+    static constexpr int WOUT_SMEM = WOUT_DERIVED ? 0 : WIN_BYTES;
     // global: NTAB x tw1 | w64 | w128 | twh; shared: ktab | tw1 | w64 | w128 | twh | window | window_out
     static constexpr int OFF_TW1 = PCH ? 0 : DTAB_BYTES;
     static constexpr int OFF_W64 = OFF_TW1 + TW1_BYTES;
@@ -134,7 +166,7 @@ struct RingGeoT {
     static constexpr int OFF_TWH = OFF_W128 + W128_BYTES;
     static constexpr int OFF_WIN = OFF_TWH + TWH_SMEM;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_SMEM;
-    static constexpr int TAB_BYTES = OFF_WOUT + WIN_SMEM;
+    static constexpr int TAB_BYTES = OFF_WOUT + WOUT_SMEM;
     static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16
                                      : (N == 1024) ? ((PCH && PVB_RING_PAIRS_1024 > 7) ? 7 : PVB_RING_PAIRS_1024)
                                      : (N == 2048) ? (PCH ? 3 : 4) : 2;     // pairs per CTA (two CTAs per SM must fit 227 KB)
@@ -146,7 +178,8 @@ struct RingGeoT {
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
     static constexpr int MIN_PAIRS = (MIN_THREADS + TP - 1) / TP;
     static constexpr int INVALID_DELTA = 0x3000;            // lands outside [0, nb) from any bin
-    static_assert(2 * (TAB_BYTES + MAX_PAIRS * PAIR_BYTES) <= 227 * 1024, "two CTAs per SM must fit the shared memory");
+    // (228 KB per SM, 1 KB of it reserved per resident CTA)
+    static_assert(2 * (TAB_BYTES + MAX_PAIRS * PAIR_BYTES + 1024) <= 228 * 1024, "two CTAs per SM must fit the shared memory");
 };
 using RingGeo = RingGeoT<1024>;
 
@@ -561,6 +594,247 @@ __device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__
     return mask;
 }
 
+// forward real-split of one (k, M-k) pair into registers: 2 X[k] -> xk, 2 X[M-k] -> xm (both channels)
+__device__ __forceinline__ void ring_split_regs(cpx2 za, cpx2 zb, float2 w, cpx2 &xk, cpx2 &xm) {
+    const float2 e_r = add2(za.re, zb.re), e_i = sub2(za.im, zb.im);
+    const float2 o_r = add2(za.im, zb.im), o_i = sub2(zb.re, za.re);
+    const cpx2 tt = cmul_s(cpx2{o_r, o_i}, w.x, w.y);
+    xk = cpx2{add2(e_r, tt.re), add2(e_i, tt.im)};
+    xm = cpx2{sub2(e_r, tt.re), sub2(tt.im, e_i)};
+}
+
+// Gather middle, step C: one descriptor per peak of this thread's run (bits of `mask`, bins b0 .. b0 + 15),
+// for one channel.  pkey / nkey: keys (2 (bin + 2048) << 16 | delta + 32768) of the nearest peaks below /
+// above the run (pkey 0: none below; nkey: a far-away bin when there is none above); krun[e]: key of bin
+// b0 + e.  See ring_one_call for the descriptor semantics.
+template <int NB, int TB, int CB, int LRW, int INVALID>
+__device__ __forceinline__ void ring_emit_descriptors(uint32_t mask, int b0, int pkey, int nkey, const int *krun,
+                                                      bool contract, int *D) {
+    constexpr int RW = 1 << LRW, TMAX = (1 << TB) - 2;
+    if (!mask) return;
+    int e = __ffs(mask) - 1;
+    mask &= mask - 1;
+    int pos = b0 + e, dl = (krun[e] & 0xFFFF) - 32768;
+    int s = 0, dp = contract ? dl : 0;                                 // no peak below: the region starts at bin 0
+    if (pkey) {
+        const int pp = (pkey >> 17) - 2048;
+        dp = (pkey & 0xFFFF) - 32768;
+        s = pos - ((pos - pp) >> 1);
+    }
+    int q = s + min(dl, dp), T = s + max(dl, dp), c = contract ? dp - dl : 0;
+#pragma unroll 1
+    for (;;) {
+        // the next peak: its region starts where this one ends
+        const bool more = mask != 0;
+        const int en = (__ffs(mask) - 1) & 15;
+        mask &= mask - 1;
+        const int keyn = more ? krun[en] : nkey;
+        const int pn = (keyn >> 17) - 2048, dn = (keyn & 0xFFFF) - 32768;
+        const int sn = pn - ((pn - pos) >> 1);
+        const int qn = sn + min(dn, dl);
+        const int qs = max(q, 0);
+        if (qs < NB) {
+            const int Tp = min(max(T, 0), TMAX) + 1;
+            const int nd = (dl == INVALID) ? 0 : -dl;                  // (an invalid peak only ever zeroes)
+            const int word = Tp | (c << TB) | int(unsigned(nd) << (TB + CB));
+            D[qs] = word;
+            const int lim = min(qn, NB);
+            // copies at the bins = 0, 1 (mod RW) inside (qs, lim): most regions have none
+            if ((((lim - 1) ^ qs) >> LRW) != 0 || (qs & (RW - 1)) == 0) {
+#pragma unroll 1
+                for (int x0 = qs & ~(RW - 1); x0 < lim; x0 += RW) {
+                    if (x0 > qs) D[x0] = word;
+                    if (x0 + 1 > qs && x0 + 1 < lim) D[x0 + 1] = word;
+                }
+            }
+        }
+        if (!more) break;
+        T = sn + max(dn, dl);
+        c = contract ? dl - dn : 0;
+        q = qn;
+        pos = pn;
+        dl = dn;
+    }
+}
+
+// Gather middle, step D: one bin of the shifted spectrum of channel `ch`.  base = pair buffer + 4 d (d: the
+// destination bin of this thread), dp1 = d + 1.  The descriptor in force is the latest one at or below d: the
+// lanes of the pair in this warp hold one aligned group of bins, ascending with the lane (MTYPE false) or
+// descending (MTYPE true); SELF: the bin is a multiple of RW, where a descriptor always is.
+template <int N, bool CONTRACT, bool MTYPE, bool SELF>
+__device__ __forceinline__ float2 ring_gather_one(const unsigned char *base, int ch, int dp1, unsigned FULL, unsigned lmask) {
+    using G = RingGeoT<N>;
+    const int w = *reinterpret_cast<const int *>(base + G::A_BYTES + ch * 4 * G::DW);
+    int got = w;
+    if (!SELF) {
+        const unsigned ball = __ballot_sync(FULL, w != 0) & lmask;
+        const int src = MTYPE ? __ffs(ball) - 1 : 31 - __clz(ball);
+        got = __shfl_sync(FULL, w, src);
+    }
+    const float *xs = reinterpret_cast<const float *>(base + ch * 4 * G::XPW) + (got >> (G::TB + G::CB));   // X[d - delta]
+    const bool zone = dp1 < (got & ((1 << G::TB) - 1));
+    float re, im;
+    if (CONTRACT) {
+        re = xs[0];
+        im = xs[2 * G::XPW];
+        if (zone) {                                                    // the previous region reaches this bin too
+            const float *x2 = xs - ((got >> G::TB) & ((1 << G::CB) - 1));
+            re += x2[0];
+            im += x2[2 * G::XPW];
+        }
+    } else {
+        re = im = 0.f;                                                 // gap between two regions
+        if (!zone) {
+            re = xs[0];
+            im = xs[2 * G::XPW];
+        }
+    }
+    return make_float2(re, im);
+}
+
+// Gather middle, step D: the shifted spectrum straight into the Hermitian C2R pre-pass (mirror of the split):
+// step j takes Y[k] and Y[M - k], k = tp + KS j (thread 0: the bins of its two self-paired butterflies), and
+// leaves the inputs of inverse pass 1 in a[] / b[].
+template <int N, bool CONTRACT>
+__device__ __forceinline__ void ring_gather_unsplit(const unsigned char *mine, const float2 *twh, int tp, int lane,
+                                                    unsigned FULL, cpx2 (&a)[8], cpx2 (&b)[8]) {
+    using G = RingGeoT<N>;
+    constexpr int M = G::M, KS = G::KS;
+    const bool l0 = tp == 0;
+    const int klo = l0 ? KS / 2 : tp, khi = l0 ? -4 * KS : tp;
+    const unsigned lem = (2u << lane) - 1u, gem = ~((1u << lane) - 1u);
+    cpx2 zk[8], zmk[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int dk = (j < 4 ? klo : khi) + KS * j, dm = M - dk;
+        const unsigned char *bk = mine + 4 * dk, *bm = mine + 4 * dm;
+        const float2 k0 = ring_gather_one<N, CONTRACT, false, false>(bk, 0, dk + 1, FULL, lem);
+        const float2 k1 = ring_gather_one<N, CONTRACT, false, false>(bk, 1, dk + 1, FULL, lem);
+        const float2 q0 = ring_gather_one<N, CONTRACT, true, false>(bm, 0, dm + 1, FULL, gem);
+        const float2 q1 = ring_gather_one<N, CONTRACT, true, false>(bm, 1, dm + 1, FULL, gem);
+        cpx2 yk{make_float2(k0.x, k1.x), make_float2(k0.y, k1.y)};
+        cpx2 ym{make_float2(q0.x, q1.x), make_float2(q0.y, q1.y)};
+        if (j == 4) {                            // thread 0: k == 0, bins 0 and N/2 enter with their real part only
+            yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
+            ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
+        }
+        const float2 *wp = twh + (j < 4 ? klo : khi) + KS * j;
+        const float2 w = G::TWH_GLOBAL ? __ldg(wp) : *wp;
+        ring_unsplit(yk, ym, w, zk[j], zmk[j]);
+    }
+    cpx2 zh, dummy;
+    {
+        const unsigned char *bh = mine + 4 * (M / 2);
+        const float2 h0 = ring_gather_one<N, CONTRACT, false, true>(bh, 0, M / 2 + 1, FULL, 0u);
+        const float2 h1 = ring_gather_one<N, CONTRACT, false, true>(bh, 1, M / 2 + 1, FULL, 0u);
+        const cpx2 y{make_float2(h0.x, h1.x), make_float2(h0.y, h1.y)};
+        const float2 w = G::TWH_GLOBAL ? __ldg(twh + M / 2) : twh[M / 2];
+        ring_unsplit(y, y, w, zh, dummy);
+    }
+    a[0] = sel(l0, zk[4], zk[0]);
+    a[1] = sel(l0, zk[5], zk[1]);
+    a[2] = sel(l0, zk[6], zk[2]);
+    a[3] = sel(l0, zk[7], zk[3]);
+    a[4] = sel(l0, zh, zk[4]);
+    a[5] = sel(l0, zmk[7], zk[5]);
+    a[6] = sel(l0, zmk[6], zk[6]);
+    a[7] = sel(l0, zmk[5], zk[7]);
+    b[0] = sel(l0, zk[0], zmk[7]);
+    b[1] = sel(l0, zk[1], zmk[6]);
+    b[2] = sel(l0, zk[2], zmk[5]);
+    b[3] = sel(l0, zk[3], zmk[4]);
+    b[4] = zmk[3];
+    b[5] = zmk[2];
+    b[6] = zmk[1];
+    b[7] = zmk[0];
+}
+
+// Peak masks of this thread's run for both channels from the squared magnitudes m0 / m1 of bins 16 tp - 2 ..
+// 16 tp + 17 (esum: the thread's share of the frame energy per channel), peak guard included (see above).
+template <int N, bool PCH>
+__device__ __forceinline__ void ring_masks(const RingParams &p, const int (&m0)[20], const int (&m1)[20], float2 esum,
+                                           uint32_t &mask0, uint32_t &mask1, unsigned char *mine, int pair, int tp,
+                                           int pin, int lane, unsigned FULL, bool has1, int t) {
+    using G = RingGeoT<N, PCH>;
+    constexpr int TP = G::TP;
+    if (p.guard_min == 0x7fffffff) {
+        mask0 = ring_peak_mask(m0);
+        mask1 = ring_peak_mask(m1);
+        if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; }          // i >= 2
+        if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); }       // i <= nb - 3
+    } else {
+        // ---- peak guard: frame energy per channel, uncertain comparisons, exact re-decision ----
+        constexpr int TPW = (TP < 32) ? TP : 32;
+#pragma unroll
+        for (int off = TPW / 2; off > 0; off >>= 1) {
+            esum = add2(esum, make_float2(__shfl_xor_sync(FULL, esum.x, off), __shfl_xor_sync(FULL, esum.y, off)));
+        }
+        int *gscr = reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16) + 4 * TP + 8;   // multi-warp pairs only
+        if constexpr (G::WPP > 1) {
+            if (lane == 0) {
+                gscr[tp >> 5] = __float_as_int(esum.x);
+                gscr[G::WPP + (tp >> 5)] = __float_as_int(esum.y);
+            }
+            pair_sync<TP>(pin);
+            esum = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < G::WPP; w++)
+                esum = add2(esum, make_float2(__int_as_float(gscr[w]), __int_as_float(gscr[G::WPP + w])));
+        }
+        constexpr float KSCALE = -16.0f * PVB_GUARD_C * PVB_GUARD_C;
+        uint32_t unc0, unc1;
+        ring_peak_masks_guarded(m0, m1, mul2(esum, bc2(KSCALE)), mask0, mask1, unc0, unc1);
+        if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; unc0 &= ~3u; unc1 &= ~3u; }
+        if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); unc0 &= ~(1u << 15); unc1 &= ~(1u << 15); }
+        // uncertain comparisons of the whole frame, per channel
+        int n0 = __reduce_add_sync(FULL, __popc(unc0)), n1 = __reduce_add_sync(FULL, __popc(unc1));
+        if constexpr (G::WPP > 1) {
+            if (lane == 0) {
+                gscr[8 + (tp >> 5)] = n0;
+                gscr[8 + G::WPP + (tp >> 5)] = n1;
+            }
+            pair_sync<TP>(pin);
+            n0 = n1 = 0;
+#pragma unroll
+            for (int w = 0; w < G::WPP; w++) {
+                n0 += gscr[8 + w];
+                n1 += gscr[8 + G::WPP + w];
+            }
+        }
+        bool redo0 = n0 >= p.guard_min, redo1 = n1 >= p.guard_min;
+        redo1 = redo1 && has1;
+        if (redo0 | redo1) {
+            // a scratch slot of 2N doubles from the pool (at least as many slots as pairs can be
+            // resident on the device, so the probe always ends)
+            int slot = 0;
+            if (tp == 0) {
+                slot = int((unsigned(pair) * 2654435761u) % unsigned(p.xslots));
+                while (atomicCAS(p.xlocks + slot, 0u, 1u) != 0u) {
+                    slot = (slot + 1 == p.xslots) ? 0 : slot + 1;
+                    __nanosleep(100);
+                }
+                __threadfence();
+                atomicAdd(p.xcount, (unsigned long long)(int(redo0) + int(redo1)));
+            }
+            if constexpr (G::WPP > 1) {
+                if (tp == 0) gscr[16] = slot;
+                pair_sync<TP>(pin);
+                slot = gscr[16];
+            } else {
+                slot = __shfl_sync(FULL, slot, (TP == 32) ? 0 : int(threadIdx.x & (32 - TP)));
+            }
+            double *xo = p.xpool + size_t(slot) * size_t(2 * N);
+            const float2 *ring = reinterpret_cast<const float2 *>(p.hist2 + size_t(pair) * (N / 2));
+            if (redo0) mask0 = ring_exact_peak_mask<N, TP>(ring, p.window2, p.xtw, p.xrev, xo, t, 0, tp, pin);
+            if (redo1) mask1 = ring_exact_peak_mask<N, TP>(ring, p.window2, p.xtw, p.xrev, xo, t, 1, tp, pin);
+            if (tp == 0) {
+                __threadfence();
+                atomicExch(p.xlocks + slot, 0u);
+            }
+        }
+    }
+}
+
 // N = frame size (512: half a warp per pair, 1024: one warp, 2048: two warps, 4096: four warps),
 // NBLK = hop / 128.
 // Registers of the first / last FFT pass are indexed by FRAME block f (128 samples), so the role
@@ -601,21 +875,23 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
     const float2 *tw1 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_TW1);
     const float2 *w64 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W64);
     // (frame 4096: twh and the windows are read from global memory, see RingGeoT::GT)
-    const float2 *twh = G::GT ? reinterpret_cast<const float2 *>(p.gtab + G::NTAB * (G::TW1_BYTES / 16) +
+    const float2 *twh = G::TWH_GLOBAL ? reinterpret_cast<const float2 *>(p.gtab + G::NTAB * (G::TW1_BYTES / 16) +
                                                                (G::W64_BYTES + G::W128_BYTES) / 16)
                               : reinterpret_cast<const float2 *>(smem_raw + G::OFF_TWH);
     const float2 *w128 = reinterpret_cast<const float2 *>(smem_raw + G::OFF_W128);   // frame 4096 only
     const float *swin = G::GT ? p.window2 : reinterpret_cast<const float *>(smem_raw + G::OFF_WIN);
     // (frame 4096: the synthesis window is the analysis window times 1 / (2 N R), a power of two, so
     // only one window table competes for L1 there)
-    const float *swout = G::GT ? p.window2 : reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
-    constexpr float WOUT_SCALE = G::GT ? 1.0f / (2.0f * float(N) * float(N / (NBLK * G::UNIT))) : 1.0f;
+    const float *swout = G::WOUT_DERIVED ? swin : reinterpret_cast<const float *>(smem_raw + G::OFF_WOUT);
+    constexpr float WOUT_SCALE = G::WOUT_DERIVED ? 1.0f / (2.0f * float(N) * float(N / (NBLK * G::UNIT))) : 1.0f;
 #define PVB_TLD2(ptr) (G::GT ? __ldg(ptr) : *(ptr))
+#define PVB_TWH(ptr) (G::TWH_GLOBAL ? __ldg(ptr) : *(ptr))
     unsigned char *mine = smem_raw + G::TAB_BYTES + size_t(pin) * G::PAIR_BYTES;
     // key table: what a peak at bin pk contributes to the region scan.  Scalar pitch factor: one table per
     // CTA, entry = position | delta.  PCH: one per pair, entry = delta of channel 0 | delta of channel 1
     // (the position is the index)
     int *ktab = PCH ? reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16 + G::SCR_BYTES) : reinterpret_cast<int *>(smem_raw);
+    (void)swout;
     float4 *ex = reinterpret_cast<float4 *>(mine);
     float4 *XQ = reinterpret_cast<float4 *>(mine);
 
@@ -674,7 +950,8 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             const int i = threadIdx.x + k * blockDim.x;
             if (first && i < G::WIN_SMEM / 16) {
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_win + 16 * i), "l"(w1 + i));
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_wout + 16 * i), "l"(w2 + i));
+                if constexpr (G::WOUT_SMEM > 0)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(s_wout + 16 * i), "l"(w2 + i));
             }
         }
         // delta = round(pk * pitchFactor) - pk in exact integer arithmetic (pv:125-127)
@@ -940,6 +1217,200 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
     dft8<false>(b);      // b[j] = Z[kB + KS j]
     pair_sync<TP>(pin);  // everyone has read the exchange slots: X may overwrite them
 
+    if constexpr (G::GATHER) {
+    // =====================================================================================================
+    // Gather middle.  Regions of influence in DESTINATION space: region i (peak p_i, delta_i, sources
+    // [s_i, s_{i+1}), s_i = p_i - floor((p_i - p_{i-1}) / 2), s_0 = 0, pv:132-141) lands on
+    // [s_i + delta_i, s_{i+1} + delta_i).  With q_i = s_i + min(delta_i, delta_{i-1}) and
+    // T_i = s_i + max(delta_i, delta_{i-1}) the destination axis is cut at the q_i, and inside [q_i, q_{i+1})
+    //     d <  T_i :  contracting: Y[d] = X[d - delta_i] + X[d - delta_{i-1}]   (two regions overlap)
+    //                 expanding:   Y[d] = 0                                      (gap between two regions)
+    //     d >= T_i :  Y[d] = X[d - delta_i]
+    // (pitch factors >= 0.75: never more than two regions on one bin).  A peak whose shifted position is
+    // beyond nb (pv:127, only while expanding) has a huge delta: the same formulas give q = end of the previous
+    // image and T = "never", i.e. zeros to the end, and later peaks fall outside [0, nb).
+    //  A. the split writes X as four planes of words (the first stale level, bundle:394-438, behind bin M:
+    //     all four operands of a stale slot sit in one thread) and |X|^2 as (ch0, ch1) pairs;
+    //  B. every thread reads the magnitudes of its run of 16 bins (+ 2 on each side): peak masks, peak guard;
+    //  C. every thread walks the peaks of its run and stores one 32-bit descriptor per peak
+    //     (T' | c << TB | -delta << (TB + CB), c = delta_{i-1} - delta_i) at D[max(q_i, 0)], and copies of it at
+    //     every bin = 0 or 1 (mod RW) inside (q_i, q_{i+1}), RW = lanes of a pair in one warp: every aligned
+    //     group of RW destination bins then has a descriptor at its first and at its second bin;
+    //  D. the Hermitian pre-pass takes Y[tp + KS j] and Y[M - tp - KS j] in step j: the RW lanes cover one
+    //     aligned group (thread 0's bins are multiples of RW, where a descriptor always is), so the latest
+    //     descriptor at or below a bin is one ballot and one shuffle away, nothing is carried from step to
+    //     step, and the shifted spectrum goes from X to registers without ever existing in shared memory.
+    // tests/ring_kernel_model.py::gather_rows_kernel is the numpy blueprint (checked against the oracle).
+    // =====================================================================================================
+    constexpr int XPW = G::XPW, TB = G::TB, CB = G::CB, RW = 1 << G::LRW;
+    float *xp = reinterpret_cast<float *>(mine);                                  // planes re0 | re1 | im0 | im1
+    float2 *mg = reinterpret_cast<float2 *>(mine + G::A_BYTES);                   // |X|^2, bin k at unit k + (k >> 4) + 3
+    int *D0 = reinterpret_cast<int *>(mine + G::A_BYTES), *D1 = D0 + G::DW;       // descriptors (over the magnitudes)
+    const bool contract = p.pitch_factor < 1.0f;
+    const int klo = l0 ? KS / 2 : tp, khi = l0 ? -4 * KS : tp;                    // bin of slot j: klo / khi + KS j
+    const int tlo = klo, thi = khi;
+    {
+        // ---- A: real split in registers -> X planes, magnitudes, stale bins -----------------------------------
+        float *xk_lo = xp + klo, *xk_hi = xp + khi;                               // + KS j
+        float *xm_lo = xp + (M - klo), *xm_hi = xp + (M - khi);                   // - KS j
+        float2 *uk_lo = mg + (klo + (klo >> 4) + 3), *uk_hi = mg + (khi + (khi >> 4) + 3);           // + SS j
+        float2 *um_lo = mg + ((M - klo) + ((M - klo) >> 4) + 3), *um_hi = mg + ((M - khi) + ((M - khi) >> 4) + 3);   // - SS j
+        auto put = [&](float *xw, float2 *mu, const cpx2 &v) {
+            xw[0] = v.re.x; xw[XPW] = v.re.y; xw[2 * XPW] = v.im.x; xw[3 * XPW] = v.im.y;
+            *mu = fma2(v.re, v.re, mul2(v.im, v.im));                             // pv:82-92, float32
+        };
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const int j4 = jj + 4;
+            cpx2 k0, m0v, k4, m4;
+            {
+                const cpx2 za = sel(l0, b[jj], a[jj]);
+                ring_split_regs(za, b[7 - jj], PVB_TWH(twh + tlo + KS * jj), k0, m0v);
+            }
+            {
+                const cpx2 za = sel(l0, a[jj], a[j4]);
+                const cpx2 zb = sel(l0, a[(12 - j4) & 7], b[7 - j4]);
+                ring_split_regs(za, zb, PVB_TWH(twh + thi + KS * j4), k4, m4);
+            }
+            put(xk_lo + KS * jj, uk_lo + SS * jj, k0);
+            put(xm_lo - KS * jj, um_lo - SS * jj, m0v);
+            put(xk_hi + KS * j4, uk_hi + SS * j4, k4);
+            put(xm_hi - KS * j4, um_hi - SS * j4, m4);
+            if (contract) {
+                // first stale level (what _realTransform4 leaves in slot N/2 + q, rebuilt from the valid half):
+                // S[q] = ((X[q] - X[N/4 + q]) + conj(X[M - q] - X[N/4 - q])) conj(W_N^{2q}) / 4.  Slots jj and
+                // jj + 4 of a thread hold bins k, k + N/4, M - k, N/4 - k: q = tp, tp + KS (from k) and
+                // 2 KS - tp, KS - tp (from M - k).  Thread 0's bins pair differently (see below).
+                const bool fromk = jj < 2;
+                const int q = (jj == 0) ? tp : (jj == 1) ? tp + KS : (jj == 2) ? 2 * KS - tp : KS - tp;
+                const cpx2 &A = fromk ? k0 : m4, &Bv = fromk ? k4 : m0v, &Cv = fromk ? m0v : k4, &Dv = fromk ? m4 : k0;
+                const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, Dv.re));
+                const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, Dv.im));
+                const float2 w = PVB_TWH(twh + 2 * q);
+                const cpx2 sv = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
+                if (!l0) {
+                    float *xe = xp + M + q;
+                    xe[0] = sv.re.x; xe[XPW] = sv.re.y; xe[2 * XPW] = sv.im.x; xe[3 * XPW] = sv.im.y;
+                }
+            }
+        }
+        if (l0) {
+            cpx2 hk, hm;
+            ring_split_regs(a[4], a[4], PVB_TWH(twh + M / 2), hk, hm);
+            put(xp + M / 2, mg + (M / 2 + M / 32 + 3), hm);
+        }
+    }
+    pair_sync<TP>(pin);
+
+    uint32_t mask0, mask1;
+    if (!(xskip & 1)) {
+        // ---- B: squared magnitudes of the run (bins 16 tp - 2 .. 16 tp + 17), peak masks, peak guard ---------
+        int m0[20], m1[20];
+        float2 esum = make_float2(0.f, 0.f);
+        {
+            const float2 *mrun = mg + 17 * tp;                                    // unit of bin 16 tp - 2
+#pragma unroll
+            for (int i = 0; i < 20; i++) {
+                const float2 v = mrun[(i < 2) ? i : (i < 18) ? i + 1 : i + 2];
+                m0[i] = __float_as_int(v.x);
+                m1[i] = __float_as_int(v.y);
+                if (i >= 2 && i < 18) esum = add2(esum, v);                       // own run: energy of the frame
+            }
+        }
+        ring_masks<N, PCH>(p, m0, m1, esum, mask0, mask1, mine, pair, tp, pin, lane, FULL, has1, t);
+        // thread 0 rebuilds the three stale bins whose operands sit in its registers in another order
+        // (q = KS/2, KS, 3 KS/2); threads 1 .. 3 do it from the planes instead
+        if (contract && tp >= 1 && tp <= 3) {
+            const int q = (KS / 2) * tp;
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                const float *re = xp + ch * XPW, *im = xp + (2 + ch) * XPW;
+                const float sr = (re[q] - re[N / 4 + q]) + (re[M - q] - re[N / 4 - q]);
+                const float si = (im[q] - im[N / 4 + q]) - (im[M - q] - im[N / 4 - q]);
+                const float2 w = PVB_TWH(twh + 2 * q);
+                const float wr = 0.25f * w.x, wi = -0.25f * w.y;
+                // (same operation order as cmul_s)
+                xp[ch * XPW + M + q] = fmaf(sr, wr, -(si * wi));
+                xp[(2 + ch) * XPW + M + q] = fmaf(sr, wi, si * wr);
+            }
+        }
+    } else {
+        mask0 = mask1 = 0;
+    }
+    pair_sync<TP>(pin);          // everyone has read the magnitudes: the descriptors take their place
+    {
+        // ---- C: descriptors -------------------------------------------------------------------------------
+        {
+            int4 *dz = reinterpret_cast<int4 *>(D0);
+#pragma unroll
+            for (int i = 0; i < (2 * G::DW / 4 + TP - 1) / TP; i++)
+                if (tp + TP * i < 2 * G::DW / 4) dz[tp + TP * i] = make_int4(0, 0, 0, 0);
+        }
+        const int *krun = ktab + 20 * tp;                                         // keys of bins 16 tp .. + 15
+        int pk0, nk0, pk1, nk1;
+        bool any0, any1;
+        {
+            // keys of the nearest peaks below / above this thread's run (0: none below)
+            const int il0 = (31 - __clz(mask0)) & 15, if0 = (__ffs(mask0) - 1) & 15;
+            const int il1 = (31 - __clz(mask1)) & 15, if1 = (__ffs(mask1) - 1) & 15;
+            const int ol0 = krun[il0], of0 = krun[if0], ol1 = krun[il1], of1 = krun[if1];
+            const int none_above = ((2 * 8190) << 16) | 32768;                    // "peak" at +6142 with delta 0
+            if constexpr (TP <= 32) {
+                constexpr uint32_t PM = (TP == 32) ? 0xFFFFFFFFu : (TP == 16) ? 0xFFFFu : 0xFFu;
+                const int hb = (TP == 32) ? 0 : int(threadIdx.x & (32 - TP));
+                const uint32_t nz0 = (__ballot_sync(FULL, mask0 != 0) >> hb) & PM;
+                const uint32_t nz1 = (__ballot_sync(FULL, mask1 != 0) >> hb) & PM;
+                const uint32_t lt = (1u << tp) - 1u, gt = ~((2u << tp) - 1u) & PM;
+                pk0 = __shfl_sync(FULL, ol0, hb + ((31 - __clz(nz0 & lt)) & (TP - 1)));
+                nk0 = __shfl_sync(FULL, of0, hb + ((__ffs(nz0 & gt) - 1) & (TP - 1)));
+                pk1 = __shfl_sync(FULL, ol1, hb + ((31 - __clz(nz1 & lt)) & (TP - 1)));
+                nk1 = __shfl_sync(FULL, of1, hb + ((__ffs(nz1 & gt) - 1) & (TP - 1)));
+                if (!(nz0 & lt)) pk0 = 0;
+                if (!(nz0 & gt)) nk0 = none_above;
+                if (!(nz1 & lt)) pk1 = 0;
+                if (!(nz1 & gt)) nk1 = none_above;
+                any0 = nz0 != 0;
+                any1 = nz1 != 0;
+            } else {
+                constexpr int WPP = G::WPP;
+                int *scr = reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16);     // [4][TP] keys, [2][WPP] ballots
+                scr[tp] = ol0; scr[TP + tp] = of0; scr[2 * TP + tp] = ol1; scr[3 * TP + tp] = of1;
+                const uint32_t bl0 = __ballot_sync(FULL, mask0 != 0), bl1 = __ballot_sync(FULL, mask1 != 0);
+                if (lane == 0) { scr[4 * TP + (tp >> 5)] = int(bl0); scr[4 * TP + WPP + (tp >> 5)] = int(bl1); }
+                pair_sync<TP>(pin);
+                const int *bal0 = scr + 4 * TP, *bal1 = bal0 + WPP;
+                const int tb0 = ring_thread_below<WPP>(bal0, tp), ta0 = ring_thread_above<WPP>(bal0, tp);
+                const int tb1 = ring_thread_below<WPP>(bal1, tp), ta1 = ring_thread_above<WPP>(bal1, tp);
+                pk0 = (tb0 >= 0) ? scr[tb0] : 0;
+                nk0 = (ta0 >= 0) ? scr[TP + ta0] : none_above;
+                pk1 = (tb1 >= 0) ? scr[2 * TP + tb1] : 0;
+                nk1 = (ta1 >= 0) ? scr[3 * TP + ta1] : none_above;
+                any0 = ring_thread_last<WPP>(bal0) >= 0;
+                any1 = ring_thread_last<WPP>(bal1) >= 0;
+            }
+        }
+        pair_sync<TP>(pin);      // the descriptor arrays are zero
+        ring_emit_descriptors<NB, TB, CB, G::LRW, G::INVALID_DELTA>(mask0, 16 * tp, pk0, nk0, krun, contract, D0);
+        ring_emit_descriptors<NB, TB, CB, G::LRW, G::INVALID_DELTA>(mask1, 16 * tp, pk1, nk1, krun, contract, D1);
+        // a channel without peaks: the shifted spectrum is zero (pv:121).  Rare (silence): its planes are
+        // zeroed and every group gets a descriptor that reads them.
+        if (!any0 || !any1) {
+            pair_sync<TP>(pin);
+#pragma unroll 1
+            for (int ch = 0; ch < 2; ch++) {
+                if (ch ? any1 : any0) continue;
+                for (int i = tp; i < XPW; i += TP) xp[ch * XPW + i] = xp[(2 + ch) * XPW + i] = 0.f;
+                int *Dc = ch ? D1 : D0;
+                for (int x = RW * tp; x <= M; x += RW * TP) Dc[x] = Dc[x + 1] = 1;
+            }
+        }
+    }
+    pair_sync<TP>(pin);
+
+    // ---- D: gather + Hermitian C2R pre-pass in registers (mirror of the split) -----------------------------
+    if (contract) ring_gather_unsplit<N, true>(mine, twh, tp, lane, FULL, a, b);
+    else ring_gather_unsplit<N, false>(mine, twh, tp, lane, FULL, a, b);
+    } else {
     // ---- real split in registers -> XQ (2x scaled) --------------------------------------------------
     // slot j pairs (a[j], b[7-j]) at k = tp + KS j.  thread 0: j < 4: (b[j], b[7-j]) at k = KS/2 + KS j;
     // j >= 4: (a[j-4], a[(12-j)&7]) at k = KS (j-4); plus the self pair k = M/2 (a[4]).
@@ -951,15 +1422,15 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const cpx2 za = sel(l0, b[j], a[j]);
-        ring_split(za, b[7 - j], PVB_TLD2(twh + tlo + KS * j), XQ + sAlo + SS * j, XQ + sBlo - SS * j);
+        ring_split(za, b[7 - j], PVB_TWH(twh + tlo + KS * j), XQ + sAlo + SS * j, XQ + sBlo - SS * j);
     }
 #pragma unroll
     for (int j = 4; j < 8; j++) {
         const cpx2 za = sel(l0, a[j - 4], a[j]);
         const cpx2 zb = sel(l0, a[(12 - j) & 7], b[7 - j]);
-        ring_split(za, zb, PVB_TLD2(twh + thi + KS * j), XQ + sAhi + SS * j, XQ + sBhi - SS * j);
+        ring_split(za, zb, PVB_TWH(twh + thi + KS * j), XQ + sAhi + SS * j, XQ + sBhi - SS * j);
     }
-    if (l0) ring_split(a[4], a[4], PVB_TLD2(twh + M / 2), XQ + M / 2 + M / 32, XQ + M / 2 + M / 32);
+    if (l0) ring_split(a[4], a[4], PVB_TWH(twh + M / 2), XQ + M / 2 + M / 32, XQ + M / 2 + M / 32);
     pair_sync<TP>(pin);
 
     // ---- peaks, regions of influence, shift (pv:95-173) -------------------------------------------------
@@ -987,82 +1458,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 m1[i] = __float_as_int(mg.y);
                 if (i >= 2 && i < 18) esum = add2(esum, mg);          // own run: energy of the frame
             }
-            if (p.guard_min == 0x7fffffff) {
-                mask0 = ring_peak_mask(m0);
-                mask1 = ring_peak_mask(m1);
-                if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; }          // i >= 2
-                if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); }       // i <= nb - 3
-            } else {
-                // ---- peak guard: frame energy per channel, uncertain comparisons, exact re-decision ----
-                constexpr int TPW = (TP < 32) ? TP : 32;
-#pragma unroll
-                for (int off = TPW / 2; off > 0; off >>= 1) {
-                    esum = add2(esum, make_float2(__shfl_xor_sync(FULL, esum.x, off), __shfl_xor_sync(FULL, esum.y, off)));
-                }
-                int *gscr = reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16) + 4 * TP + 8;   // multi-warp pairs only
-                if constexpr (G::WPP > 1) {
-                    if (lane == 0) {
-                        gscr[tp >> 5] = __float_as_int(esum.x);
-                        gscr[G::WPP + (tp >> 5)] = __float_as_int(esum.y);
-                    }
-                    pair_sync<TP>(pin);
-                    esum = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int w = 0; w < G::WPP; w++)
-                        esum = add2(esum, make_float2(__int_as_float(gscr[w]), __int_as_float(gscr[G::WPP + w])));
-                }
-                constexpr float KSCALE = -16.0f * PVB_GUARD_C * PVB_GUARD_C;
-                uint32_t unc0, unc1;
-                ring_peak_masks_guarded(m0, m1, mul2(esum, bc2(KSCALE)), mask0, mask1, unc0, unc1);
-                if (tp == 0) { mask0 &= ~3u; mask1 &= ~3u; unc0 &= ~3u; unc1 &= ~3u; }
-                if (tp == TP - 1) { mask0 &= ~(1u << 15); mask1 &= ~(1u << 15); unc0 &= ~(1u << 15); unc1 &= ~(1u << 15); }
-                // uncertain comparisons of the whole frame, per channel
-                int n0 = __reduce_add_sync(FULL, __popc(unc0)), n1 = __reduce_add_sync(FULL, __popc(unc1));
-                if constexpr (G::WPP > 1) {
-                    if (lane == 0) {
-                        gscr[8 + (tp >> 5)] = n0;
-                        gscr[8 + G::WPP + (tp >> 5)] = n1;
-                    }
-                    pair_sync<TP>(pin);
-                    n0 = n1 = 0;
-#pragma unroll
-                    for (int w = 0; w < G::WPP; w++) {
-                        n0 += gscr[8 + w];
-                        n1 += gscr[8 + G::WPP + w];
-                    }
-                }
-                bool redo0 = n0 >= p.guard_min, redo1 = n1 >= p.guard_min;
-                redo1 = redo1 && has1;
-                if (redo0 | redo1) {
-                    // a scratch slot of 2N doubles from the pool (at least as many slots as pairs can be
-                    // resident on the device, so the probe always ends)
-                    int slot = 0;
-                    if (tp == 0) {
-                        slot = int((unsigned(pair) * 2654435761u) % unsigned(p.xslots));
-                        while (atomicCAS(p.xlocks + slot, 0u, 1u) != 0u) {
-                            slot = (slot + 1 == p.xslots) ? 0 : slot + 1;
-                            __nanosleep(100);
-                        }
-                        __threadfence();
-                        atomicAdd(p.xcount, (unsigned long long)(int(redo0) + int(redo1)));
-                    }
-                    if constexpr (G::WPP > 1) {
-                        if (tp == 0) gscr[16] = slot;
-                        pair_sync<TP>(pin);
-                        slot = gscr[16];
-                    } else {
-                        slot = __shfl_sync(FULL, slot, (TP == 32) ? 0 : int(threadIdx.x & (32 - TP)));
-                    }
-                    double *xo = p.xpool + size_t(slot) * size_t(2 * N);
-                    const float2 *ring = reinterpret_cast<const float2 *>(p.hist2 + size_t(pair) * (N / 2));
-                    if (redo0) mask0 = ring_exact_peak_mask<N, TP>(ring, p.window2, p.xtw, p.xrev, xo, t, 0, tp, pin);
-                    if (redo1) mask1 = ring_exact_peak_mask<N, TP>(ring, p.window2, p.xtw, p.xrev, xo, t, 1, tp, pin);
-                    if (tp == 0) {
-                        __threadfence();
-                        atomicExch(p.xlocks + slot, 0u);
-                    }
-                }
-            }
+            ring_masks<N, PCH>(p, m0, m1, esum, mask0, mask1, mine, pair, tp, pin, lane, FULL, has1, t);
         }
 
         int dst0[16], dst1[16];
@@ -1170,7 +1566,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 const cpx2 Cv = unpack4(XQ[sm]), D = unpack4(XQ[sm - QO]);         // bins M - q, N/4 - q
                 const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, D.re));
                 const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, D.im));
-                const float2 w = PVB_TLD2(twh + 2 * qq);
+                const float2 w = PVB_TWH(twh + 2 * qq);
                 const cpx2 sv = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
                 if (q) ext[i] = pack4(sv);
             }
@@ -1274,13 +1670,13 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
                 ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
             }
-            const float2 w = PVB_TLD2(twh + (j < 4 ? tlo : thi) + KS * j);
+            const float2 w = PVB_TWH(twh + (j < 4 ? tlo : thi) + KS * j);
             ring_unsplit(yk, ym, w, zk[j], zmk[j]);
         }
         cpx2 zh, dummy;
         {
             const cpx2 y = ring_load_planes<G::XQ_SLOTS>(mine, M / 2 + ((M / 2) >> YS));
-            ring_unsplit(y, y, PVB_TLD2(twh + M / 2), zh, dummy);
+            ring_unsplit(y, y, PVB_TWH(twh + M / 2), zh, dummy);
         }
         a[0] = sel(l0, zk[4], zk[0]);
         a[1] = sel(l0, zk[5], zk[1]);
@@ -1299,6 +1695,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
         b[6] = zmk[1];
         b[7] = zmk[0];
     }
+    }   // scatter middle
     pair_sync<TP>(pin);  // everyone has read Y: the exchange slots may overwrite it
 
     // ---- inverse pass 1 (DIT): butterflies A and B over k3, twiddle conj(W_64^{k2 m3}) -------------------
@@ -1393,7 +1790,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 // by nbOverlaps (pv:65-67, ola:153) in one multiply (the scales are powers of two)
                 const int fb = PVB_FB(j);
                 float2 wo = PVB_TLD2(reinterpret_cast<const float2 *>(wol + 2 * TPH * h + 128 * fb));
-                if constexpr (G::GT) wo = make_float2(wo.x * WOUT_SCALE, wo.y * WOUT_SCALE);
+                if constexpr (G::WOUT_DERIVED) wo = make_float2(wo.x * WOUT_SCALE, wo.y * WOUT_SCALE);
                 const float4 qv = q[RT * h + j];
                 const float2 y0 = fma2(x[j].re, bc2(wo.x), make_float2(qv.x, qv.y));
                 const float2 y1 = fma2(x[j].im, bc2(wo.y), make_float2(qv.z, qv.w));
@@ -1416,6 +1813,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #undef PVB_RING_IDX
 #undef PVB_COL
 #undef PVB_TLD2
+#undef PVB_TWH
 }
 
 // N = frame size (512: half a warp per pair, 1024: one warp, 2048: two warps, 4096: four warps),

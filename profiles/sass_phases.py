@@ -35,6 +35,12 @@ for name, mark in sub:
         if mark in l:
             bounds.append((i + 1, name))
             break
+for name, mark in [("g:split+mags+stale", "---- A: real split in registers -> X planes"), ("g:mags+masks", "---- B: squared magnitudes of the run"),
+                   ("g:descriptors", "---- C: descriptors"), ("g:gather+unsplit", "---- D: gather + Hermitian C2R pre-pass in registers")]:
+    for i, l in enumerate(lines):
+        if mark in l:
+            bounds.append((i + 1, name))
+            break
 bounds.sort()
 BODY = (next(i + 1 for i, l in enumerate(lines) if "__device__ __forceinline__ bool ring_one_call" in l),
         next(i + 1 for i, l in enumerate(lines) if "#undef PVB_NOT_DUMP" in l))
@@ -56,6 +62,7 @@ with tempfile.TemporaryDirectory() as td:
 cur_fn, cur_line, in_fn = None, 0, False
 block, block_open = [], False
 cnt = collections.defaultdict(collections.Counter)
+seq = []                       # (phase, opcode) of every instruction of the function, in SASS order
 pending = None
 for l in sass.split("\n"):
     m = re.match(r"\.text\.(\S+):", l)
@@ -88,7 +95,12 @@ for l in sass.split("\n"):
             w = re.search(r"\.(64|128)", op)
             base = base + (w.group(1) if w else "32")
         cnt[phase_of(cur_line)][base] += 1
+        seq.append((phase_of(cur_line), op))
 
+if os.environ.get("SASS_PHASES_SEQ"):
+    with open(os.environ["SASS_PHASES_SEQ"], "w") as f:
+        for ph, op in seq:
+            f.write(f"{ph}\t{op}\n")
 CLASSES = [("mem", lambda o: o[:3] in ("LDS", "STS", "LDG", "STG", "ATO", "RED")), ("fp", lambda o: o[0] == "F" or o in ("HADD2", "HFMA2", "MUFU", "DADD", "DMUL", "DFMA")),
            ("shfl/vote", lambda o: o in ("SHFL", "VOTE", "VOTEU", "REDUX", "MATCH", "BAR", "WARPSYNC", "NANOSLEEP", "BSYNC", "BSSY")),]
 tot = collections.Counter()

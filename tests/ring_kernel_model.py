@@ -84,6 +84,7 @@ class Conflicts:
 
     def __init__(self):
         self.worst = {}
+        self.sparse = {}
 
     gather_log = None       # experiments: byte addresses (-1: lane idle) per 64-bit gather access
     scatter_log = None      # experiments: list of (destination bins, active lanes) per 32-bit scatter access
@@ -97,6 +98,22 @@ class Conflicts:
             byte_addr = np.concatenate([byte_addr + q * self.pair_bytes for q in range(4)])
         for w0 in range(0, byte_addr.size, 32):          # one warp at a time
             self._warp(name, byte_addr[w0:w0 + 32], width)
+
+    def note_sparse(self, name, word_idx):
+        """32-bit accesses with idle lanes (index -1): wavefronts per warp access accumulated as
+        (count, total) in self.sparse[name]"""
+        word_idx = np.asarray(word_idx).reshape(-1)
+        for w0 in range(0, word_idx.size, 32):
+            a = word_idx[w0:w0 + 32]
+            a = a[a >= 0]
+            if a.size == 0:
+                continue
+            banks = {}
+            for x in set(int(v) for v in a):
+                banks.setdefault(x % 32, set()).add(x)
+            wf = max(len(v) for v in banks.values())
+            c = self.sparse.setdefault(name, [0, 0])
+            c[0] += 1; c[1] += wf
 
     def _warp(self, name, byte_addr, width):
         assert byte_addr.size == 32
@@ -294,6 +311,166 @@ def gather_shift_lanes(g: Geo, xfull, mask, prev_before, next_after, dtab, contr
                     if len(srcs) > which:
                         addr[L] = 8 * (srcs[which] + (srcs[which] >> 4))
                 cf.gather_log.append(addr)
+    return Y
+
+
+def desc_layout(g: Geo):
+    """bit fields of the 32-bit region descriptors of gather_rows_kernel: T' in the low TB bits, the overlap
+    c in the next CB bits, -delta (signed) above"""
+    TB = int(np.log2(g.N))                 # T' = clamp(T, 0, 2^TB - 2) + 1 <= N - 1 (never zero: marks "present")
+    CB = 9                                  # overlap of two regions while contracting: <= (nb / 4) + 1 bins
+    return TB, CB
+
+
+def gather_rows_kernel(g: Geo, xfull, mask, prev_before, next_after, dtab, contract, cf: Conflicts | None = None,
+                       stats: dict | None = None):
+    """BLUEPRINT of the gather middle of pv_kernel_ring.cuh (PVB_RING_GATHER), thread by thread.
+
+    Regions of influence in DESTINATION space.  Region i (peak p_i, delta_i, sources [s_i, s_{i+1}),
+    s_i = p_i - floor((p_i - p_{i-1}) / 2), s_0 = 0) lands on [s_i + delta_i, s_{i+1} + delta_i).  With
+    q_i = s_i + min(delta_i, delta_{i-1}) and T_i = s_i + max(delta_i, delta_{i-1}) the destination axis is
+    cut at the q_i, and inside [q_i, q_{i+1}):
+        d <  T_i :  contracting: Y[d] = X[d - delta_i] + X[d - delta_{i-1}]   (the two regions overlap)
+                    expanding:   Y[d] = 0                                      (gap between the regions)
+        d >= T_i :  Y[d] = X[d - delta_i]
+    (pitch factors >= 0.75: never more than two regions on one bin).  A peak whose shifted position is
+    beyond nb (pv:127, only while expanding) has delta = INVALID (huge): the same formulas give q = end of the
+    previous image and T = "never", i.e. zeros to the end, and later peaks fall outside [0, nb).
+
+    A. Every thread walks the peaks of its SOURCE run and stores one 32-bit descriptor
+       (T' | c << TB | -delta << (TB + CB)) at D[max(q_i, 0)], and copies of it at every bin = 0 or 1
+       (mod RW) strictly inside (q_i, q_{i+1}) (RW = lanes of a pair in one warp): then every aligned
+       group of RW destination bins starts with a descriptor, at its first AND second bin.
+    B. Destinations are taken in the order the Hermitian pre-pass wants them: step j, thread tp holds
+       Y[tp + KS j] and Y[M - tp - KS j].  The RW lanes of a warp cover an aligned group (lane 0 of the
+       group holds an unrelated bin that is = 0 (mod RW), so its own descriptor is always there): the
+       latest descriptor at or below a bin comes from a ballot and one shuffle, nothing is carried from
+       step to step, and the shifted spectrum never exists in shared memory.
+    """
+    N, M, NB, TP, KS = g.N, g.M, g.NB, g.TP, g.KS
+    RW = min(TP, 32)
+    TB, CB = desc_layout(g)
+    TMAX = (1 << TB) - 2
+    DSZ = ((NB + RW - 1) // RW) * RW + RW
+    D = np.zeros(DSZ, np.int64)
+    n_src = xfull.shape[0]
+    st_addr = []                                        # descriptor stores: (iteration, lane, word index)
+    any_peak = bool((np.asarray(mask) != 0).any())
+    big = 1 << 20
+    for L in range(TP):                                # ---- A: descriptors --------------------------------
+        pp = int(prev_before[L]); has_prev = pp >= 0
+        bits = [e for e in range(16) if (int(mask[L]) >> e) & 1]
+        for it, e in enumerate(bits):
+            p = 16 * L + e
+            nxt = 16 * L + bits[it + 1] if it + 1 < len(bits) else int(next_after[L])
+            has_next = nxt < 20000
+            delta = int(dtab[p])
+            dprev = int(dtab[pp]) if has_prev else (delta if contract else 0)
+            s = p - ((p - pp) >> 1) if has_prev else 0
+            q = s + min(delta, dprev)
+            T = s + max(delta, dprev)
+            c = abs(dprev - delta) if contract else 0
+            if has_next:
+                dn = int(dtab[nxt])
+                qn = (nxt - ((nxt - p) >> 1)) + min(dn, delta)
+            else:
+                qn = big
+            if contract:
+                assert delta <= dprev and c < (1 << CB), (delta, dprev)
+                assert q >= 0 or c == 0
+                # never three regions on one bin: the next image starts after this overlap zone
+                assert qn >= T, "three regions overlap (pitch factor < 0.75?)"
+            qs = max(q, 0)
+            if qs >= NB:
+                continue
+            Tp = min(max(T, 0), TMAX) + 1
+            ndl = 0 if delta == INVALID_DELTA else -delta   # (an invalid peak's descriptor is all "zero zone")
+            word = Tp | (c << TB) | ((ndl & ((1 << (32 - TB - CB)) - 1)) << (TB + CB))
+            assert word != 0 and D[qs] == 0, "two regions start at one destination bin"
+            D[qs] = word
+            st_addr.append((it, L, qs))
+            lim = min(qn, NB)
+            r = qs // RW
+            while RW * r < lim:
+                for x in (RW * r, RW * r + 1):
+                    if qs < x < lim:
+                        assert D[x] == 0
+                        D[x] = word
+                        st_addr.append((it + 100 * (x - RW * r + 1), L, x))
+                r += 1
+            pp, has_prev = p, True
+    if not any_peak:
+        zero_forever = (TMAX + 1)
+        for r in range(0, DSZ // RW):
+            D[RW * r] = zero_forever; D[RW * r + 1] = zero_forever
+    if stats is not None:
+        stats.setdefault("desc_stores", []).append(len(st_addr))
+        stats.setdefault("peak_iters", []).append(max((bin(int(m)).count("1") for m in mask), default=0))
+
+    # ---- B: gather in the order of the Hermitian pre-pass ---------------------------------------------
+    sh = TB + CB
+    def fields(w):
+        Tp = w & ((1 << TB) - 1)
+        c = (w >> TB) & ((1 << CB) - 1)
+        nd = w >> sh
+        if nd >= 1 << (31 - sh):
+            nd -= 1 << (32 - sh)
+        return Tp, c, -nd
+    Y = np.zeros(NB, C64)
+    T_ = np.arange(TP)
+    gathers = []
+    for j in range(8):
+        dk = np.where(T_ == 0, (KS // 2 + KS * j) if j < 4 else KS * (j - 4), T_ + KS * j)
+        gathers.append(("k", dk)); gathers.append(("m", M - dk))
+    gathers.append(("k", np.full(TP, M // 2)))
+    for kind, dd in gathers:
+        words = D[dd]
+        present = words != 0
+        addr0 = np.full(TP, -1); addr1 = np.full(TP, -1)
+        for seg in range(0, TP, RW):                   # one warp (or the pair's part of a warp) at a time
+            for l in range(RW):
+                L = seg + l
+                d = int(dd[L])
+                if kind == "k":
+                    cand = [k for k in range(l + 1) if present[seg + k]]
+                    assert cand, "no descriptor at or below (k)"
+                    src = cand[-1]
+                else:
+                    cand = [k for k in range(l, RW) if present[seg + k]]
+                    assert cand, "no descriptor at or below (m)"
+                    src = cand[0]
+                if L != seg + src and l != 0:
+                    # the lane that serves must hold a bin at or below ours, in our group
+                    assert int(dd[seg + src]) <= d and d - int(dd[seg + src]) < RW, (kind, L, src)
+                Tp, c, delta = fields(int(words[seg + src]))
+                zone = d + 1 < Tp
+                if contract:
+                    b = d - delta
+                    v = xfull[b]; addr0[L] = b
+                    if zone:
+                        v = v + xfull[b - c]; addr1[L] = b - c
+                else:
+                    v = 0
+                    if not zone:
+                        b = d - delta
+                        assert 0 <= b < n_src
+                        v = xfull[b]; addr0[L] = b
+                # reference semantics: a region never reads beyond the sources that exist
+                if 0 <= d < NB:
+                    Y[d] = v
+        if cf is not None:
+            cf.note_sparse("gather_ld", addr0)
+            if contract:
+                cf.note_sparse("gather_ld2", addr1)
+            cf.note_sparse("desc_ld", dd)
+    if cf is not None:
+        its = sorted(set(i for i, _, _ in st_addr))
+        for it in its:
+            a = np.full(TP, -1)
+            for i, L, x in st_addr:
+                if i == it:
+                    a[L] = x
+            cf.note_sparse("desc_st", a)
     return Y
 
 
@@ -500,7 +677,7 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None, 
                 if cf and contract:
                     cf.note("stale_ld", xslot(qq) * 16, 16); cf.note("stale_ld_m", xslot(M - qq) * 16, 16)
 
-        if MIDDLE in ("gather", "gather_lanes"):
+        if MIDDLE in ("gather", "gather_lanes", "gather_rows2"):
             xfull = np.zeros(M + N // 8 + 1, C64)
             xfull[:M + 1] = Xc[xslot(np.arange(M + 1))]
             for i in range(4):
@@ -508,7 +685,10 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None, 
                 sel_ = (q > 0) if contract else np.zeros(TP, bool)
                 xfull[M + q[sel_]] = ext[i][sel_]
             peaks = [int(b0[L]) + e for L in range(TP) for e in range(16) if (int(mask[L]) >> e) & 1]
-            if MIDDLE == "gather_lanes":
+            if MIDDLE == "gather_rows2":
+                Yc = gather_rows_kernel(g, xfull if contract else xfull[:M + 1], mask, prev_before, next_after,
+                                        dtab, contract, cf, capture)
+            elif MIDDLE == "gather_lanes":
                 Yc = gather_shift_lanes(g, xfull if contract else xfull[:M + 1], mask, prev_before, next_after,
                                         dtab, contract, cf)
             else:

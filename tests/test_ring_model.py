@@ -71,3 +71,47 @@ def test_gather_middle_prototype_matches_oracle(oracle, monkeypatch, frame, hop,
     got = model.run(x, pf, hop, frame=frame)
     assert _rms(ref) > 1e-2
     assert _rms(got - ref) <= 2e-8
+
+
+@pytest.mark.parametrize("frame,hop,pf,calls", [
+    (1024, 256, 0.8, 9), (1024, 256, 0.75, 9), (1024, 256, 1.25, 8), (1024, 256, 3.0, 7), (1024, 256, 1.0, 6),
+    (1024, 128, 17.0, 10), (1024, 512, 2.0, 5), (256, 64, 0.8, 12), (512, 128, 1.3, 8), (2048, 512, 1.5, 6),
+    (2048, 512, 0.77, 6),
+])
+def test_gather_rows_blueprint_matches_oracle(oracle, monkeypatch, frame, hop, pf, calls):
+    """the gather middle of pv_kernel_ring.cuh (PVB_RING_GATHER) restated thread by thread: 32-bit region
+    descriptors in destination space (T' | overlap | -delta), copies at the first two bins of every aligned
+    group of lanes, destinations taken in the order of the Hermitian pre-pass (model.gather_rows_kernel)"""
+    monkeypatch.setattr(model, "MIDDLE", "gather_rows2")
+    x = signals.channels(5, 2, calls * hop)
+    ref = oracle.OracleProcessor(frame, hop, 2).run(x, np.float32(pf))
+    got = model.run(x, pf, hop, frame=frame)
+    assert _rms(ref) > 1e-2
+    assert _rms(got - ref) <= 2e-8
+
+
+@pytest.mark.parametrize("pf", [0.75, 0.8, 0.93, 1.0, 1.07, 1.5, 2.0, 5.0, 40.0])
+@pytest.mark.parametrize("kind", ["tones", "silence_then_tone", "sine", "silence", "impulse"])
+def test_gather_rows_blueprint_equals_scatter_model(monkeypatch, pf, kind):
+    """few peaks, long regions, regions that start below bin 0 or end beyond nb, no peaks at all: the gather
+    blueprint and the scatter model (same float32 spectrum) give bit-identical output"""
+    hop, calls = 256, 7
+    n = calls * hop
+    if kind == "tones":
+        x = signals.channels(3, 2, n, noise=0.0)
+    elif kind == "silence_then_tone":
+        x = np.stack([signals.silence_then_tone(1, n, 700), signals.silence_then_tone(2, n, 1300)])
+    elif kind == "sine":
+        x = np.stack([signals.bin_centred_sine(n, 1024, 37), signals.bin_centred_sine(n, 1024, 300, amp=0.2)])
+    elif kind == "silence":
+        x = np.zeros((2, n), np.float32)
+        x[1] = signals.channel(9, n)
+    else:
+        x = np.zeros((2, n), np.float32)
+        x[0, 900] = 1.0
+        x[1, 100::333] = 0.5
+    monkeypatch.setattr(model, "MIDDLE", "scatter")
+    want = model.run(x, pf, hop)
+    monkeypatch.setattr(model, "MIDDLE", "gather_rows2")
+    got = model.run(x, pf, hop)
+    assert np.array_equal(want, got)
