@@ -1240,7 +1240,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
     //     aligned group (thread 0's bins are multiples of RW, where a descriptor always is), so the latest
     //     descriptor at or below a bin is one ballot and one shuffle away, nothing is carried from step to
     //     step, and the shifted spectrum goes from X to registers without ever existing in shared memory.
-    // tests/ring_kernel_model.py::gather_rows_kernel is the numpy blueprint (checked against the oracle).
+    // tests/ring_kernel_model.py::gather_rows_kernel is the numpy blueprint of these four steps.
     // =====================================================================================================
     constexpr int XPW = G::XPW, TB = G::TB, CB = G::CB, RW = 1 << G::LRW;
     float *xp = reinterpret_cast<float *>(mine);                                  // planes re0 | re1 | im0 | im1
