@@ -639,7 +639,7 @@ OTHER_CONFIGS = [(2048, 512, 2048, 1.5), (1024, 256, 32768, 1.25),
                  (4096, 1024, 8192, 1.2), (2048, 128, 2048, 1.2)]
 
 
-def quick_config(local, frame, hop, C, pf, peak, steps=300, warm=40):
+def quick_config(local, frame, hop, C, pf, peak, steps=300, warm=40, **options):
     """Device-resident throughput of one configuration, measured like `value`: instances rotated so
     that state + io exceed L2, one stream, CUDA events around `steps` launches."""
     import numpy as np
@@ -655,9 +655,10 @@ def quick_config(local, frame, hop, C, pf, peak, steps=300, warm=40):
     host = signals.channels(0, C, nblk * hop)
     blocks = torch.from_numpy(np.ascontiguousarray(host.reshape(C, nblk, hop).transpose(1, 0, 2))).cuda()
     outs = [torch.empty((C, hop), dtype=torch.float32, device="cuda") for _ in range(rotate)]
-    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local, inputs_ready=1) for _ in range(rotate)]
-    stream = torch.cuda.current_stream()
+    procs = [phaze_b200.BatchedPhaseVocoder(C, frame, hop, device=local, inputs_ready=1, **options) for _ in range(rotate)]
+    stream = torch.cuda.Stream()        # (stream 0 would mean "the handle's own stream" to the library)
     sptr = stream.cuda_stream
+    torch.cuda.synchronize()
 
     def step(i):
         procs[i % rotate].process_device(blocks[i % nblk].data_ptr(), outs[i % rotate].data_ptr(), pitch, sptr)
@@ -666,7 +667,8 @@ def quick_config(local, frame, hop, C, pf, peak, steps=300, warm=40):
         step(i)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda._sleep(int(3e6))        # gate: the whole sequence is queued before the GPU starts on it
+    with torch.cuda.stream(stream):
+        torch.cuda._sleep(int(3e6))    # gate: the whole sequence is queued before the GPU starts on it
     for i in range(warm):
         step(i)
     ev0.record(stream)

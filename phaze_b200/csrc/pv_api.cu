@@ -251,6 +251,11 @@ bool fast_range(const pvb::FrameParams &fp) {
     return fp.pf_shift >= 1 && fp.pitch_factor >= 0.75f && fp.pitch_factor <= 64.0f && fp.overlaps <= 32;
 }
 bool warp_kernel_applies(int n, const pvb::FrameParams &fp) { return n == 1024 && fast_range(fp); }
+// ring-order kernel, DEEP instances (pv_kernel_ring.cuh): scalar pitch factors in [0.5, 0.75) -- stale slots up
+// to N/2 + N/4 - 1 rebuilt from the windowed frame, colliding regions through shared-memory atomics
+bool deep_range(int n, const pvb::FrameParams &fp) {
+    return !fp.pf_ch && n >= 512 && fp.pf_shift >= 1 && fp.pitch_factor >= 0.5f && fp.pitch_factor < 0.75f && fp.overlaps <= 32;
+}
 
 template <int N>
 cudaError_t launch_cta_n(const pvb::FrameParams &fp, const float *window_out, cudaStream_t s) {
@@ -348,7 +353,7 @@ KernelFamily pick_kernel(const pvb_processor *h, const pvb::FrameParams &fp) {
         if (first <= K_RING && h->pf_fast && fp.overlaps <= 32 && ring_geometry_ok(h)) return K_RING;
         return K_GENERIC;
     }
-    if (first <= K_RING && fast_range(fp) && ring_geometry_ok(h)) return K_RING;
+    if (first <= K_RING && (fast_range(fp) || deep_range(h->n, fp)) && ring_geometry_ok(h)) return K_RING;
     if (first <= K_WARP && warp_kernel_applies(h->n, fp)) return K_WARP;
     if (first <= K_CTA && fast_range(fp)) return K_CTA;
     return K_GENERIC;
@@ -475,6 +480,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     l.pdl = h->opt_launch_mode != 2;
     l.pch = fp.pf_ch != nullptr;
     l.multi = num_hops > 1;
+    l.deep = !fp.pf_ch && !fast_range(fp);                                   // pick_kernel admitted it: [0.5, 0.75)
     l.stream = s;
     pvb::RingParams rp = make_ring_params(h, fp, s, input_ready, num_hops);
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
@@ -719,7 +725,7 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         // how many consecutive calls this launch does: all that remain (up to the end of their copy
         // group on the pipelined host path) when the ring-order kernel takes them, else one
         int hops = 1;
-        if (p->channels > 0 && !pf_host && p->opt_many_mode == 1 && ring_kernel_applies(p, fp)) {
+        if (p->channels > 0 && !pf_host && p->opt_many_mode == 1 && ring_kernel_applies(p, fp) && fast_range(fp)) {
             hops = num_calls - k;
             if (hooks && hops > hooks->group - k % hooks->group) hops = hooks->group - k % hooks->group;
             if (hops > MAX_HOPS_PER_LAUNCH) hops = MAX_HOPS_PER_LAUNCH;
@@ -1159,7 +1165,7 @@ const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
                                 "pvb::pv_process_kernel<4096>"};
     const int idx = p->n == 256 ? 0 : p->n == 512 ? 1 : p->n == 1024 ? 2 : p->n == 2048 ? 3 : 4;
     switch (pick_kernel(p, fp)) {
-        case K_RING: return "pvb::pv_process_ring_kernel";
+        case K_RING: return fast_range(fp) ? "pvb::pv_process_ring_kernel" : "pvb::pv_process_ring_kernel (deep)";
         case K_WARP: return "pvb::pv_process_warp_kernel";
         case K_CTA: return cta[idx];
         case K_GENERIC: break;

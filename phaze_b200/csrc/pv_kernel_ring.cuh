@@ -81,6 +81,16 @@ namespace pvb {
 #ifndef PVB_RING_BULK_TABLES
 #define PVB_RING_BULK_TABLES 1
 #endif
+// Frame 1024: the exchange between forward passes 1 and 2 (and between inverse passes 2 and 3) goes through
+// TENSOR MEMORY instead of shared memory.  tcgen05.st.32x32b puts register j of lane L at (lane L, column j);
+// tcgen05.ld.16x256b hands thread t the columns 2 (t % 4) + {0, 1} (+ 8 g) of lanes t / 4 and t / 4 + 8
+// (measured: profiles/tmem/tmem_probe.cu): together they swap two lane bits with two register bits, which is
+// exactly what these two exchanges need once pass 2 runs with the lanes renumbered t = 4 m3 + a.  The data path
+// of tensor memory is separate from the load/store pipe this kernel is bound by, and an 8 KB round trip costs
+// 46 SM-cycles at 14 warps per SM against 88 through shared memory (profiles/tmem/tmem_bw.cu).
+#ifndef PVB_RING_TMEM
+#define PVB_RING_TMEM 0
+#endif
 
 // PCH: per-channel pitch factors (pvb_process_pf): the key table becomes per pair (two deltas per bin)
 template <int N_, bool PCH_ = false>
@@ -147,6 +157,8 @@ struct RingGeoT {
     static constexpr int PAIR_RAW = BUF_SLOTS * 16 + SCR_BYTES + KT_BYTES;
     static constexpr int PAIR_PAD = (TP < 32) ? ((TP == 16 ? 64 : 32) + 128 - PAIR_RAW % 128) % 128 : 0;
     static constexpr int PAIR_BYTES = PAIR_RAW + PAIR_PAD;
+    static constexpr int DEEP_BYTES = N;                    // DEEP instances: N/8 windowed samples of both channels per pair
+    static constexpr int DEEP_PAIRS_CAP = (N == 2048) ? 3 : 0;  // DEEP: pairs per CTA that keep two CTAs per SM (0: as usual)
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
     static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
     static constexpr int TW1_BYTES = R1 * TW1_ROW * 8;      // tw1[k1][n] = W_M^{n k1}, n < 64
@@ -171,7 +183,8 @@ struct RingGeoT {
     static constexpr int OFF_TWH = OFF_W128 + W128_BYTES;
     static constexpr int OFF_WIN = OFF_TWH + TWH_SMEM;
     static constexpr int OFF_WOUT = OFF_WIN + WIN_SMEM;
-    static constexpr int OFF_MBAR = OFF_WOUT + WOUT_SMEM;    // mbarrier of the bulk table copies
+    static constexpr bool TMEMX = PVB_RING_TMEM && (N_ == 1024);   // exchanges through tensor memory (one warp per pair)
+    static constexpr int OFF_MBAR = OFF_WOUT + WOUT_SMEM;    // mbarrier of the bulk table copies (+ 8: tensor-memory base)
     static constexpr int TAB_BYTES = OFF_MBAR + 16;
     static constexpr int MAX_PAIRS = (N == 256) ? 32 : (N == 512) ? 16
                                      : (N == 1024) ? ((PCH && PVB_RING_PAIRS_1024 > 7) ? 7 : PVB_RING_PAIRS_1024)
@@ -600,6 +613,46 @@ __device__ __noinline__ uint32_t ring_exact_peak_mask(const float2 *__restrict__
     return mask;
 }
 
+// ---- tensor memory as an exchange buffer (frame 1024, see PVB_RING_TMEM) ---------------------------------------
+__device__ __forceinline__ uint32_t f2u(float x) { return __float_as_uint(x); }
+// word w of a packed two-channel complex value: re0, re1, im0, im1
+__device__ __forceinline__ uint32_t cpx2_word(const cpx2 &v, int w) {
+    return f2u(w == 0 ? v.re.x : w == 1 ? v.re.y : w == 2 ? v.im.x : v.im.y);
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t ta, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(ta), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t ta, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(ta) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t ta, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(ta) : "memory");
+}
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t ta, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(ta), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Exchange slot (16 bytes) of element e (0 .. 63) of row k1 (0 .. 7) between passes 2 and 3 when pass 2 runs
+// with the lanes renumbered: 8 e + a bank term that makes both the stores of pass 2 (a quarter-warp holds
+// k1 & 3 = 0 .. 3 and two consecutive e) and the loads of pass 3 (a quarter-warp holds k1 = 0 .. 7 of one e)
+// conflict free.  512 slots, no padding.
+__device__ __forceinline__ int tmx_slot(int k1, int e) { return 8 * e + ((2 * (k1 & 3) + (k1 >> 2) + (e & 1)) & 7); }
+
 // forward real-split of one (k, M-k) pair into registers: 2 X[k] -> xk, 2 X[M-k] -> xm (both channels)
 __device__ __forceinline__ void ring_split_regs(cpx2 za, cpx2 zb, float2 w, cpx2 &xk, cpx2 &xm) {
     const float2 e_r = add2(za.re, zb.re), e_i = sub2(za.im, zb.im);
@@ -858,9 +911,19 @@ __device__ __forceinline__ void ring_masks(const RingParams &p, const int (&m0)[
 // launch (no flags, no waits: the pair itself wrote the state it reads).  In phase 2 the thread indices
 // pass through an identity the compiler cannot see through: the body then re-derives its index arithmetic
 // at every call instead of hoisting dozens of indices out of the loop and spilling.
-template <int N, int NBLK, bool PCH, int PHASE>
+// DEEP: pitch factors in [0.5, 0.75).  The shift then reads the stale slots N/2 + q for q up to N/4 - 1 (below
+// 0.75 only q < N/8, the first level) and more than two regions can land on one bin.  Slots beyond the first
+// level hold outputs of SMALLER sub-transforms of fft.js's radix-4 recursion (bundle:394-438 writes only outputs
+// 0 .. L/2 of every length-L block): walking the block tree gives (L, r, s, o) with
+//     slot = DFT_L(xw[r m + s])[o] = sum_{m < L} xw[r m + s] W_L^{o m},   r = N / L in {16, 64, 256, 1024},
+// a sum of L windowed frame samples that all have n = 10 or 14 (mod 16).  Pass 1 leaves those N/8 samples in a
+// per-pair scratch in frame order, the thread that owns slot q sums them (only when the slot lands inside [0, nb)
+// after the last peak's shift), turns the result to ring order (times W_N^{(N/2 + q) t}) and adds it; every
+// store of the shift becomes a shared-memory atomic add on the zero-filled planes.
+template <int N, int NBLK, bool PCH, int PHASE, bool DEEP = false>
 __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hopi, bool live) {
     using G = RingGeoT<N, PCH>;
+    static_assert(!DEEP || (PHASE == 0 && !PCH && N >= 512 && !(PVB_RING_GATHER && N == 1024)), "DEEP: scalar pitch factor, one call per launch, frame 512 and up");
     constexpr bool MULTI = PHASE != 0;
     constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -900,6 +963,10 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
     (void)swout;
     float4 *ex = reinterpret_cast<float4 *>(mine);
     float4 *XQ = reinterpret_cast<float4 *>(mine);
+    // DEEP: windowed frame samples n = 10, 14 (mod 16) of both channels, sample n at 2 (n >> 4) + ((n >> 2) & 1);
+    // behind the pairs' buffers (the launcher adds DEEP_BYTES per pair to the dynamic shared memory)
+    float2 *dsc = reinterpret_cast<float2 *>(smem_raw + G::TAB_BYTES + size_t(blockDim.x / TP) * G::PAIR_BYTES + size_t(pin) * G::DEEP_BYTES);
+    (void)dsc;
 
     const int c0 = 2 * pair;
     const bool has1 = c0 + 1 < p.num_channels;
@@ -1152,6 +1219,14 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 #endif
+    // this warp's window of the CTA's tensor memory: its 32 lanes, 64 columns (allocated in the kernel's prologue)
+    uint32_t tmx = 0;
+    if constexpr (G::TMEMX) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t w = threadIdx.x >> 5;
+        tmx = *reinterpret_cast<const volatile uint32_t *>(smem_raw + G::OFF_MBAR + 8) + ((32u * (w & 3u)) << 16) + 64u * (w >> 2);
+    }
+    (void)tmx;
     if (!live) return false;    // no CTA-wide barriers below (MULTI: none before the next call's)
 
     if (xstagger > 0 && (pin & 1)) __nanosleep(unsigned(xstagger));
@@ -1180,17 +1255,37 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 x[j].re = mul2(make_float2(v.x, v.y), bc2(w.x));
                 x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
             }
+            if constexpr (DEEP) {
+                // x[j].re is the windowed frame sample 128 f + 2 c of both channels, c = float4 column of the block
+                const int c = cn + TPH * h;
+                if ((c & 5) == 5) {
+#pragma unroll
+                    for (int j = 0; j < RT; j++) dsc[16 * PVB_FB(j) + 2 * (c >> 3) + ((c >> 1) & 1)] = x[j].re;
+                }
+            }
             dft_r<RT, false>(x);
 #pragma unroll
             for (int k1 = 1; k1 < RT; k1++) {
                 const float2 w = tw1[G::TW1_ROW * (row0 + k1) + nl];  // W_M^{(n + 64 toff) k1} (W_32^{s k1})
                 x[k1] = cmul_s(x[k1], w.x, w.y);
             }
+            if constexpr (G::TMEMX) {
+                // lane = this thread, column = (w & 1) | (k1 & 3) << 1 | (w >> 1) << 3 | h << 4 | (k1 >> 2) << 5
+                // for word w of x[k1] of butterfly h: pass 2 then finds k1 & 3 in its lane number
+#pragma unroll
+                for (int k1hi = 0; k1hi < 2; k1hi++) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) v[i] = cpx2_word(x[((i >> 1) & 3) + 4 * k1hi], (i & 1) | ((i >> 3) << 1));
+                    tmem_st_32x32b_x16(tmx + 16 * h + 32 * k1hi, v);
+                }
+            } else {
 #pragma unroll
             for (int k1 = 0; k1 < RT; k1++) ex[G::RS * (row0 + k1) + nl + (G::G8 - 8) * (nl >> 3)] = pack4(x[k1]);
+            }
         }
     }
-    pair_sync<TP>(pin);
+    if constexpr (!G::TMEMX) pair_sync<TP>(pin);
 
     // warm L2 with the overlap-add ring lines the tail of this kernel adds to (the slot that is
     // only written, ring [t - hop, t), is skipped)
@@ -1207,8 +1302,10 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
     const int m3l = tp & 7;
     if (!(xskip & 2)) {
         float2 w2[8];
+        if constexpr (!G::TMEMX) {
 #pragma unroll
         for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + m3l];              // W_64^{m3 k2}
+        }
         if constexpr (NSPL == 2) {
             // rows k' and 16 + k' hold E_0 and E_1 (twiddled); X[k'] = E_0 + E_1 and
             // X[k' + 16] = (E_0 - E_1) W_128^n (-1)^toff, n = m3 + 8 m2; both rows are this thread's
@@ -1234,6 +1331,37 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 b0[G::G8 * k2] = pack4(x0[k2]);
                 b1[G::G8 * k2] = pack4(x1[k2]);
             }
+        } else if constexpr (G::TMEMX) {
+            // lanes renumbered for this pass: t = 4 m3 + a does the butterflies (k1 = a + 4 h, m3) over m2.
+            // Load s of the two gives register 4 g + 2 b0 + w0 = column 2 a + w0 + 8 g of lane m3 + 8 (b0 + 2 s):
+            // word w0 | (g & 1) << 1 of x[k1 = a + 4 (g >> 2)] of pass-1 thread m3 + 8 (m2 & 3), butterfly m2 >> 2
+            // = (g >> 1) & 1, with m2 & 3 = b0 + 2 s.
+            const int ta_ = tp & 3, tm3 = tp >> 2;
+            uint32_t v0[32], v1[32];
+            tmem_wait_st();
+            tmem_ld_16x256b_x8(tmx, v0);
+            tmem_ld_16x256b_x8(tmx + (16u << 16), v1);
+            tmem_wait_ld();
+#pragma unroll
+            for (int k2 = 1; k2 < 8; k2++) w2[k2] = w64[8 * k2 + tm3];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                cpx2 x[8];
+#pragma unroll
+                for (int m2 = 0; m2 < 8; m2++) {
+                    const uint32_t *vv = ((m2 >> 1) & 1) ? v1 : v0;
+                    const int g0 = ((m2 >> 2) << 1) | (h << 2), i0 = 2 * (m2 & 1);
+                    x[m2].re = make_float2(__uint_as_float(vv[4 * g0 + i0]), __uint_as_float(vv[4 * g0 + i0 + 1]));
+                    x[m2].im = make_float2(__uint_as_float(vv[4 * (g0 | 1) + i0]), __uint_as_float(vv[4 * (g0 | 1) + i0 + 1]));
+                }
+                dft8<false>(x);
+#pragma unroll
+                for (int k2 = 1; k2 < 8; k2++) x[k2] = cmul_s(x[k2], w2[k2].x, w2[k2].y);
+                // row k1 = a + 4 h, element m3 + 8 k2
+                float4 *bp = ex + 8 * tm3 + ((2 * ta_ + h + (tm3 & 1)) & 7);
+#pragma unroll
+                for (int k2 = 0; k2 < 8; k2++) bp[64 * k2] = pack4(x[k2]);
+            }
         } else {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -1258,10 +1386,19 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
     const int exA = G::RS * (tp & (R1 - 1)) + G::G8 * (tp >> G::LR1);
     const int exB = G::RS * (kB & (R1 - 1)) + G::G8 * (kB >> G::LR1);
     cpx2 a[8], b[8];
+    if constexpr (G::TMEMX) {
+        // row k1 = k & 7, elements 8 (k >> 3) + c of the renumbered pass 2 (tmx_slot)
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            a[c] = unpack4(ex[tmx_slot(tp & 7, 8 * (tp >> 3) + c)]);
+            b[c] = unpack4(ex[tmx_slot(kB & 7, 8 * (kB >> 3) + c)]);
+        }
+    } else {
 #pragma unroll
     for (int c = 0; c < 8; c++) {
         a[c] = unpack4(ex[exA + c]);
         b[c] = unpack4(ex[exB + c]);
+    }
     }
     dft8<false>(a);      // a[j] = Z[tp + KS j]
     dft8<false>(b);      // b[j] = Z[kB + KS j]
@@ -1589,11 +1726,11 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             dl1 = (lk1 & 0xFFFF) - 32768;
             // both scans run unconditionally (a channel without peaks ends up with every bin on the
             // dump slot): two independent instruction streams the scheduler can interleave
-            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask0, 16 * tp, pk0, nk0, rk, contract0 ? int(0x80000000u) : 0, dst0);
+            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask0, 16 * tp, pk0, nk0, rk, (contract0 && !DEEP) ? int(0x80000000u) : 0, dst0);
             if constexpr (PCH)
                 ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk1, contract1 ? int(0x80000000u) : 0, dst1);
             else
-                ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk, contract1 ? int(0x80000000u) : 0, dst1);
+                ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1);
         }
 
         // sources into registers: own run, bin M and the first stale level (what _realTransform4
@@ -1604,12 +1741,11 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
         float4 ext[4];
         ext[0] = ext[1] = ext[2] = ext[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (l0) ext[0] = XQ[G::SM];
+        float4 ext4 = make_float4(0.f, 0.f, 0.f, 0.f);               // DEEP: slot N/2 + N/8 (thread 0)
+        (void)ext4;
         if (contract && !(xskip & 32)) {
             constexpr int QO = N / 4 + N / 64;                        // slots between bins k and k + N/4
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int q = tp + TP * i;
-                const int qq = q ? q : 1;
+            auto level1 = [&](int qq) {
                 const int sq = qq + (qq >> 4);                        // slot of bin q
                 const int sm = G::SM - qq - ((qq + 15) >> 4);         // slot of bin M - q
                 const cpx2 A = unpack4(XQ[sq]), Bv = unpack4(XQ[sq + QO]);         // bins q, N/4 + q
@@ -1617,14 +1753,20 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 const float2 sr = add2(sub2(A.re, Bv.re), sub2(Cv.re, D.re));
                 const float2 si = sub2(sub2(A.im, Bv.im), sub2(Cv.im, D.im));
                 const float2 w = PVB_TWH(twh + 2 * qq);
-                const cpx2 sv = cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y);
-                if (q) ext[i] = pack4(sv);
+                return pack4(cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y));
+            };
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int q = tp + TP * i;
+                const float4 sv = level1(q ? q : 1);
+                if (q) ext[i] = sv;
             }
+            if constexpr (DEEP) { if (l0) ext4 = level1(N / 8); }
         }
         pair_sync<TP>(pin);      // every thread holds its sources: the buffer becomes Y
         // (PVB_RING_EXACT: while contracting every bin of [0, nb) is stored exactly once in the first
         // sub-step, provided both channels have peaks)
-        if (!(PVB_RING_EXACT && contract && any0 && any1) && !(xskip & 8)) {
+        if ((DEEP || !(PVB_RING_EXACT && contract && any0 && any1)) && !(xskip & 8)) {
 #pragma unroll
             for (int i = 0; i < 17; i++) XQ[tp + TP * i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tp < 2) XQ[17 * TP + tp] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1637,6 +1779,71 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #else
 #define PVB_NOT_DUMP(d) true
 #endif
+        if constexpr (DEEP) {
+            // any number of regions may land on one bin: every store is an atomic add on the zero-filled planes
+            constexpr int DUMPB = 4 * (G::XQ_SLOTS - 1);
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                if (dst0[e] != DUMPB) {
+                    atomicAdd(reinterpret_cast<float *>(mine + dst0[e]), xv[e].x);
+                    atomicAdd(reinterpret_cast<float *>(mine + dst0[e] + 2 * PL), xv[e].z);
+                }
+                if (dst1[e] != DUMPB) {
+                    atomicAdd(reinterpret_cast<float *>(mine + dst1[e] + PL), xv[e].y);
+                    atomicAdd(reinterpret_cast<float *>(mine + dst1[e] + 3 * PL), xv[e].w);
+                }
+            }
+            auto add_ext = [&](int q, const float4 &v) {
+                const int d0 = M + q + dl0, d1 = M + q + dl1;
+                if (any0 && unsigned(d0) < unsigned(NB)) {
+                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS))), v.x);
+                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS)) + 2 * PL), v.z);
+                }
+                if (any1 && unsigned(d1) < unsigned(NB)) {
+                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + PL), v.y);
+                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + 3 * PL), v.w);
+                }
+            };
+#pragma unroll
+            for (int i = 0; i < 4; i++) add_ext(tp + TP * i, ext[i]);
+            // slots N/2 + q, N/8 <= q < N/4
+            constexpr int LOG2N = (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : 12;
+            constexpr int L0 = (LOG2N & 1) ? 2 : 4;                  // smallest block of the radix-4 recursion
+#pragma unroll 1
+            for (int i = 4; i < 8; i++) {
+                const int q = tp + TP * i;
+                const bool need = (any0 && M + q + dl0 < NB) || (any1 && M + q + dl1 < NB);
+                if (!need) continue;
+                if (q == N / 8) { add_ext(q, ext4); continue; }      // last slot of the first level
+                int lg = LOG2N, r = 1, sq_ = 0, o = M + q;
+                while ((1 << lg) > L0 && o > (1 << (lg - 1))) {
+                    const int sb = o >> (lg - 2);
+                    o -= sb << (lg - 2);
+                    sq_ += r * sb;
+                    r <<= 2;
+                    lg -= 2;
+                }
+                const float2 *sp_ = dsc + 2 * (sq_ >> 4) + ((sq_ >> 2) & 1);      // xw[r m + s], m at stride r / 8
+                const int stride = r >> 3, kstep = (o * r) & (N - 1), L = 1 << lg;
+                cpx2 acc;
+                acc.re = acc.im = make_float2(0.f, 0.f);
+                int k = 0;
+                for (int m = 0; m < L; m++) {
+                    const float2 xs = sp_[m * stride];
+                    float2 w = PVB_TWH(twh + (k & (M - 1)));
+                    if (k & M) w = make_float2(-w.x, -w.y);
+                    acc.re = fma2(xs, bc2(w.x), acc.re);
+                    acc.im = fma2(xs, bc2(w.y), acc.im);
+                    k = (k + kstep) & (N - 1);
+                }
+                // frame order -> ring order: U[b] = X[b] W_N^{b t}, b = N/2 + q (t is a multiple of 64); the
+                // spectrum in shared memory is 2 U (the real split leaves the factor to the synthesis window)
+                const int kr = (q * t) & (N - 1);
+                float2 wr = PVB_TWH(twh + (kr & (M - 1)));
+                if (kr & M) wr = make_float2(-wr.x, -wr.y);
+                add_ext(q, pack4(cmul_s(acc, 2.0f * wr.x, 2.0f * wr.y)));
+            }
+        } else {
         // first sub-step: plain stores (pairwise disjoint destinations)
         if (!(xskip & 16))
 #pragma unroll
@@ -1699,6 +1906,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 }
             }
         }
+        }   // !DEEP
     }
     pair_sync<TP>(pin);
 
@@ -1873,7 +2081,8 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 // the calls, its state goes back and forth through L1 / L2 instead of HBM (one DRAM round trip of the
 // rings per launch instead of per call), completion flags are taken and released once, and only the
 // first-pass twiddle table is re-staged per call.  Bit-identical to num_hops single launches.
-template <int N, int NBLK, bool PCH = false, bool MULTI = false>
+// DEEP: pitch factors in [0.5, 0.75) (see ring_one_call); scalar pitch factor, one call per launch.
+template <int N, int NBLK, bool PCH = false, bool MULTI = false, bool DEEP = false>
 __global__ void __launch_bounds__((MULTI ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP,
                                   RingGeoT<N, PCH>::CTAS_PER_SM)
 pv_process_ring_kernel(const RingParams p) {
@@ -1881,6 +2090,18 @@ pv_process_ring_kernel(const RingParams p) {
     const int tp = threadIdx.x % TP, pin = threadIdx.x / TP;
     const int pair = blockIdx.x * (blockDim.x / TP) + pin;
     bool live = 2 * pair < p.num_channels;
+    using G_ = RingGeoT<N, PCH>;
+    if constexpr (G_::TMEMX) {
+        // 128 columns of tensor memory per CTA (two CTAs per SM: 256 of 512): one warp allocates, the base
+        // address reaches the others through shared memory behind the CTA barrier that follows the frame loads
+        extern __shared__ __align__(16) unsigned char smem_k[];
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;"
+                         ::"r"(unsigned(__cvta_generic_to_shared(smem_k + G_::OFF_MBAR + 8))) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
 #ifdef PVB_EXPERIMENTS
     if (p.stamps && threadIdx.x == 0) {
         unsigned long long now;
@@ -1893,7 +2114,7 @@ pv_process_ring_kernel(const RingParams p) {
 #pragma unroll 1
         for (int hopi = 1; hopi < p.num_hops; hopi++) live = ring_one_call<N, NBLK, PCH, 2>(p, hopi, live);
     } else {
-        live = ring_one_call<N, NBLK, PCH, 0>(p, 0, live);
+        live = ring_one_call<N, NBLK, PCH, 0, DEEP>(p, 0, live);
     }
 #ifdef PVB_EXPERIMENTS
     if (p.stamps && threadIdx.x == 0) {
@@ -1902,19 +2123,31 @@ pv_process_ring_kernel(const RingParams p) {
         atomicMax(p.stamps + 1, now);
     }
 #endif
-    if (!live) return;
-    // release: state and output of this pair are complete for call my_seq.  The pair barrier orders
-    // every thread's stores before thread 0's release store, which is cumulative at gpu scope;
-    // PVB_RING_LANE_FENCE=1 additionally fences in every thread (the first version of this code).
+    if (live) {
+        // release: state and output of this pair are complete for call my_seq.  The pair barrier orders
+        // every thread's stores before thread 0's release store, which is cumulative at gpu scope;
+        // PVB_RING_LANE_FENCE=1 additionally fences in every thread (the first version of this code).
 #if PVB_RING_LANE_FENCE
-    __threadfence();
+        __threadfence();
 #endif
-    pair_sync<TP>(pin);
-    if (tp == 0)
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done + pair), "r"(p.my_seq) : "memory");
-    // flag mode skipped the wait at the top: take it here, where the previous grid is long gone, so
-    // that completion stays transitive along the stream
-    if (p.flag_mode) asm volatile("griddepcontrol.wait;" ::: "memory");
+        pair_sync<TP>(pin);
+        if (tp == 0)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done + pair), "r"(p.my_seq) : "memory");
+        // flag mode skipped the wait at the top: take it here, where the previous grid is long gone, so
+        // that completion stays transitive along the stream
+        if (p.flag_mode) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+    if constexpr (G_::TMEMX) {
+        // every warp of the CTA is done with its window: the allocating warp frees the columns
+        extern __shared__ __align__(16) unsigned char smem_k[];
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tb = *reinterpret_cast<const volatile uint32_t *>(smem_k + G_::OFF_MBAR + 8);
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tb) : "memory");
+        }
+    }
 }
 
 // tables the ring-order kernel copies into shared memory: NJ first-pass twiddle tables

@@ -86,7 +86,7 @@ def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
     """K consecutive calls in one submission: with PVB_OPT_MANY_MODE = 1 they share
     kernel launches where the ring-order kernel applies (each pair loops over the hops, state stays in
     L1 / L2); elsewhere
-    (hop 64 at frame 1024, pitch factor 0.5) it is K launches.  Both must equal K single calls bit for
+    (hop 64 at frame 1024, pitch factor 0.5: the ring-order kernel's DEEP instances) it is K launches.  Both must equal K single calls bit for
     bit, through the host entry point (copies pipelined in groups) and the device entry point."""
     import torch
     from phaze_b200 import BatchedPhaseVocoder
@@ -100,7 +100,7 @@ def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
         many = np.concatenate([b.process_many(blocks[:3], pf), b.process_many(blocks[3:], pf)])
         assert a.time_cursor == b.time_cursor == calls * hop
         kernel = b.kernel_name(np.float32(pf))
-        ring = "ring" in kernel
+        ring = "ring" in kernel and "(deep)" not in kernel
         assert b.kernel_launches < calls if ring else b.kernel_launches == calls
         din = torch.from_numpy(blocks).cuda()
         dout = torch.empty_like(din)
@@ -108,9 +108,10 @@ def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
         c.process_device(din.data_ptr(), dout.data_ptr(), pf, None, num_calls=calls)
         c.sync()
         dev = dout.cpu().numpy()
-    if "pv_process_kernel" in kernel:
-        # the generic kernel adds colliding regions with shared-memory atomics: the order, and so the last
-        # bit, is not reproducible from run to run
+    if "pv_process_kernel" in kernel or "(deep)" in kernel:
+        # the generic kernel, and the ring-order kernel's instances for pitch factors in [0.5, 0.75), add
+        # colliding regions with shared-memory atomics: the order, and so the last bit, is not reproducible
+        # from run to run
         assert np.abs(one - many).max() <= 1e-6 and np.abs(one - dev).max() <= 1e-6
     else:
         assert np.array_equal(one, many)
