@@ -157,7 +157,11 @@ struct RingGeoT {
     static constexpr int PAIR_RAW = BUF_SLOTS * 16 + SCR_BYTES + KT_BYTES;
     static constexpr int PAIR_PAD = (TP < 32) ? ((TP == 16 ? 64 : 32) + 128 - PAIR_RAW % 128) % 128 : 0;
     static constexpr int PAIR_BYTES = PAIR_RAW + PAIR_PAD;
-    static constexpr int DEEP_BYTES = N;                    // DEEP instances: N/8 windowed samples of both channels per pair
+    // DEEP instances, per pair: N/8 windowed samples of both channels, then W_N^{16 j} for j < N/16 (the twiddles
+    // of the sub-transform sums are all multiples of 16: read from twh they would all sit in one bank)
+    // (frame 4096: only the half table W_N^{16 j}, j < N/32, fits beside two CTAs per SM; the other half is its negative)
+    static constexpr bool T16_HALF = (N == 4096);
+    static constexpr int DEEP_BYTES = N + (T16_HALF ? N / 4 : N / 2);
     static constexpr int DEEP_PAIRS_CAP = (N == 2048) ? 3 : 0;  // DEEP: pairs per CTA that keep two CTAs per SM (0: as usual)
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
     static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
@@ -1256,6 +1260,12 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 x[j].im = mul2(make_float2(v.z, v.w), bc2(w.y));
             }
             if constexpr (DEEP) {
+                if (h == 0) {
+                    float2 *t16 = dsc + N / 8;
+                    const float2 wv = PVB_TWH(twh + 16 * tp);
+                    t16[tp] = wv;
+                    if constexpr (!G::T16_HALF) t16[tp + TP] = make_float2(-wv.x, -wv.y);     // W_N^{16 (tp + TP)} = -W_N^{16 tp}
+                }
                 // x[j].re is the windowed frame sample 128 f + 2 c of both channels, c = float4 column of the block
                 const int c = cn + TPH * h;
                 if ((c & 5) == 5) {
@@ -1824,17 +1834,20 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                     lg -= 2;
                 }
                 const float2 *sp_ = dsc + 2 * (sq_ >> 4) + ((sq_ >> 2) & 1);      // xw[r m + s], m at stride r / 8
-                const int stride = r >> 3, kstep = (o * r) & (N - 1), L = 1 << lg;
+                // W_L^{o m} = W_N^{16 j}, j = (o r / 16) m mod N/16
+                const float2 *t16 = dsc + N / 8;
+                const int stride = r >> 3, kstep = (o * (r >> 4)) & (N / 16 - 1), L = 1 << lg;
                 cpx2 acc;
                 acc.re = acc.im = make_float2(0.f, 0.f);
                 int k = 0;
+#pragma unroll 4
                 for (int m = 0; m < L; m++) {
-                    const float2 xs = sp_[m * stride];
-                    float2 w = PVB_TWH(twh + (k & (M - 1)));
-                    if (k & M) w = make_float2(-w.x, -w.y);
+                    float2 xs = sp_[m * stride];
+                    const float2 w = t16[G::T16_HALF ? (k & (TP - 1)) : k];
+                    if (G::T16_HALF && (k & TP)) xs = make_float2(-xs.x, -xs.y);
                     acc.re = fma2(xs, bc2(w.x), acc.re);
                     acc.im = fma2(xs, bc2(w.y), acc.im);
-                    k = (k + kstep) & (N - 1);
+                    k = (k + kstep) & (N / 16 - 1);
                 }
                 // frame order -> ring order: U[b] = X[b] W_N^{b t}, b = N/2 + q (t is a multiple of 64); the
                 // spectrum in shared memory is 2 U (the real split leaves the factor to the synthesis window)
