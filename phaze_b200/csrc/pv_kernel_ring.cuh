@@ -162,7 +162,6 @@ struct RingGeoT {
     // (frame 4096: only the half table W_N^{16 j}, j < N/32, fits beside two CTAs per SM; the other half is its negative)
     static constexpr bool T16_HALF = (N == 4096);
     static constexpr int DEEP_BYTES = N + (T16_HALF ? N / 4 : N / 2);
-    static constexpr int DEEP_PAIRS_CAP = (N == 2048) ? 3 : 0;  // DEEP: pairs per CTA that keep two CTAs per SM (0: as usual)
     // CTA-shared tables (bytes), in this order at the start of dynamic shared memory
     static constexpr int TW1_ROW = 72;                      // float2 per row of tw1 (row stride = 16 banks mod 32)
     static constexpr int TW1_BYTES = R1 * TW1_ROW * 8;      // tw1[k1][n] = W_M^{n k1}, n < 64
@@ -388,9 +387,13 @@ __device__ __forceinline__ void ring_peak_masks_guarded(const int (&m0)[20], con
 // sub-step, everything else is stored first (right halves are pairwise disjoint after the shift,
 // and so are left halves, for pitch factors >= 0.75).
 // The integer pipe runs at half rate, so this loop is written for the fewest ALU operations.
-template <int DUMP, int YS>
+// COLOUR (DEEP instances, pitch factors in [0.5, 0.75)): the low two bits of dst carry the ordinal of the owning
+// peak mod 3 instead (col3 = (peaks below this run - 1) mod 3 on entry).  Peaks are at least 3 bins apart, so for
+// pitch factors >= 0.5 the images of regions i and i + 3 never overlap: three ordered sub-steps, one per colour,
+// have pairwise disjoint destinations each.
+template <int DUMP, int YS, bool COLOUR = false>
 __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey, int nkey, const int (&rk)[16],
-                                                int second_flag, int (&dst)[16]) {
+                                                int second_flag, int (&dst)[16], int col3 = 0) {
     int nx[16];
 #pragma unroll
     for (int e = 15; e >= 0; e--) {
@@ -401,13 +404,20 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
     const int cb = b0 - 32768;
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-        if ((mask >> e) & 1u) pkey = rk[e];                          // last peak at or below bin e
+        if ((mask >> e) & 1u) {
+            pkey = rk[e];                                            // last peak at or below bin e
+            if constexpr (COLOUR) col3 = (col3 == 2) ? 0 : col3 + 1;
+        }
         // next - b <= b - prev  <=>  2 next' + 2 prev' (+ carry of the low halves) < 4 b' + 2
         const int tt = nx[e] + pkey - thr0;
         const bool take_next = tt < ((4 * e) << 16);
         const int okey = take_next ? nx[e] : pkey;
         const int d = (okey & 0xFFFF) + cb + e;
         const unsigned slot = min(unsigned(d + (d >> YS)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
+        if constexpr (COLOUR) {
+            const int cn_ = col3 + (take_next ? 1 : 0);
+            dst[e] = int(4u * slot) | (cn_ == 3 ? 0 : cn_);
+        } else {
 #if PVB_RING_EXACT
         // w = -(T - 1) 2^16 + (delta_next + delta_prev), T = 4 b + 2 - 2 next - 2 prev (even; >= 2 on a
         // left half), deltas <= 0 while contracting  =>  -T = (w >> 16) & ~1; collide <=> T <= 4 c
@@ -418,6 +428,7 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
 #else
         dst[e] = int(4u * slot) | ((tt - ((4 * e) << 16)) & second_flag);
 #endif
+        }
     }
 }
 
@@ -1734,13 +1745,36 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             }
             dl0 = (lk0 & 0xFFFF) - 32768;
             dl1 = (lk1 & 0xFFFF) - 32768;
+            int col0 = 0, col1 = 0;                                   // DEEP: (peaks below this thread's run - 1) mod 3
+            if constexpr (DEEP) {
+                // peaks below this thread's run, both channels in one word (at most N/6 peaks per channel)
+                constexpr int W = (TP < 32) ? TP : 32;
+                const int cnt = __popc(mask0) | (__popc(mask1) << 16);
+                int inc = cnt;
+#pragma unroll
+                for (int d = 1; d < W; d <<= 1) {
+                    const int v = __shfl_up_sync(FULL, inc, d, W);
+                    if ((lane & (W - 1)) >= d) inc += v;
+                }
+                int below = inc - cnt;
+                if constexpr (G::WPP > 1) {
+                    int *wtot = reinterpret_cast<int *>(mine + G::BUF_SLOTS * 16) + 4 * TP + 8 + 20;
+                    if (lane == 31) wtot[tp >> 5] = inc;
+                    pair_sync<TP>(pin);
+#pragma unroll
+                    for (int w = 0; w < G::WPP - 1; w++)
+                        if (w < (tp >> 5)) below += wtot[w];
+                }
+                col0 = ((below & 0xFFFF) + 2) % 3;
+                col1 = ((below >> 16) + 2) % 3;
+            }
             // both scans run unconditionally (a channel without peaks ends up with every bin on the
             // dump slot): two independent instruction streams the scheduler can interleave
-            ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask0, 16 * tp, pk0, nk0, rk, (contract0 && !DEEP) ? int(0x80000000u) : 0, dst0);
+            ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask0, 16 * tp, pk0, nk0, rk, (contract0 && !DEEP) ? int(0x80000000u) : 0, dst0, col0);
             if constexpr (PCH)
                 ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk1, contract1 ? int(0x80000000u) : 0, dst1);
             else
-                ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1);
+                ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask1, 16 * tp, pk1, nk1, rk, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1, col1);
         }
 
         // sources into registers: own run, bin M and the first stale level (what _realTransform4
@@ -1790,33 +1824,79 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #define PVB_NOT_DUMP(d) true
 #endif
         if constexpr (DEEP) {
-            // any number of regions may land on one bin: every store is an atomic add on the zero-filled planes
+            // up to three regions (i, i + 1, i + 2) land on one bin: one sub-step per colour = ordinal of the owning
+            // peak mod 3 (low bits of dst), each with pairwise disjoint destinations (loads of a batch issued before
+            // its first store).
             constexpr int DUMPB = 4 * (G::XQ_SLOTS - 1);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-                if (dst0[e] != DUMPB) {
-                    atomicAdd(reinterpret_cast<float *>(mine + dst0[e]), xv[e].x);
-                    atomicAdd(reinterpret_cast<float *>(mine + dst0[e] + 2 * PL), xv[e].z);
-                }
-                if (dst1[e] != DUMPB) {
-                    atomicAdd(reinterpret_cast<float *>(mine + dst1[e] + PL), xv[e].y);
-                    atomicAdd(reinterpret_cast<float *>(mine + dst1[e] + 3 * PL), xv[e].w);
+                if (dst0[e] == DUMPB + (dst0[e] & 3)) dst0[e] = -1;   // outside [0, nb): no colour matches
+                if (dst1[e] == DUMPB + (dst1[e] & 3)) dst1[e] = -1;
+            }
+            // the last region's sources from bin N/2 up to the end of the first stale level go first (plain stores
+            // onto the zero-filled planes: nothing else has been written yet), which ends their live ranges
+            {
+                auto put_ext = [&](int q, const float4 &v) {
+                    const int d0 = M + q + dl0, d1 = M + q + dl1;
+                    if (any0 && unsigned(d0) < unsigned(NB)) {
+                        float *y = reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS)));
+                        y[0] = v.x;
+                        y[PL / 2] = v.z;
+                    }
+                    if (any1 && unsigned(d1) < unsigned(NB)) {
+                        float *y = reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + PL);
+                        y[0] = v.y;
+                        y[PL / 2] = v.w;
+                    }
+                };
+#pragma unroll
+                for (int i = 0; i < 4; i++) put_ext(tp + TP * i, ext[i]);
+                if (l0) put_ext(N / 8, ext4);
+            }
+#pragma unroll 1
+            for (int col = 0; col < 3; col++) {
+                pair_sync<TP>(pin);
+                unsigned char *minec = mine - col;                    // cancels the colour bits of dst
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    float o0r[4], o0i[4], o1r[4], o1i[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int e = 4 * g + i;
+                        o0r[i] = o0i[i] = o1r[i] = o1i[i] = 0.f;
+                        if ((dst0[e] & 3) == col) { o0r[i] = *reinterpret_cast<float *>(minec + dst0[e]); o0i[i] = *reinterpret_cast<float *>(minec + dst0[e] + 2 * PL); }
+                        if ((dst1[e] & 3) == col) { o1r[i] = *reinterpret_cast<float *>(minec + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(minec + dst1[e] + 3 * PL); }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int e = 4 * g + i;
+                        if ((dst0[e] & 3) == col) {
+                            *reinterpret_cast<float *>(minec + dst0[e]) = o0r[i] + xv[e].x;
+                            *reinterpret_cast<float *>(minec + dst0[e] + 2 * PL) = o0i[i] + xv[e].z;
+                        }
+                        if ((dst1[e] & 3) == col) {
+                            *reinterpret_cast<float *>(minec + dst1[e] + PL) = o1r[i] + xv[e].y;
+                            *reinterpret_cast<float *>(minec + dst1[e] + 3 * PL) = o1i[i] + xv[e].w;
+                        }
+                    }
                 }
             }
+            // the last region's sources beyond the first stale level (distinct destinations, everything else is complete)
+            pair_sync<TP>(pin);
             auto add_ext = [&](int q, const float4 &v) {
                 const int d0 = M + q + dl0, d1 = M + q + dl1;
                 if (any0 && unsigned(d0) < unsigned(NB)) {
-                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS))), v.x);
-                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS)) + 2 * PL), v.z);
+                    float *y = reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS)));
+                    y[0] += v.x;
+                    y[PL / 2] += v.z;
                 }
                 if (any1 && unsigned(d1) < unsigned(NB)) {
-                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + PL), v.y);
-                    atomicAdd(reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + 3 * PL), v.w);
+                    float *y = reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + PL);
+                    y[0] += v.y;
+                    y[PL / 2] += v.w;
                 }
             };
-#pragma unroll
-            for (int i = 0; i < 4; i++) add_ext(tp + TP * i, ext[i]);
-            // slots N/2 + q, N/8 <= q < N/4
+            // slots N/2 + q, N/8 < q < N/4
             constexpr int LOG2N = (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : 12;
             constexpr int L0 = (LOG2N & 1) ? 2 : 4;                  // smallest block of the radix-4 recursion
 #pragma unroll 1
@@ -1824,7 +1904,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 const int q = tp + TP * i;
                 const bool need = (any0 && M + q + dl0 < NB) || (any1 && M + q + dl1 < NB);
                 if (!need) continue;
-                if (q == N / 8) { add_ext(q, ext4); continue; }      // last slot of the first level
+                if (q == N / 8) continue;                            // last slot of the first level: stored above
                 int lg = LOG2N, r = 1, sq_ = 0, o = M + q;
                 while ((1 << lg) > L0 && o > (1 << (lg - 1))) {
                     const int sb = o >> (lg - 2);
@@ -2096,7 +2176,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 // first-pass twiddle table is re-staged per call.  Bit-identical to num_hops single launches.
 // DEEP: pitch factors in [0.5, 0.75) (see ring_one_call); scalar pitch factor, one call per launch.
 template <int N, int NBLK, bool PCH = false, bool MULTI = false, bool DEEP = false>
-__global__ void __launch_bounds__((MULTI ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP,
+__global__ void __launch_bounds__(((MULTI || DEEP) ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP,
                                   RingGeoT<N, PCH>::CTAS_PER_SM)
 pv_process_ring_kernel(const RingParams p) {
     constexpr int TP = RingGeoT<N, PCH>::TP;

@@ -16,7 +16,7 @@ namespace {
 template <int N, bool PCH, bool MULTI, bool DEEP, int... NBLKS>
 cudaError_t launch_t(const RingParams &rp, const RingLaunch &l) {
     using G = RingGeoT<N, PCH>;
-    constexpr int CAP = MULTI ? G::MULTI_PAIRS : (DEEP && G::DEEP_PAIRS_CAP) ? G::DEEP_PAIRS_CAP : G::MAX_PAIRS;   // what the kernel's launch bounds (and two CTAs per SM) allow
+    constexpr int CAP = (MULTI || DEEP) ? G::MULTI_PAIRS : G::MAX_PAIRS;   // what the kernel's launch bounds (and two CTAs per SM) allow
     int ppc = l.ppc;
     if (ppc < G::MIN_PAIRS || ppc > CAP) ppc = CAP;
     cudaLaunchConfig_t cfg = {};

@@ -108,10 +108,9 @@ def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
         c.process_device(din.data_ptr(), dout.data_ptr(), pf, None, num_calls=calls)
         c.sync()
         dev = dout.cpu().numpy()
-    if "pv_process_kernel" in kernel or "(deep)" in kernel:
-        # the generic kernel, and the ring-order kernel's instances for pitch factors in [0.5, 0.75), add
-        # colliding regions with shared-memory atomics: the order, and so the last bit, is not reproducible
-        # from run to run
+    if "pv_process_kernel" in kernel:
+        # the generic kernel adds colliding regions with shared-memory atomics: the order, and so the last
+        # bit, is not reproducible from run to run
         assert np.abs(one - many).max() <= 1e-6 and np.abs(one - dev).max() <= 1e-6
     else:
         assert np.array_equal(one, many)

@@ -24,9 +24,8 @@ def _run_both(oracle, N, hop, C, pf, calls, first_channel=0, sig=None, **options
         got_many = pv.run(x, pf)
         assert 0 < pv.kernel_launches <= calls
         kernel = pv.kernel_name(pf)
-    if "pv_process_kernel" in kernel or "(deep)" in kernel:
-        # the generic kernel (and the ring-order kernel's instances for pitch factors in [0.5, 0.75)) add colliding
-        # regions with shared-memory atomics: the last bit depends on their order
+    if "pv_process_kernel" in kernel:
+        # the generic kernel adds colliding regions with shared-memory atomics: the last bit depends on their order
         assert np.abs(got - got_many).max() <= 1e-6
     else:
         assert np.array_equal(got, got_many), "calls sharing a launch differ from one launch per call"
