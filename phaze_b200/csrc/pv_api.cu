@@ -45,7 +45,8 @@ struct pvb_processor {
     // per-channel pitch factors (pvb_process_pf): last array uploaded, its device copy, its range
     std::vector<float> h_pf;
     float *d_pf = nullptr;
-    bool pf_fast = false;            // every channel inside the ring-order kernel's range
+    bool pf_fast = false;            // every channel inside the ring-order kernel's range [0.75, 64]
+    bool pf_deep = false;            // every channel inside [0.5, 64]: the ring-order kernel's DEEP instances
     // pvb_set_option
     int opt_kernel = 0, opt_launch_mode = 0, opt_inputs_ready = 0, opt_peak_guard = 0, opt_many_mode = 0;
     cudaStream_t last_stream = nullptr;   // stream of the most recent submission (state entry points wait for it)
@@ -350,7 +351,7 @@ KernelFamily pick_kernel(const pvb_processor *h, const pvb::FrameParams &fp) {
     if (fp.pf_ch) {
         // per-channel pitch factors: the ring-order kernel when every channel is in its range, else the
         // generic kernel (the only other family that reads pf_ch)
-        if (first <= K_RING && h->pf_fast && fp.overlaps <= 32 && ring_geometry_ok(h)) return K_RING;
+        if (first <= K_RING && (h->pf_fast || (h->pf_deep && h->n >= 512)) && fp.overlaps <= 32 && ring_geometry_ok(h)) return K_RING;
         return K_GENERIC;
     }
     if (first <= K_RING && (fast_range(fp) || deep_range(h->n, fp)) && ring_geometry_ok(h)) return K_RING;
@@ -480,7 +481,7 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     l.pdl = h->opt_launch_mode != 2;
     l.pch = fp.pf_ch != nullptr;
     l.multi = num_hops > 1;
-    l.deep = !fp.pf_ch && !fast_range(fp);                                   // pick_kernel admitted it: [0.5, 0.75)
+    l.deep = fp.pf_ch ? !h->pf_fast : !fast_range(fp);         // pick_kernel admitted it: pitch factors down to 0.5                                   // pick_kernel admitted it: [0.5, 0.75)
     l.stream = s;
     pvb::RingParams rp = make_ring_params(h, fp, s, input_ready, num_hops);
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
@@ -673,11 +674,12 @@ int upload_pitch_factors(pvb_processor *p, const float *pf_host, cudaStream_t s)
         }
     }
     p->h_pf.assign(pf_host, pf_host + c);
-    p->pf_fast = true;
+    p->pf_fast = p->pf_deep = true;
     for (size_t i = 0; i < c; i++) {
         int m = 0, sh = 0;
         split_pitch_factor(pf_host[i], &m, &sh);
         if (!(sh >= 1 && pf_host[i] >= 0.75f && pf_host[i] <= 64.0f)) p->pf_fast = false;
+        if (!(sh >= 1 && pf_host[i] >= 0.5f && pf_host[i] <= 64.0f)) p->pf_deep = false;
     }
     // (pageable source: the runtime stages it before returning, so h_pf may change right after)
     PVB_CUDA(p, cudaMemcpyAsync(p->d_pf, p->h_pf.data(), c * sizeof(float), cudaMemcpyHostToDevice, s));

@@ -195,6 +195,9 @@ struct RingGeoT {
     // MULTI kernels (a loop over process() calls around the body) need more than 128 registers per thread
     // to stay out of local memory: three quarters of the pairs per CTA, 168 registers
     static constexpr int MULTI_PAIRS = (N == 4096) ? 2 : (3 * MAX_PAIRS) / 4 + ((N == 1024) ? 1 : 0);
+    // DEEP instances share the launch bounds of MULTI (168 registers where that leaves two CTAs per SM); frame 4096
+    // with per-pair key tables: one pair per CTA (three CTAs per SM instead of one CTA of two pairs)
+    static constexpr int DEEP_PAIRS = (N == 4096 && PCH) ? 1 : MULTI_PAIRS;
     static constexpr int CTAS_PER_SM = 2;                   // frame 4096: 30 KB of tables + 2 x 36 KB per CTA
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
@@ -938,7 +941,7 @@ __device__ __forceinline__ void ring_masks(const RingParams &p, const int (&m0)[
 template <int N, int NBLK, bool PCH, int PHASE, bool DEEP = false>
 __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hopi, bool live) {
     using G = RingGeoT<N, PCH>;
-    static_assert(!DEEP || (PHASE == 0 && !PCH && N >= 512 && !(PVB_RING_GATHER && N == 1024)), "DEEP: scalar pitch factor, one call per launch, frame 512 and up");
+    static_assert(!DEEP || (PHASE == 0 && N >= 512 && !(PVB_RING_GATHER && N == 1024)), "DEEP: one call per launch, frame 512 and up");
     constexpr bool MULTI = PHASE != 0;
     constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1772,7 +1775,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             // dump slot): two independent instruction streams the scheduler can interleave
             ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask0, 16 * tp, pk0, nk0, rk, (contract0 && !DEEP) ? int(0x80000000u) : 0, dst0, col0);
             if constexpr (PCH)
-                ring_owner_scan<G::XQ_SLOTS - 1, G::YS>(mask1, 16 * tp, pk1, nk1, rk1, contract1 ? int(0x80000000u) : 0, dst1);
+                ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask1, 16 * tp, pk1, nk1, rk1, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1, col1);
             else
                 ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask1, 16 * tp, pk1, nk1, rk, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1, col1);
         }
@@ -2174,7 +2177,8 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 // the calls, its state goes back and forth through L1 / L2 instead of HBM (one DRAM round trip of the
 // rings per launch instead of per call), completion flags are taken and released once, and only the
 // first-pass twiddle table is re-staged per call.  Bit-identical to num_hops single launches.
-// DEEP: pitch factors in [0.5, 0.75) (see ring_one_call); scalar pitch factor, one call per launch.
+// DEEP: pitch factors down to 0.5 (see ring_one_call); scalar (then in [0.5, 0.75)) or per channel (PCH: every
+// channel in [0.5, 64]), one call per launch.
 template <int N, int NBLK, bool PCH = false, bool MULTI = false, bool DEEP = false>
 __global__ void __launch_bounds__(((MULTI || DEEP) ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP,
                                   RingGeoT<N, PCH>::CTAS_PER_SM)

@@ -16,7 +16,7 @@ namespace {
 template <int N, bool PCH, bool MULTI, bool DEEP, int... NBLKS>
 cudaError_t launch_t(const RingParams &rp, const RingLaunch &l) {
     using G = RingGeoT<N, PCH>;
-    constexpr int CAP = (MULTI || DEEP) ? G::MULTI_PAIRS : G::MAX_PAIRS;   // what the kernel's launch bounds (and two CTAs per SM) allow
+    constexpr int CAP = DEEP ? G::DEEP_PAIRS : MULTI ? G::MULTI_PAIRS : G::MAX_PAIRS;   // what the kernel's launch bounds (and two CTAs per SM) allow
     int ppc = l.ppc;
     if (ppc < G::MIN_PAIRS || ppc > CAP) ppc = CAP;
     cudaLaunchConfig_t cfg = {};
@@ -51,23 +51,27 @@ cudaError_t configure_t() {
 // (inside templates so that a frame size without the DEEP instance does not instantiate it)
 template <int N, bool DEEPOK, int... NBLKS>
 cudaError_t launch_deep_t(const RingParams &rp, const RingLaunch &l) {
-    if constexpr (DEEPOK) return launch_t<N, false, false, true, NBLKS...>(rp, l);
+    if constexpr (DEEPOK) return l.pch ? launch_t<N, true, false, true, NBLKS...>(rp, l) : launch_t<N, false, false, true, NBLKS...>(rp, l);
     else return cudaErrorInvalidValue;
 }
 template <int N, bool DEEPOK, int... NBLKS>
 cudaError_t configure_deep_t() {
-    if constexpr (DEEPOK) return configure_t<N, false, false, true, NBLKS...>();
-    else return cudaSuccess;
+    if constexpr (DEEPOK) {
+        const cudaError_t e = configure_t<N, false, false, true, NBLKS...>();
+        return e == cudaSuccess ? configure_t<N, true, false, true, NBLKS...>() : e;
+    } else {
+        return cudaSuccess;
+    }
 }
 
 }  // namespace
 
 // instances per (frame, hop): scalar pitch factor, per-channel pitch factors, several calls per launch, and
-// (frame 512 and up) the scalar instance for pitch factors in [0.5, 0.75) (DEEP)
+// (frame 512 and up) the DEEP instances (pitch factors down to 0.5), scalar and per channel
 #define PVB_RING_DEFINE(N, DEEPOK, ...)                                                             \
     cudaError_t ring_launch_##N(const RingParams &rp, const RingLaunch &l) {                        \
         if (l.deep)                                                                                 \
-            return (l.pch || l.multi) ? cudaErrorInvalidValue : launch_deep_t<N, DEEPOK, __VA_ARGS__>(rp, l); \
+            return l.multi ? cudaErrorInvalidValue : launch_deep_t<N, DEEPOK, __VA_ARGS__>(rp, l);  \
         if (l.pch) return l.multi ? cudaErrorInvalidValue : launch_t<N, true, false, false, __VA_ARGS__>(rp, l); \
         return l.multi ? launch_t<N, false, true, false, __VA_ARGS__>(rp, l)                        \
                        : launch_t<N, false, false, false, __VA_ARGS__>(rp, l);                      \

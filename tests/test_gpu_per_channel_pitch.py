@@ -49,6 +49,38 @@ def test_per_channel_pitch_in_ring_range(oracle, N, hop, C):
     assert per_channel.max() <= RMS_EXPECTED
 
 
+@pytest.mark.parametrize("N,hop,C", [(1024, 256, 9), (2048, 128, 6), (2048, 512, 7), (512, 128, 37), (4096, 1024, 5)])
+def test_per_channel_pitch_down_to_one_half(oracle, N, hop, C):
+    """factors in [0.5, 0.75) for some channels, above for others (both kinds in one pair): the ring-order
+    kernel's DEEP instances with per-pair key tables, one launch per call, no state re-layout"""
+    from phaze_b200 import BatchedPhaseVocoder
+    calls = 2 * (N // hop) + 5
+    rng = np.random.default_rng(N + 3 * hop)
+    pf = rng.uniform(0.5, 1.5, C).astype(np.float32)
+    pf[0], pf[1], pf[2], pf[3], pf[4] = (np.float32(v) for v in (0.5, 1.25, 0.62, 0.74, 0.9))
+    x = signals.channels(160, C, calls * hop)
+    ref = _oracle_per_channel(oracle, N, hop, x, pf)
+    with BatchedPhaseVocoder(C, N, hop) as pv:
+        got = pv.run_pf(x, pf)
+        assert pv.kernel_launches == calls
+        st = pv.get_state()
+    per_channel = np.sqrt(np.mean(np.square((got - ref).astype(np.float64)), axis=1))
+    print(f"N={N} hop={hop} C={C}: worst channel rms err {per_channel.max():.3e}")
+    assert per_channel.max() <= RMS_EXPECTED
+
+
+def test_uniform_array_in_deep_range_equals_scalar_call_bitwise():
+    """pitch_factors[c] == f in [0.5, 0.75) for every c must give the bits of pvb_process(..., f)"""
+    from phaze_b200 import BatchedPhaseVocoder
+    N, hop, C, calls = 1024, 256, 11, 9
+    x = signals.channels(141, C, calls * hop)
+    for f in (0.5, 0.66):
+        with BatchedPhaseVocoder(C, N, hop) as a, BatchedPhaseVocoder(C, N, hop) as b:
+            want = a.run(x, np.float32(f))
+            got = b.run_pf(x, np.full(C, f, np.float32))
+        assert np.array_equal(got, want)
+
+
 def test_per_channel_pitch_changes_every_call_and_leaves_the_range(oracle):
     """factors that change from call to call (k-rate automation) and wander outside [0.75, 64] for some
     channels and calls: those calls run on the generic kernel, state is re-laid in between"""
