@@ -40,7 +40,9 @@ METRIC = "STFT frames/sec (1024-pt, hop 256) at 4096 ch; achieved HBM GB/s vs pe
 def workload_name(channels, frame, hop, pitch):
     tag = {(1024, 256, 4096, 0.8): " (BASELINE configs[1])", (2048, 512, 2048, 1.5): " (BASELINE configs[2]: 1024 stereo streams)",
            (1024, 256, 32768, 1.25): " (BASELINE configs[3], all channels on one GPU)",
-           (2048, 128, 2048, 1.2): " (the reference's own frame / hop)"}.get((frame, hop, channels, round(float(pitch), 3)), "")
+           (2048, 128, 2048, 1.2): " (the reference's own frame / hop)",
+           (1024, 256, 4096, 0.6): " (low end of the demo's pitch slider: DEEP instances)",
+           (1024, 256, 4096, 0.5): " (bottom of the demo's pitch slider: DEEP instances)"}.get((frame, hop, channels, round(float(pitch), 3)), "")
     if not tag and channels == 8192 and hop * 4 == frame:
         tag = " (BASELINE configs[4] sweep)"
     return f"{channels} mono channels per GPU, frame {frame} / hop {hop}, pitchFactor {pitch}{tag}"
@@ -636,7 +638,9 @@ def run_e2e(procs, blocks_np, C, hop, pitch, K, CPS, dist):
 # BASELINE configs 3, 4 (one shard's worth per launch) and 5, plus the reference's own 2048 / 128
 OTHER_CONFIGS = [(2048, 512, 2048, 1.5), (1024, 256, 32768, 1.25),
                  (256, 64, 8192, 1.2), (512, 128, 8192, 1.2), (1024, 256, 8192, 1.2), (2048, 512, 8192, 1.2),
-                 (4096, 1024, 8192, 1.2), (2048, 128, 2048, 1.2)]
+                 (4096, 1024, 8192, 1.2), (2048, 128, 2048, 1.2),
+                 # the low end of the demo's pitch slider (www/index.html:23): the ring-order kernel's DEEP instances
+                 (1024, 256, 4096, 0.6), (1024, 256, 4096, 0.5)]
 
 
 def quick_config(local, frame, hop, C, pf, peak, steps=300, warm=40, **options):
