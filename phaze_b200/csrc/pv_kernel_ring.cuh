@@ -57,6 +57,11 @@ namespace pvb {
 #ifndef PVB_RING_PAIRS_1024
 #define PVB_RING_PAIRS_1024 7
 #endif
+// pairs per CTA of the MULTI (several calls per launch) and DEEP instances at frame 1024: 6 -> 168 registers,
+// 7 -> 144 registers (4096 channels then fill exactly one wave of 293 CTAs on 296 slots)
+#ifndef PVB_RING_MULTI_PAIRS_1024
+#define PVB_RING_MULTI_PAIRS_1024 6
+#endif
 // Destinations outside [0, nb) are clamped to one write-only "dump" word per plane instead of being
 // predicated off (one integer operation less per bin): several lanes may store to it at once, which
 // compute-sanitizer's racecheck reports as write-after-write hazards.  -DPVB_RING_NO_DUMP=1 predicates
@@ -194,10 +199,13 @@ struct RingGeoT {
                                      : (N == 2048) ? (PCH ? 3 : 4) : 2;     // pairs per CTA (two CTAs per SM must fit 227 KB)
     // MULTI kernels (a loop over process() calls around the body) need more than 128 registers per thread
     // to stay out of local memory: three quarters of the pairs per CTA, 168 registers
-    static constexpr int MULTI_PAIRS = (N == 4096) ? 2 : (3 * MAX_PAIRS) / 4 + ((N == 1024) ? 1 : 0);
+    static constexpr int MULTI_PAIRS = (N == 4096) ? 2 : (N == 1024) ? PVB_RING_MULTI_PAIRS_1024 : (3 * MAX_PAIRS) / 4;
     // DEEP instances share the launch bounds of MULTI (168 registers where that leaves two CTAs per SM); frame 4096
     // with per-pair key tables: one pair per CTA (three CTAs per SM instead of one CTA of two pairs)
     static constexpr int DEEP_PAIRS = (N == 4096 && PCH) ? 1 : MULTI_PAIRS;
+    // registers per thread of those instances: what two CTAs of MULTI_PAIRS pairs leave (168 at 192 threads, 144 at
+    // 224, 128 at 256); the one-call instances stay at 128
+    static constexpr int BIG_REGS = ((65536 / (2 * MULTI_PAIRS * TP)) / 8) * 8;
     static constexpr int CTAS_PER_SM = 2;                   // frame 4096: 30 KB of tables + 2 x 36 KB per CTA
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
@@ -2180,8 +2188,8 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 // DEEP: pitch factors down to 0.5 (see ring_one_call); scalar (then in [0.5, 0.75)) or per channel (PCH: every
 // channel in [0.5, 64]), one call per launch.
 template <int N, int NBLK, bool PCH = false, bool MULTI = false, bool DEEP = false>
-__global__ void __launch_bounds__(((MULTI || DEEP) ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP,
-                                  RingGeoT<N, PCH>::CTAS_PER_SM)
+__global__ void __launch_bounds__(((MULTI || DEEP) ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP)
+__maxnreg__(((MULTI || DEEP) ? RingGeoT<N, PCH>::BIG_REGS : 128))     // two CTAs per SM either way
 pv_process_ring_kernel(const RingParams p) {
     constexpr int TP = RingGeoT<N, PCH>::TP;
     const int tp = threadIdx.x % TP, pin = threadIdx.x / TP;

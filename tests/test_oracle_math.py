@@ -84,3 +84,65 @@ def test_bad_sizes_rejected(oracle):
         oracle.OracleProcessor(1000, 250, 1)
     with pytest.raises(ValueError):
         oracle.real_transform(np.zeros(48, np.float32))
+
+
+def _walk_block_tree(n, pos):
+    """(L, r, s, o): slot `pos` of the realTransform output holds DFT_L(x[r m + s])[o] (bundle:394-438 writes
+    only outputs 0 .. L/2 of every length-L block of the radix-4 recursion); pv_kernel_ring.cuh, DEEP instances"""
+    l0 = 4 if int(np.log2(n)) % 2 == 0 else 2
+    L, r, s, o = n, 1, 0, pos
+    while L > l0 and o > L // 2:
+        q = L // 4
+        sb = o // q
+        o -= sb * q
+        s += r * sb
+        r *= 4
+        L = q
+    return L, r, s, o
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_deep_stale_slots_are_sums_of_frame_samples(oracle, n):
+    """what the ring-order kernel's DEEP instances compute for pitch factors in [0.5, 0.75): every slot
+    N/2 + q, q < N/4, is a sum of L samples x[r m + s]; beyond the first level all of them have
+    n = 10 or 14 (mod 16) and sit in the kernel's scratch at 2 (n >> 4) + ((n >> 2) & 1), stride r / 8"""
+    x = np.random.default_rng(5 * n).uniform(-1, 1, n).astype(np.float32)
+    X = oracle.real_transform(x)
+    xd = x.astype(np.float64)
+    keep = np.flatnonzero((np.arange(n) % 16 == 10) | (np.arange(n) % 16 == 14))
+    scratch = np.zeros(n // 8)
+    scratch[2 * (keep >> 4) + ((keep >> 2) & 1)] = xd[keep]
+    worst = 0.0
+    for q in range(1, n // 4):
+        L, r, s, o = _walk_block_tree(n, n // 2 + q)
+        m = np.arange(L)
+        if q <= n // 8:
+            assert (L, r, s) == (n // 4, 4, 2)                      # first level: rebuilt from the valid half instead
+            samples = xd[r * m + s]
+        else:
+            assert r >= 16 and s % 16 in (10, 14)
+            samples = scratch[2 * (s >> 4) + ((s >> 2) & 1) + (r // 8) * m]
+        worst = max(worst, abs(np.sum(samples * np.exp(-2j * np.pi * o * m / L)) - X[n // 2 + q]))
+    assert worst < 1e-10
+
+
+def test_three_colours_suffice_for_pitch_factors_from_one_half():
+    """DEEP instances add colliding regions in three ordered sub-steps (ordinal of the owning peak mod 3): with
+    peaks at least 3 bins apart (pv:95-116) and pitch factors >= 0.5 the images of regions i and i + 3 never
+    overlap (pv:119-147), so at most three regions land on one bin"""
+    rng = np.random.default_rng(11)
+    n, nb = 1024, 513
+    for trial in range(3000):
+        peaks, p = [], 2 + int(rng.integers(0, 4))
+        while p < n // 2 - 2:
+            peaks.append(p)
+            p += 3 + (int(rng.geometric(0.5)) - 1 if rng.random() < 0.8 else int(rng.integers(0, 40)))
+        pf = np.float32(rng.choice([0.5, 0.5000001, 0.51, 0.55, 0.6, 0.66, 0.7, 0.7499, rng.uniform(0.5, 0.75)]))
+        delta = [int(np.floor(p * float(pf) + 0.5)) - p for p in peaks]
+        img = []
+        for i, p in enumerate(peaks):
+            s = 0 if i == 0 else p - (p - peaks[i - 1]) // 2
+            e = n if i == len(peaks) - 1 else p + -(-(peaks[i + 1] - p) // 2)
+            img.append((max(s + delta[i], 0), min(e + delta[i], nb)))
+        for i in range(len(peaks) - 3):
+            assert img[i + 3][0] >= img[i][1]
