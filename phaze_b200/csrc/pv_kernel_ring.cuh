@@ -57,8 +57,10 @@ namespace pvb {
 #ifndef PVB_RING_PAIRS_1024
 #define PVB_RING_PAIRS_1024 7
 #endif
-// pairs per CTA of the MULTI (several calls per launch) and DEEP instances at frame 1024: 6 -> 168 registers,
-// 7 -> 144 registers (4096 channels then fill exactly one wave of 293 CTAs on 296 slots)
+// pairs per CTA of the MULTI (several calls per launch) and DEEP instances at frame 1024: 6 -> 168 registers.
+// (7 at 144 registers would fill one wave with 4096 channels, but 14 warps of 144 registers do not fit the four
+// 16 K-register files of an SM -- one sub-partition gets four warps -- so only one CTA becomes resident: measured
+// 2x slower, profiles/r02_ab_m7.txt)
 #ifndef PVB_RING_MULTI_PAIRS_1024
 #define PVB_RING_MULTI_PAIRS_1024 6
 #endif
