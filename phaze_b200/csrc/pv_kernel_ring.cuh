@@ -202,12 +202,13 @@ struct RingGeoT {
     // MULTI kernels (a loop over process() calls around the body) need more than 128 registers per thread
     // to stay out of local memory: three quarters of the pairs per CTA, 168 registers
     static constexpr int MULTI_PAIRS = (N == 4096) ? 2 : (N == 1024) ? PVB_RING_MULTI_PAIRS_1024 : (3 * MAX_PAIRS) / 4;
-    // DEEP instances share the launch bounds of MULTI (168 registers where that leaves two CTAs per SM); frame 4096
-    // with per-pair key tables: one pair per CTA (three CTAs per SM instead of one CTA of two pairs)
-    static constexpr int DEEP_PAIRS = (N == 4096 && PCH) ? 1 : MULTI_PAIRS;
+    // DEEP instances share the launch bounds of MULTI (168 registers where that leaves two CTAs per SM); frame 4096:
+    // one pair per CTA, three CTAs per SM at 168 registers (two pairs per CTA would mean 128 registers and spills)
+    static constexpr int DEEP_PAIRS = (N == 4096) ? 1 : MULTI_PAIRS;
     // registers per thread of those instances: what two CTAs of MULTI_PAIRS pairs leave (168 at 192 threads, 144 at
     // 224, 128 at 256); the one-call instances stay at 128
     static constexpr int BIG_REGS = ((65536 / (2 * MULTI_PAIRS * TP)) / 8) * 8;
+    static constexpr int DEEP_REGS = (N == 4096) ? 168 : BIG_REGS;   // frame 4096: three CTAs of one pair per SM
     static constexpr int CTAS_PER_SM = 2;                   // frame 4096: 30 KB of tables + 2 x 36 KB per CTA
     static constexpr int MAX_WARPS = MAX_PAIRS;             // (frame 1024: one warp per pair)
     static constexpr int MIN_THREADS = 128;                 // trip counts of the staging loops assume this
@@ -1820,6 +1821,45 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             }
             if constexpr (DEEP) { if (l0) ext4 = level1(N / 8); }
         }
+        // DEEP: the second stale level while X is still there.  Slot N/2 + q, q = N/8 + tp + TP i: for even i
+        // (every thread) and for odd i (thread 0) the block-tree walk stops at L = N/16, r = 16, s = 2 + 4 sb,
+        // sb = 2 + i / 2, o = q - sb N/16 <= N/32, and DFT_L(xw[16 m + s])[o] = 1/16 sum_u W_N^{-s (o + u L)} X[o + u L]
+        // (X extended Hermitian above N/2): 16 terms from the spectrum instead of N/16 frame samples.  In ring
+        // order nothing changes: (o + u L) - (N/2 + q) is a multiple of L and t of 16.
+        float4 ext2[4];
+        (void)ext2;
+        if constexpr (DEEP) {
+#pragma unroll
+            for (int ip = 0; ip < 4; ip++) {
+                ext2[ip] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int q = N / 8 + tp + TP * ip;
+                const bool lvl2 = ((ip & 1) == 0 || l0) && q != N / 8;
+                const bool need = (any0 && M + q + dl0 < NB) || (any1 && M + q + dl1 < NB);
+                if (lvl2 && need) {
+                    constexpr int L16 = N / 16;
+                    const int sb = 2 + (ip >> 1), o = q - sb * L16, sx = 2 + 4 * sb;
+                    cpx2 acc;
+                    acc.re = acc.im = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const int idx = o + u * L16;
+                        const bool mir = (u > 8) || (u == 8 && o != 0);                  // bins above N/2: conj X[N - idx]
+                        const int b = mir ? N - idx : idx;
+                        const cpx2 xv = unpack4(XQ[b + (b >> 4)]);
+                        const float2 xi = mir ? make_float2(-xv.im.x, -xv.im.y) : xv.im;
+                        const int k = (sx * idx) & (N - 1);
+                        float2 w = PVB_TWH(twh + (k & (M - 1)));
+                        if (k & M) w = make_float2(-w.x, -w.y);
+                        // + (xr + j xi) conj(w)
+                        acc.re = fma2(xv.re, bc2(w.x), acc.re);
+                        acc.re = fma2(xi, bc2(w.y), acc.re);
+                        acc.im = fma2(xi, bc2(w.x), acc.im);
+                        acc.im = fma2(xv.re, bc2(-w.y), acc.im);
+                    }
+                    ext2[ip] = make_float4(0.0625f * acc.re.x, 0.0625f * acc.re.y, 0.0625f * acc.im.x, 0.0625f * acc.im.y);
+                }
+            }
+        }
         pair_sync<TP>(pin);      // every thread holds its sources: the buffer becomes Y
         // (PVB_RING_EXACT: while contracting every bin of [0, nb) is stored exactly once in the first
         // sub-step, provided both channels have peaks)
@@ -1846,7 +1886,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 if (dst0[e] == DUMPB + (dst0[e] & 3)) dst0[e] = -1;   // outside [0, nb): no colour matches
                 if (dst1[e] == DUMPB + (dst1[e] & 3)) dst1[e] = -1;
             }
-            // the last region's sources from bin N/2 up to the end of the first stale level go first (plain stores
+            // the last region's sources from bin N/2 up to the end of the first and all of the second stale level go first (plain stores
             // onto the zero-filled planes: nothing else has been written yet), which ends their live ranges
             {
                 auto put_ext = [&](int q, const float4 &v) {
@@ -1865,6 +1905,9 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #pragma unroll
                 for (int i = 0; i < 4; i++) put_ext(tp + TP * i, ext[i]);
                 if (l0) put_ext(N / 8, ext4);
+#pragma unroll
+                for (int ip = 0; ip < 4; ip++)                       // second level (zeros where not needed / not level 2)
+                    if (((ip & 1) == 0 || l0) && !(ip == 0 && l0)) put_ext(N / 8 + tp + TP * ip, ext2[ip]);
             }
 #pragma unroll 1
             for (int col = 0; col < 3; col++) {
@@ -1918,6 +1961,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 const bool need = (any0 && M + q + dl0 < NB) || (any1 && M + q + dl1 < NB);
                 if (!need) continue;
                 if (q == N / 8) continue;                            // last slot of the first level: stored above
+                if ((i & 1) == 0 || l0) continue;                    // second level: from the spectrum, stored above
                 int lg = LOG2N, r = 1, sq_ = 0, o = M + q;
                 while ((1 << lg) > L0 && o > (1 << (lg - 1))) {
                     const int sb = o >> (lg - 2);
@@ -2190,8 +2234,8 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 // DEEP: pitch factors down to 0.5 (see ring_one_call); scalar (then in [0.5, 0.75)) or per channel (PCH: every
 // channel in [0.5, 64]), one call per launch.
 template <int N, int NBLK, bool PCH = false, bool MULTI = false, bool DEEP = false>
-__global__ void __launch_bounds__(((MULTI || DEEP) ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP)
-__maxnreg__(((MULTI || DEEP) ? RingGeoT<N, PCH>::BIG_REGS : 128))     // two CTAs per SM either way
+__global__ void __launch_bounds__((DEEP ? RingGeoT<N, PCH>::DEEP_PAIRS : MULTI ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP)
+__maxnreg__((DEEP ? RingGeoT<N, PCH>::DEEP_REGS : MULTI ? RingGeoT<N, PCH>::BIG_REGS : 128))     // two CTAs per SM either way
 pv_process_ring_kernel(const RingParams p) {
     constexpr int TP = RingGeoT<N, PCH>::TP;
     const int tp = threadIdx.x % TP, pin = threadIdx.x / TP;

@@ -1,6 +1,6 @@
 """Pitch factors in [0.5, 0.75): the ring-order kernel's DEEP instances against the generic kernel
 (PVB_OPT_KERNEL = generic), device-resident, measured like bench.py's other_configs.
-    python profiles/deep_ab.py [channels]"""
+    python profiles/deep_ab.py [channels [frame]]"""
 import json
 import os
 import sys
@@ -10,7 +10,10 @@ import bench  # noqa: E402
 
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 peak, _ = bench.measured_peak()
+ONLY = int(sys.argv[2]) if len(sys.argv) > 2 else 0        # optional: one frame size
 for frame, hop in ((1024, 256), (2048, 512), (2048, 128), (512, 128), (4096, 1024)):
+    if ONLY and frame != ONLY:
+        continue
     ch = C if frame <= 1024 else C * 1024 // frame
     for pf in (0.5, 0.6, 0.7, 0.74, 0.8):
         row = {}

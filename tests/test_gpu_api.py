@@ -236,6 +236,8 @@ def test_full_size_config3_properties(oracle):
     (1024, 256, 8192, 1.2),
     (2048, 512, 8192, 0.8),
     (4096, 1024, 8192, 1.2),       # 2048 CTAs of 2 pairs
+    (1024, 256, 4096, 0.6),        # the headline channel count at the low end of the demo's pitch range: DEEP instances
+    (2048, 128, 2048, 0.5),        # the reference's own frame / hop at the bottom of that range
 ])
 def test_full_size_configs_4_and_5(oracle, N, hop, C, pf):
     """BASELINE configs 4 and 5 at their full channel counts (the grid-size edges the small parity cases do
