@@ -255,7 +255,8 @@ bool warp_kernel_applies(int n, const pvb::FrameParams &fp) { return n == 1024 &
 // ring-order kernel, DEEP instances (pv_kernel_ring.cuh): scalar pitch factors in [0.5, 0.75) -- stale slots up
 // to N/2 + N/4 - 1 rebuilt from the windowed frame, colliding regions through shared-memory atomics
 bool deep_range(int n, const pvb::FrameParams &fp) {
-    return !fp.pf_ch && n >= 512 && fp.pf_shift >= 1 && fp.pitch_factor >= 0.5f && fp.pitch_factor < 0.75f && fp.overlaps <= 32;
+    (void)n;
+    return !fp.pf_ch && fp.pf_shift >= 1 && fp.pitch_factor >= 0.5f && fp.pitch_factor < 0.75f && fp.overlaps <= 32;
 }
 
 template <int N>
@@ -351,7 +352,7 @@ KernelFamily pick_kernel(const pvb_processor *h, const pvb::FrameParams &fp) {
     if (fp.pf_ch) {
         // per-channel pitch factors: the ring-order kernel when every channel is in its range, else the
         // generic kernel (the only other family that reads pf_ch)
-        if (first <= K_RING && (h->pf_fast || (h->pf_deep && h->n >= 512)) && fp.overlaps <= 32 && ring_geometry_ok(h)) return K_RING;
+        if (first <= K_RING && (h->pf_fast || h->pf_deep) && fp.overlaps <= 32 && ring_geometry_ok(h)) return K_RING;
         return K_GENERIC;
     }
     if (first <= K_RING && (fast_range(fp) || deep_range(h->n, fp)) && ring_geometry_ok(h)) return K_RING;

@@ -952,7 +952,7 @@ __device__ __forceinline__ void ring_masks(const RingParams &p, const int (&m0)[
 template <int N, int NBLK, bool PCH, int PHASE, bool DEEP = false>
 __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hopi, bool live) {
     using G = RingGeoT<N, PCH>;
-    static_assert(!DEEP || (PHASE == 0 && N >= 512 && !(PVB_RING_GATHER && N == 1024)), "DEEP: one call per launch, frame 512 and up");
+    static_assert(!DEEP || (PHASE == 0 && !(PVB_RING_GATHER && N == 1024)), "DEEP: one call per launch");
     constexpr bool MULTI = PHASE != 0;
     constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1291,11 +1291,20 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                     t16[tp] = wv;
                     if constexpr (!G::T16_HALF) t16[tp + TP] = make_float2(-wv.x, -wv.y);     // W_N^{16 (tp + TP)} = -W_N^{16 tp}
                 }
-                // x[j].re is the windowed frame sample 128 f + 2 c of both channels, c = float4 column of the block
-                const int c = cn + TPH * h;
-                if ((c & 5) == 5) {
+                if constexpr (HB) {
+                    // frame 256: the rings may be rotated by half a block; frame sample of a ring position at run time
 #pragma unroll
-                    for (int j = 0; j < RT; j++) dsc[16 * PVB_FB(j) + 2 * (c >> 3) + ((c >> 1) & 1)] = x[j].re;
+                    for (int j = 0; j < RT; j++) {
+                        const int n = (2 * PVB_RING_IDX(h, PVB_FB(j)) - t) & (N - 1);
+                        if (((n >> 1) & 5) == 5) dsc[2 * (n >> 4) + ((n >> 2) & 1)] = x[j].re;
+                    }
+                } else {
+                    // x[j].re is the windowed frame sample 128 f + 2 c of both channels, c = float4 column of the block
+                    const int c = cn + TPH * h;
+                    if ((c & 5) == 5) {
+#pragma unroll
+                        for (int j = 0; j < RT; j++) dsc[16 * PVB_FB(j) + 2 * (c >> 3) + ((c >> 1) & 1)] = x[j].re;
+                    }
                 }
             }
             dft_r<RT, false>(x);
@@ -1953,7 +1962,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 }
             };
             // slots N/2 + q, N/8 < q < N/4
-            constexpr int LOG2N = (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : 12;
+            constexpr int LOG2N = (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : 12;
             constexpr int L0 = (LOG2N & 1) ? 2 : 4;                  // smallest block of the radix-4 recursion
 #pragma unroll 1
             for (int i = 4; i < 8; i++) {

@@ -67,7 +67,7 @@ cudaError_t configure_deep_t() {
 }  // namespace
 
 // instances per (frame, hop): scalar pitch factor, per-channel pitch factors, several calls per launch, and
-// (frame 512 and up) the DEEP instances (pitch factors down to 0.5), scalar and per channel
+// the DEEP instances (pitch factors down to 0.5), scalar and per channel
 #define PVB_RING_DEFINE(N, DEEPOK, ...)                                                             \
     cudaError_t ring_launch_##N(const RingParams &rp, const RingLaunch &l) {                        \
         if (l.deep)                                                                                 \
@@ -85,7 +85,7 @@ cudaError_t configure_deep_t() {
     }
 
 #if PVB_RING_INST_N == 256
-PVB_RING_DEFINE(256, false, 1, 2)
+PVB_RING_DEFINE(256, true, 1, 2)
 #elif PVB_RING_INST_N == 512
 PVB_RING_DEFINE(512, true, 1, 2)
 #elif PVB_RING_INST_N == 1024

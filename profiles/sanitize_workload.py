@@ -23,7 +23,7 @@ def rms(a):
 def deep(worst):
     """pitch factors in [0.5, 0.75): the DEEP instances (three coloured sub-steps of the shift, sub-transform sums
     from the per-pair scratch), scalar and per channel"""
-    for N, hop in [(512, 128), (1024, 256), (2048, 128), (2048, 512), (4096, 1024)]:
+    for N, hop in [(256, 64), (512, 128), (1024, 256), (2048, 128), (2048, 512), (4096, 1024)]:
         C, calls = 7, 2 * (N // hop) + 3
         x = signals.channels(50, C, calls * hop)
         for pf in (0.5, 0.62, 0.74):

@@ -49,7 +49,7 @@ def test_per_channel_pitch_in_ring_range(oracle, N, hop, C):
     assert per_channel.max() <= RMS_EXPECTED
 
 
-@pytest.mark.parametrize("N,hop,C", [(1024, 256, 9), (2048, 128, 6), (2048, 512, 7), (512, 128, 37), (4096, 1024, 5)])
+@pytest.mark.parametrize("N,hop,C", [(1024, 256, 9), (2048, 128, 6), (2048, 512, 7), (512, 128, 37), (256, 64, 70), (4096, 1024, 5)])
 def test_per_channel_pitch_down_to_one_half(oracle, N, hop, C):
     """factors in [0.5, 0.75) for some channels, above for others (both kinds in one pair): the ring-order
     kernel's DEEP instances with per-pair key tables, one launch per call, no state re-layout"""
