@@ -127,7 +127,8 @@ enum {
        A family that does not cover the handle's frame / hop / pitch factor falls through to the next
        one, exactly like auto.  Exists for tests and A/B measurements.
        Ranges: ring-order -- hop a multiple of 128 samples (frame 256: 64), hop <= frame / 2, pitch factors in
-       [0.5, 64] (below 0.75: its DEEP instances; scalar or per channel); families
+       [0.33, 64] (below 0.75: its DEEP instances; scalar or per channel; below 0.5 colliding regions are added with
+       shared-memory atomics, so the last bit of a result can differ from run to run); families
        2 and 3 -- pitch factors in [0.75, 64], any hop with at most 32 overlaps; generic -- everything. */
     PVB_OPT_KERNEL = 1,
     /* How consecutive launches are chained: 0 auto (programmatic dependent launch + per-pair completion

@@ -46,7 +46,8 @@ struct pvb_processor {
     std::vector<float> h_pf;
     float *d_pf = nullptr;
     bool pf_fast = false;            // every channel inside the ring-order kernel's range [0.75, 64]
-    bool pf_deep = false;            // every channel inside [0.5, 64]: the ring-order kernel's DEEP instances
+    bool pf_deep = false;            // every channel inside [0.33, 64]: the ring-order kernel's DEEP instances
+    bool pf_half = false;            // every channel inside [0.5, 64]: the DEEP instances with ordered sub-steps
     // pvb_set_option
     int opt_kernel = 0, opt_launch_mode = 0, opt_inputs_ready = 0, opt_peak_guard = 0, opt_many_mode = 0;
     cudaStream_t last_stream = nullptr;   // stream of the most recent submission (state entry points wait for it)
@@ -252,11 +253,12 @@ bool fast_range(const pvb::FrameParams &fp) {
     return fp.pf_shift >= 1 && fp.pitch_factor >= 0.75f && fp.pitch_factor <= 64.0f && fp.overlaps <= 32;
 }
 bool warp_kernel_applies(int n, const pvb::FrameParams &fp) { return n == 1024 && fast_range(fp); }
-// ring-order kernel, DEEP instances (pv_kernel_ring.cuh): scalar pitch factors in [0.5, 0.75) -- stale slots up
-// to N/2 + N/4 - 1 rebuilt from the windowed frame, colliding regions through shared-memory atomics
+// ring-order kernel, DEEP instances (pv_kernel_ring.cuh): scalar pitch factors in [0.33, 0.75) -- stale slots up
+// to N/2 + N/3 rebuilt from the spectrum / the windowed frame; colliding regions in three ordered sub-steps
+// (from 0.5) or through shared-memory atomics (below)
 bool deep_range(int n, const pvb::FrameParams &fp) {
     (void)n;
-    return !fp.pf_ch && fp.pf_shift >= 1 && fp.pitch_factor >= 0.5f && fp.pitch_factor < 0.75f && fp.overlaps <= 32;
+    return !fp.pf_ch && fp.pf_shift >= 1 && fp.pitch_factor >= 0.33f && fp.pitch_factor < 0.75f && fp.overlaps <= 32;
 }
 
 template <int N>
@@ -482,7 +484,8 @@ cudaError_t launch_ring(const pvb_processor *h, const pvb::FrameParams &fp, cuda
     l.pdl = h->opt_launch_mode != 2;
     l.pch = fp.pf_ch != nullptr;
     l.multi = num_hops > 1;
-    l.deep = fp.pf_ch ? !h->pf_fast : !fast_range(fp);         // pick_kernel admitted it: pitch factors down to 0.5                                   // pick_kernel admitted it: [0.5, 0.75)
+    // pick_kernel admitted it: 1 = pitch factors down to 0.5, 2 = down to 0.33
+    l.deep = fp.pf_ch ? (h->pf_fast ? 0 : h->pf_half ? 1 : 2) : (fast_range(fp) ? 0 : fp.pitch_factor >= 0.5f ? 1 : 2);                                   // pick_kernel admitted it: [0.5, 0.75)
     l.stream = s;
     pvb::RingParams rp = make_ring_params(h, fp, s, input_ready, num_hops);
     const_cast<pvb_processor *>(h)->ring_seq = rp.my_seq;       // the launch below stores it into done[]
@@ -675,12 +678,13 @@ int upload_pitch_factors(pvb_processor *p, const float *pf_host, cudaStream_t s)
         }
     }
     p->h_pf.assign(pf_host, pf_host + c);
-    p->pf_fast = p->pf_deep = true;
+    p->pf_fast = p->pf_deep = p->pf_half = true;
     for (size_t i = 0; i < c; i++) {
         int m = 0, sh = 0;
         split_pitch_factor(pf_host[i], &m, &sh);
         if (!(sh >= 1 && pf_host[i] >= 0.75f && pf_host[i] <= 64.0f)) p->pf_fast = false;
-        if (!(sh >= 1 && pf_host[i] >= 0.5f && pf_host[i] <= 64.0f)) p->pf_deep = false;
+        if (!(sh >= 1 && pf_host[i] >= 0.33f && pf_host[i] <= 64.0f)) p->pf_deep = false;
+        if (!(pf_host[i] >= 0.5f)) p->pf_half = false;
     }
     // (pageable source: the runtime stages it before returning, so h_pf may change right after)
     PVB_CUDA(p, cudaMemcpyAsync(p->d_pf, p->h_pf.data(), c * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -1168,7 +1172,8 @@ const char *pvb_kernel_name(const pvb_processor *p, float pitch_factor) {
                                 "pvb::pv_process_kernel<4096>"};
     const int idx = p->n == 256 ? 0 : p->n == 512 ? 1 : p->n == 1024 ? 2 : p->n == 2048 ? 3 : 4;
     switch (pick_kernel(p, fp)) {
-        case K_RING: return fast_range(fp) ? "pvb::pv_process_ring_kernel" : "pvb::pv_process_ring_kernel (deep)";
+        case K_RING: return fast_range(fp) ? "pvb::pv_process_ring_kernel"
+                            : pitch_factor >= 0.5f ? "pvb::pv_process_ring_kernel (deep)" : "pvb::pv_process_ring_kernel (deep, atomics)";
         case K_WARP: return "pvb::pv_process_warp_kernel";
         case K_CTA: return cta[idx];
         case K_GENERIC: break;

@@ -949,10 +949,13 @@ __device__ __forceinline__ void ring_masks(const RingParams &p, const int (&m0)[
 // per-pair scratch in frame order, the thread that owns slot q sums them (only when the slot lands inside [0, nb)
 // after the last peak's shift), turns the result to ring order (times W_N^{(N/2 + q) t}) and adds it; every
 // store of the shift becomes a shared-memory atomic add on the zero-filled planes.
-template <int N, int NBLK, bool PCH, int PHASE, bool DEEP = false>
+template <int N, int NBLK, bool PCH, int PHASE, int DEEP = 0>
 __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hopi, bool live) {
     using G = RingGeoT<N, PCH>;
     static_assert(!DEEP || (PHASE == 0 && !(PVB_RING_GATHER && N == 1024)), "DEEP: one call per launch");
+    // DEEP == 1: every pitch factor of the pair >= 0.5 (three coloured sub-steps); 2: down to 0.33 (atomics, and
+    // the stale slots of the quarter 3N/4 + o)
+    constexpr bool COLOURS = DEEP == 1, WIDE = DEEP == 2;
     constexpr bool MULTI = PHASE != 0;
     constexpr int M = G::M, NB = G::NB, TP = G::TP, R1 = G::R1, KS = G::KS, SS = G::SS, NJ = G::NJ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1769,7 +1772,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             dl0 = (lk0 & 0xFFFF) - 32768;
             dl1 = (lk1 & 0xFFFF) - 32768;
             int col0 = 0, col1 = 0;                                   // DEEP: (peaks below this thread's run - 1) mod 3
-            if constexpr (DEEP) {
+            if constexpr (COLOURS) {
                 // peaks below this thread's run, both channels in one word (at most N/6 peaks per channel)
                 constexpr int W = (TP < 32) ? TP : 32;
                 const int cnt = __popc(mask0) | (__popc(mask1) << 16);
@@ -1793,11 +1796,11 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             }
             // both scans run unconditionally (a channel without peaks ends up with every bin on the
             // dump slot): two independent instruction streams the scheduler can interleave
-            ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask0, 16 * tp, pk0, nk0, rk, (contract0 && !DEEP) ? int(0x80000000u) : 0, dst0, col0);
+            ring_owner_scan<G::XQ_SLOTS - 1, G::YS, COLOURS>(mask0, 16 * tp, pk0, nk0, rk, (contract0 && !DEEP) ? int(0x80000000u) : 0, dst0, col0);
             if constexpr (PCH)
-                ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask1, 16 * tp, pk1, nk1, rk1, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1, col1);
+                ring_owner_scan<G::XQ_SLOTS - 1, G::YS, COLOURS>(mask1, 16 * tp, pk1, nk1, rk1, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1, col1);
             else
-                ring_owner_scan<G::XQ_SLOTS - 1, G::YS, DEEP>(mask1, 16 * tp, pk1, nk1, rk, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1, col1);
+                ring_owner_scan<G::XQ_SLOTS - 1, G::YS, COLOURS>(mask1, 16 * tp, pk1, nk1, rk, (contract1 && !DEEP) ? int(0x80000000u) : 0, dst1, col1);
         }
 
         // sources into registers: own run, bin M and the first stale level (what _realTransform4
@@ -1869,6 +1872,33 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 }
             }
         }
+        // DEEP, pitch factors below 0.5 (down to 0.33: the reference's demo divides a pitch in [0.5, 1.5] by a speed
+        // in [0.5, 1.5], main.js:82,93): the last region reaches slots N/2 + q up to q = N/3, i.e. into the quarter
+        // 3N/4 + o of the output, which holds DFT_{N/4}(xw[4 m + 3])[o] for o <= N/8 (bundle:394-438):
+        //   1/4 W_N^{-3 o} (X[o] - j X[N/4 + o] - conj X[N/2 - o] + j conj X[N/4 - o]);  q = N/4 + tp + TP i, i < 3
+        constexpr bool wide = WIDE;
+        float4 ext3[3];
+        (void)ext3;
+        if constexpr (WIDE) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                ext3[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int o = tp + TP * i, q = N / 4 + o;
+                const bool need = (any0 && M + q + dl0 < NB) || (any1 && M + q + dl1 < NB);
+                if (wide && need) {
+                    constexpr int QO = N / 4 + N / 64;                // slots between bins k and k + N/4
+                    const int so = o + (o >> 4);                      // slot of bin o
+                    const int sm = G::SM - o - ((o + 15) >> 4);       // slot of bin M - o
+                    const cpx2 A = unpack4(XQ[so]), Bv = unpack4(XQ[so + QO]);         // bins o, N/4 + o
+                    const cpx2 Cv = unpack4(XQ[sm]), D = unpack4(XQ[sm - QO]);         // bins M - o, N/4 - o
+                    // (A - conj C) + j (conj D - B)
+                    const float2 sr = add2(sub2(A.re, Cv.re), add2(Bv.im, D.im));
+                    const float2 si = add2(add2(A.im, Cv.im), sub2(D.re, Bv.re));
+                    const float2 w = PVB_TWH(twh + 3 * o);
+                    ext3[i] = pack4(cmul_s(cpx2{sr, si}, 0.25f * w.x, -0.25f * w.y));
+                }
+            }
+        }
         pair_sync<TP>(pin);      // every thread holds its sources: the buffer becomes Y
         // (PVB_RING_EXACT: while contracting every bin of [0, nb) is stored exactly once in the first
         // sub-step, provided both channels have peaks)
@@ -1917,7 +1947,27 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #pragma unroll
                 for (int ip = 0; ip < 4; ip++)                       // second level (zeros where not needed / not level 2)
                     if (((ip & 1) == 0 || l0) && !(ip == 0 && l0)) put_ext(N / 8 + tp + TP * ip, ext2[ip]);
+                if constexpr (WIDE) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) put_ext(N / 4 + tp + TP * i, ext3[i]);
+                }
             }
+            if constexpr (WIDE) {
+                // below 0.5 any number of regions can land on one bin (a wide region's right half reaches over
+                // several narrow neighbours): shared-memory atomic adds on top of the stores above
+                pair_sync<TP>(pin);
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    if (dst0[e] >= 0) {
+                        atomicAdd(reinterpret_cast<float *>(mine + (dst0[e] & ~3)), xv[e].x);
+                        atomicAdd(reinterpret_cast<float *>(mine + (dst0[e] & ~3) + 2 * PL), xv[e].z);
+                    }
+                    if (dst1[e] >= 0) {
+                        atomicAdd(reinterpret_cast<float *>(mine + (dst1[e] & ~3) + PL), xv[e].y);
+                        atomicAdd(reinterpret_cast<float *>(mine + (dst1[e] & ~3) + 3 * PL), xv[e].w);
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int col = 0; col < 3; col++) {
                 pair_sync<TP>(pin);
@@ -2240,9 +2290,9 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 // the calls, its state goes back and forth through L1 / L2 instead of HBM (one DRAM round trip of the
 // rings per launch instead of per call), completion flags are taken and released once, and only the
 // first-pass twiddle table is re-staged per call.  Bit-identical to num_hops single launches.
-// DEEP: pitch factors down to 0.5 (see ring_one_call); scalar (then in [0.5, 0.75)) or per channel (PCH: every
-// channel in [0.5, 64]), one call per launch.
-template <int N, int NBLK, bool PCH = false, bool MULTI = false, bool DEEP = false>
+// DEEP: 1 = pitch factors down to 0.5, 2 = down to 0.33 (see ring_one_call); scalar (then below 0.75) or per
+// channel (PCH: every channel in [0.5, 64] / [0.33, 64]), one call per launch.
+template <int N, int NBLK, bool PCH = false, bool MULTI = false, int DEEP = 0>
 __global__ void __launch_bounds__((DEEP ? RingGeoT<N, PCH>::DEEP_PAIRS : MULTI ? RingGeoT<N, PCH>::MULTI_PAIRS : RingGeoT<N, PCH>::MAX_PAIRS) * RingGeoT<N, PCH>::TP)
 __maxnreg__((DEEP ? RingGeoT<N, PCH>::DEEP_REGS : MULTI ? RingGeoT<N, PCH>::BIG_REGS : 128))     // two CTAs per SM either way
 pv_process_ring_kernel(const RingParams p) {

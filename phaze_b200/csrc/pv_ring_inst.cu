@@ -13,7 +13,7 @@ namespace pvb {
 namespace {
 
 // NBLK counts role units of RingGeoT<N>::UNIT samples (64 at frame 256, else 128)
-template <int N, bool PCH, bool MULTI, bool DEEP, int... NBLKS>
+template <int N, bool PCH, bool MULTI, int DEEP, int... NBLKS>
 cudaError_t launch_t(const RingParams &rp, const RingLaunch &l) {
     using G = RingGeoT<N, PCH>;
     constexpr int CAP = DEEP ? G::DEEP_PAIRS : MULTI ? G::MULTI_PAIRS : G::MAX_PAIRS;   // what the kernel's launch bounds (and two CTAs per SM) allow
@@ -38,7 +38,7 @@ cudaError_t launch_t(const RingParams &rp, const RingLaunch &l) {
     return e;
 }
 
-template <int N, bool PCH, bool MULTI, bool DEEP, int... NBLKS>
+template <int N, bool PCH, bool MULTI, int DEEP, int... NBLKS>
 cudaError_t configure_t() {
     cudaError_t e = cudaSuccess;
     (void)std::initializer_list<int>{
@@ -51,14 +51,21 @@ cudaError_t configure_t() {
 // (inside templates so that a frame size without the DEEP instance does not instantiate it)
 template <int N, bool DEEPOK, int... NBLKS>
 cudaError_t launch_deep_t(const RingParams &rp, const RingLaunch &l) {
-    if constexpr (DEEPOK) return l.pch ? launch_t<N, true, false, true, NBLKS...>(rp, l) : launch_t<N, false, false, true, NBLKS...>(rp, l);
-    else return cudaErrorInvalidValue;
+    if constexpr (DEEPOK) {
+        if (l.deep == 2) return l.pch ? launch_t<N, true, false, 2, NBLKS...>(rp, l) : launch_t<N, false, false, 2, NBLKS...>(rp, l);
+        return l.pch ? launch_t<N, true, false, 1, NBLKS...>(rp, l) : launch_t<N, false, false, 1, NBLKS...>(rp, l);
+    } else {
+        return cudaErrorInvalidValue;
+    }
 }
 template <int N, bool DEEPOK, int... NBLKS>
 cudaError_t configure_deep_t() {
     if constexpr (DEEPOK) {
-        const cudaError_t e = configure_t<N, false, false, true, NBLKS...>();
-        return e == cudaSuccess ? configure_t<N, true, false, true, NBLKS...>() : e;
+        cudaError_t e = configure_t<N, false, false, 1, NBLKS...>();
+        if (e == cudaSuccess) e = configure_t<N, true, false, 1, NBLKS...>();
+        if (e == cudaSuccess) e = configure_t<N, false, false, 2, NBLKS...>();
+        if (e == cudaSuccess) e = configure_t<N, true, false, 2, NBLKS...>();
+        return e;
     } else {
         return cudaSuccess;
     }
@@ -72,14 +79,14 @@ cudaError_t configure_deep_t() {
     cudaError_t ring_launch_##N(const RingParams &rp, const RingLaunch &l) {                        \
         if (l.deep)                                                                                 \
             return l.multi ? cudaErrorInvalidValue : launch_deep_t<N, DEEPOK, __VA_ARGS__>(rp, l);  \
-        if (l.pch) return l.multi ? cudaErrorInvalidValue : launch_t<N, true, false, false, __VA_ARGS__>(rp, l); \
-        return l.multi ? launch_t<N, false, true, false, __VA_ARGS__>(rp, l)                        \
-                       : launch_t<N, false, false, false, __VA_ARGS__>(rp, l);                      \
+        if (l.pch) return l.multi ? cudaErrorInvalidValue : launch_t<N, true, false, 0, __VA_ARGS__>(rp, l); \
+        return l.multi ? launch_t<N, false, true, 0, __VA_ARGS__>(rp, l)                        \
+                       : launch_t<N, false, false, 0, __VA_ARGS__>(rp, l);                      \
     }                                                                                               \
     cudaError_t ring_configure_##N() {                                                              \
-        cudaError_t e = configure_t<N, false, false, false, __VA_ARGS__>();                         \
-        if (e == cudaSuccess) e = configure_t<N, true, false, false, __VA_ARGS__>();                \
-        if (e == cudaSuccess) e = configure_t<N, false, true, false, __VA_ARGS__>();                \
+        cudaError_t e = configure_t<N, false, false, 0, __VA_ARGS__>();                         \
+        if (e == cudaSuccess) e = configure_t<N, true, false, 0, __VA_ARGS__>();                \
+        if (e == cudaSuccess) e = configure_t<N, false, true, 0, __VA_ARGS__>();                \
         if (e == cudaSuccess) e = configure_deep_t<N, DEEPOK, __VA_ARGS__>();                       \
         return e;                                                                                   \
     }

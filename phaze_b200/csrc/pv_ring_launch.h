@@ -16,7 +16,7 @@ struct RingLaunch {
     bool pdl;             // programmatic dependent launch allowed
     bool pch;             // per-channel pitch factors (RingParams::pf_ch)
     bool multi;           // several process() calls per launch (RingParams::num_hops; scalar pitch factor only)
-    bool deep;            // pitch factors down to 0.5: the DEEP instances (one call per launch)
+    int deep;             // 0; 1: pitch factors down to 0.5; 2: down to 0.33 -- the DEEP instances (one call per launch)
     cudaStream_t stream;
 };
 

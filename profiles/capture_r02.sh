@@ -19,9 +19,9 @@ cap() { # name, bench args: capture, summarise on the box (the reports are 13 MB
   (python profiles/ncu_summary.py $O/$1.ncu-rep 2.0; python profiles/ncu_regions.py $O/$1.ncu-rep 300; [ -n "$3" ] && python profiles/ncu_phases.py $O/$1.ncu-rep $3) > $O/$1.txt 2>&1
   rm -f $O/$1.ncu-rep
 }
-cap r02_ncu_ring_1024 "" "phaze_b200/csrc/build/ring_1024.o ILi1024ELi2ELb0ELb0ELb0EE"
-cap r02_ncu_ring_2048 "--frame 2048 --channels 2048 --pitch 1.5" "phaze_b200/csrc/build/ring_2048.o ILi2048ELi4ELb0ELb0ELb0EE"
-cap r02_ncu_ring_1024_deep "--pitch 0.6" "phaze_b200/csrc/build/ring_1024.o ILi1024ELi2ELb0ELb0ELb1EE"
+cap r02_ncu_ring_1024 "" "phaze_b200/csrc/build/ring_1024.o ILi1024ELi2ELb0ELb0ELi0EE"
+cap r02_ncu_ring_2048 "--frame 2048 --channels 2048 --pitch 1.5" "phaze_b200/csrc/build/ring_2048.o ILi2048ELi4ELb0ELb0ELi0EE"
+cap r02_ncu_ring_1024_deep "--pitch 0.6" "phaze_b200/csrc/build/ring_1024.o ILi1024ELi2ELb0ELb0ELi1EE"
 cap r02_ncu_ring_512 "--frame 512 --channels 8192 --pitch 1.2"
 cap r02_ncu_ring_256 "--frame 256 --channels 8192 --pitch 1.2"
 cap r02_ncu_ring_4096 "--frame 4096 --channels 8192 --pitch 1.2"

@@ -15,7 +15,7 @@ for frame, hop in ((1024, 256), (2048, 512), (2048, 128), (512, 128), (4096, 102
     if ONLY and frame != ONLY:
         continue
     ch = C if frame <= 1024 else C * 1024 // frame
-    for pf in (0.5, 0.6, 0.7, 0.74, 0.8):
+    for pf in (0.34, 0.4, 0.45, 0.5, 0.6, 0.7, 0.74, 0.8):
         row = {}
         for name, opts in (("ring", {}), ("generic", {"kernel": "generic"})):
             r = bench.quick_config(0, frame, hop, ch, pf, peak, steps=100, warm=20, **opts)

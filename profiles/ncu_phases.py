@@ -8,7 +8,7 @@ import collections, csv, io, os, subprocess, sys, tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 rep = sys.argv[1]
 obj = sys.argv[2] if len(sys.argv) > 2 else os.path.join(HERE, "..", "phaze_b200/csrc/build/ring_1024.o")
-want = sys.argv[3] if len(sys.argv) > 3 else "ILi1024ELi2ELb0ELb0ELb0EE"
+want = sys.argv[3] if len(sys.argv) > 3 else "ILi1024ELi2ELb0ELb0ELi0EE"
 with tempfile.NamedTemporaryFile("r", suffix=".seq") as tf:
     subprocess.run([sys.executable, os.path.join(HERE, "sass_phases.py"), obj, want], check=True,
                    env=dict(os.environ, SASS_PHASES_SEQ=tf.name), stdout=subprocess.DEVNULL)

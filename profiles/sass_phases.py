@@ -9,7 +9,7 @@ import collections, os, re, subprocess, sys, tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 obj = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "phaze_b200/csrc/build/ring_1024.o")
-want = sys.argv[2] if len(sys.argv) > 2 else "ILi1024ELi2ELb0ELb0ELb0EE"
+want = sys.argv[2] if len(sys.argv) > 2 else "ILi1024ELi2ELb0ELb0ELi0EE"
 src = os.path.join(ROOT, "phaze_b200/csrc/pv_kernel_ring.cuh")
 
 MARKS = [("tables+flags", "CTA-shared tables: asynchronous"), ("frame loads", "---- frame loads"),

@@ -80,7 +80,7 @@ def test_pitch_factor_takes_last_element():
 
 
 @pytest.mark.parametrize("N,hop,pf", [(1024, 256, 0.8), (2048, 512, 1.5), (2048, 128, 0.8), (256, 64, 1.2),
-                                      (512, 128, 0.9), (4096, 1024, 1.25), (1024, 64, 0.8), (1024, 256, 0.5)])
+                                      (512, 128, 0.9), (4096, 1024, 1.25), (1024, 64, 0.8), (1024, 256, 0.5), (1024, 256, 0.4)])
 @pytest.mark.parametrize("K", [4, 16, 64, 70])
 def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
     """K consecutive calls in one submission: with PVB_OPT_MANY_MODE = 1 they share
@@ -100,7 +100,7 @@ def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
         many = np.concatenate([b.process_many(blocks[:3], pf), b.process_many(blocks[3:], pf)])
         assert a.time_cursor == b.time_cursor == calls * hop
         kernel = b.kernel_name(np.float32(pf))
-        ring = "ring" in kernel and "(deep)" not in kernel
+        ring = "ring" in kernel and "(deep" not in kernel
         assert b.kernel_launches < calls if ring else b.kernel_launches == calls
         din = torch.from_numpy(blocks).cuda()
         dout = torch.empty_like(din)
@@ -108,9 +108,9 @@ def test_process_many_is_bit_identical_to_single_calls(N, hop, pf, K):
         c.process_device(din.data_ptr(), dout.data_ptr(), pf, None, num_calls=calls)
         c.sync()
         dev = dout.cpu().numpy()
-    if "pv_process_kernel" in kernel:
-        # the generic kernel adds colliding regions with shared-memory atomics: the order, and so the last
-        # bit, is not reproducible from run to run
+    if "pv_process_kernel" in kernel or "atomics" in kernel:
+        # the generic kernel (and the ring-order kernel below pitch factor 0.5) adds colliding regions with
+        # shared-memory atomics: the order, and so the last bit, is not reproducible from run to run
         assert np.abs(one - many).max() <= 1e-6 and np.abs(one - dev).max() <= 1e-6
     else:
         assert np.array_equal(one, many)

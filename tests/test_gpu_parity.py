@@ -24,8 +24,9 @@ def _run_both(oracle, N, hop, C, pf, calls, first_channel=0, sig=None, **options
         got_many = pv.run(x, pf)
         assert 0 < pv.kernel_launches <= calls
         kernel = pv.kernel_name(pf)
-    if "pv_process_kernel" in kernel:
-        # the generic kernel adds colliding regions with shared-memory atomics: the last bit depends on their order
+    if "pv_process_kernel" in kernel or "atomics" in kernel:
+        # the generic kernel (and the ring-order kernel below pitch factor 0.5) adds colliding regions with
+        # shared-memory atomics: the last bit depends on their order
         assert np.abs(got - got_many).max() <= 1e-6
     else:
         assert np.array_equal(got, got_many), "calls sharing a launch differ from one launch per call"
@@ -78,7 +79,7 @@ def test_parity_1024_all_kernels(oracle, pf, kernel):
     assert err <= RMS_EXPECTED
 
 
-@pytest.mark.parametrize("pf", [0.5, 0.6, 0.34])
+@pytest.mark.parametrize("pf", [0.5, 0.6, 0.34, 0.3, 0.2])
 def test_parity_deep_stale(oracle, pf):
     """pitch factors below 0.75 read past the first level of stale upper bins."""
     x, ref, got = _run_both(oracle, 1024, 256, 4, np.float32(pf), 14)
@@ -96,6 +97,22 @@ def test_parity_ring_deep(oracle, N, hop, pf):
     from phaze_b200 import BatchedPhaseVocoder
     with BatchedPhaseVocoder(3, N, hop) as pv:
         assert "(deep)" in pv.kernel_name(np.float32(pf))
+    x, ref, got = _run_both(oracle, N, hop, 3, np.float32(pf), 2 * (N // hop) + 6)
+    err = _rms(got - ref)
+    print(f"N={N} hop={hop} pf={pf}: rms err {err:.3e}, out rms {_rms(ref):.3e}")
+    assert _rms(ref) > 1e-3
+    assert err <= RMS_EXPECTED
+
+
+@pytest.mark.parametrize("N,hop", [(256, 64), (512, 128), (1024, 256), (1024, 128), (2048, 512), (2048, 128), (4096, 1024)])
+@pytest.mark.parametrize("pf", [0.33, 0.33333334, 0.4, 0.45, 0.4999])
+def test_parity_ring_deep_below_one_half(oracle, N, hop, pf):
+    """the rest of the demo's reachable range (pitch slider / speed slider, main.js:82,93: down to 0.5 / 1.5): the
+    last region reads into the quarter 3N/4 + o of the realTransform output (DFT_{N/4}(xw[4m+3])), and any number
+    of regions can land on one bin (shared-memory atomics)"""
+    from phaze_b200 import BatchedPhaseVocoder
+    with BatchedPhaseVocoder(3, N, hop) as pv:
+        assert "(deep, atomics)" in pv.kernel_name(np.float32(pf))
     x, ref, got = _run_both(oracle, N, hop, 3, np.float32(pf), 2 * (N // hop) + 6)
     err = _rms(got - ref)
     print(f"N={N} hop={hop} pf={pf}: rms err {err:.3e}, out rms {_rms(ref):.3e}")
@@ -252,7 +269,7 @@ def test_layout_changes_mid_stream(oracle, N, hop):
     a paused block, a checkpoint round trip and a time-cursor jump happen in between."""
     from phaze_b200 import BatchedPhaseVocoder
     C = 5
-    plan = [(0.8, 5), (0.4, 3), (1.2, 4), (0.6, 2), (0.45, 2), (0.9, 6)]     # 0.6: the ring-order kernel's DEEP instances
+    plan = [(0.8, 5), (0.3, 3), (1.2, 4), (0.6, 2), (0.25, 2), (0.9, 6)]     # 0.6: the ring-order kernel's DEEP instances; 0.3, 0.25: generic
     total = sum(n for _, n in plan)
     x = signals.channels(3, C, total * hop)
     ref_p = oracle.OracleProcessor(N, hop, C)
