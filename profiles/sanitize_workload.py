@@ -26,15 +26,16 @@ def deep(worst):
     for N, hop in [(256, 64), (512, 128), (1024, 256), (2048, 128), (2048, 512), (4096, 1024)]:
         C, calls = 7, 2 * (N // hop) + 3
         x = signals.channels(50, C, calls * hop)
-        for pf in (0.5, 0.62, 0.74):
+        for pf in (0.36, 0.5, 0.62, 0.74):
             ref = oracle_lib.OracleProcessor(N, hop, C).run(x, np.float32(pf))
             with BatchedPhaseVocoder(C, N, hop) as pv:
-                assert "(deep)" in pv.kernel_name(np.float32(pf))
+                assert "(deep" in pv.kernel_name(np.float32(pf))
                 worst = max(worst, rms(pv.run(x, np.float32(pf)) - ref))
-        pfs = np.linspace(0.5, 1.3, C).astype(np.float32)
-        ref = np.concatenate([oracle_lib.OracleProcessor(N, hop, 1).run(x[c:c + 1], pfs[c]) for c in range(C)])
-        with BatchedPhaseVocoder(C, N, hop) as pv:
-            worst = max(worst, rms(pv.run_pf(x, pfs) - ref))
+        for lo in (0.5, 0.34):
+            pfs = np.linspace(lo, 1.3, C).astype(np.float32)
+            ref = np.concatenate([oracle_lib.OracleProcessor(N, hop, 1).run(x[c:c + 1], pfs[c]) for c in range(C)])
+            with BatchedPhaseVocoder(C, N, hop) as pv:
+                worst = max(worst, rms(pv.run_pf(x, pfs) - ref))
         print(f"deep: frame {N} hop {hop}: worst rms error so far {worst:.3e}", flush=True)
     return worst
 
