@@ -650,7 +650,9 @@ struct DeviceGuard {
 struct CallHooks {
     virtual void before(int k, cudaStream_t s) = 0;
     virtual void after(int k, cudaStream_t s) = 0;
-    int group = 1;      // calls [g * group, (g + 1) * group) share their copies: they may share a launch too
+    // copy groups: calls [first[k], last[k]) share their copies (they may share a launch too)
+    std::vector<int> first, last;
+    int left_in_group(int k) const { return last[k] - k; }
 };
 
 // sticky device error (a completion flag that never arrived): the handle refuses further work
@@ -734,7 +736,7 @@ int submit(pvb_processor *p, const float *in_dev, float *out_dev, int num_calls,
         int hops = 1;
         if (p->channels > 0 && !pf_host && p->opt_many_mode == 1 && ring_kernel_applies(p, fp) && fast_range(fp)) {
             hops = num_calls - k;
-            if (hooks && hops > hooks->group - k % hooks->group) hops = hooks->group - k % hooks->group;
+            if (hooks && hops > hooks->left_in_group(k)) hops = hooks->left_in_group(k);
             if (hops > MAX_HOPS_PER_LAUNCH) hops = MAX_HOPS_PER_LAUNCH;
         }
         if (hooks) for (int j = k; j < k + hops; j++) hooks->before(j, s);
@@ -980,8 +982,8 @@ int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t 
         cudaError_t err = cudaSuccess;
         void note(cudaError_t e) { if (err == cudaSuccess) err = e; }
         void before(int k, cudaStream_t s) override {
-            if (in && k % group == 0) {
-                const int n = (calls - k < group) ? calls - k : group;
+            if (in && first[k] == k) {
+                const int n = last[k] - k;
                 note(cudaMemcpyAsync(p->d_in + k * block, in + k * block, n * block * sizeof(float),
                                      cudaMemcpyHostToDevice, p->s_in));
                 note(cudaEventRecord(p->ev_in[k], p->s_in));
@@ -989,19 +991,41 @@ int32_t pvb_process_many(pvb_processor *p, const float *in, float *out, int32_t 
             }
         }
         void after(int k, cudaStream_t s) override {
-            if ((k + 1) % group == 0 || k + 1 == calls) {
-                const int first = k - (k % group);
+            if (k + 1 == last[k]) {
+                const int f = first[k];
                 note(cudaEventRecord(p->ev_done[k], s));
                 note(cudaStreamWaitEvent(p->s_out, p->ev_done[k], 0));
-                note(cudaMemcpyAsync(out + first * block, p->d_out + first * block,
-                                     (k + 1 - first) * block * sizeof(float), cudaMemcpyDeviceToHost, p->s_out));
+                note(cudaMemcpyAsync(out + f * block, p->d_out + f * block,
+                                     (k + 1 - f) * block * sizeof(float), cudaMemcpyDeviceToHost, p->s_out));
             }
         }
     } pipe;
     pipe.p = p; pipe.in = in; pipe.out = out; pipe.block = block; pipe.calls = num_calls;
-    pipe.group = (block * sizeof(float) >= (size_t(16) << 20)) ? 1
-                 : int((size_t(16) << 20) / (block * sizeof(float)));
-    if (pipe.group > 8) pipe.group = 8;
+    int group = (block * sizeof(float) >= (size_t(16) << 20)) ? 1
+                : int((size_t(16) << 20) / (block * sizeof(float)));
+    if (group > 8) group = 8;
+    {
+        // the pipeline fills with the first input group and drains with the last output group: those ramp
+        // (1, 1, 2, ... calls) so that only a single call's copy is exposed at either end of a submission
+        std::vector<int> ramp, sizes;
+        int ramp_sum = 0;
+        for (int r = 1, i = 0; r < group; i++) {           // 1, 1, 2, 4, ... (< group)
+            ramp.push_back(r);
+            ramp_sum += r;
+            if (i >= 1) r *= 2;
+        }
+        if (num_calls < 2 * ramp_sum + 2 * group) { ramp.clear(); ramp_sum = 0; }
+        sizes = ramp;
+        for (int left = num_calls - 2 * ramp_sum; left > 0; left -= group) sizes.push_back(left < group ? left : group);
+        for (size_t i = ramp.size(); i-- > 0;) sizes.push_back(ramp[i]);
+        pipe.first.resize(num_calls);
+        pipe.last.resize(num_calls);
+        int k0 = 0;
+        for (int n : sizes) {
+            for (int j = k0; j < k0 + n; j++) { pipe.first[j] = k0; pipe.last[j] = k0 + n; }
+            k0 += n;
+        }
+    }
     // (every launch waits for the event of its input copy before it becomes eligible)
     rc = submit(p, in ? p->d_in : nullptr, p->d_out, num_calls, pitch_factor, p->stream, true, &pipe);
     if (rc != PVB_OK) return rc;
