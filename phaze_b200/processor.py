@@ -99,7 +99,7 @@ class BatchedPhaseVocoder:
     def set_option(self, name: str, value) -> None:
         """pvb_set_option: kernel ("auto" | "ring" | "warp" | "cta" | "generic"), launch_mode (0 flags,
         1 grid-wide wait, 2 plain launches), inputs_ready (0 | 1), peak_guard (0 auto, 1 off, 2 always,
-        3 strict), many_mode (0: consecutive calls share launches, 1: one launch per call)."""
+        3 strict), many_mode (0: one launch per call, 1: consecutive calls of a submission share launches)."""
         if name == "kernel" and isinstance(value, str):
             value = self._KERNELS[value]
         _lib.check(self._h, self._lib.pvb_set_option(self._h, self._OPTIONS[name], int(value)))
