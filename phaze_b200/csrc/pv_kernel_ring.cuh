@@ -341,6 +341,48 @@ __device__ __forceinline__ cpx2 ring_load_planes(const unsigned char *mine, int 
     return cpx2{make_float2(y[0], y[PLW]), make_float2(y[2 * PLW], y[3 * PLW])};
 }
 
+// Layout of the shifted spectrum Y.  PVB_RING_Y64 = 0 (default): four planes of 32-bit words (re0 | re1 | im0 | im1),
+// bin d at word d + (d >> YSHIFT).  1 (`make y64`): two planes (one per channel) of (re, im) pairs at the same slot
+// numbers: the scatter and its read-add-store sub-steps move one 64-bit word per bin and channel instead of two
+// 32-bit ones (half the load / store instructions there; a model of the lanes' destinations gives 3.5 instead of
+// 3.8 wavefronts per (re, im) pair), and the Hermitian pre-pass reads two 64-bit words per bin instead of four
+// 32-bit ones, but has to re-pair (re0, im0), (re1, im1) into (re0, re1), (im0, im1).  Measured (parity-green on all
+// 475 GPU tests, profiles/r02_ab_y64.txt): 15.92 against 15.94 us per launch at pitch 0.8, 14.44 against 14.21 at
+// 1.2 -- the wavefronts, not the instructions, are what the middle costs.  Kept as a measured alternative.
+#ifndef PVB_RING_Y64
+#define PVB_RING_Y64 0
+#endif
+template <int XQS>
+struct RingY {
+    static constexpr int SB = PVB_RING_Y64 ? 8 : 4;      // bytes per slot
+    static constexpr int PLB = SB * XQS;                 // bytes per plane
+    // `at`: address of the slot in plane 0
+    static __device__ __forceinline__ void store(unsigned char *at, int ch, float re, float im) {
+        if constexpr (PVB_RING_Y64) {
+            *reinterpret_cast<float2 *>(at + ch * PLB) = make_float2(re, im);
+        } else {
+            *reinterpret_cast<float *>(at + ch * PLB) = re;
+            *reinterpret_cast<float *>(at + (2 + ch) * PLB) = im;
+        }
+    }
+    static __device__ __forceinline__ float2 load(const unsigned char *at, int ch) {
+        if constexpr (PVB_RING_Y64) {
+            return *reinterpret_cast<const float2 *>(at + ch * PLB);
+        } else {
+            return make_float2(*reinterpret_cast<const float *>(at + ch * PLB), *reinterpret_cast<const float *>(at + (2 + ch) * PLB));
+        }
+    }
+    static __device__ __forceinline__ void atomic_add(unsigned char *at, int ch, float re, float im) {
+        atomicAdd(reinterpret_cast<float *>(at + ch * PLB), re);
+        atomicAdd(reinterpret_cast<float *>(at + (PVB_RING_Y64 ? ch * PLB + 4 : (2 + ch) * PLB)), im);
+    }
+    // one bin of both channels for the Hermitian pre-pass
+    static __device__ __forceinline__ cpx2 load_bin(const unsigned char *mine, int slot) {
+        const float2 a = load(mine + SB * slot, 0), b = load(mine + SB * slot, 1);
+        return cpx2{make_float2(a.x, b.x), make_float2(a.y, b.y)};
+    }
+};
+
 // error model of the float32 forward transform (see "Peak guard" below): |dX_k| <= a |X_k| + c ||X||_2
 #define PVB_GUARD_A 3.0e-7f
 #define PVB_GUARD_C 5.5e-8f
@@ -416,6 +458,7 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
     }
     const int thr0 = (4 * (b0 + 2048) + 2) << 16;
     const int cb = b0 - 32768;
+    constexpr unsigned YB = PVB_RING_Y64 ? 8u : 4u;                  // bytes per destination slot
 #pragma unroll
     for (int e = 0; e < 16; e++) {
         if ((mask >> e) & 1u) {
@@ -430,7 +473,7 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
         const unsigned slot = min(unsigned(d + (d >> YS)), unsigned(DUMP));     // d < 0 or d >= nb: dump slot
         if constexpr (COLOUR) {
             const int cn_ = col3 + (take_next ? 1 : 0);
-            dst[e] = int(4u * slot) | (cn_ == 3 ? 0 : cn_);
+            dst[e] = int(YB * slot) | (cn_ == 3 ? 0 : cn_);
         } else {
 #if PVB_RING_EXACT
         // w = -(T - 1) 2^16 + (delta_next + delta_prev), T = 4 b + 2 - 2 next - 2 prev (even; >= 2 on a
@@ -438,9 +481,9 @@ __device__ __forceinline__ void ring_owner_scan(uint32_t mask, int b0, int pkey,
         const int w = tt - ((4 * e) << 16);
         const int c4 = 4 * int(short(pkey - nx[e]));
         const int q = ((w >> 16) & ~1) + c4;
-        dst[e] = int(4u * slot) | (w & ~q & second_flag);
+        dst[e] = int(YB * slot) | (w & ~q & second_flag);
 #else
-        dst[e] = int(4u * slot) | ((tt - ((4 * e) << 16)) & second_flag);
+        dst[e] = int(YB * slot) | ((tt - ((4 * e) << 16)) & second_flag);
 #endif
         }
     }
@@ -1909,9 +1952,9 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             pair_sync<TP>(pin);
         }
 
-        constexpr int PL = 4 * G::XQ_SLOTS;                           // bytes per plane
+        using Y = RingY<G::XQ_SLOTS>;
 #if PVB_RING_NO_DUMP
-#define PVB_NOT_DUMP(d) (((d) & 0x7fffffff) != 4 * (G::XQ_SLOTS - 1))
+#define PVB_NOT_DUMP(d) (((d) & 0x7fffffff) != Y::SB * (G::XQ_SLOTS - 1))
 #else
 #define PVB_NOT_DUMP(d) true
 #endif
@@ -1919,7 +1962,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             // up to three regions (i, i + 1, i + 2) land on one bin: one sub-step per colour = ordinal of the owning
             // peak mod 3 (low bits of dst), each with pairwise disjoint destinations (loads of a batch issued before
             // its first store).
-            constexpr int DUMPB = 4 * (G::XQ_SLOTS - 1);
+            constexpr int DUMPB = Y::SB * (G::XQ_SLOTS - 1);
 #pragma unroll
             for (int e = 0; e < 16; e++) {
                 if (dst0[e] == DUMPB + (dst0[e] & 3)) dst0[e] = -1;   // outside [0, nb): no colour matches
@@ -1930,16 +1973,8 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             {
                 auto put_ext = [&](int q, const float4 &v) {
                     const int d0 = M + q + dl0, d1 = M + q + dl1;
-                    if (any0 && unsigned(d0) < unsigned(NB)) {
-                        float *y = reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS)));
-                        y[0] = v.x;
-                        y[PL / 2] = v.z;
-                    }
-                    if (any1 && unsigned(d1) < unsigned(NB)) {
-                        float *y = reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + PL);
-                        y[0] = v.y;
-                        y[PL / 2] = v.w;
-                    }
+                    if (any0 && unsigned(d0) < unsigned(NB)) Y::store(mine + Y::SB * (d0 + (d0 >> G::YS)), 0, v.x, v.z);
+                    if (any1 && unsigned(d1) < unsigned(NB)) Y::store(mine + Y::SB * (d1 + (d1 >> G::YS)), 1, v.y, v.w);
                 };
 #pragma unroll
                 for (int i = 0; i < 4; i++) put_ext(tp + TP * i, ext[i]);
@@ -1958,14 +1993,8 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 pair_sync<TP>(pin);
 #pragma unroll
                 for (int e = 0; e < 16; e++) {
-                    if (dst0[e] >= 0) {
-                        atomicAdd(reinterpret_cast<float *>(mine + (dst0[e] & ~3)), xv[e].x);
-                        atomicAdd(reinterpret_cast<float *>(mine + (dst0[e] & ~3) + 2 * PL), xv[e].z);
-                    }
-                    if (dst1[e] >= 0) {
-                        atomicAdd(reinterpret_cast<float *>(mine + (dst1[e] & ~3) + PL), xv[e].y);
-                        atomicAdd(reinterpret_cast<float *>(mine + (dst1[e] & ~3) + 3 * PL), xv[e].w);
-                    }
+                    if (dst0[e] >= 0) Y::atomic_add(mine + (dst0[e] & ~3), 0, xv[e].x, xv[e].z);
+                    if (dst1[e] >= 0) Y::atomic_add(mine + (dst1[e] & ~3), 1, xv[e].y, xv[e].w);
                 }
             } else
 #pragma unroll 1
@@ -1974,25 +2003,19 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
                 unsigned char *minec = mine - col;                    // cancels the colour bits of dst
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    float o0r[4], o0i[4], o1r[4], o1i[4];
+                    float2 o0[4], o1[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int e = 4 * g + i;
-                        o0r[i] = o0i[i] = o1r[i] = o1i[i] = 0.f;
-                        if ((dst0[e] & 3) == col) { o0r[i] = *reinterpret_cast<float *>(minec + dst0[e]); o0i[i] = *reinterpret_cast<float *>(minec + dst0[e] + 2 * PL); }
-                        if ((dst1[e] & 3) == col) { o1r[i] = *reinterpret_cast<float *>(minec + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(minec + dst1[e] + 3 * PL); }
+                        o0[i] = o1[i] = make_float2(0.f, 0.f);
+                        if ((dst0[e] & 3) == col) o0[i] = Y::load(minec + dst0[e], 0);
+                        if ((dst1[e] & 3) == col) o1[i] = Y::load(minec + dst1[e], 1);
                     }
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int e = 4 * g + i;
-                        if ((dst0[e] & 3) == col) {
-                            *reinterpret_cast<float *>(minec + dst0[e]) = o0r[i] + xv[e].x;
-                            *reinterpret_cast<float *>(minec + dst0[e] + 2 * PL) = o0i[i] + xv[e].z;
-                        }
-                        if ((dst1[e] & 3) == col) {
-                            *reinterpret_cast<float *>(minec + dst1[e] + PL) = o1r[i] + xv[e].y;
-                            *reinterpret_cast<float *>(minec + dst1[e] + 3 * PL) = o1i[i] + xv[e].w;
-                        }
+                        if ((dst0[e] & 3) == col) Y::store(minec + dst0[e], 0, o0[i].x + xv[e].x, o0[i].y + xv[e].z);
+                        if ((dst1[e] & 3) == col) Y::store(minec + dst1[e], 1, o1[i].x + xv[e].y, o1[i].y + xv[e].w);
                     }
                 }
             }
@@ -2001,14 +2024,14 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             auto add_ext = [&](int q, const float4 &v) {
                 const int d0 = M + q + dl0, d1 = M + q + dl1;
                 if (any0 && unsigned(d0) < unsigned(NB)) {
-                    float *y = reinterpret_cast<float *>(mine + 4 * (d0 + (d0 >> G::YS)));
-                    y[0] += v.x;
-                    y[PL / 2] += v.z;
+                    unsigned char *at = mine + Y::SB * (d0 + (d0 >> G::YS));
+                    const float2 o = Y::load(at, 0);
+                    Y::store(at, 0, o.x + v.x, o.y + v.z);
                 }
                 if (any1 && unsigned(d1) < unsigned(NB)) {
-                    float *y = reinterpret_cast<float *>(mine + 4 * (d1 + (d1 >> G::YS)) + PL);
-                    y[0] += v.y;
-                    y[PL / 2] += v.w;
+                    unsigned char *at = mine + Y::SB * (d1 + (d1 >> G::YS));
+                    const float2 o = Y::load(at, 1);
+                    Y::store(at, 1, o.x + v.y, o.y + v.w);
                 }
             };
             // slots N/2 + q, N/8 < q < N/4
@@ -2057,33 +2080,21 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
         if (!(xskip & 16))
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-            if (dst0[e] >= 0 && PVB_NOT_DUMP(dst0[e])) {
-                *reinterpret_cast<float *>(mine + dst0[e]) = xv[e].x;
-                *reinterpret_cast<float *>(mine + dst0[e] + 2 * PL) = xv[e].z;
-            }
-            if (dst1[e] >= 0 && PVB_NOT_DUMP(dst1[e])) {
-                *reinterpret_cast<float *>(mine + dst1[e] + PL) = xv[e].y;
-                *reinterpret_cast<float *>(mine + dst1[e] + 3 * PL) = xv[e].w;
-            }
+            if (dst0[e] >= 0 && PVB_NOT_DUMP(dst0[e])) Y::store(mine + dst0[e], 0, xv[e].x, xv[e].z);
+            if (dst1[e] >= 0 && PVB_NOT_DUMP(dst1[e])) Y::store(mine + dst1[e], 1, xv[e].y, xv[e].w);
         }
         if (any0) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int d = M + tp + TP * i + dl0;
-                if (unsigned(d) < unsigned(NB)) {
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS))) = ext[i].x;
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS)) + 2 * PL) = ext[i].z;
-                }
+                if (unsigned(d) < unsigned(NB)) Y::store(mine + Y::SB * (d + (d >> G::YS)), 0, ext[i].x, ext[i].z);
             }
         }
         if (any1) {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int d = M + tp + TP * i + dl1;
-                if (unsigned(d) < unsigned(NB)) {
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS)) + PL) = ext[i].y;
-                    *reinterpret_cast<float *>(mine + 4 * (d + (d >> G::YS)) + 3 * PL) = ext[i].w;
-                }
+                if (unsigned(d) < unsigned(NB)) Y::store(mine + Y::SB * (d + (d >> G::YS)), 1, ext[i].y, ext[i].w);
             }
         }
         if (contract && !(xskip & 4)) {
@@ -2093,25 +2104,19 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
             unsigned char *mine2 = mine + 0x80000000u;                // cancels the flag bit of dst
 #pragma unroll
             for (int g = 0; g < 2; g++) {
-                float o0r[8], o0i[8], o1r[8], o1i[8];
+                float2 o0[8], o1[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int e = 8 * g + i;
-                    o0r[i] = o0i[i] = o1r[i] = o1i[i] = 0.f;
-                    if (dst0[e] < 0 && PVB_NOT_DUMP(dst0[e])) { o0r[i] = *reinterpret_cast<float *>(mine2 + dst0[e]); o0i[i] = *reinterpret_cast<float *>(mine2 + dst0[e] + 2 * PL); }
-                    if (dst1[e] < 0 && PVB_NOT_DUMP(dst1[e])) { o1r[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + PL); o1i[i] = *reinterpret_cast<float *>(mine2 + dst1[e] + 3 * PL); }
+                    o0[i] = o1[i] = make_float2(0.f, 0.f);
+                    if (dst0[e] < 0 && PVB_NOT_DUMP(dst0[e])) o0[i] = Y::load(mine2 + dst0[e], 0);
+                    if (dst1[e] < 0 && PVB_NOT_DUMP(dst1[e])) o1[i] = Y::load(mine2 + dst1[e], 1);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int e = 8 * g + i;
-                    if (dst0[e] < 0 && PVB_NOT_DUMP(dst0[e])) {
-                        *reinterpret_cast<float *>(mine2 + dst0[e]) = o0r[i] + xv[e].x;
-                        *reinterpret_cast<float *>(mine2 + dst0[e] + 2 * PL) = o0i[i] + xv[e].z;
-                    }
-                    if (dst1[e] < 0 && PVB_NOT_DUMP(dst1[e])) {
-                        *reinterpret_cast<float *>(mine2 + dst1[e] + PL) = o1r[i] + xv[e].y;
-                        *reinterpret_cast<float *>(mine2 + dst1[e] + 3 * PL) = o1i[i] + xv[e].w;
-                    }
+                    if (dst0[e] < 0 && PVB_NOT_DUMP(dst0[e])) Y::store(mine2 + dst0[e], 0, o0[i].x + xv[e].x, o0[i].y + xv[e].z);
+                    if (dst1[e] < 0 && PVB_NOT_DUMP(dst1[e])) Y::store(mine2 + dst1[e], 1, o1[i].x + xv[e].y, o1[i].y + xv[e].w);
                 }
             }
         }
@@ -2132,7 +2137,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int sa = (j < 4 ? yAlo : yAhi) + YSS * j, sb = (j < 4 ? yBlo : yBhi) - YSS * j;
-            cpx2 yk = ring_load_planes<G::XQ_SLOTS>(mine, sa), ym = ring_load_planes<G::XQ_SLOTS>(mine, sb);
+            cpx2 yk = RingY<G::XQ_SLOTS>::load_bin(mine, sa), ym = RingY<G::XQ_SLOTS>::load_bin(mine, sb);
             if (j == 4) {                        // thread 0: k == 0, bins 0 and N/2 enter with their real part only
                 yk.im = make_float2(l0 ? 0.f : yk.im.x, l0 ? 0.f : yk.im.y);
                 ym.im = make_float2(l0 ? 0.f : ym.im.x, l0 ? 0.f : ym.im.y);
@@ -2142,7 +2147,7 @@ __device__ __forceinline__ bool ring_one_call(const RingParams &p, const int hop
         }
         cpx2 zh, dummy;
         {
-            const cpx2 y = ring_load_planes<G::XQ_SLOTS>(mine, M / 2 + ((M / 2) >> YS));
+            const cpx2 y = RingY<G::XQ_SLOTS>::load_bin(mine, M / 2 + ((M / 2) >> YS));
             ring_unsplit(y, y, PVB_TWH(twh + M / 2), zh, dummy);
         }
         a[0] = sel(l0, zk[4], zk[0]);
