@@ -146,3 +146,38 @@ def test_three_colours_suffice_for_pitch_factors_from_one_half():
             img.append((max(s + delta[i], 0), min(e + delta[i], nb)))
         for i in range(len(peaks) - 3):
             assert img[i + 3][0] >= img[i][1]
+
+
+@pytest.mark.parametrize("n", [256, 1024, 4096])
+def test_second_stale_level_from_the_spectrum(oracle, n):
+    """DEEP instances: slots N/2 + q of the second level (block-tree walk stops at L = N/16, r = 16) are
+    1/16 sum_u W_N^{-s (o + u L)} X[o + u L] over the Hermitian-extended spectrum: 16 terms instead of N/16 samples"""
+    x = np.random.default_rng(9 * n).uniform(-1, 1, n).astype(np.float32)
+    X = oracle.real_transform(x)
+    m = n // 2
+    full = np.concatenate([X[:m + 1], np.conj(X[1:m][::-1])])           # X[k] for k < N from the valid half
+    L = n // 16
+    worst, seen = 0.0, 0
+    for q in range(n // 8 + 1, n // 4):
+        Lw, r, s, o = _walk_block_tree(n, m + q)
+        if r != 16:
+            continue
+        assert Lw == L and s in (10, 14) and o <= n // 32
+        idx = o + L * np.arange(16)
+        rebuilt = np.sum(full[idx] * np.exp(2j * np.pi * s * idx / n)) / 16
+        worst = max(worst, abs(rebuilt - X[m + q]))
+        seen += 1
+    assert seen == 2 * (n // 32) + 1 and worst < 1e-10
+
+
+@pytest.mark.parametrize("n", [256, 1024, 4096])
+def test_quarter_three_slots_from_the_spectrum(oracle, n):
+    """DEEP instances below pitch factor 0.5: slot 3N/4 + o, o <= N/8, holds DFT_{N/4}(x[4m + 3])[o] =
+    1/4 W_N^{-3 o} (X[o] - j X[N/4 + o] - conj X[N/2 - o] + j conj X[N/4 - o])"""
+    x = np.random.default_rng(13 * n).uniform(-1, 1, n).astype(np.float32)
+    X = oracle.real_transform(x)
+    m = n // 2
+    o = np.arange(0, n // 8 + 1)
+    rebuilt = 0.25 * np.exp(2j * np.pi * 3 * o / n) * (X[o] - 1j * X[n // 4 + o] - np.conj(X[m - o]) + 1j * np.conj(X[n // 4 - o]))
+    assert np.abs(rebuilt - X[3 * n // 4 + o]).max() < 1e-11
+    assert np.abs(X[3 * n // 4 + o] - np.fft.fft(x.astype(np.float64)[3::4])[: n // 8 + 1]).max() < 1e-10
