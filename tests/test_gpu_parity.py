@@ -337,6 +337,37 @@ def test_flag_mode_chained_handles_and_back_to_back(oracle, N, hop):
     assert _rms(got_b - ref_b) <= RMS_EXPECTED
 
 
+@pytest.mark.parametrize("N,hop", [(1024, 256), (256, 64), (2048, 128), (4096, 1024)])
+def test_flag_mode_chain_across_kernel_instances(oracle, N, hop):
+    """One handle called back to back on a stream while the pitch factor wanders over the ring-order kernel's
+    three instance kinds (>= 0.75; [0.5, 0.75): ordered sub-steps; < 0.5: atomics) -- they use different CTA shapes
+    (7 / 6 pairs per CTA at frame 1024), and consecutive launches overlap: each pair must still wait for ITS previous
+    call's flag, whichever instance wrote it."""
+    import torch
+    from phaze_b200 import BatchedPhaseVocoder
+    C, calls = 45, 30
+    plan = [0.8, 0.8, 0.6, 0.62, 0.4, 0.8, 0.5, 0.36, 1.3, 0.74, 0.75, 0.49]
+    x = signals.channels(11, C, calls * hop)
+    orc = oracle.OracleProcessor(N, hop, C)
+    ref = np.empty_like(x)
+    for k in range(calls):
+        s = slice(k * hop, (k + 1) * hop)
+        ref[:, s] = orc.process_packed(x[:, s], np.float32(plan[k % len(plan)]))
+    stream = torch.cuda.Stream()
+    xin = torch.from_numpy(np.ascontiguousarray(x.reshape(C, calls, hop).transpose(1, 0, 2))).cuda()
+    out = torch.empty((calls, C, hop), dtype=torch.float32, device="cuda")
+    with BatchedPhaseVocoder(C, N, hop, inputs_ready=1) as pv:
+        torch.cuda.synchronize()
+        for k in range(calls):
+            pv.process_device(xin[k].data_ptr(), out[k].data_ptr(), np.float32(plan[k % len(plan)]), stream.cuda_stream)
+        stream.synchronize()
+        assert pv.ring_stuck_count == 0 and pv.kernel_launches == calls
+    got = out.cpu().numpy().transpose(1, 0, 2).reshape(C, calls * hop)
+    err = _rms(got - ref)
+    print(f"N={N} hop={hop}: rms err {err:.3e}")
+    assert err <= RMS_EXPECTED
+
+
 def test_flag_mode_chained_through_deep_buffer(oracle):
     """Two handles chained through a [K][C][hop] buffer, K = 24 calls per submission, few channels
     (tiny grids: many launches are co-resident) and a faster second handle: B's call j reads what
