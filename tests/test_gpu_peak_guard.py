@@ -48,7 +48,7 @@ def test_parity_noise_floor(oracle, N, hop, pf, noise):
 
 
 @pytest.mark.parametrize("N,hop", [(256, 64), (512, 128), (1024, 256), (1024, 128), (2048, 512), (4096, 1024)])
-@pytest.mark.parametrize("pf", [0.75, 0.8, 1.5])
+@pytest.mark.parametrize("pf", [0.4, 0.6, 0.75, 0.8, 1.5])
 def test_parity_clean_tones_every_frame_size(oracle, N, hop, pf):
     """noise-free tones at every frame size of the ring-order kernel (sub-warp pairs, one warp, two
     and four warps per pair), odd channel count"""
