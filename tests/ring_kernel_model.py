@@ -474,6 +474,68 @@ def gather_rows_kernel(g: Geo, xfull, mask, prev_before, next_after, dtab, contr
     return Y
 
 
+def walk_block_tree(n, pos):
+    """(L, r, s, o): slot `pos` of fft.js's realTransform output holds DFT_L(xw[r m + s])[o] (bundle:394-438 writes
+    only outputs 0 .. L/2 of every length-L block of the radix-4 recursion)"""
+    l0 = 4 if int(np.log2(n)) % 2 == 0 else 2
+    L, r, s, o = n, 1, 0, pos
+    while L > l0 and o > L // 2:
+        q = L // 4
+        sb = o // q
+        o -= sb * q
+        s += r * sb
+        r *= 4
+        L = q
+    return L, r, s, o
+
+
+def deep_shift(g: Geo, Xc, ring, win, tw, t, mask, prev_before, next_after, dtab, d_last, pf):
+    """The middle of the kernel's DEEP instances for one channel.  Xc: spectrum slots (2x scaled, ring order);
+    ring: the channel's history ring [N] (sample n of the frame at (n + t) mod N).  Returns Y[0 .. nb)."""
+    N, M, NB, TP, T = g.N, g.M, g.NB, g.TP, g.T
+    Xv = Xc[xslot(np.arange(M + 1))]
+    full = np.concatenate([Xv, np.conj(Xv[1:M][::-1])]).astype(C64)              # Hermitian extension, k < N
+    n = np.arange(N)
+    xw = (ring[(n + t) % N].astype(F32) * win).astype(F32)                       # windowed frame, frame order
+
+    def stale(q):                                                                # slot N/2 + q in the kernel's units
+        if q == 0:
+            return Xv[M]
+        L, r, s, o = walk_block_tree(N, M + q)
+        if r == 4:                                                               # quarters s = 2 (q <= N/8) and s = 3 (q >= N/4)
+            idx = o + L * np.arange(4)
+            return C64(0.25 * np.sum(full[idx] * np.conj(tw[(s * idx) % N])))
+        if r == 16:                                                              # second level: 16 terms of the spectrum
+            idx = o + L * np.arange(16)
+            return C64(np.sum(full[idx] * np.conj(tw[(s * idx) % N])) / 16)
+        m = np.arange(L)                                                         # deeper: L <= N/64 frame samples
+        acc = np.sum(xw[r * m + s].astype(C64) * tw[(o * r * m) % N])
+        return C64(2 * acc * tw[((M + q) * t) % N])                              # frame order -> ring order, 2x scale
+
+    # owner (ordinal of the peak) and destination of every bin of every run
+    peaks = np.array([int(16 * L + e) for L in range(TP) for e in range(16) if (int(mask[L]) >> e) & 1])
+    b = np.arange(16 * TP)
+    hi = np.searchsorted(peaks, b, side="right")                                 # first peak above b
+    lo = hi - 1
+    take_next = (lo < 0) | ((hi < len(peaks)) & (peaks[np.minimum(hi, len(peaks) - 1)] - b <= b - peaks[np.maximum(lo, 0)]))
+    ordinal = np.where(take_next, hi, lo)
+    dest = b + dtab[peaks[ordinal]]
+    Y = np.zeros(NB + 1, C64)
+    ok = (dest >= 0) & (dest < NB)
+    if pf >= 0.5:
+        for colour in range(3):                                                  # pairwise disjoint inside a sub-step
+            sel = ok & (ordinal % 3 == colour)
+            assert len(set(dest[sel].tolist())) == int(sel.sum()), "two writers for one bin inside a coloured sub-step"
+            Y[dest[sel]] += Xv[b[sel]]
+    else:
+        np.add.at(Y, dest[ok], Xv[b[ok]])
+    for q in range(0, N // 3 + 2):                                               # the last region beyond bin N/2 - 1
+        d = M + q + d_last
+        if 0 <= d < NB:
+            Y[d] += stale(q)
+    return Y[:NB]
+
+
 def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None, capture: dict | None = None):
     """One process() call of one channel pair.  hist2/acc2: [N][2] float32 rings (modified in
     place), inblk: [2][hop] or None (paused), t = timeCursor (multiple of hop).  Returns out[2][hop]."""
@@ -661,6 +723,14 @@ def step(g: Geo, hist2, acc2, inblk, t, pf32, hop, cf: Conflicts | None = None, 
             if hi: next_after[L] = own_first[hi[0]]
         p_last = own_last[np.nonzero(nz)[0][-1]]
         d_last = int(dtab[p_last])
+
+        if float(pf32) < 0.75:
+            # DEEP instances (pitch factors in [0.33, 0.75)): every stale slot the last region reaches, and the
+            # scatter in three coloured sub-steps (>= 0.5) or with atomic adds (below)
+            Yd = deep_shift(g, Xc.copy(), hist2[:, ch], win, tw, t, mask, prev_before, next_after, dtab, d_last, float(pf32))
+            X[ch, :] = 0
+            X[ch, xslot(np.arange(NB))] = Yd
+            continue
 
         # extension: bin M and the first stale level (bundle:394-438), owned by the last peak
         ext = np.zeros((4, TP), C64)

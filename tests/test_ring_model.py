@@ -34,6 +34,25 @@ def test_model_matches_oracle(oracle, frame, hop, pf, calls, start):
     assert _rms(got - ref) <= 2e-8
 
 
+@pytest.mark.parametrize("frame,hop,pf,calls,start", [
+    (1024, 256, 0.6, 9, 0), (1024, 256, 0.5, 9, 3), (1024, 128, 0.7, 18, 1), (1024, 256, 0.74, 8, 0),
+    (1024, 256, 0.4, 9, 2), (1024, 256, 0.34, 9, 0), (1024, 512, 0.45, 6, 1),
+    (2048, 128, 0.55, 20, 3), (2048, 512, 0.36, 7, 0), (512, 128, 0.62, 12, 1), (512, 128, 0.4, 12, 0),
+    (4096, 1024, 0.5, 5, 1), (4096, 1024, 0.38, 5, 0), (256, 64, 0.6, 14, 1), (256, 64, 0.35, 14, 2),
+])
+def test_model_deep_instances_match_oracle(oracle, frame, hop, pf, calls, start):
+    """pitch factors in [0.33, 0.75): the stale slots the last region reaches (first level and the quarter 3N/4 + o
+    from four spectrum terms, second level from sixteen, deeper levels from N/64 or fewer windowed frame samples)
+    and the scatter in three coloured sub-steps (the model asserts that no sub-step has two writers for a bin)"""
+    x = signals.channels(21, 2, calls * hop)
+    ref_p = oracle.OracleProcessor(frame, hop, 2)
+    ref_p.time_cursor = start * hop
+    ref = ref_p.run(x, np.float32(pf))
+    got = model.run(x, pf, hop, start_calls=start, frame=frame)
+    assert _rms(ref) > 1e-3
+    assert _rms(got - ref) <= 5e-8
+
+
 def test_model_shared_memory_patterns_are_conflict_free(oracle):
     """every 128-bit exchange pattern of the three radix-8 passes and the run reads take the
     minimum number of wavefronts; the split stores at most twice that (lane 0 is special)"""
