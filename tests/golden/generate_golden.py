@@ -36,6 +36,9 @@ CASES = [
     ("c3_2048_512_pf1.5_stereo", 2048, 512, 2, 1.5, 10, 5),     # BASELINE config 3 arithmetic
     ("c4_1024_256_pf1.25", 1024, 256, 1, 1.25, 10, 7),          # BASELINE config 4 arithmetic
     ("deep_1024_256_pf0.5", 1024, 256, 1, 0.5, 8, 8),           # reads the deeper stale levels
+    ("deep_1024_256_pf0.36", 1024, 256, 1, 0.36, 8, 14),        # ... and the quarter 3N/4 + o (the demo's low end: 0.5 / 1.5)
+    ("deep_native_2048_128_pf0.6", None, None, 1, 0.6, 20, 15), # the reference as shipped, low end of its pitch slider
+    ("deep_256_64_pf0.4", 256, 64, 2, 0.4, 12, 16),
     ("sweep_256_64_pf0.8", 256, 64, 2, 0.8, 12, 9),             # BASELINE config 5 ends
     ("sweep_512_128_pf1.2", 512, 128, 1, 1.2, 10, 11),
     ("sweep_4096_1024_pf0.8", 4096, 1024, 1, 0.8, 6, 12),
@@ -109,6 +112,11 @@ def run_scenario():
 
 if __name__ == "__main__":
     only_tonal = len(sys.argv) > 1 and sys.argv[1] == "tonal"
+    if len(sys.argv) > 2 and sys.argv[1] == "only":            # python generate_golden.py only <name prefix>
+        for case in CASES:
+            if case[0].startswith(sys.argv[2]):
+                run_case(*case)
+        sys.exit(0)
     if not only_tonal:
         for case in CASES:
             run_case(*case)
